@@ -1,0 +1,161 @@
+/*
+ * sdtgpu.h — C ABI of the B200-native pregraph k-mer hashing path (libsdtgpu.so).
+ *
+ * The reference (SOAPdenovo-Trans 1.04) has no plugin/FFI interface; its seam for this path is
+ * a C function boundary inside one process.  Each entry point below names the reference
+ * interface it replaces (paths relative to /root/reference/src).  Everything is extern "C",
+ * plain pointers and sizes; no C++/torch types; every call returns 0 or an SDTGPU_E* code and
+ * never calls exit() — the C caller turns a non-zero status into the reference's
+ * printf + exit(-1) convention (check.c:31-34).
+ *
+ * Input reads are 2-bit packed in the reference's tight-string convention (seq.c:49-90): four
+ * bases per byte, first base in bits 7..6, codes A=0 C=1 T=2 G=3 (inc/def.h:39); read i starts
+ * at packed + i*stride_bytes (stride_bytes a multiple of 4, >= ceil(max_read_len/4)), which
+ * mirrors the reference's fixed-stride seqBuffer[maxReadNum][maxReadLen] (prlHashReads.c:387-395).
+ */
+#ifndef SDTGPU_H
+#define SDTGPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDTGPU_OK        0
+#define SDTGPU_EINVAL    1	/* bad argument (K even / out of range, misaligned buffer, ...) */
+#define SDTGPU_ECUDA     2	/* CUDA runtime error; see sdtgpu_last_error */
+#define SDTGPU_ENOMEM    3	/* host or device allocation failed */
+#define SDTGPU_ERANGE    4	/* ordinal / capacity limit exceeded */
+#define SDTGPU_ESTATE    5	/* call not valid in the handle's current state */
+
+typedef struct sdtgpu sdtgpu_t;
+
+/* One exported node: the reference's kmer_t (inc/newhash.h:65-77) plus bookkeeping.
+ * key[0] is the most significant word (high1), key[3] the least (low2 / the MER31 scalar).
+ * rword = r_links | linear<<24 | deleted<<25 | checked<<26 | single<<27 | twin<<28 | inEdge<<30,
+ * i.e. the raw bit-field word that follows l_links in kmer_t.  ordinal is the position of the
+ * k-mer's first instance in the reference's arrival order (read ordinal * max windows + window). */
+typedef struct sdtgpu_node {
+	uint64_t key[4];
+	uint32_t l_links;
+	uint32_t rword;
+	uint32_t count;
+	uint32_t set;		/* hash_kmer(key) % thrd_num (hashFunction.c:108, prlHashReads.c:81) */
+	uint64_t ordinal;
+} sdtgpu_node;		/* 56 bytes */
+
+/* Binary-compatible with the reference's KmerSet (inc/newhash.h:79-88).  array points to
+ * kmer_t records of node_bytes each (24 for MER31, 32 for MER63, 48 for MER127); array, flags and
+ * the struct itself come from malloc/calloc so the reference's free_Sets (newhash.c:498) can
+ * release them. */
+typedef struct sdtgpu_kmerset {
+	void *array;
+	uint32_t *flags;
+	uint64_t size;
+	uint64_t count;
+	uint64_t max;
+	double load_factor;
+	uint64_t iter_ptr;
+} sdtgpu_kmerset;
+
+typedef struct sdtgpu_stats {
+	uint64_t n_instances;	/* "kmer in reads"  (kmerCounter[0], prlHashReads.c:466,662) */
+	uint64_t n_nodes;	/* "nodes allocated" (sum of count_kmerset, prlHashReads.c:657) */
+	uint64_t n_removed;	/* "%lld kmer removed" (deLowCov, prlHashReads.c:908) */
+	uint64_t n_linear;	/* "%lld linear nodes" (Mark1in1outNode, prlHashReads.c:991) */
+	uint64_t capacity;	/* device slots */
+	uint64_t n_reads;	/* reads pushed (including those shorter than K+1, which are skipped) */
+	uint32_t n_grows;	/* device table re-hashes so far */
+	uint32_t device_key_words;	/* 1, 2 or 4 */
+} sdtgpu_stats;
+
+/* ---- life cycle.  Replaces the set-up part of prlRead2HashTable (prlHashReads.c:355-426):
+ * createFilter, the kmerBuffer/hashBanBuffer/prevc/nextc batch buffers, init_kmerset x thrd_num
+ * and creatThrds.  K odd, 13..127 (pregraph.c:38-59).  key_words is the reference build being
+ * served (1 = MER31, 2 = MER63, 4 = MER127) and fixes hash_kmer's byte count and the exported
+ * kmer_t size; the device key width is ceil(2K/64) words independently of it.
+ * capacity_hint = expected distinct k-mers (0: start small and grow by device re-hash).
+ * device = CUDA ordinal.  flags: SDTGPU_F_* */
+#define SDTGPU_F_NKMER     1u	/* the reference's -n (N_kmer): windows containing N become key 0 without links */
+int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_read_len,
+		   uint64_t capacity_hint, unsigned flags);
+void sdtgpu_destroy (sdtgpu_t *h);
+const char *sdtgpu_last_error (const sdtgpu_t *h);	/* h may be NULL: last create() failure */
+int sdtgpu_reset (sdtgpu_t *h);	/* empty the table, keep the allocation */
+
+/* ---- the hot path.  Replaces one `sendWorkSignal(2); sendWorkSignal(1);` flush
+ * (prlHashReads.c:466-471, 524-527, 561-564, 603-606, 617-619), i.e. chopKmer4read
+ * (prlHashReads.c:164-310) over the batch followed by put_kmerset (newhash.c:411-462) of every
+ * window.  lens == NULL means every read has uniform_len bases.  nmask (1 bit per base, bit 7 of
+ * byte 0 = base 0, stride mask_stride_bytes) is only read with SDTGPU_F_NKMER and may be NULL.
+ * first_read_ordinal = number of reads pushed before this batch in arrival order (needed only
+ * for export_kmersets' slot-exact layout; pass the running count).
+ * push_reads takes HOST buffers (pageable or pinned), copies them and returns once the copy is
+ * enqueued on the handle's stream; the kernels run asynchronously (the reference does not overlap
+ * parsing with hashing; doing so is allowed because the table is order-free).
+ * push_reads_device takes DEVICE pointers (16-byte aligned) and only enqueues kernels. */
+int sdtgpu_push_reads (sdtgpu_t *h, const uint8_t *packed, const uint32_t *lens, const uint8_t *nmask,
+		       uint64_t n_reads, uint32_t uniform_len, uint32_t stride_bytes, uint64_t first_read_ordinal);
+int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32_t *d_lens, const uint8_t *d_nmask,
+			      uint64_t n_reads, uint32_t uniform_len, uint32_t stride_bytes, uint64_t first_read_ordinal);
+int sdtgpu_sync (sdtgpu_t *h);
+
+/* ---- multi-GPU exchange (one process per GPU; the caller moves the bins, e.g. NCCL all-to-all).
+ * The reference's equivalent is "every worker scans the shared hashBanBuffer and keeps
+ * hash % thrd_num == id" (prlHashReads.c:79-88).  bucket_reads_device chops this rank's reads and
+ * appends each instance as a 16*ceil(W/1)-byte record to the bin of its owner rank
+ * (owner = mix(key) -> [0, n_ranks)); insert_records_device upserts received records.
+ * Record layout (little endian u64 words): key words (device_key_words, most significant first),
+ * then one meta word = ordinal << 8 | left << 4 | right  (left/right 0..3, or 4 = none).
+ * d_bins holds n_ranks bins of bin_capacity records each; d_counts[n_ranks] (u64) must be zeroed
+ * by the caller and receives the fill of each bin (a bin that would overflow is reported through
+ * SDTGPU_ERANGE at the next sdtgpu_sync). */
+size_t sdtgpu_record_bytes (const sdtgpu_t *h);
+int sdtgpu_bucket_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32_t *d_lens, const uint8_t *d_nmask,
+				uint64_t n_reads, uint32_t uniform_len, uint32_t stride_bytes, uint64_t first_read_ordinal,
+				int n_ranks, void *d_bins, uint64_t bin_capacity, uint64_t *d_counts);
+int sdtgpu_insert_records_device (sdtgpu_t *h, const void *d_records, uint64_t n_records);
+
+/* ---- post-pass.  Replaces deLowCov/thread_delow (prlHashReads.c:844-909; only when
+ * deLowKmer > 0), Mark1in1outNode/thread_mark (prlHashReads.c:911-992) and the histogram behind
+ * freqStat (prlHashReads.c:994-1023): kmerFreq[i] for i in 0..256, the reference prints 1..255.
+ * May be called once per table; push after finalize is SDTGPU_ESTATE. */
+int sdtgpu_finalize (sdtgpu_t *h, int deLowKmer, int64_t kmerFreq[257], sdtgpu_stats *stats);
+int sdtgpu_get_stats (sdtgpu_t *h, sdtgpu_stats *stats);
+
+/* ---- hand-back.  export_nodes copies every node (unordered unless sort_by_ordinal) to host
+ * memory; thrd_num fixes node.set.  export_kmersets builds thrd_num reference KmerSets whose
+ * (set, slot) layout is exactly what the reference's own init_kmerset(1024,0.77f) + put_kmerset
+ * sequence would have produced for the same reads in the same order (newhash.c:160-193,
+ * 293-462), which is what node2edge.c:46, cutTipPreGraph.c:1012 and prlRead2path.c:817 consume.
+ * sets must point to thrd_num pointers; each receives a malloc'ed sdtgpu_kmerset. */
+int sdtgpu_export_count (sdtgpu_t *h, uint64_t *n_nodes);
+int sdtgpu_export_nodes (sdtgpu_t *h, int thrd_num, int sort_by_ordinal, sdtgpu_node *out, uint64_t max_nodes, uint64_t *n_nodes);
+int sdtgpu_export_kmersets (sdtgpu_t *h, int thrd_num, sdtgpu_kmerset **sets);
+/* the host half of export_kmersets, usable on nodes merged from several ranks */
+int sdtgpu_build_kmersets (const sdtgpu_node *nodes, uint64_t n_nodes, int key_words, int thrd_num,
+			   const uint64_t *set_last_ordinal /* [thrd_num] or NULL */, sdtgpu_kmerset **sets);
+void sdtgpu_free_kmersets (sdtgpu_kmerset **sets, int thrd_num);
+
+/* ---- measurement hooks */
+void *sdtgpu_stream (sdtgpu_t *h);	/* the cudaStream_t all work of this handle is enqueued on */
+/* device time (ms, CUDA events on the handle's stream) and launch count accumulated by the insert
+ * kernels since the last call with reset != 0 */
+int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *insert_launches, uint64_t *all_launches);
+
+/* ---- synthetic reads on the device (bench/test utility; bit-identical to synth.py).
+ * d_tr_bases: uint8 codes of all transcripts; d_starts u64[T]; d_lengths u32[T]; d_cum u64[T]. */
+int sdtgpu_synth_reads_device (int device, void *stream, const uint8_t *d_tr_bases, const uint64_t *d_starts,
+			       const uint32_t *d_lengths, const uint64_t *d_cum, uint32_t n_transcripts,
+			       uint64_t seed, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len,
+			       uint32_t stride_bytes, uint8_t *d_packed_out);
+
+/* reference helpers restated for host callers (tests bind them) */
+uint64_t sdtgpu_hash_kmer (const uint64_t key[4], int key_words);	/* hashFunction.c:108 */
+int sdtgpu_version (void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

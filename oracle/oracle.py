@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.sdto_run_set_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sdto_run_dump.argtypes = [C.c_void_p, C.c_void_p]
         L.sdto_run_destroy.argtypes = [C.c_void_p]
+        L.sdto_run_set_max_read_len.argtypes = [C.c_void_p, C.c_int]
+        L.sdto_run_first_ordinals.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -101,21 +103,23 @@ def chop_read(codes: np.ndarray, K: int, key_words: int, n_kmer: int = 0):
 
 
 class OracleResult:
-    def __init__(self, records, nodes, instances, removed, linear, freq, set_info):
+    def __init__(self, records, nodes, instances, removed, linear, freq, set_info, first_ordinals=None):
         self.records = records          # RECORD array in (set, slot) order
+        self.first_ordinals = first_ordinals  # uint64 per record: read index * (max_read_len-K+1) + window
         self.nodes, self.instances, self.removed, self.linear = nodes, instances, removed, linear
         self.kmerfreq = freq            # int64[257]
         self.set_info = set_info        # uint64[thrd_num, 3] size, count, max
 
 
 def run_hashing(reads: np.ndarray, lens: np.ndarray, K: int, key_words: int, thrd_num: int = 8,
-                deLowKmer: int = 0, n_kmer: int = 0, batches: int = 1) -> OracleResult:
+                deLowKmer: int = 0, n_kmer: int = 0, batches: int = 1, max_read_len: int = 0) -> OracleResult:
     """The oracle's prlRead2HashTable on in-memory reads (`reads`[n, L] base codes, `lens`[n])."""
     L = lib()
     reads = np.ascontiguousarray(reads, dtype=np.uint8)
     lens = np.ascontiguousarray(lens, dtype=np.uint32)
     n, width = reads.shape if reads.ndim == 2 else (0, 0)
     h = L.sdto_run_create(K, key_words, thrd_num, n_kmer)
+    L.sdto_run_set_max_read_len(h, max_read_len or width)
     try:
         step = max((n + batches - 1) // batches, 1)
         for a in range(0, n, step):
@@ -133,7 +137,10 @@ def run_hashing(reads: np.ndarray, lens: np.ndarray, K: int, key_words: int, thr
         info = np.zeros((thrd_num, 3), dtype=np.uint64)
         for t in range(thrd_num):
             L.sdto_run_set_info(h, t, info[t].ctypes.data)
-        return OracleResult(rec, nodes, L.sdto_run_instances(h), L.sdto_run_removed(h), L.sdto_run_linear(h), freq, info)
+        first = np.zeros(nodes, dtype=np.uint64)
+        if nodes:
+            L.sdto_run_first_ordinals(h, first.ctypes.data)
+        return OracleResult(rec, nodes, L.sdto_run_instances(h), L.sdto_run_removed(h), L.sdto_run_linear(h), freq, info, first)
     finally:
         L.sdto_run_destroy(h)
 

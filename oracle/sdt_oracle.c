@@ -259,7 +259,7 @@ int sdto_chop_read (const uint8_t *src, int len, int K, int key_words, int N_kme
 #define R_SINGLE  0x08000000u
 #define R_LINKS   0x00FFFFFFu
 
-typedef struct { sdto_kmer seq; uint32_t l_links, rword, count; } node_t;
+typedef struct { sdto_kmer seq; uint32_t l_links, rword, count; uint64_t first; } node_t;	/* first: test bookkeeping (ordinal of the first instance), not part of kmer_t */
 typedef struct {
 	node_t *array;
 	uint32_t *flags;
@@ -398,7 +398,7 @@ static void set_encap (set_t *s, uint64_t num, int key_words)	/* encap_kmerset, 
 	free (oldf);
 }
 
-static void set_put (set_t *s, sdto_kmer seq, unsigned left, unsigned right, int key_words)	/* put_kmerset, newhash.c:411-462 */
+static void set_put (set_t *s, sdto_kmer seq, unsigned left, unsigned right, int key_words, uint64_t ordinal)	/* put_kmerset, newhash.c:411-462 */
 {
 	uint64_t hc;
 	set_encap (s, 1, key_words);
@@ -413,6 +413,7 @@ static void set_put (set_t *s, sdto_kmer seq, unsigned left, unsigned right, int
 			m->seq = seq;
 			m->rword = R_SINGLE;
 			m->count = 1;
+			m->first = ordinal;
 			if (left < 4)
 				m->l_links |= 1u << (6 * left);
 			if (right < 4)
@@ -450,7 +451,8 @@ static void set_put (set_t *s, sdto_kmer seq, unsigned left, unsigned right, int
 struct sdto_run {
 	int K, key_words, thrd_num, N_kmer;
 	set_t **sets;
-	uint64_t instances, removed, linear;
+	uint64_t instances, removed, linear, reads_seen;
+	int max_read_len;
 	int64_t freq[257];
 	sdto_kmer *kbuf;
 	uint8_t *pbuf, *nbuf;
@@ -462,6 +464,7 @@ sdto_run *sdto_run_create (int K, int key_words, int thrd_num, int N_kmer)
 	sdto_run *r = (sdto_run *) calloc (1, sizeof *r);
 	int i;
 	r->K = K; r->key_words = key_words; r->thrd_num = thrd_num; r->N_kmer = N_kmer;
+	r->max_read_len = 1 << 16;
 	r->sets = (set_t **) malloc (sizeof (set_t *) * thrd_num);
 	for (i = 0; i < thrd_num; i++)
 		r->sets[i] = set_init (1024, 0.77f);	/* prlHashReads.c:402-416 */
@@ -489,9 +492,11 @@ void sdto_run_push (sdto_run *r, const uint8_t *bases, const uint64_t *offsets, 
 		for (i = 0; i < n; i++)
 		{	/* owner = hashBan % thrd_num (prlHashReads.c:81); per-set order = instance order */
 			uint64_t h = sdto_hash_kmer (r->kbuf[i], r->key_words);
-			set_put (r->sets[h % r->thrd_num], r->kbuf[i], r->pbuf[i], r->nbuf[i], r->key_words);
+			set_put (r->sets[h % r->thrd_num], r->kbuf[i], r->pbuf[i], r->nbuf[i], r->key_words,
+				 (r->reads_seen + t) * (uint64_t) (r->max_read_len - r->K + 1) + (uint64_t) i);
 		}
 	}
+	r->reads_seen += n_reads;
 }
 
 void sdto_run_finalize (sdto_run *r, int deLowKmer)
@@ -601,6 +606,20 @@ void sdto_run_dump (const sdto_run *r, sdto_record *out)
 			n++;
 		}
 	}
+}
+
+/* test bookkeeping: ordinal (read index * (max_read_len-K+1) + window) of each node's first
+ * instance, in dump order; max_read_len must be set before the first push */
+void sdto_run_set_max_read_len (sdto_run *r, int max_read_len) { r->max_read_len = max_read_len; }
+
+void sdto_run_first_ordinals (const sdto_run *r, uint64_t *out)
+{
+	uint64_t n = 0, p;
+	int t;
+	for (t = 0; t < r->thrd_num; t++)
+		for (p = 0; p < r->sets[t]->size; p++)
+			if (!F_NULL (r->sets[t]->flags, p))
+				out[n++] = r->sets[t]->array[p].first;
 }
 
 void sdto_run_destroy (sdto_run *r)

@@ -1,0 +1,751 @@
+// sdtgpu.cu — C ABI (include/sdtgpu.h) over the sm_100a kernels in sdt_kernels.cuh.
+// Host-side plumbing only: streams, staging, capacity management, launches, D2H of results.
+// There is NO CPU fallback: every entry point either runs the CUDA path or returns an error.
+#include "../../include/sdtgpu.h"
+#include "sdt_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sdt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Staging
+{
+	uint8_t *d_packed = nullptr, *d_mask = nullptr;
+	u32 *d_lens = nullptr;
+	size_t cap_packed = 0, cap_mask = 0, cap_lens = 0;
+	cudaEvent_t free_ev = nullptr;	// recorded on the compute stream after the kernel that read this buffer
+	cudaEvent_t ready_ev = nullptr;	// recorded on the copy stream after the H2D copies
+};
+
+}	// namespace
+
+struct sdtgpu
+{
+	int device = 0, K = 0, key_words = 0, W = 0, max_read_len = 0;
+	u32 maxwin = 0;
+	unsigned flags = 0;
+	void *table = nullptr;
+	u64 cap = 0;
+	bool grow_mode = false;
+	Counters *d_ctr = nullptr;
+	Counters *h_ctr = nullptr;	// pinned mirror
+	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	Staging stage[2];
+	int next_stage = 0;
+	int sm_count = 0;
+	u64 pushed_upper = 0;	// upper bound of instances pushed (host-side arithmetic)
+	u64 n_reads = 0;
+	u32 n_grows = 0;
+	bool finalized = false;
+	int deLowKmer = 0;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+	std::vector<cudaEvent_t> ev_pool;
+	u64 insert_launches = 0, all_launches = 0;
+	double insert_ms_acc = 0;
+	std::string err;
+};
+
+namespace {
+
+#define CK(h, call)                                                                                     \
+	do                                                                                              \
+	{                                                                                               \
+		cudaError_t e_ = (call);                                                                \
+		if (e_ != cudaSuccess)                                                                  \
+		{                                                                                       \
+			char b_[512];                                                                   \
+			snprintf (b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString (e_), __FILE__, __LINE__); \
+			(h)->err = b_;                                                                  \
+			return e_ == cudaErrorMemoryAllocation ? SDTGPU_ENOMEM : SDTGPU_ECUDA;          \
+		}                                                                                       \
+	} while (0)
+
+size_t slot_bytes (int W) { return W == 4 ? sizeof (Slot4) : 32; }
+
+int fail (sdtgpu *h, int code, const char *msg)
+{
+	h->err = msg;
+	return code;
+}
+
+template <int W> void launch_init (sdtgpu *h, void *table, u64 cap)
+{
+	const u64 want = (cap + BLOCK - 1) / BLOCK;
+	const unsigned grid = (unsigned) std::min<u64> (want, (u64) h->sm_count * 16);
+	init_table_kernel<W><<<grid, BLOCK, 0, h->stream>>> (static_cast<typename SlotOf<W>::type *> (table), cap);
+	h->all_launches++;
+}
+
+int init_table (sdtgpu *h, void *table, u64 cap)
+{
+	switch (h->W)
+	{
+	case 1: launch_init<1> (h, table, cap); break;
+	case 2: launch_init<2> (h, table, cap); break;
+	default: launch_init<4> (h, table, cap); break;
+	}
+	CK (h, cudaGetLastError ());
+	return SDTGPU_OK;
+}
+
+template <int W> void launch_rehash (sdtgpu *h, void *old, u64 old_cap, void *neu, u64 cap)
+{
+	typedef typename SlotOf<W>::type S;
+	const unsigned grid = (unsigned) std::min<u64> ((old_cap + BLOCK - 1) / BLOCK, (u64) h->sm_count * 16);
+	rehash_kernel<W><<<grid, BLOCK, 0, h->stream>>> (static_cast<const S *> (old), old_cap, static_cast<S *> (neu), cap);
+	h->all_launches++;
+}
+
+int read_counters (sdtgpu *h)
+{
+	CK (h, cudaMemcpyAsync (h->h_ctr, h->d_ctr, sizeof (Counters), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	return SDTGPU_OK;
+}
+
+// Keep the load factor bounded before `incoming` more instances are inserted.  With a capacity
+// hint the table is sized once (load <= 0.5 at the hinted count) and only re-hashed if the hint
+// turns out too small; without one it starts small and doubles, like the reference's
+// encap_kmerset (newhash.c:293-409) but on the device.
+int ensure_capacity (sdtgpu *h, u64 incoming)
+{
+	const double max_load = 0.70;
+	if ((double) (h->pushed_upper + incoming) <= max_load * (double) h->cap)
+		return SDTGPU_OK;	// even if every instance were distinct the table stays below max_load
+	int rc = read_counters (h);
+	if (rc)
+		return rc;
+	const u64 nodes = h->h_ctr->n_nodes;
+	if ((double) (nodes + incoming) <= max_load * (double) h->cap)
+		return SDTGPU_OK;
+	u64 new_cap = std::max<u64> (h->cap * 2, (u64) ((double) (nodes + incoming) / 0.45) + 1024);
+	void *neu = nullptr;
+	CK (h, cudaMalloc (&neu, new_cap * slot_bytes (h->W)));
+	rc = init_table (h, neu, new_cap);
+	if (rc)
+		return rc;
+	switch (h->W)
+	{
+	case 1: launch_rehash<1> (h, h->table, h->cap, neu, new_cap); break;
+	case 2: launch_rehash<2> (h, h->table, h->cap, neu, new_cap); break;
+	default: launch_rehash<4> (h, h->table, h->cap, neu, new_cap); break;
+	}
+	CK (h, cudaGetLastError ());
+	CK (h, cudaStreamSynchronize (h->stream));
+	CK (h, cudaFree (h->table));
+	h->table = neu;
+	h->cap = new_cap;
+	h->n_grows++;
+	return SDTGPU_OK;
+}
+
+cudaEvent_t get_event (sdtgpu *h)
+{
+	if (!h->ev_pool.empty ())
+	{
+		cudaEvent_t e = h->ev_pool.back ();
+		h->ev_pool.pop_back ();
+		return e;
+	}
+	cudaEvent_t e = nullptr;
+	cudaEventCreate (&e);
+	return e;
+}
+
+u32 pick_tile_reads (u32 stride_bytes)
+{
+	u32 t = (16384u / stride_bytes) & ~3u;
+	return std::max (4u, std::min ((u32) MAX_TILE_READS, t));
+}
+
+size_t insert_smem_bytes (const ReadBatch &rb, bool nmode)
+{
+	const size_t sw = rb.stride_bytes / 4, mw = nmode ? (rb.mask_stride + 3) / 4 : 0;
+	return 4 * (2 * TILE_PAD + rb.tile_reads * sw + rb.tile_reads + 4 + rb.tile_reads * mw);
+}
+
+template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const ReadBatch &rb, const Bins &bins)
+{
+	typedef typename SlotOf<W>::type S;
+	auto kern = insert_reads_kernel<W, NMODE, MODE>;
+	const size_t smem = insert_smem_bytes (rb, NMODE);
+	if (smem > 48 * 1024)
+		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	int occ = 0;
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, BLOCK, smem));
+	if (occ < 1)
+		return fail (h, SDTGPU_EINVAL, "read stride too large for one shared-memory tile");
+	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
+	const unsigned grid = (unsigned) std::min<u64> (n_tiles, (u64) h->sm_count * occ);
+	cudaEvent_t e0 = get_event (h), e1 = get_event (h);
+	CK (h, cudaEventRecord (e0, h->stream));
+	kern<<<grid, BLOCK, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, rb, bins, h->d_ctr);
+	CK (h, cudaGetLastError ());
+	CK (h, cudaEventRecord (e1, h->stream));
+	h->timing.emplace_back (e0, e1);
+	h->insert_launches++;
+	h->all_launches++;
+	return SDTGPU_OK;
+}
+
+template <int MODE> int launch_insert (sdtgpu *h, const ReadBatch &rb, const Bins &bins)
+{
+	const bool nmode = (h->flags & SDTGPU_F_NKMER) && rb.nmask;
+	switch (h->W)
+	{
+	case 1: return nmode ? launch_insert_t<1, true, MODE> (h, rb, bins) : launch_insert_t<1, false, MODE> (h, rb, bins);
+	case 2: return nmode ? launch_insert_t<2, true, MODE> (h, rb, bins) : launch_insert_t<2, false, MODE> (h, rb, bins);
+	default: return nmode ? launch_insert_t<4, true, MODE> (h, rb, bins) : launch_insert_t<4, false, MODE> (h, rb, bins);
+	}
+}
+
+int make_batch (sdtgpu *h, ReadBatch &rb, const uint8_t *d_packed, const u32 *d_lens, const uint8_t *d_nmask,
+		u64 n_reads, u32 uniform_len, u32 stride_bytes, u64 first_read_ordinal)
+{
+	if (h->finalized)
+		return fail (h, SDTGPU_ESTATE, "push after finalize");
+	if (stride_bytes == 0 || (stride_bytes & 3) || (u64) stride_bytes * 4 < (u64) h->max_read_len)
+		return fail (h, SDTGPU_EINVAL, "stride_bytes must be a multiple of 4 and hold max_read_len bases");
+	if (((uintptr_t) d_packed & 15) || ((uintptr_t) d_lens & 3))
+		return fail (h, SDTGPU_EINVAL, "device read buffers must be 16-byte aligned");
+	if (!d_lens && uniform_len == 0 && n_reads)
+		return fail (h, SDTGPU_EINVAL, "lens == NULL needs uniform_len");
+	const u64 ord_limit = h->W == 2 ? ORD40_NONE : (1ull << 56);	// meta word keeps 56 bits of ordinal
+	if ((first_read_ordinal + n_reads) >= ord_limit / h->maxwin)
+		return fail (h, SDTGPU_ERANGE, "instance ordinal would overflow the slot's ordinal field");
+	rb.packed = d_packed;
+	rb.lens = d_lens;
+	rb.nmask = (h->flags & SDTGPU_F_NKMER) ? d_nmask : nullptr;
+	rb.n_reads = n_reads;
+	rb.first_read_ordinal = first_read_ordinal;
+	rb.uniform_len = uniform_len;
+	rb.stride_bytes = stride_bytes;
+	rb.mask_stride = stride_bytes / 2;	// 1 bit per base for stride_bytes * 4 bases
+	rb.tile_reads = pick_tile_reads (stride_bytes);
+	rb.K = h->K;
+	rb.max_read_len = (u32) h->max_read_len;
+	rb.maxwin = h->maxwin;
+	return SDTGPU_OK;
+}
+
+u64 instances_upper (const sdtgpu *h, u64 n_reads, u32 uniform_len, bool have_lens)
+{
+	const u32 len = have_lens ? (u32) h->max_read_len : std::min (uniform_len, (u32) h->max_read_len);
+	return len >= (u32) h->K + 1 ? n_reads * (u64) (len - h->K + 1) : 0;
+}
+
+int ensure_stage (sdtgpu *h, Staging &s, size_t packed, size_t lens, size_t mask)
+{
+	if (packed > s.cap_packed)
+	{
+		if (s.d_packed)
+			CK (h, cudaFree (s.d_packed));
+		s.cap_packed = packed + packed / 4 + 4096;
+		CK (h, cudaMalloc (&s.d_packed, s.cap_packed));
+	}
+	if (lens > s.cap_lens)
+	{
+		if (s.d_lens)
+			CK (h, cudaFree (s.d_lens));
+		s.cap_lens = lens + lens / 4 + 4096;
+		CK (h, cudaMalloc (&s.d_lens, s.cap_lens));
+	}
+	if (mask > s.cap_mask)
+	{
+		if (s.d_mask)
+			CK (h, cudaFree (s.d_mask));
+		s.cap_mask = mask + mask / 4 + 4096;
+		CK (h, cudaMalloc (&s.d_mask, s.cap_mask));
+	}
+	return SDTGPU_OK;
+}
+
+// ---- hash_kmer restated for the export partition (hashFunction.c:83-122): CRC-32 table arithmetic
+// carried in a signed int (arithmetic >> 8), over the raw bytes of the reference's Kmer object.
+__constant__ int c_crc[256];
+int h_crc[256];
+bool h_crc_ready = false;
+
+void crc_table_host ()
+{
+	if (h_crc_ready)
+		return;
+	for (unsigned n = 0; n < 256; n++)
+	{
+		unsigned c = n;
+		for (int k = 0; k < 8; k++)
+			c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+		h_crc[n] = (int) c;
+	}
+	h_crc_ready = true;
+}
+
+__host__ __device__ inline u32 hash_kmer_impl (const uint64_t *key, int key_words, const int *tab)
+{
+	int crc = ~0;
+	for (int w = 4 - key_words; w < 4; w++)
+		for (int b = 0; b < 8; b++)
+		{
+			const int byte = (int) (signed char) (unsigned char) (key[w] >> (8 * b));
+			crc = tab[(crc ^ byte) & 0xff] ^ (crc >> 8);
+		}
+	crc = ~crc;
+	return (u32) crc & 0x00ffffffu;
+}
+
+template <int W>
+__global__ void __launch_bounds__ (BLOCK)
+export_kernel (const typename SlotOf<W>::type *table, u64 cap, int key_words, int thrd_num, int deLowKmer,
+	       sdtgpu_node *out, u64 max_nodes, Counters *ctr)
+{
+	for (u64 base = blockIdx.x * (u64) BLOCK; base < cap; base += (u64) gridDim.x * BLOCK)
+	{
+		const u64 i = base + threadIdx.x;
+		const bool occ = i < cap && SlotIO<W>::occupied (table + i);
+		const unsigned m = __ballot_sync (0xFFFFFFFFu, occ);
+		if (!m)
+			continue;
+		const int lane = threadIdx.x & 31;
+		u64 pos = 0;
+		if (lane == 0)
+			pos = atomicAdd (&ctr->export_cursor, (u64) __popc (m));
+		pos = __shfl_sync (0xFFFFFFFFu, pos, 0) + __popc (m & ((1u << lane) - 1u));
+		if (!occ || pos >= max_nodes)
+			continue;
+		Key<W> k;
+		u32 L, R, count;
+		u64 ord;
+		SlotIO<W>::get (table + i, k, L, R, count, ord);
+		sdtgpu_node n;
+#pragma unroll
+		for (int q = 0; q < 4; q++)
+			n.key[q] = q < 4 - W ? 0 : k.w[q - (4 - W)];
+		u32 in_num = 0, out_num = 0;
+#pragma unroll
+		for (int b = 0; b < 4; b++)
+		{
+			in_num += ((L >> (6 * b)) & 63) > 0;
+			out_num += ((R >> (6 * b)) & 63) > 0;
+		}
+		u32 rword = R;
+		if (in_num == 1 && out_num == 1)
+			rword |= 0x01000000u;	// linear  (thread_mark, prlHashReads.c:956-960)
+		if (deLowKmer > 0 && L == 0 && R == 0)
+			rword |= 0x02000000u;	// deleted (thread_delow, prlHashReads.c:876-880)
+		if (count == 1)
+			rword |= 0x08000000u;	// single  (newhash.c:39,103,445)
+		n.l_links = L;
+		n.rword = rword;
+		n.count = count;
+		n.set = hash_kmer_impl (n.key, key_words, c_crc) % (u32) thrd_num;
+		n.ordinal = ord;
+		out[pos] = n;
+	}
+}
+
+}	// namespace
+
+// =================================================================================================
+extern "C" {
+
+int sdtgpu_version (void) { return 1; }
+
+uint64_t sdtgpu_hash_kmer (const uint64_t key[4], int key_words)
+{
+	crc_table_host ();
+	return hash_kmer_impl (key, key_words, h_crc);
+}
+
+const char *sdtgpu_last_error (const sdtgpu_t *h) { return h ? h->err.c_str () : g_create_error.c_str (); }
+
+int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_read_len, uint64_t capacity_hint, unsigned flags)
+{
+	if (!out)
+		return SDTGPU_EINVAL;
+	*out = nullptr;
+	if ((key_words != 1 && key_words != 2 && key_words != 4) || !(K & 1) || K < 13 || K > 32 * key_words - 1)
+	{
+		g_create_error = "K must be odd, 13 <= K <= 32*key_words-1, key_words in {1,2,4} (pregraph.c:38-59)";
+		return SDTGPU_EINVAL;
+	}
+	if (max_read_len < K + 1)
+	{
+		g_create_error = "max_read_len must be at least K+1";
+		return SDTGPU_EINVAL;
+	}
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount (&n_dev);
+	if (e != cudaSuccess || device < 0 || device >= n_dev)
+	{
+		g_create_error = std::string ("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString (e) : "bad ordinal");
+		return SDTGPU_ECUDA;
+	}
+	sdtgpu *h = new sdtgpu ();
+	h->device = device; h->K = K; h->key_words = key_words; h->max_read_len = max_read_len; h->flags = flags;
+	h->W = K <= 31 ? 1 : (K <= 63 ? 2 : 4);
+	h->maxwin = (u32) (max_read_len - K + 1);
+	auto bail = [&](int rc) { g_create_error = h->err; sdtgpu_destroy (h); return rc; };
+	auto body = [&]() -> int {
+		CK (h, cudaSetDevice (device));
+		cudaDeviceProp prop;
+		CK (h, cudaGetDeviceProperties (&prop, device));
+		h->sm_count = prop.multiProcessorCount;
+		CK (h, cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking));
+		CK (h, cudaStreamCreateWithFlags (&h->copy_stream, cudaStreamNonBlocking));
+		for (auto &s : h->stage)
+		{
+			CK (h, cudaEventCreateWithFlags (&s.free_ev, cudaEventDisableTiming));
+			CK (h, cudaEventCreateWithFlags (&s.ready_ev, cudaEventDisableTiming));
+		}
+		CK (h, cudaMalloc (&h->d_ctr, sizeof (Counters)));
+		CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
+		CK (h, cudaMallocHost (&h->h_ctr, sizeof (Counters)));
+		memset (h->h_ctr, 0, sizeof (Counters));
+		crc_table_host ();
+		CK (h, cudaMemcpyToSymbol (c_crc, h_crc, sizeof h_crc));
+		h->grow_mode = capacity_hint == 0;
+		h->cap = capacity_hint ? std::max<u64> (capacity_hint * 2, 1024) : (1ull << 20);
+		CK (h, cudaMalloc (&h->table, h->cap * slot_bytes (h->W)));
+		int rc = init_table (h, h->table, h->cap);
+		if (rc)
+			return rc;
+		CK (h, cudaStreamSynchronize (h->stream));
+		return SDTGPU_OK;
+	};
+	int rc = body ();
+	if (rc)
+		return bail (rc);
+	*out = h;
+	return SDTGPU_OK;
+}
+
+void sdtgpu_destroy (sdtgpu_t *h)
+{
+	if (!h)
+		return;
+	cudaSetDevice (h->device);
+	if (h->stream)
+		cudaStreamSynchronize (h->stream);
+	if (h->copy_stream)
+		cudaStreamSynchronize (h->copy_stream);
+	for (auto &s : h->stage)
+	{
+		cudaFree (s.d_packed); cudaFree (s.d_lens); cudaFree (s.d_mask);
+		if (s.free_ev) cudaEventDestroy (s.free_ev);
+		if (s.ready_ev) cudaEventDestroy (s.ready_ev);
+	}
+	for (auto &p : h->timing) { cudaEventDestroy (p.first); cudaEventDestroy (p.second); }
+	for (auto e : h->ev_pool) cudaEventDestroy (e);
+	cudaFree (h->table);
+	cudaFree (h->d_ctr);
+	if (h->h_ctr) cudaFreeHost (h->h_ctr);
+	if (h->stream) cudaStreamDestroy (h->stream);
+	if (h->copy_stream) cudaStreamDestroy (h->copy_stream);
+	delete h;
+}
+
+int sdtgpu_reset (sdtgpu_t *h)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
+	int rc = init_table (h, h->table, h->cap);
+	if (rc)
+		return rc;
+	h->pushed_upper = 0; h->n_reads = 0; h->finalized = false; h->deLowKmer = 0;
+	return SDTGPU_OK;
+}
+
+void *sdtgpu_stream (sdtgpu_t *h) { return h ? (void *) h->stream : nullptr; }
+
+int sdtgpu_sync (sdtgpu_t *h)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	CK (h, cudaStreamSynchronize (h->copy_stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	return SDTGPU_OK;
+}
+
+int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32_t *d_lens, const uint8_t *d_nmask,
+			      uint64_t n_reads, uint32_t uniform_len, uint32_t stride_bytes, uint64_t first_read_ordinal)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	ReadBatch rb;
+	int rc = make_batch (h, rb, d_packed, d_lens, d_nmask, n_reads, uniform_len, stride_bytes, first_read_ordinal);
+	if (rc || n_reads == 0)
+		return rc;
+	const u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
+	rc = ensure_capacity (h, upper);
+	if (rc)
+		return rc;
+	h->pushed_upper += upper;
+	h->n_reads += n_reads;
+	return launch_insert<0> (h, rb, Bins ());
+}
+
+int sdtgpu_push_reads (sdtgpu_t *h, const uint8_t *packed, const uint32_t *lens, const uint8_t *nmask,
+		       uint64_t n_reads, uint32_t uniform_len, uint32_t stride_bytes, uint64_t first_read_ordinal)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	if (n_reads == 0)
+		return SDTGPU_OK;
+	if (!packed)
+		return fail (h, SDTGPU_EINVAL, "packed == NULL");
+	CK (h, cudaSetDevice (h->device));
+	const bool nmode = (h->flags & SDTGPU_F_NKMER) && nmask;
+	Staging &s = h->stage[h->next_stage];
+	h->next_stage ^= 1;
+	const size_t pbytes = (size_t) n_reads * stride_bytes, lbytes = lens ? (size_t) n_reads * 4 : 0;
+	const size_t mstride = stride_bytes / 2, mbytes = nmode ? (size_t) n_reads * mstride : 0;
+	// the kernel that last read this staging buffer must be done before it is overwritten
+	CK (h, cudaStreamWaitEvent (h->copy_stream, s.free_ev, 0));
+	if (pbytes > s.cap_packed || lbytes > s.cap_lens || mbytes > s.cap_mask)
+	{
+		CK (h, cudaEventSynchronize (s.free_ev));
+		int rc = ensure_stage (h, s, pbytes, lbytes, mbytes);
+		if (rc)
+			return rc;
+	}
+	CK (h, cudaMemcpyAsync (s.d_packed, packed, pbytes, cudaMemcpyHostToDevice, h->copy_stream));
+	if (lens)
+		CK (h, cudaMemcpyAsync (s.d_lens, lens, lbytes, cudaMemcpyHostToDevice, h->copy_stream));
+	if (nmode)
+		CK (h, cudaMemcpyAsync (s.d_mask, nmask, mbytes, cudaMemcpyHostToDevice, h->copy_stream));
+	CK (h, cudaEventRecord (s.ready_ev, h->copy_stream));
+	CK (h, cudaStreamWaitEvent (h->stream, s.ready_ev, 0));
+	int rc = sdtgpu_push_reads_device (h, s.d_packed, lens ? s.d_lens : nullptr, nmode ? s.d_mask : nullptr,
+					   n_reads, uniform_len, stride_bytes, first_read_ordinal);
+	CK (h, cudaEventRecord (s.free_ev, h->stream));
+	return rc;
+}
+
+size_t sdtgpu_record_bytes (const sdtgpu_t *h) { return h ? 8 * (size_t) (h->W + 1) : 0; }
+
+int sdtgpu_bucket_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32_t *d_lens, const uint8_t *d_nmask,
+				uint64_t n_reads, uint32_t uniform_len, uint32_t stride_bytes, uint64_t first_read_ordinal,
+				int n_ranks, void *d_bins, uint64_t bin_capacity, uint64_t *d_counts)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	if (n_ranks < 1 || !d_bins || !d_counts || ((uintptr_t) d_bins & 15))
+		return fail (h, SDTGPU_EINVAL, "bad bins");
+	CK (h, cudaSetDevice (h->device));
+	ReadBatch rb;
+	int rc = make_batch (h, rb, d_packed, d_lens, d_nmask, n_reads, uniform_len, stride_bytes, first_read_ordinal);
+	if (rc || n_reads == 0)
+		return rc;
+	Bins b;
+	b.records = static_cast<u64 *> (d_bins);
+	b.counts = reinterpret_cast<u64 *> (d_counts);
+	b.capacity = bin_capacity;
+	b.n_ranks = (u32) n_ranks;
+	h->n_reads += n_reads;
+	return launch_insert<1> (h, rb, b);
+}
+
+int sdtgpu_insert_records_device (sdtgpu_t *h, const void *d_records, uint64_t n_records)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	if (h->finalized)
+		return fail (h, SDTGPU_ESTATE, "insert after finalize");
+	if (n_records == 0)
+		return SDTGPU_OK;
+	if (!d_records || ((uintptr_t) d_records & (h->W == 1 ? 15 : 7)))
+		return fail (h, SDTGPU_EINVAL, "records must be aligned device memory (16 bytes for 1-word keys, else 8)");
+	CK (h, cudaSetDevice (h->device));
+	int rc = ensure_capacity (h, n_records);
+	if (rc)
+		return rc;
+	h->pushed_upper += n_records;
+	const unsigned grid = (unsigned) std::min<u64> ((n_records + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
+	cudaEvent_t e0 = get_event (h), e1 = get_event (h);
+	CK (h, cudaEventRecord (e0, h->stream));
+	const u64 *rec = static_cast<const u64 *> (d_records);
+	switch (h->W)
+	{
+	case 1: insert_records_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot1 *> (h->table), h->cap, rec, n_records, h->d_ctr); break;
+	case 2: insert_records_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot2 *> (h->table), h->cap, rec, n_records, h->d_ctr); break;
+	default: insert_records_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot4 *> (h->table), h->cap, rec, n_records, h->d_ctr); break;
+	}
+	CK (h, cudaGetLastError ());
+	CK (h, cudaEventRecord (e1, h->stream));
+	h->timing.emplace_back (e0, e1);
+	h->insert_launches++;
+	h->all_launches++;
+	return SDTGPU_OK;
+}
+
+static void fill_stats (sdtgpu *h, sdtgpu_stats *st)
+{
+	st->n_instances = h->h_ctr->n_instances;
+	st->n_nodes = h->h_ctr->n_nodes;
+	st->n_removed = h->h_ctr->n_removed;
+	st->n_linear = h->h_ctr->n_linear;
+	st->capacity = h->cap;
+	st->n_reads = h->n_reads;
+	st->n_grows = h->n_grows;
+	st->device_key_words = (u32) h->W;
+}
+
+int sdtgpu_get_stats (sdtgpu_t *h, sdtgpu_stats *stats)
+{
+	if (!h || !stats)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	int rc = read_counters (h);
+	if (rc)
+		return rc;
+	fill_stats (h, stats);
+	if (h->h_ctr->overflow)
+		return fail (h, SDTGPU_ERANGE, "a record bin overflowed");
+	return SDTGPU_OK;
+}
+
+int sdtgpu_finalize (sdtgpu_t *h, int deLowKmer, int64_t kmerFreq[257], sdtgpu_stats *stats)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	if (h->finalized)
+		return fail (h, SDTGPU_ESTATE, "finalize called twice");
+	if (deLowKmer < 0 || deLowKmer > 127)
+		return fail (h, SDTGPU_EINVAL, "deLowKmer is a char in the reference (0..127)");
+	CK (h, cudaSetDevice (h->device));
+	CK (h, cudaStreamSynchronize (h->copy_stream));
+	const unsigned grid = (unsigned) std::min<u64> ((h->cap + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
+	switch (h->W)
+	{
+	case 1: finalize_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot1 *> (h->table), h->cap, deLowKmer, h->d_ctr); break;
+	case 2: finalize_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot2 *> (h->table), h->cap, deLowKmer, h->d_ctr); break;
+	default: finalize_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot4 *> (h->table), h->cap, deLowKmer, h->d_ctr); break;
+	}
+	CK (h, cudaGetLastError ());
+	h->all_launches++;
+	h->finalized = true;
+	h->deLowKmer = deLowKmer;
+	int rc = read_counters (h);
+	if (rc)
+		return rc;
+	if (kmerFreq)
+		for (int i = 0; i < 257; i++)
+			kmerFreq[i] = (int64_t) h->h_ctr->freq[i];
+	if (stats)
+		fill_stats (h, stats);
+	return SDTGPU_OK;
+}
+
+int sdtgpu_export_count (sdtgpu_t *h, uint64_t *n_nodes)
+{
+	if (!h || !n_nodes)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	int rc = read_counters (h);
+	if (rc)
+		return rc;
+	*n_nodes = h->h_ctr->n_nodes;
+	return SDTGPU_OK;
+}
+
+int sdtgpu_export_nodes (sdtgpu_t *h, int thrd_num, int sort_by_ordinal, sdtgpu_node *out, uint64_t max_nodes, uint64_t *n_nodes)
+{
+	if (!h || !out || !n_nodes || thrd_num < 1)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	int rc = read_counters (h);
+	if (rc)
+		return rc;
+	const u64 n = h->h_ctr->n_nodes;
+	*n_nodes = n;
+	if (n > max_nodes)
+		return fail (h, SDTGPU_ERANGE, "export buffer too small");
+	if (n == 0)
+		return SDTGPU_OK;
+	sdtgpu_node *d_out = nullptr;
+	CK (h, cudaMalloc (&d_out, n * sizeof (sdtgpu_node)));
+	CK (h, cudaMemsetAsync (&h->d_ctr->export_cursor, 0, sizeof (u64), h->stream));
+	const unsigned grid = (unsigned) std::min<u64> ((h->cap + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
+	switch (h->W)
+	{
+	case 1: export_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot1 *> (h->table), h->cap, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
+	case 2: export_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot2 *> (h->table), h->cap, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
+	default: export_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot4 *> (h->table), h->cap, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
+	}
+	h->all_launches++;
+	cudaError_t e = cudaGetLastError ();
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync (out, d_out, n * sizeof (sdtgpu_node), cudaMemcpyDeviceToHost, h->stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize (h->stream);
+	cudaFree (d_out);
+	CK (h, e);
+	if (sort_by_ordinal)
+		std::sort (out, out + n, [](const sdtgpu_node &a, const sdtgpu_node &b) {
+			return a.set != b.set ? a.set < b.set : a.ordinal < b.ordinal;
+		});
+	return SDTGPU_OK;
+}
+
+int sdtgpu_export_kmersets (sdtgpu_t *h, int thrd_num, sdtgpu_kmerset **sets)
+{
+	if (!h || !sets || thrd_num < 1)
+		return SDTGPU_EINVAL;
+	uint64_t n = 0;
+	int rc = sdtgpu_export_count (h, &n);
+	if (rc)
+		return rc;
+	sdtgpu_node *nodes = (sdtgpu_node *) malloc (std::max<uint64_t> (n, 1) * sizeof (sdtgpu_node));
+	if (!nodes)
+		return fail (h, SDTGPU_ENOMEM, "host allocation for export failed");
+	rc = sdtgpu_export_nodes (h, thrd_num, 0, nodes, n, &n);
+	if (!rc)
+	{
+		rc = sdtgpu_build_kmersets (nodes, n, h->key_words, thrd_num, nullptr, sets);
+		if (rc)
+			h->err = "sdtgpu_build_kmersets failed";
+	}
+	free (nodes);
+	return rc;
+}
+
+int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *insert_launches, uint64_t *all_launches)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	CK (h, cudaStreamSynchronize (h->stream));
+	for (auto &p : h->timing)
+	{
+		float ms = 0;
+		CK (h, cudaEventElapsedTime (&ms, p.first, p.second));
+		h->insert_ms_acc += ms;
+		h->ev_pool.push_back (p.first);
+		h->ev_pool.push_back (p.second);
+	}
+	h->timing.clear ();
+	if (insert_ms) *insert_ms = h->insert_ms_acc;
+	if (insert_launches) *insert_launches = h->insert_launches;
+	if (all_launches) *all_launches = h->all_launches;
+	if (reset)
+	{
+		h->insert_ms_acc = 0;
+		h->insert_launches = h->all_launches = 0;
+	}
+	return SDTGPU_OK;
+}
+
+}	// extern "C"

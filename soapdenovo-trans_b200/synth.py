@@ -144,10 +144,11 @@ def pack_reads(reads: np.ndarray, lens: np.ndarray | None = None, stride: int | 
 
 
 def nmask_reads(reads: np.ndarray, stride: int | None = None) -> np.ndarray:
-    """1 bit per base (bit 7 of byte 0 = base 0) set where the base code is 4 (N with -n)."""
+    """1 bit per base (bit 7 of byte 0 = base 0) set where the base code is 4 (N with -n);
+    stride_bytes/2 bytes per read (include/sdtgpu.h)."""
     n, L = reads.shape
     stride = stride or stride_bytes(L)
-    bits = np.zeros((n, stride * 8), dtype=np.uint8)
+    bits = np.zeros((n, stride * 4), dtype=np.uint8)
     bits[:, :L] = reads == 4
     return np.packbits(bits, axis=1, bitorder="big")
 
