@@ -1,0 +1,85 @@
+"""Multi-GPU k-mer exchange: one process per GPU, k-mers sharded by owner.
+
+The reference's only parallelism is hash-partitioned shared-nothing tables (owner =
+hash_kmer % thrd_num, prlHashReads.c:81; every worker scans the whole batch, :79-88).  Here the
+same structure spans GPUs: each rank chops its own reads and buckets every instance by owner rank
+(sdtgpu_bucket_reads_device), the bins cross NVLink with one NCCL all-to-all per round
+(torch.distributed), and each rank upserts what it received (sdtgpu_insert_records_device).
+Updates are commutative, so arrival order is free and the union of the ranks' tables is the
+reference's multiset.
+
+`exchange_records` is the backend-agnostic plumbing (counts all-to-all, offsets, payload
+all-to-all); it is exercised on CPU with the gloo backend in tests/test_exchange_cpu.py.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def exchange_records(send: torch.Tensor, send_counts: torch.Tensor, recv: torch.Tensor, group=None):
+    """send: [world, cap, words] int64 bins, bin d holds send_counts[d] valid records for rank d.
+    recv: flat [recv_cap, words] int64.  Returns (n_received, recv_counts list).
+    Two collectives: a tiny all-to-all of the counts, then the variable-size payload all-to-all
+    (batched isend/irecv = one NCCL grouped send/recv; no packing copy — the bins are sent in place;
+    the same code runs on gloo for the CPU tests)."""
+    world = dist.get_world_size(group)
+    counts_host = [int(x) for x in send_counts.tolist()]
+    cap = send.shape[1]
+    if max(counts_host) > cap:
+        raise OverflowError(f"a send bin overflowed: {max(counts_host)} > {cap}")
+    sc = torch.tensor(counts_host, dtype=torch.int64, device=send.device)
+    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.tolist()]
+    total = sum(recv_counts)
+    if total > recv.shape[0]:
+        raise OverflowError(f"receive buffer too small: {total} > {recv.shape[0]}")
+    rank = dist.get_rank(group)
+    ops, off = [], 0
+    for src, n in enumerate(recv_counts):
+        seg = recv[off:off + n]
+        off += n
+        if n == 0:
+            continue
+        if src == rank:
+            seg.copy_(send[rank, :n])      # own bin: device-local copy, never touches the fabric
+        else:
+            ops.append(dist.P2POp(dist.irecv, seg, src, group=group))
+    for dst in range(world):
+        if dst != rank and counts_host[dst]:
+            ops.append(dist.P2POp(dist.isend, send[dst, :counts_host[dst]], dst, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):      # NCCL: one grouped ncclSend/ncclRecv launch
+            req.wait()
+    return total, recv_counts
+
+
+class Exchange:
+    """Round driver for bench.py / multi-rank callers.  All device work is enqueued on the table's
+    own stream (made torch's current stream, so the NCCL collectives order against it)."""
+
+    def __init__(self, pkg, g, world: int, rank: int, dev, max_round_instances: int, slack: float = 1.15):
+        self.pkg, self.world, self.rank, self.dev = pkg, world, rank, dev
+        self.words = g.record_bytes() // 8
+        self.cap = int(max_round_instances / world * slack) + 65536
+        self.send = torch.empty((world, self.cap, self.words), dtype=torch.int64, device=dev)
+        self.counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        self.recv = torch.empty((int(self.cap * world), self.words), dtype=torch.int64, device=dev)
+        self.rebind(g)
+        self.nvlink_bytes = 0
+
+    def rebind(self, g):
+        self.ext = torch.cuda.ExternalStream(g.stream, device=self.dev)
+
+    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None):
+        with torch.cuda.stream(self.ext):
+            self.counts.zero_()
+            g.bucket_reads_device(d_packed, d_lens, None, n_reads, uniform_len, stride, first_read_ordinal,
+                                  self.world, self.send, self.cap, self.counts)
+            total, rc = exchange_records(self.send, self.counts, self.recv)
+            self.nvlink_bytes += (total - rc[self.rank]) * self.words * 8
+            g.insert_records_device(self.recv, total)
+
+    def flush(self, g):
+        pass
