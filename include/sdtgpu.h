@@ -88,11 +88,12 @@ int sdtgpu_reset (sdtgpu_t *h);	/* empty the table, keep the allocation */
  * (prlHashReads.c:466-471, 524-527, 561-564, 603-606, 617-619), i.e. chopKmer4read
  * (prlHashReads.c:164-310) over the batch followed by put_kmerset (newhash.c:411-462) of every
  * window.  lens == NULL means every read has uniform_len bases.  nmask (1 bit per base, bit 7 of
- * byte 0 = base 0, stride mask_stride_bytes) is only read with SDTGPU_F_NKMER and may be NULL.
+ * byte 0 = base 0, stride_bytes/2 bytes per read) is only read with SDTGPU_F_NKMER and may be NULL.
  * first_read_ordinal = number of reads pushed before this batch in arrival order (needed only
  * for export_kmersets' slot-exact layout; pass the running count).
- * push_reads takes HOST buffers (pageable or pinned), copies them and returns once the copy is
- * enqueued on the handle's stream; the kernels run asynchronously (the reference does not overlap
+ * push_reads takes HOST buffers (pageable or pinned) and returns as soon as they have been copied
+ * to the device (the caller may reuse them immediately); the copy overlaps the kernels of the
+ * previous batch and this batch's kernels run asynchronously (the reference does not overlap
  * parsing with hashing; doing so is allowed because the table is order-free).
  * push_reads_device takes DEVICE pointers (16-byte aligned) and only enqueues kernels. */
 int sdtgpu_push_reads (sdtgpu_t *h, const uint8_t *packed, const uint32_t *lens, const uint8_t *nmask,
@@ -137,6 +138,11 @@ int sdtgpu_export_kmersets (sdtgpu_t *h, int thrd_num, sdtgpu_kmerset **sets);
 int sdtgpu_build_kmersets (const sdtgpu_node *nodes, uint64_t n_nodes, int key_words, int thrd_num,
 			   const uint64_t *set_last_ordinal /* [thrd_num] or NULL */, sdtgpu_kmerset **sets);
 void sdtgpu_free_kmersets (sdtgpu_kmerset **sets, int thrd_num);
+
+/* pinned host memory for the caller's batch buffers (the reference's seqBuffer/lenBuffer role,
+ * prlHashReads.c:387-395); plain pageable memory also works with push_reads, only slower */
+int sdtgpu_host_alloc (void **out, size_t bytes);
+void sdtgpu_host_free (void *p);
 
 /* ---- measurement hooks */
 void *sdtgpu_stream (sdtgpu_t *h);	/* the cudaStream_t all work of this handle is enqueued on */

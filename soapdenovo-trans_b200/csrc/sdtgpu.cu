@@ -528,6 +528,7 @@ int sdtgpu_push_reads (sdtgpu_t *h, const uint8_t *packed, const uint32_t *lens,
 		CK (h, cudaMemcpyAsync (s.d_mask, nmask, mbytes, cudaMemcpyHostToDevice, h->copy_stream));
 	CK (h, cudaEventRecord (s.ready_ev, h->copy_stream));
 	CK (h, cudaStreamWaitEvent (h->stream, s.ready_ev, 0));
+	CK (h, cudaEventSynchronize (s.ready_ev));	// the caller's buffers are free again when we return
 	int rc = sdtgpu_push_reads_device (h, s.d_packed, lens ? s.d_lens : nullptr, nmode ? s.d_mask : nullptr,
 					   n_reads, uniform_len, stride_bytes, first_read_ordinal);
 	CK (h, cudaEventRecord (s.free_ev, h->stream));
@@ -720,6 +721,20 @@ int sdtgpu_export_kmersets (sdtgpu_t *h, int thrd_num, sdtgpu_kmerset **sets)
 	}
 	free (nodes);
 	return rc;
+}
+
+int sdtgpu_host_alloc (void **out, size_t bytes)
+{
+	if (!out)
+		return SDTGPU_EINVAL;
+	*out = nullptr;
+	return cudaMallocHost (out, bytes ? bytes : 1) == cudaSuccess ? SDTGPU_OK : SDTGPU_ENOMEM;
+}
+
+void sdtgpu_host_free (void *p)
+{
+	if (p)
+		cudaFreeHost (p);
 }
 
 int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *insert_launches, uint64_t *all_launches)
