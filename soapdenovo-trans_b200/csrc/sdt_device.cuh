@@ -224,10 +224,12 @@ template <> struct Table<1>
 				links = 0;	// seeds only; a racing writer just makes the CAS below retry
 				sord = EMPTY64;
 			}
+			// returning atomics first, fire-and-forget REDs last: a RED queued ahead of a CAS on the
+			// same sector halves the throughput (tools/randacc_bench.cu, profiles/r1_randacc_bench.txt)
+			links_update48 (&s->links, links, left, right);
 			red_add_u32 (&s->count, 1u);
 			if (ord < sord)
 				red_min_u64 (&s->ord, ord);
-			links_update48 (&s->links, links, left, right);
 			return created;
 		next:
 			if (++idx == cap)
@@ -258,7 +260,6 @@ template <> struct Table<2>
 				ordL = ORD40_NONE << 24;
 				rc = 0;
 			}
-			red_add_u32 (&s->count, 1u);
 			{	// ord (min) and the four left counters share one 64-bit CAS word
 				u64 seen = ordL;
 				for (;;)
@@ -290,6 +291,7 @@ template <> struct Table<2>
 					seen = old;
 				}
 			}
+			red_add_u32 (&s->count, 1u);	// REDs after the returning atomics (see Table<1>)
 			return created;
 		next:
 			if (++idx == cap)
@@ -333,10 +335,10 @@ template <> struct Table<4>
 					goto next;
 				ld128 (&s->links, links, sord);
 			}
+			links_update48 (&s->links, links, left, right);
 			red_add_u32 (&s->count, 1u);
 			if (ord < sord)
 				red_min_u64 (&s->ord, ord);
-			links_update48 (&s->links, links, left, right);
 			return created;
 		next:
 			if (++idx == cap)

@@ -43,6 +43,11 @@ struct sdtgpu
 	int next_stage = 0;
 	int sm_count = 0;
 	u64 pushed_upper = 0;	// upper bound of instances pushed (host-side arithmetic)
+	// lagging snapshot of the node counter, so that the capacity check never has to drain the stream
+	u64 *h_nodes_snap = nullptr;	// pinned
+	cudaEvent_t snap_ev = nullptr;
+	bool snap_pending = false;
+	u64 snap_pushed = 0, known_nodes = 0, known_at = 0;
 	u64 n_reads = 0;
 	u32 n_grows = 0;
 	bool finalized = false;
@@ -112,19 +117,31 @@ int read_counters (sdtgpu *h)
 	return SDTGPU_OK;
 }
 
-// Keep the load factor bounded before `incoming` more instances are inserted.  With a capacity
-// hint the table is sized once (load <= 0.5 at the hinted count) and only re-hashed if the hint
-// turns out too small; without one it starts small and doubles, like the reference's
-// encap_kmerset (newhash.c:293-409) but on the device.
+// Keep the load factor bounded before `incoming` more instances are inserted.  The table never
+// fills beyond max_load even if every incoming instance were a new key.  With a capacity hint the
+// table is sized once (load <= 0.5 at the hinted count); without one it starts small and grows by
+// device re-hash, like the reference's encap_kmerset (newhash.c:293-409).  The check uses a
+// lagging snapshot of the device's node counter (copied asynchronously after every launch), so
+// the steady state costs no stream synchronisation.
 int ensure_capacity (sdtgpu *h, u64 incoming)
 {
-	const double max_load = 0.70;
-	if ((double) (h->pushed_upper + incoming) <= max_load * (double) h->cap)
-		return SDTGPU_OK;	// even if every instance were distinct the table stays below max_load
+	const double max_load = 0.90;
+	if (h->snap_pending && cudaEventQuery (h->snap_ev) == cudaSuccess)
+	{
+		h->snap_pending = false;
+		h->known_nodes = *h->h_nodes_snap;
+		h->known_at = h->snap_pushed;
+	}
+	const u64 bound = h->known_nodes + (h->pushed_upper - h->known_at);	// >= nodes in the table now
+	if ((double) (bound + incoming) <= max_load * (double) h->cap)
+		return SDTGPU_OK;
 	int rc = read_counters (h);
 	if (rc)
 		return rc;
 	const u64 nodes = h->h_ctr->n_nodes;
+	h->known_nodes = nodes;
+	h->known_at = h->pushed_upper;
+	h->snap_pending = false;
 	if ((double) (nodes + incoming) <= max_load * (double) h->cap)
 		return SDTGPU_OK;
 	u64 new_cap = std::max<u64> (h->cap * 2, (u64) ((double) (nodes + incoming) / 0.45) + 1024);
@@ -145,6 +162,17 @@ int ensure_capacity (sdtgpu *h, u64 incoming)
 	h->table = neu;
 	h->cap = new_cap;
 	h->n_grows++;
+	return SDTGPU_OK;
+}
+
+int snapshot_nodes (sdtgpu *h)
+{
+	if (h->snap_pending)
+		return SDTGPU_OK;
+	CK (h, cudaMemcpyAsync (h->h_nodes_snap, &h->d_ctr->n_nodes, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaEventRecord (h->snap_ev, h->stream));
+	h->snap_pending = true;
+	h->snap_pushed = h->pushed_upper;
 	return SDTGPU_OK;
 }
 
@@ -408,6 +436,8 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 		}
 		CK (h, cudaMalloc (&h->d_ctr, sizeof (Counters)));
 		CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
+		CK (h, cudaMallocHost (&h->h_nodes_snap, sizeof (u64)));
+		CK (h, cudaEventCreateWithFlags (&h->snap_ev, cudaEventDisableTiming));
 		CK (h, cudaMallocHost (&h->h_ctr, sizeof (Counters)));
 		memset (h->h_ctr, 0, sizeof (Counters));
 		crc_table_host ();
@@ -448,6 +478,8 @@ void sdtgpu_destroy (sdtgpu_t *h)
 	cudaFree (h->table);
 	cudaFree (h->d_ctr);
 	if (h->h_ctr) cudaFreeHost (h->h_ctr);
+	if (h->h_nodes_snap) cudaFreeHost (h->h_nodes_snap);
+	if (h->snap_ev) cudaEventDestroy (h->snap_ev);
 	if (h->stream) cudaStreamDestroy (h->stream);
 	if (h->copy_stream) cudaStreamDestroy (h->copy_stream);
 	delete h;
@@ -463,6 +495,10 @@ int sdtgpu_reset (sdtgpu_t *h)
 	if (rc)
 		return rc;
 	h->pushed_upper = 0; h->n_reads = 0; h->finalized = false; h->deLowKmer = 0;
+	if (h->snap_pending)
+		CK (h, cudaEventSynchronize (h->snap_ev));
+	h->snap_pending = false;
+	h->known_nodes = h->known_at = h->snap_pushed = 0;
 	return SDTGPU_OK;
 }
 
@@ -494,7 +530,8 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 		return rc;
 	h->pushed_upper += upper;
 	h->n_reads += n_reads;
-	return launch_insert<0> (h, rb, Bins ());
+	rc = launch_insert<0> (h, rb, Bins ());
+	return rc ? rc : snapshot_nodes (h);
 }
 
 int sdtgpu_push_reads (sdtgpu_t *h, const uint8_t *packed, const uint32_t *lens, const uint8_t *nmask,
@@ -589,7 +626,7 @@ int sdtgpu_insert_records_device (sdtgpu_t *h, const void *d_records, uint64_t n
 	h->timing.emplace_back (e0, e1);
 	h->insert_launches++;
 	h->all_launches++;
-	return SDTGPU_OK;
+	return snapshot_nodes (h);
 }
 
 static void fill_stats (sdtgpu *h, sdtgpu_stats *st)
