@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--batch-reads", type=int, default=1 << 22)
+    ap.add_argument("--partitioned", action="store_true", help="experimental staged/partitioned insert path")
     args = ap.parse_args()
 
     import sdt_pkg
@@ -184,7 +185,7 @@ def main():
     batch = args.batch_reads
 
     # ---- pilot pass with a generous table to learn the distinct count, then size load <= 0.5
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(0.5 * instances_rank) + 1024, device=local_rank)
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(0.25 * instances_rank) + 1024, device=local_rank, partitioned=args.partitioned)
     ext = torch.cuda.ExternalStream(g.stream, device=dev)
 
     exch = None
@@ -203,13 +204,14 @@ def main():
                 exch.round(gg, d_packed[a:b], b - a, L, stride, 2 * first_pair + a)
         if exch is not None:
             exch.flush(gg)
+        gg.sync()      # end of the step: everything staged has been inserted (flushes the epoch)
 
     one_step(g)
     st = g.stats()
     distinct = st.n_nodes
     assert (exch is not None) or st.n_instances == instances_rank, (st.n_instances, instances_rank)
     g.close()
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(distinct * 1.02) + 1024, device=local_rank)
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(distinct * 1.02) + 1024, device=local_rank, partitioned=args.partitioned)
     ext = torch.cuda.ExternalStream(g.stream, device=dev)
     if exch is not None:
         exch.rebind(g)
@@ -235,8 +237,11 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     ms = e0.elapsed_time(e1)
-    insert_ms, insert_launches, all_launches = g.kernel_time(reset=True)
+    chk = g.stats()
+    assert exch is not None or (chk.n_instances == instances_rank and chk.n_nodes == distinct), (chk.n_instances, chk.n_nodes)
     st = g.stats()
+    cat_ms, cat_launches = g.kernel_times(reset=False)
+    insert_ms, insert_launches, all_launches = g.kernel_time(reset=True)
     t = torch.tensor([ms, float(st.n_instances), float(st.n_nodes)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -301,8 +306,10 @@ def main():
                        "batch_reads": batch,
                        "l2": "table (>= 2x distinct x slot bytes) and reads are far larger than the 126 MB L2; table is reset every step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": None, "kernel": "insert_reads_kernel" if world == 1 else "insert_records_kernel+insert_reads_kernel(bucket)",
-                         "bytes_per_instance": bpi, "kernel_ms_per_launch": ker_ms, "peak_source": peak_src},
+                         "traffic": None, "kernel": ("insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if world == 1 else "insert_records_kernel",
+                         "bytes_per_instance": bpi, "kernel_ms_per_launch": ker_ms, "peak_source": peak_src,
+                         "kernel_ms_per_step": {"insert": cat_ms[0] / args.steps, "partition_count": cat_ms[1] / args.steps,
+                                                "partition_scatter": cat_ms[2] / args.steps}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(all_launches),
             "clocks": sampler.summary(),
         }

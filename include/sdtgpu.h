@@ -78,6 +78,9 @@ typedef struct sdtgpu_stats {
  * capacity_hint = expected distinct k-mers (0: start small and grow by device re-hash).
  * device = CUDA ordinal.  flags: SDTGPU_F_* */
 #define SDTGPU_F_NKMER     1u	/* the reference's -n (N_kmer): windows containing N become key 0 without links */
+#define SDTGPU_F_PARTITIONED 2u	/* experimental: stage records, radix-partition them by table slot range and
+				 * insert bucket by bucket (L2-resident table regions) instead of the default
+				 * single-pass insert; measured slower on B200 */
 int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_read_len,
 		   uint64_t capacity_hint, unsigned flags);
 void sdtgpu_destroy (sdtgpu_t *h);
@@ -149,6 +152,8 @@ void *sdtgpu_stream (sdtgpu_t *h);	/* the cudaStream_t all work of this handle i
 /* device time (ms, CUDA events on the handle's stream) and launch count accumulated by the insert
  * kernels since the last call with reset != 0 */
 int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *insert_launches, uint64_t *all_launches);
+/* per kernel class: [0] insert (direct, staged or records), [1] partition count pass, [2] partition scatter pass */
+int sdtgpu_kernel_times (sdtgpu_t *h, int reset, double ms[3], uint64_t launches[3]);
 
 /* ---- synthetic reads on the device (bench/test utility; bit-identical to synth.py).
  * d_tr_bases: uint8 codes of all transcripts; d_starts u64[T]; d_lengths u32[T]; d_cum u64[T]. */

@@ -160,40 +160,74 @@ __device__ __forceinline__ u32 base_at (const u32 *rd, int b)
 }
 
 // ------------------------------------------------------------------------------------------------
-// table slots.  Link counters are the reference's 6-bit saturating counters (update_kmer,
-// newhash.c:71-96): left[i] at bits 6i, right[i] at bits 24+6i of `links` (W = 1, 4) or split
-// into L24 / R24 (W = 2).  count is the reference's wrapping u32 (newhash.c:75).  ord is the
-// smallest instance ordinal seen, used only to reproduce the reference's slot order at export.
-struct __align__(32) Slot1 { u64 key; u64 links; u64 ord; u32 count; u32 pad; };
-struct __align__(32) Slot2 { u64 key[2]; u64 ordL; u32 R; u32 count; };	// ordL = ord40 << 24 | L24
-struct __align__(64) Slot4 { u64 key[4]; u64 links; u64 ord; u32 count; u32 pad; u64 pad2; };
+// table slots: key words + one 16-byte payload, everything of a slot in one 32-byte DRAM sector
+// for K <= 63 (two sectors for K <= 127).
+//   payload word 0 = ord40 << 24 | L24      L24 = the four left  link counters, 6 bits each
+//   payload word 1 = count32 << 32 | R24    R24 = the four right link counters
+// Link counters are the reference's saturating 6-bit counters (update_kmer, newhash.c:71-96),
+// count its wrapping u32 (newhash.c:75); ord is the smallest instance ordinal seen, kept only so
+// that the export can reproduce the reference's slot order.
+struct __align__(16) Payload { u64 ordL; u32 R; u32 count; };
+struct __align__(32) Slot1 { u64 key; u64 pad; Payload p; };
+struct __align__(32) Slot2 { u64 key[2]; Payload p; };
+struct __align__(64) Slot4 { u64 key[4]; Payload p; u64 pad[2]; };
 
 template <int W> struct SlotOf;
 template <> struct SlotOf<1> { typedef Slot1 type; };
 template <> struct SlotOf<2> { typedef Slot2 type; };
 template <> struct SlotOf<4> { typedef Slot4 type; };
 
-__device__ __forceinline__ u64 links_inc48 (u64 links, u32 left, u32 right)
+static constexpr u64 PAYLOAD0_INIT = ORD40_NONE << 24;
+
+__device__ __forceinline__ u32 sat_inc24 (u32 links, u32 base)
 {
-	if (left < 4 && ((links >> (6 * left)) & 63) < LINK_SAT)
-		links += 1ull << (6 * left);
-	if (right < 4 && ((links >> (24 + 6 * right)) & 63) < LINK_SAT)
-		links += 1ull << (24 + 6 * right);
+	if (base < 4 && ((links >> (6 * base)) & 63) < LINK_SAT)
+		links += 1u << (6 * base);
 	return links;
 }
 
-__device__ __forceinline__ void links_update48 (u64 *p, u64 seen, u32 left, u32 right)
-{	// CAS loop that stops for good once both addressed counters are saturated
-	for (;;)
+// One instance into a slot's payload.  Fast path: ONE 128-bit CAS carries count+1, both link
+// increments and the ordinal minimum (a hash-table insert costs what its L2 requests cost:
+// tools/randacc_bench.cu, ld + CAS128 17 G/s vs ld + CAS64 + RED 12 G/s on random slots).
+// If the CAS loses a race the key is contended (a hot k-mer): fall back to per-field atomics,
+// which never retry on account of count (RED) and stop for good once a link counter saturates.
+__device__ __forceinline__ void payload_update (Payload *p, u64 s0, u64 s1, u32 left, u32 right, u64 ord)
+{
 	{
-		const u64 want = links_inc48 (seen, left, right);
-		if (want == seen)
+		const u64 o = min (s0 >> 24, ord);
+		const u64 w0 = (o << 24) | sat_inc24 ((u32) s0 & 0xFFFFFFu, left);
+		const u64 w1 = ((s1 + (1ull << 32)) & 0xFFFFFFFF00000000ull) | sat_inc24 ((u32) s1 & 0xFFFFFFu, right);
+		u64 o0, o1;
+		if (cas128 (p, s0, s1, w0, w1, o0, o1))
 			return;
-		const u64 old = atomicCAS (p, seen, want);
-		if (old == seen)
-			return;
-		seen = old;
+		s0 = o0;
+		s1 = o1;
 	}
+	for (;;)
+	{	// ordinal minimum + left counters
+		const u64 o = min (s0 >> 24, ord);
+		const u64 want = (o << 24) | sat_inc24 ((u32) s0 & 0xFFFFFFu, left);
+		if (want == s0)
+			break;
+		const u64 old = atomicCAS (&p->ordL, s0, want);
+		if (old == s0)
+			break;
+		s0 = old;
+	}
+	if (right < 4)
+	{
+		u32 seen = (u32) s1;
+		for (;;)
+		{
+			if (((seen >> (6 * right)) & 63) >= LINK_SAT)
+				break;
+			const u32 old = atomicCAS (&p->R, seen, seen + (1u << (6 * right)));
+			if (old == seen)
+				break;
+			seen = old;
+		}
+	}
+	red_add_u32 (&p->count, 1u);	// fire-and-forget RED last (a RED queued ahead of a CAS halves the rate)
 }
 
 // upsert of one instance; returns 1 if this call created the node.  The table must never be
@@ -209,9 +243,9 @@ template <> struct Table<1>
 		for (;;)
 		{
 			Slot1 *s = tab + idx;
-			u64 sk, links, sord, cnt;
+			u64 sk, pad, s0, s1;
 			int created = 0;
-			ld256 (s, sk, links, sord, cnt);
+			ld256 (s, sk, pad, s0, s1);
 			if (sk != key)
 			{
 				if (sk != EMPTY64)
@@ -221,15 +255,10 @@ template <> struct Table<1>
 					created = 1;
 				else if (sk != key)
 					goto next;
-				links = 0;	// seeds only; a racing writer just makes the CAS below retry
-				sord = EMPTY64;
+				s0 = PAYLOAD0_INIT;	// seeds only; a racing writer just makes the CAS retry
+				s1 = 0;
 			}
-			// returning atomics first, fire-and-forget REDs last: a RED queued ahead of a CAS on the
-			// same sector halves the throughput (tools/randacc_bench.cu, profiles/r1_randacc_bench.txt)
-			links_update48 (&s->links, links, left, right);
-			red_add_u32 (&s->count, 1u);
-			if (ord < sord)
-				red_min_u64 (&s->ord, ord);
+			payload_update (&s->p, s0, s1, left, right, ord);
 			return created;
 		next:
 			if (++idx == cap)
@@ -246,9 +275,9 @@ template <> struct Table<2>
 		for (;;)
 		{
 			Slot2 *s = tab + idx;
-			u64 k0, k1, ordL, rc;
+			u64 k0, k1, s0, s1;
 			int created = 0;
-			ld256 (s, k0, k1, ordL, rc);
+			ld256 (s, k0, k1, s0, s1);
 			if (k0 != k.w[0] || k1 != k.w[1])
 			{
 				if (k0 != EMPTY64 || k1 != EMPTY64)
@@ -257,41 +286,10 @@ template <> struct Table<2>
 					created = 1;
 				else if (k0 != k.w[0] || k1 != k.w[1])
 					goto next;
-				ordL = ORD40_NONE << 24;
-				rc = 0;
+				s0 = PAYLOAD0_INIT;
+				s1 = 0;
 			}
-			{	// ord (min) and the four left counters share one 64-bit CAS word
-				u64 seen = ordL;
-				for (;;)
-				{
-					u64 o = seen >> 24, L = seen & 0xFFFFFFull;
-					if (ord < o)
-						o = ord;
-					if (left < 4 && ((L >> (6 * left)) & 63) < LINK_SAT)
-						L += 1ull << (6 * left);
-					const u64 want = (o << 24) | L;
-					if (want == seen)
-						break;
-					const u64 old = atomicCAS (&s->ordL, seen, want);
-					if (old == seen)
-						break;
-					seen = old;
-				}
-			}
-			if (right < 4)
-			{
-				u32 seen = (u32) rc;
-				for (;;)
-				{
-					if (((seen >> (6 * right)) & 63) >= LINK_SAT)
-						break;
-					const u32 old = atomicCAS (&s->R, seen, seen + (1u << (6 * right)));
-					if (old == seen)
-						break;
-					seen = old;
-				}
-			}
-			red_add_u32 (&s->count, 1u);	// REDs after the returning atomics (see Table<1>)
+			payload_update (&s->p, s0, s1, left, right, ord);
 			return created;
 		next:
 			if (++idx == cap)
@@ -308,7 +306,7 @@ template <> struct Table<4>
 		for (;;)
 		{
 			Slot4 *s = tab + idx;
-			u64 a0, a1, links = 0, sord = EMPTY64;
+			u64 a0, a1, s0 = PAYLOAD0_INIT, s1 = 0;
 			int created = 0;
 			ld128 (&s->key[0], a0, a1);
 			if (a0 == EMPTY64 && a1 == LOCKED64)
@@ -333,12 +331,9 @@ template <> struct Table<4>
 				ld128 (&s->key[2], b0, b1);
 				if (b0 != k.w[2] || b1 != k.w[3])
 					goto next;
-				ld128 (&s->links, links, sord);
+				ld128 (&s->p, s0, s1);
 			}
-			links_update48 (&s->links, links, left, right);
-			red_add_u32 (&s->count, 1u);
-			if (ord < sord)
-				red_min_u64 (&s->ord, ord);
+			payload_update (&s->p, s0, s1, left, right, ord);
 			return created;
 		next:
 			if (++idx == cap)

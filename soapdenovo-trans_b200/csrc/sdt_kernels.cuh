@@ -6,6 +6,11 @@
 //                         (read, offset) space and upserts them into the table.  MODE 1 writes
 //                         (key, meta) records into per-owner bins instead (the send side of the
 //                         multi-GPU exchange; prlHashReads.c:79-88 is the reference's partition).
+//                         MODE 2 / MODE 3 are the two passes of the exact radix partition by table
+//                         slot range (count, then scatter): the staged records of one bucket all
+//                         fall into one L2-sized region of the table.
+//   insert_staged_kernel  upserts staged records bucket by bucket, so that the table region being
+//                         updated stays L2-resident (tools/randacc_bench.cu: 3-4x the random rate).
 //   insert_records_kernel the receive side: upsert records produced by MODE 1 on any rank.
 //   init / rehash / finalize / export kernels: table maintenance and the post-pass
 //                         (thread_delow prlHashReads.c:844-887, thread_mark :911-967).
@@ -140,6 +145,37 @@ template <int W> __device__ __forceinline__ void emit_record (const Bins &bins, 
 	}
 }
 
+template <int W> __device__ __forceinline__ void store_record (u64 *rec, const Key<W> &key, u32 left, u32 right, u64 ord)
+{
+	const u64 meta = (ord << 8) | (left << 4) | right;
+	if constexpr (W == 1)
+		*reinterpret_cast<ulonglong2 *> (rec) = make_ulonglong2 (key.w[0], meta);
+	else
+	{
+#pragma unroll
+		for (int i = 0; i < W; i++)
+			rec[i] = key.w[i];
+		rec[W] = meta;
+	}
+}
+
+template <int W> __device__ __forceinline__ void load_record (const u64 *rec, Key<W> &key, u64 &meta)
+{
+	if constexpr (W == 1)
+	{
+		const ulonglong2 v = *reinterpret_cast<const ulonglong2 *> (rec);
+		key.w[0] = v.x;
+		meta = v.y;
+	}
+	else
+	{
+#pragma unroll
+		for (int q = 0; q < W; q++)
+			key.w[q] = rec[q];
+		meta = rec[W];
+	}
+}
+
 template <int W, bool NMODE, int MODE>
 __global__ void __launch_bounds__ (BLOCK)
 insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bins bins, Counters *ctr)
@@ -151,6 +187,8 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 	u32 *tile = smem + TILE_PAD;
 	u32 *prefix = smem + TILE_PAD + rb.tile_reads * sw + TILE_PAD;	// tile_reads + 1 entries
 	u32 *mtile = prefix + rb.tile_reads + 4;
+	u32 *hist = mtile + rb.tile_reads * mw;	// MODE 2 / 3: bins.n_ranks counters (MODE 3: + u64 bases behind them)
+	u64 *base = reinterpret_cast<u64 *> (hist + ((bins.n_ranks + 1) & ~1u));
 	__shared__ u32 warp_sums[BLOCK / 32];
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
 	const int K = rb.K;
@@ -162,6 +200,9 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		smem[tid] = 0;
 		smem[TILE_PAD + rb.tile_reads * sw + tid] = 0;
 	}
+	if (MODE == 2 || MODE == 3)
+		for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
+			hist[b] = 0;
 
 	for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x)
 	{
@@ -242,6 +283,10 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		__syncthreads ();
 		instances += (tid == 0) ? total : 0;
 
+		// MODE 3 walks the tile twice: sweep 0 counts the tile's records per bucket, one global atomic
+		// per non-empty bucket then reserves their space, sweep 1 writes the records
+		for (int sweep = (MODE == 3 ? 0 : 1); sweep < 2; sweep++)
+		{
 		for (u32 w = tid; w < total; w += BLOCK)
 		{
 			u32 r, j, len;
@@ -272,10 +317,51 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 			const u64 ord = (rb.first_read_ordinal + r0 + r) * rb.maxwin + j;
 			if (MODE == 0)
 				created += Table<W>::upsert (table, cap, key, left, right, ord);
-			else
+			else if (MODE == 1)
 				emit_record<W> (bins, key, left, right, ord, key_hash<W> (key));
+			else if (MODE == 2)	// partition pass 1: how many records per slot-range bucket
+				atomicAdd (&hist[(u32) __umul64hi (key_hash<W> (key), (u64) bins.n_ranks)], 1u);
+			else
+			{	// partition pass 2: exact scatter, cursors were initialised to the bucket offsets
+				const u32 b = (u32) __umul64hi (key_hash<W> (key), (u64) bins.n_ranks);
+				if (sweep == 0)
+					atomicAdd (&hist[b], 1u);
+				else
+				{
+					const u64 pos = base[b] + atomicAdd (&hist[b], 1u);
+					store_record<W> (bins.records + pos * (W + 1), key, left, right, ord);
+				}
+			}
+		}
+		if (MODE == 3)
+		{
+			__syncthreads ();
+			if (sweep == 0)
+			{
+				for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
+				{
+					const u32 c = hist[b];
+					if (c)
+					{
+						base[b] = atomicAdd (bins.counts + b, (u64) c);
+						hist[b] = 0;
+					}
+				}
+				__syncthreads ();
+			}
+			else
+				for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
+					hist[b] = 0;
+		}
 		}
 		__syncthreads ();	// the tile is overwritten by the next iteration
+	}
+	if (MODE == 2)
+	{
+		__syncthreads ();
+		for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
+			if (hist[b])
+				atomicAdd (bins.counts + b, (u64) hist[b]);
 	}
 	// ---- counters: one atomic per warp
 #pragma unroll
@@ -285,6 +371,163 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		atomicAdd (&ctr->n_nodes, (u64) created);
 	if (MODE == 0 && tid == 0 && instances)	// bucketed instances are counted by the rank that inserts them
 		atomicAdd (&ctr->n_instances, instances);
+}
+
+// ------------------------------------------------------------------------------------------------
+// staged (partitioned) insert
+static constexpr int STAGE_CHUNK = 1024;	// records per work item
+static constexpr int MAX_SEGMENTS = 64;		// batches per epoch
+
+struct Staged
+{
+	const u64 *seg_records[MAX_SEGMENTS];	// record base of each batch
+	const u64 *seg_offsets;			// [n_segments][P + 1] exclusive bucket offsets (records) of each batch
+	const u64 *chunk_prefix;		// [P * n_segments + 1] exclusive prefix of work items, bucket-major
+	u64 *next_chunk;			// work-stealing cursor (zeroed at the start of an epoch)
+	u64 node_limit;				// stop handing out chunks once the table holds this many nodes
+	u32 n_segments, P;
+};
+
+// offsets[s][b] (exclusive scan of counts[b]) for ONE batch, cursors[b] = base + offsets[b]; one CTA
+__global__ void __launch_bounds__ (1024)
+bucket_scan_kernel (const u64 *counts, u32 P, u64 base, u64 *offsets, u64 *cursors)
+{
+	__shared__ u64 part[1024];
+	__shared__ u64 carry;
+	if (threadIdx.x == 0)
+		carry = 0;
+	__syncthreads ();
+	for (u32 b0 = 0; b0 < P; b0 += 1024)
+	{
+		const u32 b = b0 + threadIdx.x;
+		const u64 c = b < P ? counts[b] : 0;
+		part[threadIdx.x] = c;
+		__syncthreads ();
+		for (int d = 1; d < 1024; d <<= 1)
+		{
+			const u64 y = threadIdx.x >= (u32) d ? part[threadIdx.x - d] : 0;
+			__syncthreads ();
+			part[threadIdx.x] += y;
+			__syncthreads ();
+		}
+		const u64 excl = carry + part[threadIdx.x] - c;
+		if (b < P)
+		{
+			offsets[b] = excl;
+			cursors[b] = base + excl;
+		}
+		__syncthreads ();
+		if (threadIdx.x == 1023)
+			carry += part[1023];
+		__syncthreads ();
+	}
+	if (threadIdx.x == 0)
+		offsets[P] = carry;
+}
+
+// chunk_prefix over (bucket-major, segment-minor) work items; one CTA
+__global__ void __launch_bounds__ (1024)
+chunk_prefix_kernel (const u64 *seg_offsets, u32 n_segments, u32 P, u64 *chunk_prefix)
+{
+	__shared__ u64 part[1024];
+	__shared__ u64 carry;
+	const u32 n = P * n_segments;
+	if (threadIdx.x == 0)
+		carry = 0;
+	__syncthreads ();
+	for (u32 i0 = 0; i0 < n; i0 += 1024)
+	{
+		const u32 i = i0 + threadIdx.x;
+		u64 c = 0;
+		if (i < n)
+		{
+			const u32 b = i / n_segments, t = i - b * n_segments;
+			const u64 *off = seg_offsets + (u64) t * (P + 1);
+			c = (off[b + 1] - off[b] + STAGE_CHUNK - 1) / STAGE_CHUNK;
+		}
+		part[threadIdx.x] = c;
+		__syncthreads ();
+		for (int d = 1; d < 1024; d <<= 1)
+		{
+			const u64 y = threadIdx.x >= (u32) d ? part[threadIdx.x - d] : 0;
+			__syncthreads ();
+			part[threadIdx.x] += y;
+			__syncthreads ();
+		}
+		if (i < n)
+			chunk_prefix[i] = carry + part[threadIdx.x] - c;
+		__syncthreads ();
+		if (threadIdx.x == 1023)
+			carry += part[1023];
+		__syncthreads ();
+	}
+	if (threadIdx.x == 0)
+		chunk_prefix[n] = carry;
+}
+
+// Chunks are handed out in bucket order, so at any moment all CTAs update the same few table
+// regions.  The number of distinct keys in an epoch is not known in advance: when the live node
+// count reaches node_limit the kernel stops taking chunks; the host grows the table and relaunches
+// (next_chunk persists), so the table can never fill up while a launch is running.
+template <int W>
+__global__ void __launch_bounds__ (BLOCK)
+insert_staged_kernel (typename SlotOf<W>::type *table, u64 cap, Staged st, Counters *ctr)
+{
+	__shared__ u64 s_chunk;
+	__shared__ u32 s_created;
+	const u32 n_items = st.P * st.n_segments;
+	const u64 total = st.chunk_prefix[n_items];
+	u64 done = 0;
+	if (threadIdx.x == 0)
+		s_created = 0;
+	for (;;)
+	{
+		if (threadIdx.x == 0)
+		{
+			const u64 live = *reinterpret_cast<volatile u64 *> (&ctr->n_nodes);
+			s_chunk = live >= st.node_limit ? ~0ull : atomicAdd (st.next_chunk, 1ull);
+		}
+		__syncthreads ();
+		const u64 c = s_chunk;
+		if (c >= total)
+			break;
+		u32 lo = 0, hi = n_items - 1;	// largest item with chunk_prefix[item] <= c
+		while (lo < hi)
+		{
+			const u32 mid = (lo + hi + 1) >> 1;
+			if (st.chunk_prefix[mid] <= c)
+				lo = mid;
+			else
+				hi = mid - 1;
+		}
+		const u32 b = lo / st.n_segments, t = lo - b * st.n_segments;
+		const u64 *off = st.seg_offsets + (u64) t * (st.P + 1);
+		const u64 first = off[b] + (c - st.chunk_prefix[lo]) * STAGE_CHUNK;
+		const u64 last = min (first + STAGE_CHUNK, off[b + 1]);
+		const u64 *recs = st.seg_records[t];
+		u32 created = 0;
+		for (u64 i = first + threadIdx.x; i < last; i += BLOCK)
+		{
+			Key<W> key;
+			u64 meta;
+			load_record<W> (recs + i * (W + 1), key, meta);
+			created += Table<W>::upsert (table, cap, key, (u32) (meta >> 4) & 15u, (u32) meta & 15u, meta >> 8);
+		}
+		if (created)
+			atomicAdd (&s_created, created);
+		__syncthreads ();
+		if (threadIdx.x == 0)
+		{
+			done += last - first;
+			if (s_created)
+			{
+				atomicAdd (&ctr->n_nodes, (u64) s_created);
+				s_created = 0;
+			}
+		}
+	}
+	if (threadIdx.x == 0 && done)
+		atomicAdd (&ctr->n_instances, done);
 }
 
 template <int W>
@@ -326,77 +569,57 @@ insert_records_kernel (typename SlotOf<W>::type *table, u64 cap, const u64 *reco
 
 // ------------------------------------------------------------------------------------------------
 // slot accessors shared by init / rehash / finalize / export
-template <int W> struct SlotIO;
-
-template <> struct SlotIO<1>
+template <int W> struct SlotIO
 {
-	static __device__ __forceinline__ void init (Slot1 *s) { *reinterpret_cast<uint4 *> (s) = make_uint4 (~0u, ~0u, 0, 0); *(reinterpret_cast<uint4 *> (s) + 1) = make_uint4 (~0u, ~0u, 0, 0); }
-	static __device__ __forceinline__ bool occupied (const Slot1 *s) { return s->key != EMPTY64; }
-	static __device__ __forceinline__ void get (const Slot1 *s, Key<1> &k, u32 &L, u32 &R, u32 &count, u64 &ord)
+	typedef typename SlotOf<W>::type S;
+	static __device__ __forceinline__ void init (S *s)
 	{
-		k.w[0] = s->key; L = (u32) (s->links & 0xFFFFFF); R = (u32) ((s->links >> 24) & 0xFFFFFF); count = s->count; ord = s->ord;
+		uint4 *q = reinterpret_cast<uint4 *> (s);
+		const uint4 ones = make_uint4 (~0u, ~0u, ~0u, ~0u);
+		const uint4 pay = make_uint4 ((u32) PAYLOAD0_INIT, (u32) (PAYLOAD0_INIT >> 32), 0, 0);
+		if constexpr (W == 4)
+		{
+			q[0] = ones; q[1] = ones; q[2] = pay; q[3] = make_uint4 (0, 0, 0, 0);
+		}
+		else
+		{
+			q[0] = ones; q[1] = pay;
+		}
 	}
-	static __device__ __forceinline__ void set_links (Slot1 *s, u32 L, u32 R) { s->links = (u64) L | ((u64) R << 24); }
-	static __device__ __forceinline__ void put (Slot1 *s, const Key<1> &k, u32 L, u32 R, u32 count, u64 ord)
+	static __device__ __forceinline__ const u64 *keyp (const S *s) { return reinterpret_cast<const u64 *> (s); }
+	static __device__ __forceinline__ bool occupied (const S *s)
 	{
-		s->links = (u64) L | ((u64) R << 24); s->ord = ord; s->count = count;
+		if constexpr (W == 1)
+			return keyp (s)[0] != EMPTY64;
+		else
+			return !(keyp (s)[0] == EMPTY64 && keyp (s)[1] == EMPTY64);
 	}
-	static __device__ __forceinline__ bool claim (Slot1 *s, const Key<1> &k) { return atomicCAS (&s->key, EMPTY64, k.w[0]) == EMPTY64; }
-};
-
-template <> struct SlotIO<2>
-{
-	static __device__ __forceinline__ void init (Slot2 *s)
-	{
-		*reinterpret_cast<uint4 *> (s) = make_uint4 (~0u, ~0u, ~0u, ~0u);
-		const u64 ordL = ORD40_NONE << 24;
-		*(reinterpret_cast<uint4 *> (s) + 1) = make_uint4 ((u32) ordL, (u32) (ordL >> 32), 0, 0);
-	}
-	static __device__ __forceinline__ bool occupied (const Slot2 *s) { return !(s->key[0] == EMPTY64 && s->key[1] == EMPTY64); }
-	static __device__ __forceinline__ void get (const Slot2 *s, Key<2> &k, u32 &L, u32 &R, u32 &count, u64 &ord)
-	{
-		k.w[0] = s->key[0]; k.w[1] = s->key[1]; L = (u32) (s->ordL & 0xFFFFFF); R = s->R & 0xFFFFFF; count = s->count; ord = s->ordL >> 24;
-	}
-	static __device__ __forceinline__ void set_links (Slot2 *s, u32 L, u32 R) { s->ordL = (s->ordL & ~0xFFFFFFull) | L; s->R = R; }
-	static __device__ __forceinline__ void put (Slot2 *s, const Key<2> &k, u32 L, u32 R, u32 count, u64 ord)
-	{
-		s->ordL = (ord << 24) | L; s->R = R; s->count = count;
-	}
-	static __device__ __forceinline__ bool claim (Slot2 *s, const Key<2> &k)
-	{
-		u64 a, b;
-		return cas128 (s, EMPTY64, EMPTY64, k.w[0], k.w[1], a, b);
-	}
-};
-
-template <> struct SlotIO<4>
-{
-	static __device__ __forceinline__ void init (Slot4 *s)
-	{
-		uint4 *p = reinterpret_cast<uint4 *> (s);
-		p[0] = make_uint4 (~0u, ~0u, ~0u, ~0u);
-		p[1] = make_uint4 (~0u, ~0u, ~0u, ~0u);
-		p[2] = make_uint4 (0, 0, ~0u, ~0u);
-		p[3] = make_uint4 (0, 0, 0, 0);
-	}
-	static __device__ __forceinline__ bool occupied (const Slot4 *s) { return !(s->key[0] == EMPTY64 && s->key[1] == EMPTY64); }
-	static __device__ __forceinline__ void get (const Slot4 *s, Key<4> &k, u32 &L, u32 &R, u32 &count, u64 &ord)
+	static __device__ __forceinline__ void get (const S *s, Key<W> &k, u32 &L, u32 &R, u32 &count, u64 &ord)
 	{
 #pragma unroll
-		for (int i = 0; i < 4; i++)
-			k.w[i] = s->key[i];
-		L = (u32) (s->links & 0xFFFFFF); R = (u32) ((s->links >> 24) & 0xFFFFFF); count = s->count; ord = s->ord;
+		for (int i = 0; i < W; i++)
+			k.w[i] = keyp (s)[i];
+		L = (u32) (s->p.ordL & 0xFFFFFF); R = s->p.R & 0xFFFFFF; count = s->p.count; ord = s->p.ordL >> 24;
 	}
-	static __device__ __forceinline__ void set_links (Slot4 *s, u32 L, u32 R) { s->links = (u64) L | ((u64) R << 24); }
-	static __device__ __forceinline__ void put (Slot4 *s, const Key<4> &k, u32 L, u32 R, u32 count, u64 ord)
+	static __device__ __forceinline__ void set_links (S *s, u32 L, u32 R) { s->p.ordL = (s->p.ordL & ~0xFFFFFFull) | L; s->p.R = R; }
+	// rehash only: keys are unique there, so claiming the first 8 / 16 bytes is enough
+	static __device__ __forceinline__ bool claim (S *s, const Key<W> &k)
 	{
-		s->key[2] = k.w[2]; s->key[3] = k.w[3];
-		s->links = (u64) L | ((u64) R << 24); s->ord = ord; s->count = count;
+		if constexpr (W == 1)
+			return atomicCAS (reinterpret_cast<u64 *> (s), EMPTY64, k.w[0]) == EMPTY64;
+		else
+		{
+			u64 a, b;
+			return cas128 (s, EMPTY64, EMPTY64, k.w[0], k.w[1], a, b);
+		}
 	}
-	static __device__ __forceinline__ bool claim (Slot4 *s, const Key<4> &k)
-	{	// rehash only: keys are unique, so claiming the first half is enough (put() writes the rest)
-		u64 a, b;
-		return cas128 (&s->key[0], EMPTY64, EMPTY64, k.w[0], k.w[1], a, b);
+	static __device__ __forceinline__ void put (S *s, const Key<W> &k, u32 L, u32 R, u32 count, u64 ord)
+	{
+		if constexpr (W == 4)
+		{
+			s->key[2] = k.w[2]; s->key[3] = k.w[3];
+		}
+		s->p.ordL = (ord << 24) | L; s->p.R = R; s->p.count = count;
 	}
 };
 

@@ -52,10 +52,21 @@ struct sdtgpu
 	u32 n_grows = 0;
 	bool finalized = false;
 	int deLowKmer = 0;
-	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+	// partitioned (staged) insert: records of an epoch are radix-partitioned by table slot range
+	bool direct = true;		// default; SDTGPU_F_PARTITIONED selects the staged path
+	u64 *staging = nullptr;		// records, (W + 1) u64 each
+	u64 staging_cap = 0, staging_used = 0, staged_upper = 0;	// in records
+	u32 P = 0;			// buckets of the current epoch
+	u64 *d_counts = nullptr, *d_cursors = nullptr, *d_seg_offsets = nullptr, *d_chunk_prefix = nullptr, *d_next_chunk = nullptr;
+	const u64 *seg_records[MAX_SEGMENTS];
+	u32 n_segments = 0;
+	double region_bytes = 16.0 * 1024 * 1024;
+	struct Timed { cudaEvent_t e0, e1; int cat; };
+	std::vector<Timed> timing;
+	double cat_ms[3] = { 0, 0, 0 };
+	u64 cat_launches[3] = { 0, 0, 0 };
 	std::vector<cudaEvent_t> ev_pool;
-	u64 insert_launches = 0, all_launches = 0;
-	double insert_ms_acc = 0;
+	u64 all_launches = 0;
 	std::string err;
 };
 
@@ -195,17 +206,17 @@ u32 pick_tile_reads (u32 stride_bytes)
 	return std::max (4u, std::min ((u32) MAX_TILE_READS, t));
 }
 
-size_t insert_smem_bytes (const ReadBatch &rb, bool nmode)
+size_t insert_smem_bytes (const ReadBatch &rb, bool nmode, size_t hist_bins)
 {
 	const size_t sw = rb.stride_bytes / 4, mw = nmode ? (rb.mask_stride + 3) / 4 : 0;
-	return 4 * (2 * TILE_PAD + rb.tile_reads * sw + rb.tile_reads + 4 + rb.tile_reads * mw);
+	return 4 * (2 * TILE_PAD + rb.tile_reads * sw + rb.tile_reads + 4 + rb.tile_reads * mw + hist_bins);
 }
 
 template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const ReadBatch &rb, const Bins &bins)
 {
 	typedef typename SlotOf<W>::type S;
 	auto kern = insert_reads_kernel<W, NMODE, MODE>;
-	const size_t smem = insert_smem_bytes (rb, NMODE);
+	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : (MODE == 3 ? 3 * (size_t) bins.n_ranks + 4 : 0));
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
@@ -219,8 +230,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 	kern<<<grid, BLOCK, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, rb, bins, h->d_ctr);
 	CK (h, cudaGetLastError ());
 	CK (h, cudaEventRecord (e1, h->stream));
-	h->timing.emplace_back (e0, e1);
-	h->insert_launches++;
+	h->timing.push_back ({ e0, e1, MODE == 2 ? 1 : (MODE == 3 || MODE == 1 ? 2 : 0) });
 	h->all_launches++;
 	return SDTGPU_OK;
 }
@@ -247,7 +257,7 @@ int make_batch (sdtgpu *h, ReadBatch &rb, const uint8_t *d_packed, const u32 *d_
 		return fail (h, SDTGPU_EINVAL, "device read buffers must be 16-byte aligned");
 	if (!d_lens && uniform_len == 0 && n_reads)
 		return fail (h, SDTGPU_EINVAL, "lens == NULL needs uniform_len");
-	const u64 ord_limit = h->W == 2 ? ORD40_NONE : (1ull << 56);	// meta word keeps 56 bits of ordinal
+	const u64 ord_limit = ORD40_NONE;	// the slot keeps 40 bits of ordinal
 	if ((first_read_ordinal + n_reads) >= ord_limit / h->maxwin)
 		return fail (h, SDTGPU_ERANGE, "instance ordinal would overflow the slot's ordinal field");
 	rb.packed = d_packed;
@@ -380,6 +390,168 @@ export_kernel (const typename SlotOf<W>::type *table, u64 cap, int key_words, in
 	}
 }
 
+// ---- partitioned insert -----------------------------------------------------------------------
+static constexpr u32 MAX_BUCKETS = 4096;
+
+int alloc_staging (sdtgpu *h, u64 want_records)
+{
+	size_t free_b = 0, total_b = 0;
+	CK (h, cudaMemGetInfo (&free_b, &total_b));
+	const size_t rec = 8 * (size_t) (h->W + 1);
+	double budget = (h->grow_mode ? 0.25 : 0.45) * (double) free_b;
+	if (const char *e = getenv ("SDTGPU_STAGING_MB"))
+		budget = atof (e) * 1024.0 * 1024.0;
+	u64 records = (u64) (budget / (double) rec);
+	records = std::max<u64> (records, 1u << 20);
+	(void) want_records;
+	CK (h, cudaMalloc (&h->staging, records * rec));
+	h->staging_cap = records;
+	CK (h, cudaMalloc (&h->d_counts, MAX_BUCKETS * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_cursors, MAX_BUCKETS * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_seg_offsets, (size_t) MAX_SEGMENTS * (MAX_BUCKETS + 1) * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_chunk_prefix, ((size_t) MAX_SEGMENTS * MAX_BUCKETS + 1) * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_next_chunk, sizeof (u64)));
+	if (const char *e = getenv ("SDTGPU_REGION_MB"))
+		if (atof (e) > 0)
+			h->region_bytes = atof (e) * 1024.0 * 1024.0;
+	return SDTGPU_OK;
+}
+
+template <int W> int launch_staged (sdtgpu *h, const Staged &st, unsigned max_grid)
+{
+	typedef typename SlotOf<W>::type S;
+	int occ = 0;
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, insert_staged_kernel<W>, BLOCK, 0));
+	const unsigned grid = std::max (1u, std::min ((unsigned) (h->sm_count * std::max (occ, 1)), max_grid));
+	cudaEvent_t e0 = get_event (h), e1 = get_event (h);
+	CK (h, cudaEventRecord (e0, h->stream));
+	insert_staged_kernel<W><<<grid, BLOCK, 0, h->stream>>> (static_cast<S *> (h->table), h->cap, st, h->d_ctr);
+	CK (h, cudaGetLastError ());
+	CK (h, cudaEventRecord (e1, h->stream));
+	h->timing.push_back ({ e0, e1, 0 });
+	h->all_launches++;
+	return SDTGPU_OK;
+}
+
+int grow_table (sdtgpu *h, u64 new_cap)
+{
+	void *neu = nullptr;
+	CK (h, cudaMalloc (&neu, new_cap * slot_bytes (h->W)));
+	int rc = init_table (h, neu, new_cap);
+	if (rc)
+		return rc;
+	switch (h->W)
+	{
+	case 1: launch_rehash<1> (h, h->table, h->cap, neu, new_cap); break;
+	case 2: launch_rehash<2> (h, h->table, h->cap, neu, new_cap); break;
+	default: launch_rehash<4> (h, h->table, h->cap, neu, new_cap); break;
+	}
+	CK (h, cudaGetLastError ());
+	CK (h, cudaStreamSynchronize (h->stream));
+	CK (h, cudaFree (h->table));
+	h->table = neu;
+	h->cap = new_cap;
+	h->n_grows++;
+	return SDTGPU_OK;
+}
+
+// End of an epoch: upsert everything that was staged, bucket by bucket.  The distinct count of
+// the epoch is unknown, so the kernel runs optimistically and stops itself when the table reaches
+// 85 % load; the table is then grown by device re-hash (the reference's encap_kmerset,
+// newhash.c:293-409, moved to the device) and the kernel resumes where it stopped.
+int flush_epoch (sdtgpu *h)
+{
+	if (h->n_segments == 0)
+		return SDTGPU_OK;
+	int rc;
+	chunk_prefix_kernel<<<1, 1024, 0, h->stream>>> (h->d_seg_offsets, h->n_segments, h->P, h->d_chunk_prefix);
+	CK (h, cudaGetLastError ());
+	CK (h, cudaMemsetAsync (h->d_next_chunk, 0, sizeof (u64), h->stream));
+	h->all_launches++;
+	Staged st;
+	memset (&st, 0, sizeof st);
+	for (u32 i = 0; i < h->n_segments; i++)
+		st.seg_records[i] = h->seg_records[i];
+	st.seg_offsets = h->d_seg_offsets;
+	st.chunk_prefix = h->d_chunk_prefix;
+	st.next_chunk = h->d_next_chunk;
+	st.n_segments = h->n_segments;
+	st.P = h->P;
+	for (;;)
+	{
+		// every CTA may finish one more chunk after the limit is seen: keep that much head room
+		const unsigned max_grid = (unsigned) std::max<u64> (1, h->cap / 8 / STAGE_CHUNK);
+		const u64 head = (u64) std::min<u64> (max_grid, (u64) h->sm_count * 8) * STAGE_CHUNK;
+		const u64 lim = (u64) (0.85 * (double) h->cap);
+		st.node_limit = lim > head ? lim - head : 1;
+		switch (h->W)
+		{
+		case 1: rc = launch_staged<1> (h, st, max_grid); break;
+		case 2: rc = launch_staged<2> (h, st, max_grid); break;
+		default: rc = launch_staged<4> (h, st, max_grid); break;
+		}
+		if (rc)
+			return rc;
+		u64 *hv = h->h_nodes_snap + 1;	// pinned scratch: next_chunk, total chunks
+		CK (h, cudaMemcpyAsync (hv, h->d_next_chunk, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (hv + 1, h->d_chunk_prefix + (size_t) h->P * h->n_segments, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (hv + 2, &h->d_ctr->n_nodes, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaStreamSynchronize (h->stream));
+		const u64 next = hv[0], total = hv[1], nodes = hv[2];
+		if (next >= total)
+			break;
+		// stopped early: project the final node count from the fraction done and re-hash
+		const double frac = std::max (0.02, (double) next / (double) total);
+		const u64 projected = (u64) ((double) nodes / frac);
+		const u64 new_cap = std::max<u64> (h->cap * 2, (u64) ((double) projected / 0.5) + 1024);
+		if ((rc = grow_table (h, new_cap)))
+			return rc;
+	}
+	h->pushed_upper += h->staged_upper;
+	h->n_segments = 0;
+	h->staging_used = 0;
+	h->staged_upper = 0;
+	h->snap_pending = false;
+	h->known_nodes = h->h_nodes_snap[3];
+	h->known_at = h->pushed_upper;
+	return SDTGPU_OK;
+}
+
+// one batch (or part of one) into the staging area: count -> scan -> scatter
+int stage_batch (sdtgpu *h, const ReadBatch &rb, u64 upper)
+{
+	int rc;
+	if (h->staging_used + upper > h->staging_cap || h->n_segments == MAX_SEGMENTS)
+		if ((rc = flush_epoch (h)))
+			return rc;
+	if (h->n_segments == 0)
+	{
+		const double table_bytes = (double) h->cap * (double) slot_bytes (h->W);
+		h->P = (u32) std::min<double> (MAX_BUCKETS, std::max (1.0, std::ceil (table_bytes / h->region_bytes)));
+	}
+	CK (h, cudaMemsetAsync (h->d_counts, 0, h->P * sizeof (u64), h->stream));
+	Bins b;
+	b.records = nullptr;
+	b.counts = h->d_counts;
+	b.capacity = 0;
+	b.n_ranks = h->P;
+	if ((rc = launch_insert<2> (h, rb, b)))
+		return rc;
+	u64 *offsets = h->d_seg_offsets + (size_t) h->n_segments * (h->P + 1);
+	bucket_scan_kernel<<<1, 1024, 0, h->stream>>> (h->d_counts, h->P, h->staging_used, offsets, h->d_cursors);
+	CK (h, cudaGetLastError ());
+	h->all_launches++;
+	b.records = h->staging;
+	b.counts = h->d_cursors;
+	if ((rc = launch_insert<3> (h, rb, b)))
+		return rc;
+	h->seg_records[h->n_segments] = h->staging + h->staging_used * (u64) (h->W + 1);
+	h->n_segments++;
+	h->staging_used += upper;
+	h->staged_upper += upper;
+	return SDTGPU_OK;
+}
+
 }	// namespace
 
 // =================================================================================================
@@ -420,6 +592,7 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 	sdtgpu *h = new sdtgpu ();
 	h->device = device; h->K = K; h->key_words = key_words; h->max_read_len = max_read_len; h->flags = flags;
 	h->W = K <= 31 ? 1 : (K <= 63 ? 2 : 4);
+	h->direct = (flags & SDTGPU_F_PARTITIONED) == 0;
 	h->maxwin = (u32) (max_read_len - K + 1);
 	auto bail = [&](int rc) { g_create_error = h->err; sdtgpu_destroy (h); return rc; };
 	auto body = [&]() -> int {
@@ -436,7 +609,7 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 		}
 		CK (h, cudaMalloc (&h->d_ctr, sizeof (Counters)));
 		CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
-		CK (h, cudaMallocHost (&h->h_nodes_snap, sizeof (u64)));
+		CK (h, cudaMallocHost (&h->h_nodes_snap, 8 * sizeof (u64)));
 		CK (h, cudaEventCreateWithFlags (&h->snap_ev, cudaEventDisableTiming));
 		CK (h, cudaMallocHost (&h->h_ctr, sizeof (Counters)));
 		memset (h->h_ctr, 0, sizeof (Counters));
@@ -473,7 +646,8 @@ void sdtgpu_destroy (sdtgpu_t *h)
 		if (s.free_ev) cudaEventDestroy (s.free_ev);
 		if (s.ready_ev) cudaEventDestroy (s.ready_ev);
 	}
-	for (auto &p : h->timing) { cudaEventDestroy (p.first); cudaEventDestroy (p.second); }
+	for (auto &p : h->timing) { cudaEventDestroy (p.e0); cudaEventDestroy (p.e1); }
+	cudaFree (h->staging); cudaFree (h->d_counts); cudaFree (h->d_cursors); cudaFree (h->d_seg_offsets); cudaFree (h->d_chunk_prefix); cudaFree (h->d_next_chunk);
 	for (auto e : h->ev_pool) cudaEventDestroy (e);
 	cudaFree (h->table);
 	cudaFree (h->d_ctr);
@@ -495,6 +669,7 @@ int sdtgpu_reset (sdtgpu_t *h)
 	if (rc)
 		return rc;
 	h->pushed_upper = 0; h->n_reads = 0; h->finalized = false; h->deLowKmer = 0;
+	h->n_segments = 0; h->staging_used = 0; h->staged_upper = 0;
 	if (h->snap_pending)
 		CK (h, cudaEventSynchronize (h->snap_ev));
 	h->snap_pending = false;
@@ -510,6 +685,9 @@ int sdtgpu_sync (sdtgpu_t *h)
 		return SDTGPU_EINVAL;
 	CK (h, cudaSetDevice (h->device));
 	CK (h, cudaStreamSynchronize (h->copy_stream));
+	int rc = flush_epoch (h);
+	if (rc)
+		return rc;
 	CK (h, cudaStreamSynchronize (h->stream));
 	return SDTGPU_OK;
 }
@@ -524,14 +702,34 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 	int rc = make_batch (h, rb, d_packed, d_lens, d_nmask, n_reads, uniform_len, stride_bytes, first_read_ordinal);
 	if (rc || n_reads == 0)
 		return rc;
-	const u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
-	rc = ensure_capacity (h, upper);
-	if (rc)
-		return rc;
-	h->pushed_upper += upper;
 	h->n_reads += n_reads;
-	rc = launch_insert<0> (h, rb, Bins ());
-	return rc ? rc : snapshot_nodes (h);
+	if (h->direct)
+	{	// single pass: every window goes straight to its (random) slot
+		const u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
+		rc = ensure_capacity (h, upper);
+		if (rc)
+			return rc;
+		h->pushed_upper += upper;
+		rc = launch_insert<0> (h, rb, Bins ());
+		return rc ? rc : snapshot_nodes (h);
+	}
+	// partitioned: stage the batch (in pieces if it is larger than the staging area)
+	if (!h->staging && (rc = alloc_staging (h, 0)))
+		return rc;
+	const u64 per_read = std::max<u64> (instances_upper (h, 1, uniform_len, d_lens != nullptr), 1);
+	const u64 max_reads = std::max<u64> ((h->staging_cap / per_read) & ~1023ull, 1024);
+	for (u64 a = 0; a < n_reads; a += max_reads)
+	{
+		ReadBatch part = rb;
+		part.n_reads = std::min<u64> (max_reads, n_reads - a);
+		part.packed = rb.packed + a * stride_bytes;
+		part.lens = rb.lens ? rb.lens + a : nullptr;
+		part.nmask = rb.nmask ? rb.nmask + a * rb.mask_stride : nullptr;
+		part.first_read_ordinal = first_read_ordinal + a;
+		if ((rc = stage_batch (h, part, part.n_reads * per_read)))
+			return rc;
+	}
+	return SDTGPU_OK;
 }
 
 int sdtgpu_push_reads (sdtgpu_t *h, const uint8_t *packed, const uint32_t *lens, const uint8_t *nmask,
@@ -607,7 +805,10 @@ int sdtgpu_insert_records_device (sdtgpu_t *h, const void *d_records, uint64_t n
 	if (!d_records || ((uintptr_t) d_records & (h->W == 1 ? 15 : 7)))
 		return fail (h, SDTGPU_EINVAL, "records must be aligned device memory (16 bytes for 1-word keys, else 8)");
 	CK (h, cudaSetDevice (h->device));
-	int rc = ensure_capacity (h, n_records);
+	int rc = flush_epoch (h);
+	if (rc)
+		return rc;
+	rc = ensure_capacity (h, n_records);
 	if (rc)
 		return rc;
 	h->pushed_upper += n_records;
@@ -623,8 +824,7 @@ int sdtgpu_insert_records_device (sdtgpu_t *h, const void *d_records, uint64_t n
 	}
 	CK (h, cudaGetLastError ());
 	CK (h, cudaEventRecord (e1, h->stream));
-	h->timing.emplace_back (e0, e1);
-	h->insert_launches++;
+	h->timing.push_back ({ e0, e1, 0 });
 	h->all_launches++;
 	return snapshot_nodes (h);
 }
@@ -646,7 +846,10 @@ int sdtgpu_get_stats (sdtgpu_t *h, sdtgpu_stats *stats)
 	if (!h || !stats)
 		return SDTGPU_EINVAL;
 	CK (h, cudaSetDevice (h->device));
-	int rc = read_counters (h);
+	int rc = flush_epoch (h);
+	if (rc)
+		return rc;
+	rc = read_counters (h);
 	if (rc)
 		return rc;
 	fill_stats (h, stats);
@@ -665,6 +868,9 @@ int sdtgpu_finalize (sdtgpu_t *h, int deLowKmer, int64_t kmerFreq[257], sdtgpu_s
 		return fail (h, SDTGPU_EINVAL, "deLowKmer is a char in the reference (0..127)");
 	CK (h, cudaSetDevice (h->device));
 	CK (h, cudaStreamSynchronize (h->copy_stream));
+	int frc = flush_epoch (h);
+	if (frc)
+		return frc;
 	const unsigned grid = (unsigned) std::min<u64> ((h->cap + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
 	switch (h->W)
 	{
@@ -692,7 +898,10 @@ int sdtgpu_export_count (sdtgpu_t *h, uint64_t *n_nodes)
 	if (!h || !n_nodes)
 		return SDTGPU_EINVAL;
 	CK (h, cudaSetDevice (h->device));
-	int rc = read_counters (h);
+	int rc = flush_epoch (h);
+	if (rc)
+		return rc;
+	rc = read_counters (h);
 	if (rc)
 		return rc;
 	*n_nodes = h->h_ctr->n_nodes;
@@ -704,7 +913,10 @@ int sdtgpu_export_nodes (sdtgpu_t *h, int thrd_num, int sort_by_ordinal, sdtgpu_
 	if (!h || !out || !n_nodes || thrd_num < 1)
 		return SDTGPU_EINVAL;
 	CK (h, cudaSetDevice (h->device));
-	int rc = read_counters (h);
+	int rc = flush_epoch (h);
+	if (rc)
+		return rc;
+	rc = read_counters (h);
 	if (rc)
 		return rc;
 	const u64 n = h->h_ctr->n_nodes;
@@ -774,28 +986,57 @@ void sdtgpu_host_free (void *p)
 		cudaFreeHost (p);
 }
 
-int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *insert_launches, uint64_t *all_launches)
+static int collect_times (sdtgpu *h)
 {
-	if (!h)
-		return SDTGPU_EINVAL;
 	CK (h, cudaSetDevice (h->device));
 	CK (h, cudaStreamSynchronize (h->stream));
 	for (auto &p : h->timing)
 	{
 		float ms = 0;
-		CK (h, cudaEventElapsedTime (&ms, p.first, p.second));
-		h->insert_ms_acc += ms;
-		h->ev_pool.push_back (p.first);
-		h->ev_pool.push_back (p.second);
+		CK (h, cudaEventElapsedTime (&ms, p.e0, p.e1));
+		h->cat_ms[p.cat] += ms;
+		h->cat_launches[p.cat]++;
+		h->ev_pool.push_back (p.e0);
+		h->ev_pool.push_back (p.e1);
 	}
 	h->timing.clear ();
-	if (insert_ms) *insert_ms = h->insert_ms_acc;
-	if (insert_launches) *insert_launches = h->insert_launches;
+	return SDTGPU_OK;
+}
+
+int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *insert_launches, uint64_t *all_launches)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	int rc = collect_times (h);
+	if (rc)
+		return rc;
+	if (insert_ms) *insert_ms = h->cat_ms[0];
+	if (insert_launches) *insert_launches = h->cat_launches[0];
 	if (all_launches) *all_launches = h->all_launches;
 	if (reset)
 	{
-		h->insert_ms_acc = 0;
-		h->insert_launches = h->all_launches = 0;
+		for (int i = 0; i < 3; i++) { h->cat_ms[i] = 0; h->cat_launches[i] = 0; }
+		h->all_launches = 0;
+	}
+	return SDTGPU_OK;
+}
+
+int sdtgpu_kernel_times (sdtgpu_t *h, int reset, double ms[3], uint64_t launches[3])
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	int rc = collect_times (h);
+	if (rc)
+		return rc;
+	for (int i = 0; i < 3; i++)
+	{
+		if (ms) ms[i] = h->cat_ms[i];
+		if (launches) launches[i] = h->cat_launches[i];
+	}
+	if (reset)
+	{
+		for (int i = 0; i < 3; i++) { h->cat_ms[i] = 0; h->cat_launches[i] = 0; }
+		h->all_launches = 0;
 	}
 	return SDTGPU_OK;
 }

@@ -20,6 +20,7 @@ NODE_DTYPE = np.dtype([("key", "<u8", (4,)), ("l_links", "<u4"), ("rword", "<u4"
 assert NODE_DTYPE.itemsize == 56
 
 F_NKMER = 1
+F_PARTITIONED = 2
 _ERR = {1: "EINVAL", 2: "ECUDA", 3: "ENOMEM", 4: "ERANGE", 5: "ESTATE"}
 
 
@@ -90,6 +91,7 @@ def library() -> C.CDLL:
     L.sdtgpu_stream.restype = vp
     L.sdtgpu_stream.argtypes = [vp]
     L.sdtgpu_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)]
+    L.sdtgpu_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.sdtgpu_synth_reads_device.argtypes = [i32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u32, u32, vp]
     _lib = L
     return L
@@ -158,12 +160,12 @@ class PregraphGPU:
     stage of `pregraph` (prlRead2HashTable, prlHashReads.c:338)."""
 
     def __init__(self, K: int, key_words: int, max_read_len: int, capacity_hint: int = 0, device: int = 0,
-                 n_kmer: bool = False):
+                 n_kmer: bool = False, partitioned: bool = False):
         self.L = library()
         self.h = C.c_void_p()
         self.K, self.key_words, self.max_read_len, self.device = K, key_words, max_read_len, device
         rc = self.L.sdtgpu_create(C.byref(self.h), device, K, key_words, max_read_len, capacity_hint,
-                                  F_NKMER if n_kmer else 0)
+                                  (F_NKMER if n_kmer else 0) | (F_PARTITIONED if partitioned else 0))
         if rc:
             raise SdtGpuError(rc, self.L.sdtgpu_last_error(None).decode())
 
@@ -247,6 +249,12 @@ class PregraphGPU:
         ms, nl, al = C.c_double(), C.c_uint64(), C.c_uint64()
         self._ck(self.L.sdtgpu_kernel_time(self.h, int(reset), C.byref(ms), C.byref(nl), C.byref(al)))
         return ms.value, nl.value, al.value
+
+    def kernel_times(self, reset: bool = True):
+        """(ms[3], launches[3]) for insert / partition-count / partition-scatter kernels."""
+        ms, nl = (C.c_double * 3)(), (C.c_uint64 * 3)()
+        self._ck(self.L.sdtgpu_kernel_times(self.h, int(reset), ms, nl))
+        return list(ms), list(nl)
 
 
 def synth_reads_device(tr_dev: dict, seed: int, first_pair: int, n_pairs: int, read_len: int, stride_bytes: int,
