@@ -114,7 +114,9 @@ int sdtgpu_sync (sdtgpu_t *h);
  * then one meta word = ordinal << 8 | left << 4 | right  (left/right 0..3, or 4 = none).
  * d_bins holds n_ranks bins of bin_capacity records each; d_counts[n_ranks] (u64) must be zeroed
  * by the caller and receives the fill of each bin (a bin that would overflow is reported through
- * SDTGPU_ERANGE at the next sdtgpu_sync). */
+ * SDTGPU_ERANGE at the next sdtgpu_sync).  bucket_reads_device is enqueued on the handle's auxiliary
+ * stream (sdtgpu_aux_stream), insert_records_device on the main one, so the send side of round r+1
+ * overlaps the inserts of round r; the caller orders the two with events. */
 size_t sdtgpu_record_bytes (const sdtgpu_t *h);
 int sdtgpu_bucket_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32_t *d_lens, const uint8_t *d_nmask,
 				uint64_t n_reads, uint32_t uniform_len, uint32_t stride_bytes, uint64_t first_read_ordinal,
@@ -148,7 +150,8 @@ int sdtgpu_host_alloc (void **out, size_t bytes);
 void sdtgpu_host_free (void *p);
 
 /* ---- measurement hooks */
-void *sdtgpu_stream (sdtgpu_t *h);	/* the cudaStream_t all work of this handle is enqueued on */
+void *sdtgpu_stream (sdtgpu_t *h);	/* the cudaStream_t the handle's insert work is enqueued on */
+void *sdtgpu_aux_stream (sdtgpu_t *h);	/* second stream: H2D copies of push_reads and bucket_reads_device kernels */
 /* device time (ms, CUDA events on the handle's stream) and launch count accumulated by the insert
  * kernels since the last call with reset != 0 */
 int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *insert_launches, uint64_t *all_launches);

@@ -39,6 +39,7 @@ struct sdtgpu
 	Counters *d_ctr = nullptr;
 	Counters *h_ctr = nullptr;	// pinned mirror
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	cudaStream_t launch_stream = nullptr;	// stream the next read kernel goes to (main unless bucketing)
 	Staging stage[2];
 	int next_stage = 0;
 	int sm_count = 0;
@@ -225,11 +226,12 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 		return fail (h, SDTGPU_EINVAL, "read stride too large for one shared-memory tile");
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
 	const unsigned grid = (unsigned) std::min<u64> (n_tiles, (u64) h->sm_count * occ);
+	cudaStream_t ls = h->launch_stream ? h->launch_stream : h->stream;
 	cudaEvent_t e0 = get_event (h), e1 = get_event (h);
-	CK (h, cudaEventRecord (e0, h->stream));
-	kern<<<grid, BLOCK, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, rb, bins, h->d_ctr);
+	CK (h, cudaEventRecord (e0, ls));
+	kern<<<grid, BLOCK, smem, ls>>> (static_cast<S *> (h->table), h->cap, rb, bins, h->d_ctr);
 	CK (h, cudaGetLastError ());
-	CK (h, cudaEventRecord (e1, h->stream));
+	CK (h, cudaEventRecord (e1, ls));
 	h->timing.push_back ({ e0, e1, MODE == 2 ? 1 : (MODE == 3 || MODE == 1 ? 2 : 0) });
 	h->all_launches++;
 	return SDTGPU_OK;
@@ -678,6 +680,7 @@ int sdtgpu_reset (sdtgpu_t *h)
 }
 
 void *sdtgpu_stream (sdtgpu_t *h) { return h ? (void *) h->stream : nullptr; }
+void *sdtgpu_aux_stream (sdtgpu_t *h) { return h ? (void *) h->copy_stream : nullptr; }
 
 int sdtgpu_sync (sdtgpu_t *h)
 {
@@ -791,7 +794,10 @@ int sdtgpu_bucket_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint
 	b.capacity = bin_capacity;
 	b.n_ranks = (u32) n_ranks;
 	h->n_reads += n_reads;
-	return launch_insert<1> (h, rb, b);
+	h->launch_stream = h->copy_stream;	// the send side runs on the auxiliary stream so that it
+	rc = launch_insert<1> (h, rb, b);	// overlaps the inserts of the previous round
+	h->launch_stream = nullptr;
+	return rc;
 }
 
 int sdtgpu_insert_records_device (sdtgpu_t *h, const void *d_records, uint64_t n_records)
@@ -989,6 +995,7 @@ void sdtgpu_host_free (void *p)
 static int collect_times (sdtgpu *h)
 {
 	CK (h, cudaSetDevice (h->device));
+	CK (h, cudaStreamSynchronize (h->copy_stream));
 	CK (h, cudaStreamSynchronize (h->stream));
 	for (auto &p : h->timing)
 	{

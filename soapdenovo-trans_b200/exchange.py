@@ -56,30 +56,42 @@ def exchange_records(send: torch.Tensor, send_counts: torch.Tensor, recv: torch.
 
 
 class Exchange:
-    """Round driver for bench.py / multi-rank callers.  All device work is enqueued on the table's
-    own stream (made torch's current stream, so the NCCL collectives order against it)."""
+    """Round driver for bench.py / multi-rank callers, software-pipelined over two buffer sets:
+    bucket(r+1) and the NCCL exchange of round r+1 run on the table's auxiliary stream while
+    insert(r) runs on its main stream; events order buffer reuse."""
 
     def __init__(self, pkg, g, world: int, rank: int, dev, max_round_instances: int, slack: float = 1.15):
         self.pkg, self.world, self.rank, self.dev = pkg, world, rank, dev
         self.words = g.record_bytes() // 8
         self.cap = int(max_round_instances / world * slack) + 65536
-        self.send = torch.empty((world, self.cap, self.words), dtype=torch.int64, device=dev)
-        self.counts = torch.zeros(world, dtype=torch.int64, device=dev)
-        self.recv = torch.empty((int(self.cap * world), self.words), dtype=torch.int64, device=dev)
+        self.send = [torch.empty((world, self.cap, self.words), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.counts = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.recv = [torch.empty((int(self.cap * world), self.words), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.inserted = [torch.cuda.Event() for _ in range(2)]     # insert(r) finished reading recv[r % 2]
+        self.received = torch.cuda.Event()
+        self.r = 0
         self.rebind(g)
         self.nvlink_bytes = 0
 
     def rebind(self, g):
-        self.ext = torch.cuda.ExternalStream(g.stream, device=self.dev)
+        self.main = torch.cuda.ExternalStream(g.stream, device=self.dev)
+        self.aux = torch.cuda.ExternalStream(g.aux_stream, device=self.dev)
 
     def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None):
-        with torch.cuda.stream(self.ext):
-            self.counts.zero_()
+        b = self.r & 1
+        self.r += 1
+        with torch.cuda.stream(self.aux):
+            self.aux.wait_event(self.inserted[b])          # buffer set b is free again
+            self.counts[b].zero_()
             g.bucket_reads_device(d_packed, d_lens, None, n_reads, uniform_len, stride, first_read_ordinal,
-                                  self.world, self.send, self.cap, self.counts)
-            total, rc = exchange_records(self.send, self.counts, self.recv)
-            self.nvlink_bytes += (total - rc[self.rank]) * self.words * 8
-            g.insert_records_device(self.recv, total)
+                                  self.world, self.send[b], self.cap, self.counts[b])
+            total, rc = exchange_records(self.send[b], self.counts[b], self.recv[b])
+            self.received.record(self.aux)
+        self.nvlink_bytes += (total - rc[self.rank]) * self.words * 8
+        with torch.cuda.stream(self.main):
+            self.main.wait_event(self.received)
+            g.insert_records_device(self.recv[b], total)
+            self.inserted[b].record(self.main)
 
     def flush(self, g):
         pass

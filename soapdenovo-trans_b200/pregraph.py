@@ -90,6 +90,8 @@ def library() -> C.CDLL:
     L.sdtgpu_free_kmersets.restype = None
     L.sdtgpu_stream.restype = vp
     L.sdtgpu_stream.argtypes = [vp]
+    L.sdtgpu_aux_stream.restype = vp
+    L.sdtgpu_aux_stream.argtypes = [vp]
     L.sdtgpu_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)]
     L.sdtgpu_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.sdtgpu_synth_reads_device.argtypes = [i32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u32, u32, vp]
@@ -195,6 +197,10 @@ class PregraphGPU:
     @property
     def stream(self) -> int:
         return int(self.L.sdtgpu_stream(self.h) or 0)
+
+    @property
+    def aux_stream(self) -> int:
+        return int(self.L.sdtgpu_aux_stream(self.h) or 0)
 
     def push_reads(self, packed, lens=None, nmask=None, n_reads=None, uniform_len=0, stride_bytes=None,
                    first_read_ordinal=0, device=False):
