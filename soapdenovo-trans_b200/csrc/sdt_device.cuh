@@ -24,14 +24,17 @@ static constexpr u64 ORD40_NONE = (1ull << 40) - 1;
 static constexpr u32 LINK_SAT = 63;	// MAX_KMER_COV, inc/newhash.h:30
 
 // ------------------------------------------------------------------------------------------------
-// memory primitives (all table traffic bypasses L1: the table is mutated by L2 atomics)
+// memory primitives (all table traffic bypasses L1: the table is mutated by L2 atomics).
+// .L2::64B: by default a missing load makes the B200 L2 fetch the whole 128-byte line (127 B of DRAM
+// reads per random 16-byte load, tools/ldvar_bench.cu); the 64-byte prefetch size is the smallest
+// the ISA offers and halves that (cudaLimitMaxL2FetchGranularity has no effect on this part).
 __device__ __forceinline__ void ld256 (const void *p, u64 &a, u64 &b, u64 &c, u64 &d)
 {
-	asm volatile ("ld.global.relaxed.gpu.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+	asm volatile ("ld.global.relaxed.gpu.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void ld128 (const void *p, u64 &a, u64 &b)
 {
-	asm volatile ("ld.global.relaxed.gpu.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+	asm volatile ("ld.global.relaxed.gpu.L2::64B.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void st128 (void *p, u64 a, u64 b)
 {
