@@ -204,7 +204,7 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		smem[tid] = 0;
 		smem[TILE_PAD + rb.tile_reads * sw + tid] = 0;
 	}
-	if (MODE == 2 || MODE == 3)
+	if (MODE != 0)
 		for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
 			hist[b] = 0;
 
@@ -287,9 +287,10 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		__syncthreads ();
 		instances += (tid == 0) ? total : 0;
 
-		// MODE 3 walks the tile twice: sweep 0 counts the tile's records per bucket, one global atomic
-		// per non-empty bucket then reserves their space, sweep 1 writes the records
-		for (int sweep = (MODE == 3 ? 0 : 1); sweep < 2; sweep++)
+		// MODE 1 / 3 walk the tile twice: sweep 0 counts the tile's records per bin, ONE global atomic per
+		// non-empty bin then reserves their space, sweep 1 writes the records (chopping twice is cheap;
+		// a contended global cursor atomic per warp was 3x slower, profiles/r1_multi_gpu.md)
+		for (int sweep = ((MODE == 3 || MODE == 1) ? 0 : 1); sweep < 2; sweep++)
 		{
 		for (u32 w = tid; w < total; w += BLOCK)
 		{
@@ -322,7 +323,17 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 			if (MODE == 0)
 				created += Table<W>::upsert (table, cap, key, left, right, ord);
 			else if (MODE == 1)
-				emit_record<W> (bins, key, left, right, ord, key_hash<W> (key));
+			{	// send side of the exchange: bin = owner rank, fixed capacity per bin
+				const u32 b = owner_of (key_hash<W> (key), bins.n_ranks);
+				if (sweep == 0)
+					atomicAdd (&hist[b], 1u);
+				else
+				{
+					const u64 pos = base[b] + atomicAdd (&hist[b], 1u);
+					if (pos < bins.capacity)	// else: the host sees counts[b] > capacity and reports it
+						store_record<W> (bins.records + ((u64) b * bins.capacity + pos) * (W + 1), key, left, right, ord);
+				}
+			}
 			else if (MODE == 2)	// partition pass 1: how many records per slot-range bucket
 				atomicAdd (&hist[(u32) __umul64hi (key_hash<W> (key), (u64) bins.n_ranks)], 1u);
 			else
@@ -337,7 +348,7 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 				}
 			}
 		}
-		if (MODE == 3)
+		if (MODE == 3 || MODE == 1)
 		{
 			__syncthreads ();
 			if (sweep == 0)

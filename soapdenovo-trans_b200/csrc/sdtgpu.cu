@@ -217,7 +217,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 {
 	typedef typename SlotOf<W>::type S;
 	auto kern = insert_reads_kernel<W, NMODE, MODE>;
-	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : (MODE == 3 ? 3 * (size_t) bins.n_ranks + 4 : 0));
+	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : ((MODE == 3 || MODE == 1) ? 3 * (size_t) bins.n_ranks + 4 : 0));
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
