@@ -29,6 +29,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_INSTANCE = {1: 64, 2: 64, 4: 96}
+# Measured on this pool's B200 with tools/randacc_bench.cu (profiles/r1_randacc_bench.txt): requests to
+# cold lines of a table >> L2 complete at 36.65 G/s no matter their kind (load, CAS, RED) or width; an
+# upsert needs at least one load and one atomic, so a single-pass insert cannot exceed half of that.
+RANDOM_REQUESTS_PER_S = 36.65e9
+MIN_REQUESTS_PER_INSTANCE = {1: 2, 2: 2, 4: 3}
 METRIC = "k-mers inserted/s in pregraph hashing"
 UNIT = "k-mer instances/s"
 
@@ -257,33 +262,56 @@ def main():
     ker_ms = insert_ms / max(insert_launches, 1)
     inst_per_launch = st.n_instances * args.steps / max(insert_launches, 1)
     achieved = inst_per_launch * bpi / (ker_ms * 1e-3) / 1e9
+    traffic = None      # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp) and world == 1 and not args.partitioned:
+        with open(tp) as f:
+            tj = json.load(f)
+        if tj.get("key_words") == st.device_key_words:
+            traffic = tj["dram_bytes_per_instance"] * inst_per_launch
 
-    # ---- e2e: HOST (pinned) buffers through the C ABI, H2D inside, counters read back (D2H)
+    # ---- e2e: HOST (pinned) buffers, H2D inside the timed region, counters read back (D2H) every step.
+    # N = 1: straight through the C ABI's host entry point (sdtgpu_push_reads).  N > 1: every rank
+    # copies its round's reads from pinned host memory, then bucket -> exchange -> insert as above.
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         h_packed = torch.empty((n_reads, stride), dtype=torch.uint8).pin_memory()
         h_packed.copy_(d_packed)
         torch.cuda.synchronize()
+        d_round = [torch.empty((min(batch, n_reads), stride), dtype=torch.uint8, device=dev) for _ in range(2)] if exch is not None else None
 
         def e2e_step():
             g.reset()
-            for a in range(0, n_reads, batch):
+            for i, a in enumerate(range(0, n_reads, batch)):
                 b = min(a + batch, n_reads)
-                g.push_reads(h_packed[a:b], None, None, n_reads=b - a, uniform_len=L, stride_bytes=stride,
-                             first_read_ordinal=a)
+                if exch is None:
+                    g.push_reads(h_packed[a:b], None, None, n_reads=b - a, uniform_len=L, stride_bytes=stride,
+                                 first_read_ordinal=a)
+                else:
+                    buf = d_round[i & 1]
+                    with torch.cuda.stream(exch.aux):
+                        exch.aux.wait_event(exch.inserted[exch.r & 1])      # same buffer parity as the exchange
+                        buf[: b - a].copy_(h_packed[a:b], non_blocking=True)
+                    exch.round(g, buf, b - a, L, stride, 2 * first_pair + a)
+            g.sync()
             return g.stats()
         e2e_step()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             s2 = e2e_step()
-        torch.cuda.synchronize()
+        barrier()
         dt = (time.perf_counter() - t0) / args.steps
-        assert s2.n_instances == instances_rank and s2.n_nodes == distinct
-        e2e = {"value": instances_rank / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_reads * stride),
-               "d2h_bytes_per_step": 2120, "ms_per_step": dt * 1e3}
-    elif world > 1:
-        e2e = None
+        assert exch is not None or (s2.n_instances == instances_rank and s2.n_nodes == distinct)
+        tt = torch.tensor([dt, float(s2.n_instances)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = tt.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = tt.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            dt, e2e_inst = float(tm[0]), float(ts[1])
+        else:
+            e2e_inst = float(s2.n_instances)
+        e2e = {"value": e2e_inst / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_reads * stride) * world,
+               "d2h_bytes_per_step": 2120 * world, "ms_per_step": dt * 1e3}
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
@@ -306,17 +334,26 @@ def main():
                        "batch_reads": batch,
                        "l2": "table (>= 2x distinct x slot bytes) and reads are far larger than the 126 MB L2; table is reset every step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": None, "kernel": ("insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if world == 1 else "insert_records_kernel",
+                         "traffic": traffic, "kernel": ("insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if world == 1 else "insert_records_kernel",
                          "bytes_per_instance": bpi, "kernel_ms_per_launch": ker_ms, "peak_source": peak_src,
+                         "random_access": {"cold_line_requests_per_s_measured": RANDOM_REQUESTS_PER_S,
+                                           "min_requests_per_instance": MIN_REQUESTS_PER_INSTANCE[st.device_key_words],
+                                           "ceiling_instances_per_s_per_gpu": RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words],
+                                           "frac_of_ceiling": (inst_per_launch / (ker_ms * 1e-3)) / (RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words]),
+                                           "source": "tools/randacc_bench.cu, profiles/r1_randacc_bench.txt"},
                          "kernel_ms_per_step": {"insert": cat_ms[0] / args.steps, "partition_count": cat_ms[1] / args.steps,
                                                 "partition_scatter": cat_ms[2] / args.steps}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(all_launches),
             "clocks": sampler.summary(),
         }
-        print(json.dumps(line))
-    g.close()
+        print(json.dumps(line), flush=True)
+    # orderly teardown: tensors that were used on the table's streams must go before the streams do
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
