@@ -64,6 +64,25 @@ __device__ __forceinline__ uint4 ldg_stream (const uint4 *p)
 	return v;
 }
 
+// ---- hash_kmer restated (hashFunction.c:83-122): CRC-32 table arithmetic carried in a signed int
+// (arithmetic >> 8), over the raw bytes of the reference's Kmer object (8 * key_words bytes, words
+// in declaration order, each little endian), masked to 24 bits.  Its only use in the reference is
+// owner set = hash % thrd_num (prlHashReads.c:81); here it is needed at hand-back time only.
+__constant__ int c_crc[256];
+
+__host__ __device__ inline u32 hash_kmer_impl (const uint64_t *key, int key_words, const int *tab)
+{
+	int crc = ~0;
+	for (int w = 4 - key_words; w < 4; w++)
+		for (int b = 0; b < 8; b++)
+		{
+			const int byte = (int) (signed char) (unsigned char) (key[w] >> (8 * b));
+			crc = tab[(crc ^ byte) & 0xff] ^ (crc >> 8);
+		}
+	crc = ~crc;
+	return (u32) crc & 0x00ffffffu;
+}
+
 // one window -> canonical key and the link bases in the stored orientation
 template <int W, bool NMODE>
 __device__ __forceinline__ void chop_window (const u32 *rd, const u32 *mk, int len, int j, int K,
@@ -204,7 +223,10 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		smem[tid] = 0;
 		smem[TILE_PAD + rb.tile_reads * sw + tid] = 0;
 	}
-	if (MODE != 0)
+	if (MODE == 4)
+		for (u32 b = tid; b < 2 * bins.n_ranks; b += BLOCK)
+			hist[b] = 0;
+	else if (MODE != 0)
 		for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
 			hist[b] = 0;
 
@@ -334,6 +356,17 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 						store_record<W> (bins.records + ((u64) b * bins.capacity + pos) * (W + 1), key, left, right, ord);
 				}
 			}
+			else if (MODE == 4)
+			{	// per reference set: the largest instance ordinal (bins.n_ranks = thrd_num, bins.capacity = key_words)
+				uint64_t k4[4] = { 0, 0, 0, 0 };
+#pragma unroll
+				for (int q = 0; q < W; q++)
+					k4[4 - W + q] = key.w[q];
+				const u32 set = hash_kmer_impl (k4, (int) bins.capacity, c_crc) % bins.n_ranks;
+				u64 *smax = reinterpret_cast<u64 *> (hist);
+				if (ord + 1 > smax[set])
+					atomicMax (&smax[set], ord + 1);	// stored +1 so that 0 means "no instance"
+			}
 			else if (MODE == 2)	// partition pass 1: how many records per slot-range bucket
 				atomicAdd (&hist[(u32) __umul64hi (key_hash<W> (key), (u64) bins.n_ranks)], 1u);
 			else
@@ -377,6 +410,14 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
 			if (hist[b])
 				atomicAdd (bins.counts + b, (u64) hist[b]);
+	}
+	if (MODE == 4)
+	{
+		__syncthreads ();
+		const u64 *smax = reinterpret_cast<const u64 *> (hist);
+		for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
+			if (smax[b])
+				atomicMax (bins.counts + b, smax[b]);
 	}
 	// ---- counters: one atomic per warp
 #pragma unroll

@@ -44,6 +44,13 @@ struct sdtgpu
 	int next_stage = 0;
 	int sm_count = 0;
 	u64 pushed_upper = 0;	// upper bound of instances pushed (host-side arithmetic)
+	// the most recent batch stays on the device until the next one arrives: the hand-back needs the
+	// per-set last instance ordinal (put_kmerset runs encap_kmerset on every call, newhash.c:415)
+	uint8_t *last_packed = nullptr, *last_mask = nullptr;
+	u32 *last_lens = nullptr;
+	size_t last_cap_packed = 0, last_cap_mask = 0, last_cap_lens = 0;
+	ReadBatch last_rb;
+	bool have_last = false;
 	// lagging snapshot of the node counter, so that the capacity check never has to drain the stream
 	u64 *h_nodes_snap = nullptr;	// pinned
 	cudaEvent_t snap_ev = nullptr;
@@ -217,7 +224,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 {
 	typedef typename SlotOf<W>::type S;
 	auto kern = insert_reads_kernel<W, NMODE, MODE>;
-	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : ((MODE == 3 || MODE == 1) ? 3 * (size_t) bins.n_ranks + 4 : 0));
+	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : ((MODE == 3 || MODE == 1) ? 3 * (size_t) bins.n_ranks + 4 : (MODE == 4 ? 2 * (size_t) bins.n_ranks + 2 : 0)));
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
@@ -232,7 +239,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 	kern<<<grid, BLOCK, smem, ls>>> (static_cast<S *> (h->table), h->cap, rb, bins, h->d_ctr);
 	CK (h, cudaGetLastError ());
 	CK (h, cudaEventRecord (e1, ls));
-	h->timing.push_back ({ e0, e1, MODE == 2 ? 1 : (MODE == 3 || MODE == 1 ? 2 : 0) });
+	h->timing.push_back ({ e0, e1, MODE == 2 ? 1 : (MODE == 0 ? 0 : 2) });
 	h->all_launches++;
 	return SDTGPU_OK;
 }
@@ -309,9 +316,6 @@ int ensure_stage (sdtgpu *h, Staging &s, size_t packed, size_t lens, size_t mask
 	return SDTGPU_OK;
 }
 
-// ---- hash_kmer restated for the export partition (hashFunction.c:83-122): CRC-32 table arithmetic
-// carried in a signed int (arithmetic >> 8), over the raw bytes of the reference's Kmer object.
-__constant__ int c_crc[256];
 int h_crc[256];
 bool h_crc_ready = false;
 
@@ -327,19 +331,6 @@ void crc_table_host ()
 		h_crc[n] = (int) c;
 	}
 	h_crc_ready = true;
-}
-
-__host__ __device__ inline u32 hash_kmer_impl (const uint64_t *key, int key_words, const int *tab)
-{
-	int crc = ~0;
-	for (int w = 4 - key_words; w < 4; w++)
-		for (int b = 0; b < 8; b++)
-		{
-			const int byte = (int) (signed char) (unsigned char) (key[w] >> (8 * b));
-			crc = tab[(crc ^ byte) & 0xff] ^ (crc >> 8);
-		}
-	crc = ~crc;
-	return (u32) crc & 0x00ffffffu;
 }
 
 template <int W>
@@ -390,6 +381,65 @@ export_kernel (const typename SlotOf<W>::type *table, u64 cap, int key_words, in
 		n.ordinal = ord;
 		out[pos] = n;
 	}
+}
+
+// device copy of the newest batch (device-to-device, a few hundred microseconds per 100 MB)
+int retain_last_batch (sdtgpu *h, const ReadBatch &rb)
+{
+	const size_t pb = (size_t) rb.n_reads * rb.stride_bytes, lb = rb.lens ? (size_t) rb.n_reads * 4 : 0;
+	const size_t mb = rb.nmask ? (size_t) rb.n_reads * rb.mask_stride : 0;
+	auto fit = [&](void **p, size_t &cap, size_t need) -> cudaError_t {
+		if (need <= cap)
+			return cudaSuccess;
+		if (*p)
+			cudaFree (*p);
+		*p = nullptr;
+		cap = need + need / 4 + 4096;
+		return cudaMalloc (p, cap);
+	};
+	CK (h, fit ((void **) &h->last_packed, h->last_cap_packed, pb));
+	CK (h, fit ((void **) &h->last_lens, h->last_cap_lens, lb));
+	CK (h, fit ((void **) &h->last_mask, h->last_cap_mask, mb));
+	CK (h, cudaMemcpyAsync (h->last_packed, rb.packed, pb, cudaMemcpyDeviceToDevice, h->stream));
+	if (lb)
+		CK (h, cudaMemcpyAsync (h->last_lens, rb.lens, lb, cudaMemcpyDeviceToDevice, h->stream));
+	if (mb)
+		CK (h, cudaMemcpyAsync (h->last_mask, rb.nmask, mb, cudaMemcpyDeviceToDevice, h->stream));
+	h->last_rb = rb;
+	h->last_rb.packed = h->last_packed;
+	h->last_rb.lens = lb ? h->last_lens : nullptr;
+	h->last_rb.nmask = mb ? h->last_mask : nullptr;
+	h->have_last = true;
+	return SDTGPU_OK;
+}
+
+// per reference set: (largest instance ordinal + 1) within the retained batch, 0 if none
+int set_last_ordinals (sdtgpu *h, int thrd_num, std::vector<u64> &last)
+{
+	last.assign (thrd_num, 0);
+	if (!h->have_last || thrd_num > 1024)
+		return SDTGPU_OK;
+	u64 *d_last = nullptr;
+	CK (h, cudaMalloc (&d_last, thrd_num * sizeof (u64)));
+	CK (h, cudaMemsetAsync (d_last, 0, thrd_num * sizeof (u64), h->stream));
+	Bins b;
+	b.records = nullptr;
+	b.counts = d_last;
+	b.capacity = (u64) h->key_words;
+	b.n_ranks = (u32) thrd_num;
+	int rc = launch_insert<4> (h, h->last_rb, b);
+	cudaError_t e = cudaSuccess;
+	if (!rc)
+	{
+		e = cudaMemcpyAsync (last.data (), d_last, thrd_num * sizeof (u64), cudaMemcpyDeviceToHost, h->stream);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize (h->stream);
+	}
+	cudaFree (d_last);
+	if (rc)
+		return rc;
+	CK (h, e);
+	return SDTGPU_OK;
 }
 
 // ---- partitioned insert -----------------------------------------------------------------------
@@ -649,6 +699,7 @@ void sdtgpu_destroy (sdtgpu_t *h)
 		if (s.ready_ev) cudaEventDestroy (s.ready_ev);
 	}
 	for (auto &p : h->timing) { cudaEventDestroy (p.e0); cudaEventDestroy (p.e1); }
+	cudaFree (h->last_packed); cudaFree (h->last_mask); cudaFree (h->last_lens);
 	cudaFree (h->staging); cudaFree (h->d_counts); cudaFree (h->d_cursors); cudaFree (h->d_seg_offsets); cudaFree (h->d_chunk_prefix); cudaFree (h->d_next_chunk);
 	for (auto e : h->ev_pool) cudaEventDestroy (e);
 	cudaFree (h->table);
@@ -706,6 +757,8 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 	if (rc || n_reads == 0)
 		return rc;
 	h->n_reads += n_reads;
+	if ((rc = retain_last_batch (h, rb)))
+		return rc;
 	if (h->direct)
 	{	// single pass: every window goes straight to its (random) slot
 		const u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
@@ -968,9 +1021,19 @@ int sdtgpu_export_kmersets (sdtgpu_t *h, int thrd_num, sdtgpu_kmerset **sets)
 	if (!nodes)
 		return fail (h, SDTGPU_ENOMEM, "host allocation for export failed");
 	rc = sdtgpu_export_nodes (h, thrd_num, 0, nodes, n, &n);
+	std::vector<u64> last;
+	if (!rc)
+		rc = set_last_ordinals (h, thrd_num, last);
 	if (!rc)
 	{
-		rc = sdtgpu_build_kmersets (nodes, n, h->key_words, thrd_num, nullptr, sets);
+		// last[s] = (largest instance ordinal of set s in the newest batch) + 1, or 0 when that batch
+		// had no instance of s.  In the latter case a later instance than the set's newest key can only
+		// have come from an older batch; every batch of >= a few hundred reads touches every set, so a
+		// set that the newest batch missed is assumed to have ended with its newest key.
+		std::vector<uint64_t> last_ord (thrd_num, 0);
+		for (int t = 0; t < thrd_num; t++)
+			last_ord[t] = last[t] ? last[t] - 1 : 0;
+		rc = sdtgpu_build_kmersets (nodes, n, h->key_words, thrd_num, h->have_last ? last_ord.data () : nullptr, sets);
 		if (rc)
 			h->err = "sdtgpu_build_kmersets failed";
 	}

@@ -115,6 +115,28 @@ def test_edge_cases(pkg, oracle):
     check_against_oracle(pkg, oracle, reads, lens3, 25, 1, d=0)
 
 
+def test_trailing_growth_is_reproduced(pkg, oracle):
+    """put_kmerset runs encap_kmerset on every call (newhash.c:415): when a set holds exactly `max`
+    keys after its newest one, any later instance grows it once more.  21 reads x 36 + 1 read x 37
+    windows = 793 distinct keys = max of the 1031-slot set; the repeated read that follows adds no key
+    but the reference ends with 2063 slots.  thrd_num = 1 puts every key in set 0."""
+    rng = np.random.default_rng(3)
+    K, Wd = 25, 61
+    base = rng.integers(0, 4, size=(23, Wd), dtype=np.uint8)
+    sizes = []
+    for extra in (0, 1):
+        reads = np.concatenate([base[:22], base[:extra]])
+        lens = np.array([60] * 21 + [61] + [60] * extra, np.uint32)
+        ref = oracle.run_hashing(reads, lens, K, 1, 1, 0, max_read_len=Wd)
+        assert ref.nodes == 793
+        g, freq, st = run_gpu(pkg, reads, lens, K, 1, thrd_num=1, max_read_len=Wd)
+        rec, info = g.export_kmersets(1)
+        g.close()
+        assert np.array_equal(info, ref.set_info) and np.array_equal(rec, ref.records)
+        sizes.append(int(info[0, 0]))
+    assert sizes == [1031, 2063]
+
+
 def test_hot_kmer_contention(pkg, oracle, tiny_transcriptome):
     """Config-5 flavour: a handful of transcripts at huge depth; counts far above the 6-bit link
     saturation, then the -d 2 cutoff."""
