@@ -130,6 +130,12 @@ int sdtgpu_insert_records_device (sdtgpu_t *h, const void *d_records, uint64_t n
 int sdtgpu_finalize (sdtgpu_t *h, int deLowKmer, int64_t kmerFreq[257], sdtgpu_stats *stats);
 int sdtgpu_get_stats (sdtgpu_t *h, sdtgpu_stats *stats);
 
+/* Order-independent fingerprint of the table (test/verification hook): out[0] = sum over nodes of
+ * mix64(key words, count, l_links, r_links) mod 2^64, out[1] = sum of counts, out[2] = set link bits
+ * (left in the low, right in the high 32 bits), out[3] = nodes.  Equal multisets give equal
+ * fingerprints regardless of insertion order, batching, capacity or sharding across GPUs. */
+int sdtgpu_table_checksum (sdtgpu_t *h, uint64_t out[4]);
+
 /* ---- hand-back.  export_nodes copies every node (unordered unless sort_by_ordinal) to host
  * memory; thrd_num fixes node.set.  export_kmersets builds thrd_num reference KmerSets whose
  * (set, slot) layout is exactly what the reference's own init_kmerset(1024,0.77f) + put_kmerset

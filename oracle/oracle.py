@@ -153,6 +153,32 @@ def sorted_multiset(rec: np.ndarray) -> np.ndarray:
     return m[order]
 
 
+def _fmix64(k: np.ndarray) -> np.ndarray:
+    k = k.astype(np.uint64)
+    k ^= k >> np.uint64(33)
+    k *= np.uint64(0xff51afd7ed558ccd)
+    k ^= k >> np.uint64(33)
+    k *= np.uint64(0xc4ceb9fe1a85ec53)
+    k ^= k >> np.uint64(33)
+    return k
+
+
+def table_checksum(rec: np.ndarray, device_key_words: int) -> np.ndarray:
+    """CPU twin of sdtgpu_table_checksum over dump records (or exported nodes): order-independent."""
+    with np.errstate(over="ignore"):
+        x = np.full(len(rec), 0x9E3779B97F4A7C15, dtype=np.uint64)
+        for q in range(4 - device_key_words, 4):
+            x = _fmix64(x ^ rec["key"][:, q])
+        L = rec["l_links"].astype(np.uint64)
+        R = (rec["rword"] & R_LINKS).astype(np.uint64)
+        x = _fmix64(x ^ ((rec["count"].astype(np.uint64) << np.uint64(32)) | L))
+        x = _fmix64(x ^ R)
+        lbits = int(np.unpackbits(np.ascontiguousarray(L).view(np.uint8)).sum())
+        rbits = int(np.unpackbits(np.ascontiguousarray(R).view(np.uint8)).sum())
+        return np.array([x.sum(dtype=np.uint64), rec["count"].astype(np.uint64).sum(dtype=np.uint64),
+                         np.uint64(lbits) + (np.uint64(rbits) << np.uint64(32)), len(rec)], dtype=np.uint64)
+
+
 # ------------------------------------------------------------------ the real reference (oracle/_ref)
 def ref_binary(key_words: int, stock: bool = False) -> str | None:
     name = ("SOAPdenovo-Trans-%dmer" if stock else "ref_hash_%d") % (31 if key_words == 1 else 127)

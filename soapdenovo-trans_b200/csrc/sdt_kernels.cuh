@@ -136,34 +136,6 @@ __device__ __forceinline__ void chop_window (const u32 *rd, const u32 *mk, int l
 	}
 }
 
-template <int W> __device__ __forceinline__ void emit_record (const Bins &bins, const Key<W> &key, u32 left, u32 right, u64 ord, u64 h)
-{
-	const u32 owner = owner_of (h, bins.n_ranks);
-	// warp-aggregated append: one atomic per (warp, destination)
-	const unsigned active = __activemask ();
-	const unsigned peers = __match_any_sync (active, owner);
-	const int leader = __ffs (peers) - 1;
-	const int lane = threadIdx.x & 31;
-	u64 base = 0;
-	if (lane == leader)
-		base = atomicAdd (bins.counts + owner, (u64) __popc (peers));
-	base = __shfl_sync (peers, base, leader);
-	const u64 pos = base + __popc (peers & ((1u << lane) - 1u));
-	if (pos >= bins.capacity)
-		return;	// the host sees counts[owner] > capacity and reports SDTGPU_ERANGE
-	u64 *rec = bins.records + ((u64) owner * bins.capacity + pos) * (W + 1);
-	const u64 meta = (ord << 8) | (left << 4) | right;
-	if constexpr (W == 1)
-		*reinterpret_cast<ulonglong2 *> (rec) = make_ulonglong2 (key.w[0], meta);
-	else
-	{
-#pragma unroll
-		for (int i = 0; i < W; i++)
-			rec[i] = key.w[i];
-		rec[W] = meta;
-	}
-}
-
 template <int W> __device__ __forceinline__ void store_record (u64 *rec, const Key<W> &key, u32 left, u32 right, u64 ord)
 {
 	const u64 meta = (ord << 8) | (left << 4) | right;
@@ -769,6 +741,51 @@ finalize_kernel (typename SlotOf<W>::type *table, u64 cap, int deLowKmer, Counte
 			atomicAdd (&ctr->n_removed, (u64) s_removed);
 		if (s_linear)
 			atomicAdd (&ctr->n_linear, (u64) s_linear);
+	}
+}
+
+// Order-independent fingerprint of the table: sums over all nodes of a 64-bit mix of
+// (key, count, l_links, r_links) and of a few plain totals.  Any two runs that hold the same
+// multiset of nodes — whatever the insertion order, batching, capacity or sharding — agree on it;
+// the oracle computes the same sums on the CPU (oracle.table_checksum).
+template <int W>
+__global__ void __launch_bounds__ (BLOCK)
+checksum_kernel (const typename SlotOf<W>::type *table, u64 cap, u64 *out /* [4] */)
+{
+	u64 h = 0, c = 0, l = 0, n = 0;
+	for (u64 i = blockIdx.x * (u64) BLOCK + threadIdx.x; i < cap; i += (u64) gridDim.x * BLOCK)
+	{
+		if (!SlotIO<W>::occupied (table + i))
+			continue;
+		Key<W> k;
+		u32 L, R, count;
+		u64 ord;
+		SlotIO<W>::get (table + i, k, L, R, count, ord);
+		u64 x = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+		for (int q = 0; q < W; q++)
+			x = fmix64 (x ^ k.w[q]);
+		x = fmix64 (x ^ (((u64) count << 32) | L));
+		x = fmix64 (x ^ R);
+		h += x;
+		c += count;
+		l += (u64) __popc (L) + ((u64) __popc (R) << 32);
+		n += 1;
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+	{
+		h += __shfl_down_sync (0xFFFFFFFFu, h, d);
+		c += __shfl_down_sync (0xFFFFFFFFu, c, d);
+		l += __shfl_down_sync (0xFFFFFFFFu, l, d);
+		n += __shfl_down_sync (0xFFFFFFFFu, n, d);
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		atomicAdd (out + 0, h);
+		atomicAdd (out + 1, c);
+		atomicAdd (out + 2, l);
+		atomicAdd (out + 3, n);
 	}
 }
 

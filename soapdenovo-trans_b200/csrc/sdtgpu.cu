@@ -1041,6 +1041,35 @@ int sdtgpu_export_kmersets (sdtgpu_t *h, int thrd_num, sdtgpu_kmerset **sets)
 	return rc;
 }
 
+int sdtgpu_table_checksum (sdtgpu_t *h, uint64_t out[4])
+{
+	if (!h || !out)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	int rc = flush_epoch (h);
+	if (rc)
+		return rc;
+	u64 *d = nullptr;
+	CK (h, cudaMalloc (&d, 4 * sizeof (u64)));
+	CK (h, cudaMemsetAsync (d, 0, 4 * sizeof (u64), h->stream));
+	const unsigned grid = (unsigned) std::min<u64> ((h->cap + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
+	switch (h->W)
+	{
+	case 1: checksum_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot1 *> (h->table), h->cap, d); break;
+	case 2: checksum_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot2 *> (h->table), h->cap, d); break;
+	default: checksum_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot4 *> (h->table), h->cap, d); break;
+	}
+	h->all_launches++;
+	cudaError_t e = cudaGetLastError ();
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync (out, d, 4 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize (h->stream);
+	cudaFree (d);
+	CK (h, e);
+	return SDTGPU_OK;
+}
+
 int sdtgpu_host_alloc (void **out, size_t bytes)
 {
 	if (!out)

@@ -93,6 +93,7 @@ def library() -> C.CDLL:
     L.sdtgpu_aux_stream.restype = vp
     L.sdtgpu_aux_stream.argtypes = [vp]
     L.sdtgpu_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)]
+    L.sdtgpu_table_checksum.argtypes = [vp, vp]
     L.sdtgpu_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.sdtgpu_synth_reads_device.argtypes = [i32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u32, u32, vp]
     _lib = L
@@ -234,6 +235,11 @@ class PregraphGPU:
         st = Stats()
         self._ck(self.L.sdtgpu_get_stats(self.h, C.byref(st)))
         return st
+
+    def table_checksum(self) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        self._ck(self.L.sdtgpu_table_checksum(self.h, out.ctypes.data))
+        return out
 
     def export_nodes(self, thrd_num: int = 8, sort_by_ordinal: bool = False) -> np.ndarray:
         n = C.c_uint64()
