@@ -193,7 +193,7 @@ def main():
     # distinct k-mers are dominated by error k-mers (a window is error-free with probability 0.99^K)
     slot_b = 64 if K > 63 else 32
     est_distinct = instances_rank * (1.0 - 0.99 ** K) * 1.03 + 6e7
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(est_distinct / 0.8 / 2) + 1024, device=local_rank, partitioned=args.partitioned)
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(est_distinct) + 1024, device=local_rank, partitioned=args.partitioned)
     ext = torch.cuda.ExternalStream(g.stream, device=dev)
 
     exch = None
@@ -219,10 +219,8 @@ def main():
     distinct = st.n_nodes
     assert (exch is not None) or st.n_instances == instances_rank, (st.n_instances, instances_rank)
     g.close()
-    free_b, _ = torch.cuda.mem_get_info(dev)
-    room = (free_b - (8 << 30) - (0 if exch is None else 0)) / slot_b          # slots that fit next to the reads and buffers
-    slots = min(2.04 * distinct, max(room, distinct / 0.85))                  # load 0.49 when it fits (C2), denser otherwise (C4)
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(slots / 2) + 1024, device=local_rank, partitioned=args.partitioned)
+    # the library sizes the table from the hint: load 0.5 up to 60 GiB, denser beyond
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(distinct * 1.02) + 1024, device=local_rank, partitioned=args.partitioned)
     ext = torch.cuda.ExternalStream(g.stream, device=dev)
     if exch is not None:
         exch.rebind(g)

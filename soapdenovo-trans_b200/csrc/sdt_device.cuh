@@ -36,6 +36,10 @@ __device__ __forceinline__ void ld128 (const void *p, u64 &a, u64 &b)
 {
 	asm volatile ("ld.global.relaxed.gpu.L2::64B.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
+__device__ __forceinline__ void st256 (void *p, u64 a, u64 b, u64 c, u64 d)
+{
+	asm volatile ("st.global.relaxed.gpu.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 __device__ __forceinline__ void st128 (void *p, u64 a, u64 b)
 {
 	asm volatile ("st.global.relaxed.gpu.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
@@ -303,36 +307,36 @@ template <> struct Table<2>
 
 template <> struct Table<4>
 {
+	// 4-word keys: no 256-bit CAS exists, so a new key is claimed by locking the slot's first half
+	// with a 128-bit CAS (EMPTY -> LOCKED) and published with ONE 256-bit store of the whole key.
+	// The key occupies exactly one 32-byte sector, probes read it with one 256-bit load, and a sector
+	// is written and read by the L2 as a unit, so a reader sees either LOCKED or the complete key:
+	// no fence, no second round trip (the first version published the halves separately behind a
+	// __threadfence() and ran config C4 at 2.0 G instances/s).
 	static __device__ __forceinline__ int upsert (Slot4 *tab, u64 cap, const Key<4> &k, u32 left, u32 right, u64 ord)
 	{
 		u64 idx = slot_of (key_hash<4> (k), cap);
 		for (;;)
 		{
 			Slot4 *s = tab + idx;
-			u64 a0, a1, s0 = PAYLOAD0_INIT, s1 = 0;
+			u64 a0, a1, b0, b1, s0 = PAYLOAD0_INIT, s1 = 0;
 			int created = 0;
-			ld128 (&s->key[0], a0, a1);
+			ld256 (&s->key[0], a0, a1, b0, b1);
 			if (a0 == EMPTY64 && a1 == LOCKED64)
 			{	// another thread is publishing this slot: look again
-				__nanosleep (32);
+				__nanosleep (20);
 				continue;
 			}
 			if (a0 == EMPTY64 && a1 == EMPTY64)
 			{
 				if (!cas128 (&s->key[0], EMPTY64, EMPTY64, EMPTY64, LOCKED64, a0, a1))
 					continue;	// lost the race: re-examine the same slot
-				st128 (&s->key[2], k.w[2], k.w[3]);
-				__threadfence ();	// second half visible before the first half is published
-				st128 (&s->key[0], k.w[0], k.w[1]);
+				st256 (&s->key[0], k.w[0], k.w[1], k.w[2], k.w[3]);
 				created = 1;
 			}
 			else
 			{
-				if (a0 != k.w[0] || a1 != k.w[1])
-					goto next;
-				u64 b0, b1;	// issued after the first half was seen published (no load speculation on the GPU)
-				ld128 (&s->key[2], b0, b1);
-				if (b0 != k.w[2] || b1 != k.w[3])
+				if (a0 != k.w[0] || a1 != k.w[1] || b0 != k.w[2] || b1 != k.w[3])
 					goto next;
 				ld128 (&s->p, s0, s1);
 			}

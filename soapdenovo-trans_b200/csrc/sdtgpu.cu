@@ -95,6 +95,17 @@ namespace {
 
 size_t slot_bytes (int W) { return W == 4 ? sizeof (Slot4) : 32; }
 
+// Slots for `nodes` expected distinct keys: load 0.5 when that fits in 60 GiB, otherwise as sparse
+// as 60 GiB allows but never denser than 0.85.  Random access over a table larger than 64 GiB is
+// 4x slower on B200 (36 G -> 9.8 G cold-line requests/s at 128 GiB, tools/randacc_bench.cu,
+// profiles/r1_randacc_bench.txt), so staying under that size beats a lower load factor.
+u64 pick_capacity (u64 nodes, size_t slot)
+{
+	const u64 fast = (60ull << 30) / slot;
+	const u64 sparse = nodes * 2, dense = (u64) ((double) nodes / 0.85) + 1;
+	return std::max<u64> (1024, std::max (dense, std::min (sparse, fast)));
+}
+
 int fail (sdtgpu *h, int code, const char *msg)
 {
 	h->err = msg;
@@ -163,7 +174,7 @@ int ensure_capacity (sdtgpu *h, u64 incoming)
 	h->snap_pending = false;
 	if ((double) (nodes + incoming) <= max_load * (double) h->cap)
 		return SDTGPU_OK;
-	u64 new_cap = std::max<u64> (h->cap * 2, (u64) ((double) (nodes + incoming) / 0.45) + 1024);
+	u64 new_cap = std::max<u64> (h->cap + h->cap / 2, pick_capacity (nodes + incoming, slot_bytes (h->W)));
 	void *neu = nullptr;
 	CK (h, cudaMalloc (&neu, new_cap * slot_bytes (h->W)));
 	rc = init_table (h, neu, new_cap);
@@ -555,7 +566,7 @@ int flush_epoch (sdtgpu *h)
 		// stopped early: project the final node count from the fraction done and re-hash
 		const double frac = std::max (0.02, (double) next / (double) total);
 		const u64 projected = (u64) ((double) nodes / frac);
-		const u64 new_cap = std::max<u64> (h->cap * 2, (u64) ((double) projected / 0.5) + 1024);
+		const u64 new_cap = std::max<u64> (h->cap + h->cap / 2, pick_capacity (projected, slot_bytes (h->W)));
 		if ((rc = grow_table (h, new_cap)))
 			return rc;
 	}
@@ -668,7 +679,7 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 		crc_table_host ();
 		CK (h, cudaMemcpyToSymbol (c_crc, h_crc, sizeof h_crc));
 		h->grow_mode = capacity_hint == 0;
-		h->cap = capacity_hint ? std::max<u64> (capacity_hint * 2, 1024) : (1ull << 20);
+		h->cap = capacity_hint ? pick_capacity (capacity_hint, slot_bytes (h->W)) : (1ull << 20);
 		CK (h, cudaMalloc (&h->table, h->cap * slot_bytes (h->W)));
 		int rc = init_table (h, h->table, h->cap);
 		if (rc)

@@ -56,12 +56,12 @@ def test_full_size_properties(pkg, oracle, name, n_pairs):
     slot = 64 if K > 63 else 32
     # distinct k-mers are dominated by error k-mers: a window is error-free with probability 0.99^K
     est = instances * (1.0 - 0.99 ** K) * 1.03 + 6e7
-    cap1 = est / 0.8                                     # first pass at load <= 0.8 (the library allocates 2 x hint)
+    cap1 = max(est / 0.85, min(2 * est, (60 << 30) / slot))     # the library's sizing rule (load 0.5 up to 60 GiB)
     if free_b < cap1 * slot + 2 * n_pairs * pkg.synth.stride_bytes(L) + 2e9:
         pytest.skip(f"{name} needs more free HBM than this box has ({free_b / 2**30:.0f} GiB)")
     tr, d_packed, stride = _device_reads(pkg, cfg, n_pairs, dev)
     try:
-        g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(cap1 / 2))
+        g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(est))
     except pkg.SdtGpuError as e:
         pytest.skip(str(e))
     _insert_all(pkg, g, d_packed, L, stride, 1 << 22)
@@ -71,7 +71,7 @@ def test_full_size_properties(pkg, oracle, name, n_pairs):
     assert st.n_instances == instances == int(fp1[1])          # conservation: "kmer in reads" == "kmer processed"
     assert st.n_nodes == int(fp1[3])
     # a different capacity, batch size and (where memory allows) the partitioned path: same multiset
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(st.n_nodes / 0.85 / 2))
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(st.n_nodes * 1.08))
     _insert_all(pkg, g, d_packed, L, stride, (1 << 21) + 4 * 12345)
     fp2 = g.table_checksum()
     g.close()

@@ -36,10 +36,10 @@ static void bench(const char* what, u64* tab, u64 cap, u64* sink)
 		printf("%-44s %-12s %7.2f G/s\n", what, mode ? "ld+CAS64" : "ld128", n / best * 1e-6);
 	}
 }
-int main()
+int main(int argc, char** argv)
 {
 	CK(cudaFree(0));
-	const size_t bytes = 16ull << 30; const u64 cap = bytes / 32;
+	const size_t bytes = (argc > 1 ? strtoull(argv[1], 0, 10) : 16ull) << 30; const u64 cap = bytes / 32;
 	u64* sink; CK(cudaMalloc(&sink, 8));
 	{ u64* t; CK(cudaMalloc(&t, bytes)); CK(cudaMemset(t, 0, bytes)); bench("cudaMalloc", t, cap, sink); CK(cudaFree(t)); }
 	CUmemAllocationProp prop = {}; prop.type = CU_MEM_ALLOCATION_TYPE_PINNED; prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE; prop.location.id = 0;
