@@ -124,6 +124,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--batch-reads", type=int, default=1 << 22)
+    ap.add_argument("--exchange", default="reads", choices=["reads", "records"],
+                    help="multi-GPU sharding: all-gather the packed reads and insert owned k-mers (default) or exchange k-mer records")
     ap.add_argument("--partitioned", action="store_true", help="experimental staged/partitioned insert path")
     args = ap.parse_args()
 
@@ -198,8 +200,11 @@ def main():
 
     exch = None
     if world > 1:
-        from soapdenovo_trans_b200.exchange import Exchange
-        exch = Exchange(pkg, g, world, rank, dev, max_round_instances=min(batch, n_reads) * nwin)
+        from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads
+        if args.exchange == "records":
+            exch = Exchange(pkg, g, world, rank, dev, max_round_instances=min(batch, n_reads) * nwin)
+        else:
+            exch = ReplicatedReads(pkg, g, world, rank, dev, max_round_reads=min(batch, n_reads), stride=stride)
 
     def one_step(gg):
         gg.reset()
@@ -332,13 +337,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers exchanged by owner (NCCL all-to-all)" if world > 1 else ""),
+            "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers sharded by owner ({'packed reads all-gathered over NCCL, every rank inserts the k-mers it owns' if args.exchange == 'reads' else 'k-mer records exchanged over NCCL'})" if world > 1 else ""),
                        "instances_per_step": total_instances, "distinct_kmers": total_nodes,
                        "table_slots_per_gpu": int(st.capacity), "slot_bytes": 64 if st.device_key_words == 4 else 32,
                        "batch_reads": batch,
                        "l2": "table (>= 2x distinct x slot bytes) and reads are far larger than the 126 MB L2; table is reset every step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": traffic, "kernel": ("insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if world == 1 else "insert_records_kernel",
+                         "traffic": traffic, "kernel": ("insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if (world == 1 or args.exchange == "reads") else "insert_records_kernel",
                          "bytes_per_instance": bpi, "kernel_ms_per_launch": ker_ms, "peak_source": peak_src,
                          "random_access": {"cold_line_requests_per_s_measured": RANDOM_REQUESTS_PER_S,
                                            "min_requests_per_instance": MIN_REQUESTS_PER_INSTANCE[st.device_key_words],

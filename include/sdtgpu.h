@@ -105,7 +105,17 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 			      uint64_t n_reads, uint32_t uniform_len, uint32_t stride_bytes, uint64_t first_read_ordinal);
 int sdtgpu_sync (sdtgpu_t *h);
 
-/* ---- multi-GPU exchange (one process per GPU; the caller moves the bins, e.g. NCCL all-to-all).
+/* ---- multi-GPU, replicated reads (the default sharding of bench.py and exchange.py).
+ * After sdtgpu_set_owner (h, rank, n_ranks) every push inserts only the instances this rank owns
+ * (owner = mix(key) -> [0, n_ranks), any owner function gives the same union).  The ranks
+ * all-gather their packed reads (28 bytes per 100-bp read over NVLink) and each chops all of them:
+ * this is exactly the reference's scheme — every worker scans the whole batch and keeps
+ * hash % thrd_num == id (prlHashReads.c:79-88) — and it needs no per-k-mer records at all; chopping
+ * is ~20x cheaper than inserting, so the redundant chop costs less than writing, sending and
+ * re-reading 16-byte records.  stats.n_instances then counts the instances this rank inserted. */
+int sdtgpu_set_owner (sdtgpu_t *h, int rank, int n_ranks);
+
+/* ---- multi-GPU, record exchange (alternative; the caller moves the bins, e.g. NCCL all-to-all).
  * The reference's equivalent is "every worker scans the shared hashBanBuffer and keeps
  * hash % thrd_num == id" (prlHashReads.c:79-88).  bucket_reads_device chops this rank's reads and
  * appends each instance as a 16*ceil(W/1)-byte record to the bin of its owner rank

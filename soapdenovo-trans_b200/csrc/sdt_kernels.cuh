@@ -34,6 +34,7 @@ struct ReadBatch
 	u32 tile_reads;		// reads per shared-memory tile (multiple of 4, <= MAX_TILE_READS)
 	int K;
 	u32 max_read_len, maxwin;	// maxwin = max_read_len - K + 1 (ordinal = read * maxwin + window)
+	u32 owner_rank, owner_ranks;	// owner_ranks > 1: insert only instances whose owner_of (mix(key)) == owner_rank
 };
 
 struct Counters
@@ -187,7 +188,7 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 	__shared__ u32 warp_sums[BLOCK / 32];
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
 	const int K = rb.K;
-	u32 created = 0;
+	u32 created = 0, owned = 0;
 	u64 instances = 0;
 
 	if (tid < TILE_PAD)
@@ -315,7 +316,13 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 			chop_window<W, NMODE> (tile + r * sw, NMODE ? (mtile + r * mw) : nullptr, (int) len, (int) j, K, key, left, right);
 			const u64 ord = (rb.first_read_ordinal + r0 + r) * rb.maxwin + j;
 			if (MODE == 0)
+			{	// replicated-reads sharding: every rank chops every read and keeps the k-mers it owns
+				// (the reference's own scheme, prlHashReads.c:79-88, with GPUs in place of threads)
+				if (rb.owner_ranks > 1 && owner_of (key_hash<W> (key), rb.owner_ranks) != rb.owner_rank)
+					continue;
+				owned++;
 				created += Table<W>::upsert (table, cap, key, left, right, ord);
+			}
 			else if (MODE == 1)
 			{	// send side of the exchange: bin = owner rank, fixed capacity per bin
 				const u32 b = owner_of (key_hash<W> (key), bins.n_ranks);
@@ -397,8 +404,19 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		created += __shfl_down_sync (0xFFFFFFFFu, created, d);
 	if ((tid & 31) == 0 && created)
 		atomicAdd (&ctr->n_nodes, (u64) created);
-	if (MODE == 0 && tid == 0 && instances)	// bucketed instances are counted by the rank that inserts them
-		atomicAdd (&ctr->n_instances, instances);
+	if (MODE == 0)
+	{	// instances are counted by the rank that inserts them
+		if (rb.owner_ranks > 1)
+		{
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1)
+				owned += __shfl_down_sync (0xFFFFFFFFu, owned, d);
+			if ((tid & 31) == 0 && owned)
+				atomicAdd (&ctr->n_instances, (u64) owned);
+		}
+		else if (tid == 0 && instances)
+			atomicAdd (&ctr->n_instances, instances);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -61,6 +61,7 @@ struct sdtgpu
 	bool finalized = false;
 	int deLowKmer = 0;
 	// partitioned (staged) insert: records of an epoch are radix-partitioned by table slot range
+	u32 owner_rank = 0, owner_ranks = 1;	// sdtgpu_set_owner
 	bool direct = true;		// default; SDTGPU_F_PARTITIONED selects the staged path
 	u64 *staging = nullptr;		// records, (W + 1) u64 each
 	u64 staging_cap = 0, staging_used = 0, staged_upper = 0;	// in records
@@ -292,6 +293,8 @@ int make_batch (sdtgpu *h, ReadBatch &rb, const uint8_t *d_packed, const u32 *d_
 	rb.K = h->K;
 	rb.max_read_len = (u32) h->max_read_len;
 	rb.maxwin = h->maxwin;
+	rb.owner_rank = h->owner_rank;
+	rb.owner_ranks = h->owner_ranks;
 	return SDTGPU_OK;
 }
 
@@ -772,7 +775,9 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 		return rc;
 	if (h->direct)
 	{	// single pass: every window goes straight to its (random) slot
-		const u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
+		u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
+		if (h->owner_ranks > 1)	// owners are a uniform hash of the key: this rank keeps ~1/n (allow 1.5x)
+			upper = upper / h->owner_ranks + upper / (2 * h->owner_ranks) + 1024;
 		rc = ensure_capacity (h, upper);
 		if (rc)
 			return rc;
@@ -835,6 +840,19 @@ int sdtgpu_push_reads (sdtgpu_t *h, const uint8_t *packed, const uint32_t *lens,
 					   n_reads, uniform_len, stride_bytes, first_read_ordinal);
 	CK (h, cudaEventRecord (s.free_ev, h->stream));
 	return rc;
+}
+
+int sdtgpu_set_owner (sdtgpu_t *h, int rank, int n_ranks)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	if (n_ranks < 1 || rank < 0 || rank >= n_ranks)
+		return fail (h, SDTGPU_EINVAL, "sdtgpu_set_owner: need 0 <= rank < n_ranks");
+	if (!h->direct && n_ranks > 1)
+		return fail (h, SDTGPU_ESTATE, "owner filtering is implemented for the single-pass insert path");
+	h->owner_rank = (u32) rank;
+	h->owner_ranks = (u32) n_ranks;
+	return SDTGPU_OK;
 }
 
 size_t sdtgpu_record_bytes (const sdtgpu_t *h) { return h ? 8 * (size_t) (h->W + 1) : 0; }

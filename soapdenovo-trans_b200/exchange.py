@@ -1,12 +1,18 @@
-"""Multi-GPU k-mer exchange: one process per GPU, k-mers sharded by owner.
+"""Multi-GPU sharding: one process per GPU, k-mers sharded by owner.
 
 The reference's only parallelism is hash-partitioned shared-nothing tables (owner =
-hash_kmer % thrd_num, prlHashReads.c:81; every worker scans the whole batch, :79-88).  Here the
-same structure spans GPUs: each rank chops its own reads and buckets every instance by owner rank
-(sdtgpu_bucket_reads_device), the bins cross NVLink with one NCCL all-to-all per round
-(torch.distributed), and each rank upserts what it received (sdtgpu_insert_records_device).
+hash_kmer % thrd_num, prlHashReads.c:81) where every worker scans the whole batch and keeps what it
+owns (:79-88).  Two ways to stretch that over GPUs live here:
+
+* `ReplicatedReads` (default): the ranks all-gather their 2-bit packed reads (28 bytes per 100-bp
+  read) over NVLink and every rank chops ALL reads but inserts only the k-mers it owns
+  (sdtgpu_set_owner).  No per-k-mer records exist; the redundant chop is ~20x cheaper than an insert.
+* `Exchange`: each rank chops only its own reads, buckets every instance as a 16-byte record by owner
+  (sdtgpu_bucket_reads_device), the bins cross NVLink with one grouped NCCL send/recv per round and
+  each rank upserts what it received (sdtgpu_insert_records_device).
+
 Updates are commutative, so arrival order is free and the union of the ranks' tables is the
-reference's multiset.
+reference's multiset either way.
 
 `exchange_records` is the backend-agnostic plumbing (counts all-to-all, offsets, payload
 all-to-all); it is exercised on CPU with the gloo backend in tests/test_exchange_cpu.py.
@@ -91,6 +97,62 @@ class Exchange:
         with torch.cuda.stream(self.main):
             self.main.wait_event(self.received)
             g.insert_records_device(self.recv[b], total)
+            self.inserted[b].record(self.main)
+
+    def flush(self, g):
+        pass
+
+
+class ReplicatedReads:
+    """Round driver of the replicated-reads sharding, pipelined over two gather buffers: the NCCL
+    all-gather of round r+1 runs on the table's auxiliary stream while the inserts of round r run on
+    its main stream."""
+
+    def __init__(self, pkg, g, world: int, rank: int, dev, max_round_reads: int, stride: int, group=None):
+        self.world, self.rank, self.dev, self.group = world, rank, dev, group
+        g.set_owner(rank, world)
+        self.buf = [torch.empty((world, max_round_reads, stride), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.lens = [torch.empty((world, max_round_reads), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.meta = [torch.empty((world, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.inserted = [torch.cuda.Event() for _ in range(2)]
+        self.received = torch.cuda.Event()
+        self.max_round_reads, self.stride, self.r = max_round_reads, stride, 0
+        self.nvlink_bytes = 0
+        self.rebind(g)
+
+    def rebind(self, g):
+        g.set_owner(self.rank, self.world)
+        self.main = torch.cuda.ExternalStream(g.stream, device=self.dev)
+        self.aux = torch.cuda.ExternalStream(g.aux_stream, device=self.dev)
+
+    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None):
+        """d_packed: this rank's reads of the round ([n_reads, stride] uint8 on the device).  Ranks may
+        bring different numbers of reads (<= max_round_reads)."""
+        b = self.r & 1
+        self.r += 1
+        with torch.cuda.stream(self.aux):
+            self.aux.wait_event(self.inserted[b])
+            mine = torch.tensor([first_read_ordinal, n_reads], dtype=torch.int64, device=self.dev)
+            dist.all_gather_into_tensor(self.meta[b].view(-1), mine, group=self.group)
+            src = d_packed
+            if n_reads != self.max_round_reads:          # NCCL all-gather wants equal contributions
+                src = self.buf[b][self.rank]
+                src[:n_reads].copy_(d_packed[:n_reads])
+            dist.all_gather_into_tensor(self.buf[b].view(-1), src.reshape(-1)[: self.max_round_reads * self.stride], group=self.group)
+            if d_lens is not None:
+                ls = self.lens[b][self.rank]
+                ls[:n_reads].copy_(d_lens[:n_reads])
+                dist.all_gather_into_tensor(self.lens[b].view(-1), ls, group=self.group)
+            meta = self.meta[b].tolist()
+            self.received.record(self.aux)
+        self.nvlink_bytes += sum(m[1] for i, m in enumerate(meta) if i != self.rank) * self.stride
+        with torch.cuda.stream(self.main):
+            self.main.wait_event(self.received)
+            for s_rank, (first, n) in enumerate(meta):
+                if n:
+                    g.push_reads(self.buf[b][s_rank], self.lens[b][s_rank] if d_lens is not None else None, None,
+                                 n_reads=int(n), uniform_len=uniform_len, stride_bytes=stride,
+                                 first_read_ordinal=int(first), device=True)
             self.inserted[b].record(self.main)
 
     def flush(self, g):

@@ -76,6 +76,7 @@ def library() -> C.CDLL:
     L.sdtgpu_sync.argtypes = [vp]
     L.sdtgpu_push_reads.argtypes = [vp, vp, vp, vp, u64, u32, u32, u64]
     L.sdtgpu_push_reads_device.argtypes = [vp, vp, vp, vp, u64, u32, u32, u64]
+    L.sdtgpu_set_owner.argtypes = [vp, i32, i32]
     L.sdtgpu_record_bytes.restype = C.c_size_t
     L.sdtgpu_record_bytes.argtypes = [vp]
     L.sdtgpu_bucket_reads_device.argtypes = [vp, vp, vp, vp, u64, u32, u32, u64, i32, vp, u64, vp]
@@ -212,6 +213,9 @@ class PregraphGPU:
             stride_bytes = packed.shape[1]
         fn = self.L.sdtgpu_push_reads_device if device else self.L.sdtgpu_push_reads
         self._ck(fn(self.h, _ptr(packed), _ptr(lens), _ptr(nmask), n_reads, uniform_len, stride_bytes, first_read_ordinal))
+
+    def set_owner(self, rank: int, n_ranks: int):
+        self._ck(self.L.sdtgpu_set_owner(self.h, rank, n_ranks))
 
     def record_bytes(self) -> int:
         return int(self.L.sdtgpu_record_bytes(self.h))

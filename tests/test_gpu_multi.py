@@ -20,13 +20,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, K, kw, L, d, out_dir):
+def _worker(rank, world, port, K, kw, L, d, out_dir, mode):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
     import sdt_pkg
     pkg = sdt_pkg.load()
-    from soapdenovo_trans_b200.exchange import Exchange
+    from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -40,7 +40,10 @@ def _worker(rank, world, port, K, kw, L, d, out_dir):
     d_packed = torch.from_numpy(synth.pack_reads(reads[lo:hi], lens[lo:hi], stride)).to(dev)
     d_lens = torch.from_numpy(lens[lo:hi].astype(np.int32)).to(dev)
     g = pkg.PregraphGPU(K, kw, L, capacity_hint=1_500_000, device=rank)
-    ex = Exchange(pkg, g, world, rank, dev, max_round_instances=2048 * (L - K + 1))
+    if mode == "records":
+        ex = Exchange(pkg, g, world, rank, dev, max_round_instances=2048 * (L - K + 1))
+    else:
+        ex = ReplicatedReads(pkg, g, world, rank, dev, max_round_reads=2048, stride=stride)
     for a in range(0, hi - lo, 2048):                            # several rounds, exercises the double buffering
         b = min(a + 2048, hi - lo)
         ex.round(g, d_packed[a:b], b - a, 0, stride, lo + a, d_lens=d_lens[a:b])
@@ -55,14 +58,15 @@ def _worker(rank, world, port, K, kw, L, d, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["reads", "records"])
 @pytest.mark.parametrize("K,kw,L,d", [(25, 1, 100, 0), (63, 4, 100, 1), (127, 4, 150, 0)])
-def test_two_gpu_union_matches_oracle(pkg, oracle, tmp_path, K, kw, L, d):
+def test_two_gpu_union_matches_oracle(pkg, oracle, tmp_path, K, kw, L, d, mode):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), K, kw, L, d, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), K, kw, L, d, str(tmp_path), mode), nprocs=world, join=True)
     synth = pkg.synth
     reads, lens = synth.make_reads(synth.make_transcriptome(40, 5), 6000, L, 77, ragged=30)
     ref = oracle.run_hashing(reads, lens, K, kw, 8, d)
