@@ -268,7 +268,7 @@ def main():
     ms_per_step = ms / args.steps
     value = total_instances / (ms_per_step * 1e-3)
     bpi = BYTES_PER_INSTANCE[st.device_key_words]
-    ker_ms = insert_ms / max(insert_launches, 1)
+    ker_ms = max(insert_ms, 1e-9) / max(insert_launches, 1)
     inst_per_launch = st.n_instances * args.steps / max(insert_launches, 1)
     achieved = inst_per_launch * bpi / (ker_ms * 1e-3) / 1e9
     traffic = None      # DRAM bytes per launch of the dominant kernel, from the committed ncu capture

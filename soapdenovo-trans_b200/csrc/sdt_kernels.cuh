@@ -22,6 +22,7 @@ namespace sdt {
 static constexpr int TILE_PAD = 8;	// u32 words of padding on both sides of the staged tile
 static constexpr int BLOCK = 256;
 static constexpr int MAX_TILE_READS = 256;
+static constexpr u32 QUEUE_WINDOWS = 2048;	// windows chopped per drain of the owned-instance queue (MODE 5)
 
 struct ReadBatch
 {
@@ -188,8 +189,12 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 	__shared__ u32 warp_sums[BLOCK / 32];
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
 	const int K = rb.K;
-	u32 created = 0, owned = 0;
-	u64 instances = 0;
+	u32 created = 0;
+	u64 instances = 0, owned = 0;
+	__shared__ u32 q_count;
+	u64 *queue = reinterpret_cast<u64 *> (hist);	// MODE 5: QUEUE_WINDOWS records of (W + 1) u64
+	if (MODE == 5 && tid == 0)
+		q_count = 0;
 
 	if (tid < TILE_PAD)
 	{
@@ -285,9 +290,12 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		// MODE 1 / 3 walk the tile twice: sweep 0 counts the tile's records per bin, ONE global atomic per
 		// non-empty bin then reserves their space, sweep 1 writes the records (chopping twice is cheap;
 		// a contended global cursor atomic per warp was 3x slower, profiles/r1_multi_gpu.md)
+		for (u32 chunk0 = 0; chunk0 < total; chunk0 += (MODE == 5 ? QUEUE_WINDOWS : total))
+		{
+		const u32 chunk1 = MODE == 5 ? min (total, chunk0 + QUEUE_WINDOWS) : total;
 		for (int sweep = ((MODE == 3 || MODE == 1) ? 0 : 1); sweep < 2; sweep++)
 		{
-		for (u32 w = tid; w < total; w += BLOCK)
+		for (u32 w = chunk0 + tid; w < chunk1; w += BLOCK)
 		{
 			u32 r, j, len;
 			if (uniform)
@@ -316,12 +324,14 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 			chop_window<W, NMODE> (tile + r * sw, NMODE ? (mtile + r * mw) : nullptr, (int) len, (int) j, K, key, left, right);
 			const u64 ord = (rb.first_read_ordinal + r0 + r) * rb.maxwin + j;
 			if (MODE == 0)
-			{	// replicated-reads sharding: every rank chops every read and keeps the k-mers it owns
-				// (the reference's own scheme, prlHashReads.c:79-88, with GPUs in place of threads)
-				if (rb.owner_ranks > 1 && owner_of (key_hash<W> (key), rb.owner_ranks) != rb.owner_rank)
-					continue;
-				owned++;
 				created += Table<W>::upsert (table, cap, key, left, right, ord);
+			else if (MODE == 5)
+			{	// replicated-reads sharding: every rank chops every read and keeps the k-mers it owns (the
+				// reference's own scheme, prlHashReads.c:79-88, with GPUs in place of threads).  Owned
+				// instances are first compacted into a shared-memory queue so that the upserts below run
+				// with full warps (filtering in place left 1 lane in n_ranks busy per memory round trip).
+				if (rb.owner_ranks <= 1 || owner_of (key_hash<W> (key), rb.owner_ranks) == rb.owner_rank)
+					store_record<W> (queue + (u64) atomicAdd (&q_count, 1u) * (W + 1), key, left, right, ord);
 			}
 			else if (MODE == 1)
 			{	// send side of the exchange: bin = owner rank, fixed capacity per bin
@@ -381,6 +391,26 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 					hist[b] = 0;
 		}
 		}
+		if (MODE == 5)
+		{	// drain the queue of owned instances with every lane busy
+			__syncthreads ();
+			const u32 nq = q_count;
+			__syncthreads ();
+			if (tid == 0)
+			{
+				q_count = 0;
+				owned += nq;
+			}
+			for (u32 i = tid; i < nq; i += BLOCK)
+			{
+				Key<W> key;
+				u64 meta;
+				load_record<W> (queue + (u64) i * (W + 1), key, meta);
+				created += Table<W>::upsert (table, cap, key, (u32) (meta >> 4) & 15u, (u32) meta & 15u, meta >> 8);
+			}
+			__syncthreads ();
+		}
+		}
 		__syncthreads ();	// the tile is overwritten by the next iteration
 	}
 	if (MODE == 2)
@@ -404,19 +434,11 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		created += __shfl_down_sync (0xFFFFFFFFu, created, d);
 	if ((tid & 31) == 0 && created)
 		atomicAdd (&ctr->n_nodes, (u64) created);
-	if (MODE == 0)
-	{	// instances are counted by the rank that inserts them
-		if (rb.owner_ranks > 1)
-		{
-#pragma unroll
-			for (int d = 16; d > 0; d >>= 1)
-				owned += __shfl_down_sync (0xFFFFFFFFu, owned, d);
-			if ((tid & 31) == 0 && owned)
-				atomicAdd (&ctr->n_instances, (u64) owned);
-		}
-		else if (tid == 0 && instances)
-			atomicAdd (&ctr->n_instances, instances);
-	}
+	// instances are counted by the rank that inserts them
+	if (MODE == 0 && tid == 0 && instances)
+		atomicAdd (&ctr->n_instances, instances);
+	if (MODE == 5 && tid == 0 && owned)
+		atomicAdd (&ctr->n_instances, owned);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -236,7 +236,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 {
 	typedef typename SlotOf<W>::type S;
 	auto kern = insert_reads_kernel<W, NMODE, MODE>;
-	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : ((MODE == 3 || MODE == 1) ? 3 * (size_t) bins.n_ranks + 4 : (MODE == 4 ? 2 * (size_t) bins.n_ranks + 2 : 0)));
+	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : ((MODE == 3 || MODE == 1) ? 3 * (size_t) bins.n_ranks + 4 : (MODE == 4 ? 2 * (size_t) bins.n_ranks + 2 : (MODE == 5 ? 2 * (size_t) QUEUE_WINDOWS * (W + 1) + 2 : 0))));
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
@@ -251,7 +251,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 	kern<<<grid, BLOCK, smem, ls>>> (static_cast<S *> (h->table), h->cap, rb, bins, h->d_ctr);
 	CK (h, cudaGetLastError ());
 	CK (h, cudaEventRecord (e1, ls));
-	h->timing.push_back ({ e0, e1, MODE == 2 ? 1 : (MODE == 0 ? 0 : 2) });
+	h->timing.push_back ({ e0, e1, MODE == 2 ? 1 : ((MODE == 0 || MODE == 5) ? 0 : 2) });
 	h->all_launches++;
 	return SDTGPU_OK;
 }
@@ -782,7 +782,9 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 		if (rc)
 			return rc;
 		h->pushed_upper += upper;
-		rc = launch_insert<0> (h, rb, Bins ());
+		// MODE 5 (chop into a shared-memory queue, then upsert with full warps) is the default also on one
+		// GPU: +3.5 % on C2 over upserting straight from the chop loop (MODE 0, SDTGPU_NO_QUEUE=1 for A/B)
+		rc = getenv ("SDTGPU_NO_QUEUE") && h->owner_ranks <= 1 ? launch_insert<0> (h, rb, Bins ()) : launch_insert<5> (h, rb, Bins ());
 		return rc ? rc : snapshot_nodes (h);
 	}
 	// partitioned: stage the batch (in pieces if it is larger than the staging area)
