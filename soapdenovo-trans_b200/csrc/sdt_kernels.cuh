@@ -22,7 +22,7 @@ namespace sdt {
 static constexpr int TILE_PAD = 8;	// u32 words of padding on both sides of the staged tile
 static constexpr int BLOCK = 256;
 static constexpr int MAX_TILE_READS = 256;
-static constexpr u32 QUEUE_WINDOWS = 2048;	// windows chopped per drain of the owned-instance queue (MODE 5)
+static constexpr u32 QUEUE_CAP = 1024;	// records in the owned-instance queue (MODE 5); tuned on C2: 512..1536 equal, 3072+ slower
 
 struct ReadBatch
 {
@@ -35,6 +35,7 @@ struct ReadBatch
 	u32 tile_reads;		// reads per shared-memory tile (multiple of 4, <= MAX_TILE_READS)
 	int K;
 	u32 max_read_len, maxwin;	// maxwin = max_read_len - K + 1 (ordinal = read * maxwin + window)
+	u32 queue_windows, queue_cap;	// MODE 5: windows chopped per drain of the owned-instance queue; its capacity (records)
 	u32 owner_rank, owner_ranks;	// owner_ranks > 1: insert only instances whose owner_of (mix(key)) == owner_rank
 };
 
@@ -290,9 +291,9 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		// MODE 1 / 3 walk the tile twice: sweep 0 counts the tile's records per bin, ONE global atomic per
 		// non-empty bin then reserves their space, sweep 1 writes the records (chopping twice is cheap;
 		// a contended global cursor atomic per warp was 3x slower, profiles/r1_multi_gpu.md)
-		for (u32 chunk0 = 0; chunk0 < total; chunk0 += (MODE == 5 ? QUEUE_WINDOWS : total))
+		for (u32 chunk0 = 0; chunk0 < total; chunk0 += (MODE == 5 ? rb.queue_windows : total))
 		{
-		const u32 chunk1 = MODE == 5 ? min (total, chunk0 + QUEUE_WINDOWS) : total;
+		const u32 chunk1 = MODE == 5 ? min (total, chunk0 + rb.queue_windows) : total;
 		for (int sweep = ((MODE == 3 || MODE == 1) ? 0 : 1); sweep < 2; sweep++)
 		{
 		for (u32 w = chunk0 + tid; w < chunk1; w += BLOCK)
@@ -331,7 +332,13 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 				// instances are first compacted into a shared-memory queue so that the upserts below run
 				// with full warps (filtering in place left 1 lane in n_ranks busy per memory round trip).
 				if (rb.owner_ranks <= 1 || owner_of (key_hash<W> (key), rb.owner_ranks) == rb.owner_rank)
-					store_record<W> (queue + (u64) atomicAdd (&q_count, 1u) * (W + 1), key, left, right, ord);
+				{
+					const u32 pos = atomicAdd (&q_count, 1u);
+					if (pos < rb.queue_cap)
+						store_record<W> (queue + (u64) pos * (W + 1), key, left, right, ord);
+					else	// more owned instances in this chunk than expected (skewed owners): insert in place
+						created += Table<W>::upsert (table, cap, key, left, right, ord);
+				}
 			}
 			else if (MODE == 1)
 			{	// send side of the exchange: bin = owner rank, fixed capacity per bin
@@ -394,12 +401,12 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		if (MODE == 5)
 		{	// drain the queue of owned instances with every lane busy
 			__syncthreads ();
-			const u32 nq = q_count;
+			const u32 nq_all = q_count, nq = min (nq_all, rb.queue_cap);
 			__syncthreads ();
 			if (tid == 0)
 			{
 				q_count = 0;
-				owned += nq;
+				owned += nq_all;
 			}
 			for (u32 i = tid; i < nq; i += BLOCK)
 			{

@@ -236,7 +236,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 {
 	typedef typename SlotOf<W>::type S;
 	auto kern = insert_reads_kernel<W, NMODE, MODE>;
-	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : ((MODE == 3 || MODE == 1) ? 3 * (size_t) bins.n_ranks + 4 : (MODE == 4 ? 2 * (size_t) bins.n_ranks + 2 : (MODE == 5 ? 2 * (size_t) QUEUE_WINDOWS * (W + 1) + 2 : 0))));
+	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : ((MODE == 3 || MODE == 1) ? 3 * (size_t) bins.n_ranks + 4 : (MODE == 4 ? 2 * (size_t) bins.n_ranks + 2 : (MODE == 5 ? 2 * (size_t) rb.queue_cap * (W + 1) + 2 : 0))));
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
@@ -293,6 +293,10 @@ int make_batch (sdtgpu *h, ReadBatch &rb, const uint8_t *d_packed, const u32 *d_
 	rb.K = h->K;
 	rb.max_read_len = (u32) h->max_read_len;
 	rb.maxwin = h->maxwin;
+	// chunk of windows chopped per drain: the queue's capacity on one GPU; with owner filtering only
+	// ~1/n of a chunk is owned, so chop 3n/4 capacities' worth (overflow is inserted in place)
+	rb.queue_cap = QUEUE_CAP;
+	rb.queue_windows = h->owner_ranks > 1 ? std::min<u32> (QUEUE_CAP * h->owner_ranks * 3 / 4, 16384) : QUEUE_CAP;
 	rb.owner_rank = h->owner_rank;
 	rb.owner_ranks = h->owner_ranks;
 	return SDTGPU_OK;
