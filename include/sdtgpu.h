@@ -118,7 +118,7 @@ int sdtgpu_set_owner (sdtgpu_t *h, int rank, int n_ranks);
 /* ---- multi-GPU, record exchange (alternative; the caller moves the bins, e.g. NCCL all-to-all).
  * The reference's equivalent is "every worker scans the shared hashBanBuffer and keeps
  * hash % thrd_num == id" (prlHashReads.c:79-88).  bucket_reads_device chops this rank's reads and
- * appends each instance as a 16*ceil(W/1)-byte record to the bin of its owner rank
+ * appends each instance as a record of sdtgpu_record_bytes() (8 * (device_key_words + 1)) to the bin of its owner rank
  * (owner = mix(key) -> [0, n_ranks)); insert_records_device upserts received records.
  * Record layout (little endian u64 words): key words (device_key_words, most significant first),
  * then one meta word = ordinal << 8 | left << 4 | right  (left/right 0..3, or 4 = none).

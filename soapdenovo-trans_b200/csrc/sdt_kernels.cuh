@@ -1,19 +1,21 @@
 // sdt_kernels.cuh — the sm_100a kernels of the pregraph hashing path.
 //
-//   insert_reads_kernel   chop (prlHashReads.c:164-310) fused with put_kmerset (newhash.c:411-462):
-//                         persistent CTAs stage tiles of 2-bit packed reads into shared memory with
-//                         16-byte vector loads, every thread takes windows of the flattened
-//                         (read, offset) space and upserts them into the table.  MODE 1 writes
-//                         (key, meta) records into per-owner bins instead (the send side of the
-//                         multi-GPU exchange; prlHashReads.c:79-88 is the reference's partition).
-//                         MODE 2 / MODE 3 are the two passes of the exact radix partition by table
-//                         slot range (count, then scatter): the staged records of one bucket all
-//                         fall into one L2-sized region of the table.
-//   insert_staged_kernel  upserts staged records bucket by bucket, so that the table region being
-//                         updated stays L2-resident (tools/randacc_bench.cu: 3-4x the random rate).
-//   insert_records_kernel the receive side: upsert records produced by MODE 1 on any rank.
-//   init / rehash / finalize / export kernels: table maintenance and the post-pass
-//                         (thread_delow prlHashReads.c:844-887, thread_mark :911-967).
+//   insert_reads_kernel<W, NMODE, MODE>
+//       chop (prlHashReads.c:164-310) fused with put_kmerset (newhash.c:411-462): persistent CTAs
+//       stage tiles of 2-bit packed reads into shared memory with 16-byte vector loads and walk the
+//       tile's flattened (read, offset) windows.  What happens to a window depends on MODE:
+//         5  the default insert: windows are chopped into a shared-memory queue of (key, meta)
+//            records, optionally filtered by owner rank (replicated-reads multi-GPU sharding), and
+//            the queue is drained with every lane issuing an upsert;
+//         0  upsert straight from the chop loop (kept for A/B, SDTGPU_NO_QUEUE=1);
+//         1  send side of the record exchange: records into per-owner bins;
+//         2, 3  count and scatter passes of the exact radix partition by table slot range
+//            (experimental partitioned path);
+//         4  per reference set, the largest instance ordinal of the batch (hand-back helper).
+//   insert_staged_kernel   upserts staged records bucket by bucket (experimental partitioned path).
+//   insert_records_kernel  receive side of the record exchange.
+//   init / rehash / finalize / export / checksum kernels: table maintenance, the post-pass
+//       (thread_delow prlHashReads.c:844-887, thread_mark :911-967) and verification.
 #pragma once
 #include "sdt_device.cuh"
 
@@ -43,7 +45,7 @@ struct Counters
 {
 	u64 n_nodes;		// distinct keys in the table
 	u64 n_instances;	// windows processed ("kmer in reads")
-	u64 overflow;		// records dropped because a bin was full (MODE 1)
+	u64 overflow;		// reserved
 	u64 n_removed, n_linear;	// finalize
 	u64 export_cursor;
 	u64 pad[2];
@@ -52,10 +54,10 @@ struct Counters
 
 struct Bins
 {
-	u64 *records;		// n_ranks x capacity x (W + 1) u64
-	u64 *counts;		// n_ranks
-	u64 capacity;
-	u32 n_ranks;
+	u64 *records;		// MODE 1: n_ranks x capacity x (W + 1) u64; MODE 3: the staging area
+	u64 *counts;		// per bin: fill (MODE 1), count (MODE 2), cursor (MODE 3), last ordinal + 1 (MODE 4)
+	u64 capacity;		// MODE 1: records per bin; MODE 4: key_words of the reference build
+	u32 n_ranks;		// bins: owner ranks (MODE 1), slot-range buckets (MODE 2, 3), reference sets (MODE 4)
 };
 
 __device__ __forceinline__ u32 bswap32 (u32 x) { return __byte_perm (x, 0, 0x0123); }
