@@ -11,6 +11,6 @@ The directory name contains a hyphen, so import it through `load()` in the repo-
 """
 from . import synth  # noqa: F401
 from .pregraph import (  # noqa: F401
-    LIB_PATH, NODE_DTYPE, PregraphGPU, SdtGpuError, build_library, hash_kmer, library, nodes_to_records,
+    LIB_PATH, NODE_DTYPE, PregraphGPU, ReadPacker, SdtGpuError, build_library, hash_kmer, library, nodes_to_records,
     read_kmersets,
 )

@@ -13,12 +13,13 @@
  *
  * What happens here, in the reference's order:
  *   1. same set-up and stdout lines as prlHashReads.c:355-367;
- *   2. every library file is read in the reference's order (openNextFile), records are parsed with
- *      the reference's rules (readseq1by1.c:122-178 FASTA, :281-340 FASTQ: first sequence line,
- *      base2int, '.' -> A, N -> G or 4 with -n, truncation to maxReadLen, reverse_seq), paired
- *      files are consumed alternately read1/read2 (prlHashReads.c:493-567);
- *   3. reads with len >= K+1 are 2-bit packed (seq.c:49-90 convention) into a pinned batch buffer;
- *      a full batch is one sdtgpu_push_reads call — the device replacement of
+ *   2. every library file is read in the reference's order (openNextFile); records are parsed and
+ *      2-bit packed (seq.c:49-90 convention) by the multi-threaded reader of include/sdtpack.h, which
+ *      restates the reference's rules (readseq1by1.c:122-178 FASTA, :281-340 FASTQ: first sequence
+ *      line, base2int, '.' -> A, N -> G or 4 with -n, truncation to maxReadLen, reverse_seq; paired
+ *      files alternate read1/read2, prlHashReads.c:493-567) straight into pinned batch buffers;
+ *   3. a batch is one sdtgpu_push_reads call (reads shorter than K+1 are skipped on the device, as
+ *      prlHashReads.c:507,539,592 skip them) — the device replacement of
  *      `sendWorkSignal(2); sendWorkSignal(1);` (prlHashReads.c:468-469, 525-526, 562-563, 604-605,
  *      618-619);
  *   4. sdtgpu_finalize = deLowCov + Mark1in1outNode + the kmerFreq histogram (prlHashReads.c:689-699);
@@ -33,6 +34,7 @@
 #include "extfunc.h"
 #include "extvab.h"
 #include "sdtgpu.h"
+#include "sdtpack.h"
 
 #ifdef MER127
 #define SDT_KEY_WORDS 4
@@ -51,11 +53,8 @@ typedef struct
 	uint32_t *lens[2];
 	int cur;
 	uint32_t stride, mstride;
-	uint64_t batch_reads, read_c, pushed_reads;
+	uint64_t batch_reads, pushed_reads;
 	long long instances;
-	char *seq;	/* one parsed read, one base code per byte */
-	char *line;
-	size_t line_cap;
 } hasher_t;
 
 static void die (hasher_t * hs, const char *what, int rc)
@@ -64,121 +63,54 @@ static void die (hasher_t * hs, const char *what, int rc)
 	exit (-1);	/* the reference's error convention, check.c:31-34 */
 }
 
-static void flush_batch (hasher_t * hs)
+/* one file (or file pair) through the parser and the GPU; returns the number of reads seen */
+static long long hash_file (hasher_t * hs, const char *path1, const char *path2, int fastq, int reverse, long long *progress)
 {
-	int rc;
-	if (!hs->read_c)
-		return;
-	rc = sdtgpu_push_reads (hs->gpu, hs->packed[hs->cur], hs->lens[hs->cur], N_kmer ? hs->nmask[hs->cur] : NULL,
-				hs->read_c, 0, hs->stride, hs->pushed_reads);
-	if (rc)
-		die (hs, "sdtgpu_push_reads", rc);
-	hs->pushed_reads += hs->read_c;
-	hs->read_c = 0;
-	hs->cur ^= 1;
-}
-
-/* one read (len >= K+1) into the current batch */
-static void add_read (hasher_t * hs, const char *seq, int len)
-{
-	uint8_t *dst = hs->packed[hs->cur] + hs->read_c * hs->stride;
-	int i;
-	memset (dst, 0, hs->stride);
-	for (i = 0; i < len; i++)
-		dst[i >> 2] |= (uint8_t) ((seq[i] & 3) << (6 - 2 * (i & 3)));
-	if (N_kmer)
+	sdtpack_reader *rd;
+	long long seen = 0;
+	int64_t n;
+	if (sdtpack_open (&rd, path1, path2, fastq, 0))
 	{
-		uint8_t *m = hs->nmask[hs->cur] + hs->read_c * hs->mstride;
-		memset (m, 0, hs->mstride);
-		for (i = 0; i < len; i++)
-			if (seq[i] == 4)
-				m[i >> 3] |= (uint8_t) (0x80 >> (i & 7));
+		printf ("Cannot open %s%s%s\n", path1, path2 ? " / " : "", path2 ? path2 : "");
+		exit (-1);
 	}
-	hs->lens[hs->cur][hs->read_c] = (uint32_t) len;
-	hs->instances += len - overlaplen + 1;
-	if (++hs->read_c == hs->batch_reads)
-		flush_batch (hs);
-}
-
-/* sequence line -> base codes, the rules of readseqInBuf/readseqfq (readseq1by1.c:147-171, 300-325) */
-static int encode_line (const char *str, char *out)
-{
-	int n = 0, i, strL = (int) strlen (str);
-	if (strL > maxReadLen)
-		strL = maxReadLen;
-	for (i = 0; i < strL; i++)
+	while ((n = sdtpack_next (rd, maxReadLen, N_kmer, reverse, hs->packed[hs->cur], hs->lens[hs->cur],
+				  N_kmer ? hs->nmask[hs->cur] : NULL, hs->batch_reads, hs->stride)) > 0)
 	{
-		const char c = str[i];
-		if ((c == 'N' || c == 'n') && N_kmer)
-			out[n++] = 4;
-		else if (c >= 'a' && c <= 'z')
-			out[n++] = base2int (c - 'a' + 'A');
-		else if (c >= 'A' && c <= 'Z')
-			out[n++] = base2int (c);
-		else if (c == '.')
-			out[n++] = base2int ('A');
-	}
-	return n;
-}
-
-static int get_line (hasher_t * hs, FILE * fp)
-{
-	ssize_t got = getline (&hs->line, &hs->line_cap, fp);
-	if (got < 0)
-		return 0;
-	while (got > 0 && (hs->line[got - 1] == '\n' || hs->line[got - 1] == '\r'))
-		hs->line[--got] = '\0';
-	return 1;
-}
-
-/* next record of a FASTA (fastq = 0) or FASTQ stream; returns 0 at end of file, else 1 and *len */
-static int next_record (hasher_t * hs, FILE * fp, int fastq, int reverse, int *len)
-{
-	const char tag = fastq ? '@' : '>';
-	int i;
-	do
-	{
-		if (!get_line (hs, fp))
-			return 0;
-	}
-	while (hs->line[0] != tag);
-	if (!get_line (hs, fp))
-		return 0;
-	*len = encode_line (hs->line, hs->seq);
-	if (fastq)
-	{	/* '+' line and quality line */
-		if (get_line (hs, fp))
-			get_line (hs, fp);
-	}
-	if (reverse && *len)
-	{	/* reverse2k, readseq1by1.c:749-764 */
-		for (i = 0; i < *len / 2; i++)
+		const uint32_t *lens = hs->lens[hs->cur];
+		int64_t t;
+		int rc;
+		for (t = 0; t < n; t++)
+			if ((int) lens[t] >= overlaplen + 1)	/* "kmer in reads", prlHashReads.c:516-518 */
+				hs->instances += (int) lens[t] - overlaplen + 1;
+		rc = sdtgpu_push_reads (hs->gpu, hs->packed[hs->cur], lens, N_kmer ? hs->nmask[hs->cur] : NULL,
+					(uint64_t) n, 0, hs->stride, hs->pushed_reads);
+		if (rc)
+			die (hs, "sdtgpu_push_reads", rc);
+		hs->pushed_reads += (uint64_t) n;
+		hs->cur ^= 1;
+		seen += n;
+		n_solexa += n;
+		while (*progress + 1000000 <= (long long) hs->pushed_reads)
 		{
-			char t = hs->seq[i];
-			hs->seq[i] = hs->seq[*len - 1 - i];
-			hs->seq[*len - 1 - i] = t;
+			*progress += 1000000;
+			printf ("--- %lldth reads\n", *progress);
 		}
-		for (i = 0; i < *len; i++)
-			hs->seq[i] = int_comp (hs->seq[i]);
 	}
-	n_solexa++;
-	return 1;
-}
-
-static void take_read (hasher_t * hs, int len, long long *i)
-{
-	if ((++(*i)) % 1000000 == 0)
-		printf ("--- %lldth reads\n", *i);
-	if (len < overlaplen + 1)	/* prlHashReads.c:507, 539, 592 */
-		return;
-	add_read (hs, hs->seq, len);
+	if (n < 0)
+	{
+		printf ("reading %s failed\n", path1);
+		exit (-1);
+	}
+	sdtpack_close (rd);
+	return seen;
 }
 
 boolean prlRead2HashTable (char *libfile, char *outfile)
 {
 	hasher_t hs;
-	long long i = 0;
-	int libNo = 0, b, rc, len;
+	long long i = 0, progress = 0;
+	int libNo = 0, b, rc;
 	time_t start_t, stop_t;
 	const char *env;
 	uint64_t hint = 0;
@@ -219,38 +151,26 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 		    sdtgpu_host_alloc ((void **) &hs.nmask[b], hs.batch_reads * hs.mstride))
 			die (&hs, "sdtgpu_host_alloc", SDTGPU_ENOMEM);
 	}
-	hs.seq = (char *) ckalloc ((maxReadLen + 1) * sizeof (char));
 	printf ("GPU pregraph hashing on device %d, K %d, %d-word keys\n", device, overlaplen, SDT_KEY_WORDS);
 
 	time (&start_t);
 	n_solexa = readNumBack = gradsCounter = 0;
 	while (openNextFile (&libNo, 0, 1))
 	{
-		const int type = lib_array[libNo].curr_type, rev = lib_array[libNo].reverse;
-		if (type == 4)
+		const LIB_INFO *lib = &lib_array[libNo];
+		const int type = lib->curr_type, rev = lib->reverse, idx = lib->curr_index - 1;	/* openFileInLib advanced it */
+		switch (type)
 		{
+		case 1:	i += hash_file (&hs, lib->a1_fname[idx], lib->a2_fname[idx], 0, rev, &progress); break;
+		case 2:	i += hash_file (&hs, lib->q1_fname[idx], lib->q2_fname[idx], 1, rev, &progress); break;
+		case 3:	i = hash_file (&hs, lib->p_fname[idx], NULL, 0, rev, &progress); break;	/* the reference restarts its counter for single files (:577) */
+		case 5:	i = hash_file (&hs, lib->s_a_fname[idx], NULL, 0, rev, &progress); break;
+		case 6:	i = hash_file (&hs, lib->s_q_fname[idx], NULL, 1, rev, &progress); break;
+		default:
 			printf ("BAM input (b=) is not supported by the GPU pregraph path\n");
 			exit (-1);
 		}
-		if (type == 1 || type == 2)
-		{	/* paired files: read1, read2, read1, ... (prlHashReads.c:493-567) */
-			int more1 = 1, more2 = 1;
-			while (more1 || more2)
-			{
-				if (more1 && (more1 = next_record (&hs, lib_array[libNo].fp1, type == 2, rev, &len)))
-					take_read (&hs, len, &i);
-				if (more2 && (more2 = next_record (&hs, lib_array[libNo].fp2, type == 2, rev, &len)))
-					take_read (&hs, len, &i);
-			}
-		}
-		else
-		{	/* p= / f= (FASTA) and q= (FASTQ): one stream (prlHashReads.c:574-611) */
-			i = 0;	/* the reference restarts its progress counter here (:577) */
-			while (next_record (&hs, lib_array[libNo].fp1, type == 6, rev, &len))
-				take_read (&hs, len, &i);
-		}
 	}
-	flush_batch (&hs);
 	if ((rc = sdtgpu_sync (hs.gpu)))
 		die (&hs, "sdtgpu_sync", rc);
 	time (&stop_t);
@@ -288,8 +208,6 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 		sdtgpu_host_free (hs.lens[b]);
 		sdtgpu_host_free (hs.nmask[b]);
 	}
-	free (hs.seq);
-	free (hs.line);
 	sdtgpu_destroy (hs.gpu);
 	return 1;
 }

@@ -45,7 +45,7 @@ class KmerSet(C.Structure):
 def build_library(force: bool = False) -> str:
     """Compiles csrc/ + host/ for sm_100a into libsdtgpu.so (in-tree, so it travels to the GPU box)."""
     srcs = [os.path.join(PKG_DIR, p) for p in ("csrc/sdtgpu.cu", "csrc/sdt_synth.cu", "csrc/sdt_device.cuh",
-                                               "csrc/sdt_kernels.cuh", "host/kmerset_builder.cpp",
+                                               "csrc/sdt_kernels.cuh", "host/kmerset_builder.cpp", "host/sdt_readpack.c", "../include/sdtpack.h",
                                                "../include/sdtgpu.h")]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
@@ -96,6 +96,11 @@ def library() -> C.CDLL:
     L.sdtgpu_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)]
     L.sdtgpu_table_checksum.argtypes = [vp, vp]
     L.sdtgpu_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.sdtpack_open.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p, i32, i32]
+    L.sdtpack_next.restype = C.c_int64
+    L.sdtpack_next.argtypes = [vp, i32, i32, i32, vp, vp, vp, u64, u32]
+    L.sdtpack_close.argtypes = [vp]
+    L.sdtpack_close.restype = None
     L.sdtgpu_synth_reads_device.argtypes = [i32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u32, u32, vp]
     _lib = L
     return L
@@ -281,3 +286,33 @@ def synth_reads_device(tr_dev: dict, seed: int, first_pair: int, n_pairs: int, r
                                              first_pair, n_pairs, read_len, stride_bytes, _ptr(out))
     if rc:
         raise SdtGpuError(rc, "sdtgpu_synth_reads_device")
+
+
+class ReadPacker:
+    """include/sdtpack.h: multi-threaded FASTA/FASTQ parser + 2-bit packer (host only)."""
+
+    def __init__(self, path1: str, path2: str | None = None, fastq: bool = False, n_threads: int = 0):
+        self.L = library()
+        self.h = C.c_void_p()
+        if self.L.sdtpack_open(C.byref(self.h), path1.encode(), path2.encode() if path2 else None, int(fastq), n_threads):
+            raise OSError(C.get_errno(), f"sdtpack_open({path1}, {path2})")
+
+    def next(self, max_read_len: int, max_reads: int, n_kmer: bool = False, reverse: bool = False, stride_bytes: int | None = None):
+        """Returns (packed[n, stride], lens[n], nmask[n, stride/2] or None); n == 0 at end of input."""
+        from .synth import stride_bytes as _sb
+        stride = stride_bytes or _sb(max_read_len)
+        packed = np.empty((max_reads, stride), dtype=np.uint8)
+        lens = np.empty(max_reads, dtype=np.uint32)
+        nmask = np.empty((max_reads, stride // 2), dtype=np.uint8) if n_kmer else None
+        n = self.L.sdtpack_next(self.h, max_read_len, int(n_kmer), int(reverse), packed.ctypes.data, lens.ctypes.data,
+                                nmask.ctypes.data if n_kmer else None, max_reads, stride)
+        if n < 0:
+            raise OSError("sdtpack_next failed")
+        return packed[:n], lens[:n], (nmask[:n] if n_kmer else None)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sdtpack_close(self.h)
+            self.h = None
+
+    __del__ = close
