@@ -61,13 +61,25 @@ u64 key_mod (const u64 key[4], int key_words, u64 size)
 	return t;
 }
 
+// Model of ONE reference KmerSet being filled in arrival order.  Slots hold the RANK of a node in
+// that order (or -1); the keys are kept in a compact rank-ordered array so that the replay touches
+// 8-32 bytes per node instead of a 56-byte export record, and both loops prefetch the random slot
+// (and key) they are about to need — the replay is bound by cache misses, not arithmetic.
 struct SetModel
 {
-	std::vector<int64_t> slot;	// node index or -1
+	std::vector<int32_t> slot;	// rank or -1   (a set holds far fewer than 2^31 nodes: ranks fit 32 bits)
+	std::vector<u64> keys;		// key_words words per rank, most significant first (only the words of the build)
 	u64 size = 0, count = 0, max = 0;
 	double load = 0;
 	int key_words = 1;
-	const sdtgpu_node *nodes = nullptr;
+
+	u64 mod_of (size_t rank) const
+	{
+		u64 k4[4] = { 0, 0, 0, 0 };
+		for (int w = 0; w < key_words; w++)
+			k4[4 - key_words + w] = keys[rank * key_words + w];
+		return key_mod (k4, key_words, size);
+	}
 
 	void init ()
 	{
@@ -102,15 +114,24 @@ struct SetModel
 		std::vector<uint8_t> taken (n, 0);	// new-table occupancy ("null" bit cleared)
 		size = n;
 		max = (u64) ((double) n * load);
+		const u64 AHEAD = 12;
 		for (u64 i = 0; i < old_size; i++)
 		{
+			if (i + 2 * AHEAD < old_size && slot[i + 2 * AHEAD] >= 0)
+				__builtin_prefetch (&keys[(size_t) slot[i + 2 * AHEAD] * key_words]);
+			if (i + AHEAD < old_size && pending[i + AHEAD])
+			{
+				const u64 h = mod_of ((size_t) slot[i + AHEAD]);
+				__builtin_prefetch (&taken[h]);
+				__builtin_prefetch (&slot[h]);
+			}
 			if (!pending[i])
 				continue;
-			int64_t carry = slot[i];
+			int32_t carry = slot[i];
 			pending[i] = 0;
 			for (;;)
 			{
-				u64 hc = key_mod (nodes[carry].key, key_words, size);
+				u64 hc = mod_of ((size_t) carry);
 				while (taken[hc])
 					if (++hc == size)
 						hc = 0;
@@ -133,15 +154,22 @@ struct SetModel
 				slot[i] = -1;
 	}
 
-	void put_new (int64_t idx)
-	{	// put_kmerset for a key known to be absent, newhash.c:411-440
-		grow (1);
-		u64 hc = key_mod (nodes[idx].key, key_words, size);
-		while (slot[hc] >= 0)
-			if (++hc == size)
-				hc = 0;
-		slot[hc] = idx;
-		count++;
+	// put_kmerset for keys known to be absent (newhash.c:411-440), ranks first..last-1 in order
+	void put_all (size_t n_ranks)
+	{
+		const size_t AHEAD = 12;
+		for (size_t r = 0; r < n_ranks; r++)
+		{
+			grow (1);
+			if (r + AHEAD < n_ranks)
+				__builtin_prefetch (&slot[mod_of (r + AHEAD)]);	// (a growth in between just wastes the hint)
+			u64 hc = mod_of (r);
+			while (slot[hc] >= 0)
+				if (++hc == size)
+					hc = 0;
+			slot[hc] = (int32_t) r;
+			count++;
+		}
 	}
 };
 
@@ -164,13 +192,28 @@ extern "C" int sdtgpu_build_kmersets (const sdtgpu_node *nodes, uint64_t n_nodes
 	std::vector<int> status (thrd_num, SDTGPU_OK);
 	auto work = [&](int t) {
 		std::vector<int64_t> &ord = order[t];
-		std::sort (ord.begin (), ord.end (), [&](int64_t a, int64_t b) { return nodes[a].ordinal < nodes[b].ordinal; });
+		if (ord.size () >= 0x7FFFFFFFull)
+		{
+			status[t] = SDTGPU_ERANGE;
+			sets[t] = nullptr;
+			return;
+		}
+		{	// arrival order = ascending first-instance ordinal; sort (ordinal, index) pairs, not indices
+			std::vector<std::pair<u64, int64_t>> keyed (ord.size ());
+			for (size_t i = 0; i < ord.size (); i++)
+				keyed[i] = std::make_pair ((u64) nodes[ord[i]].ordinal, ord[i]);
+			std::sort (keyed.begin (), keyed.end ());
+			for (size_t i = 0; i < ord.size (); i++)
+				ord[i] = keyed[i].second;
+		}
 		SetModel m;
 		m.key_words = key_words;
-		m.nodes = nodes;
+		m.keys.resize (ord.size () * (size_t) key_words);
+		for (size_t i = 0; i < ord.size (); i++)
+			for (int w = 0; w < key_words; w++)
+				m.keys[i * key_words + w] = nodes[ord[i]].key[4 - key_words + w];
 		m.init ();
-		for (int64_t idx : ord)
-			m.put_new (idx);
+		m.put_all (ord.size ());
 		// put_kmerset evaluates encap_kmerset on EVERY call, also for instances of known keys
 		// (newhash.c:415): if instances of this set arrived after its last new key, one more
 		// growth step may have happened.
@@ -191,10 +234,9 @@ extern "C" int sdtgpu_build_kmersets (const sdtgpu_node *nodes, uint64_t n_nodes
 		memset (flags, 0x55, fwords * 4);	// every entry "null" (newhash.c:190-191, newhash.h:47)
 		for (u64 p = 0; p < m.size; p++)
 		{
-			const int64_t idx = m.slot[p];
-			if (idx < 0)
+			if (m.slot[p] < 0)
 				continue;
-			const sdtgpu_node &n = nodes[idx];
+			const sdtgpu_node &n = nodes[ord[(size_t) m.slot[p]]];
 			char *rec = array + p * nb;
 			memcpy (rec, &n.key[4 - key_words], 8 * (size_t) key_words);	// Kmer words in declaration order (def.h:45-59)
 			memcpy (rec + 8 * key_words, &n.l_links, 4);
