@@ -155,6 +155,11 @@ int sdtgpu_table_checksum (sdtgpu_t *h, uint64_t out[4]);
 int sdtgpu_export_count (sdtgpu_t *h, uint64_t *n_nodes);
 int sdtgpu_export_nodes (sdtgpu_t *h, int thrd_num, int sort_by_ordinal, sdtgpu_node *out, uint64_t max_nodes, uint64_t *n_nodes);
 int sdtgpu_export_kmersets (sdtgpu_t *h, int thrd_num, sdtgpu_kmerset **sets);
+/* Per reference set: the largest instance ordinal among ALL instances of the newest batch (owner
+ * filtering does not apply), 0 for a set that batch did not touch — the set_last_ordinal input of
+ * sdtgpu_build_kmersets when nodes of several GPUs are merged (put_kmerset runs encap_kmerset on
+ * every call, newhash.c:415).  SDTGPU_ESTATE if no batch was pushed. */
+int sdtgpu_last_ordinals (sdtgpu_t *h, int thrd_num, uint64_t *out);
 /* the host half of export_kmersets, usable on nodes merged from several ranks */
 int sdtgpu_build_kmersets (const sdtgpu_node *nodes, uint64_t n_nodes, int key_words, int thrd_num,
 			   const uint64_t *set_last_ordinal /* [thrd_num] or NULL */, sdtgpu_kmerset **sets);

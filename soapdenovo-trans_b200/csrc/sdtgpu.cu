@@ -1076,6 +1076,23 @@ int sdtgpu_export_kmersets (sdtgpu_t *h, int thrd_num, sdtgpu_kmerset **sets)
 	return rc;
 }
 
+int sdtgpu_last_ordinals (sdtgpu_t *h, int thrd_num, uint64_t *out)
+{
+	if (!h || !out || thrd_num < 1)
+		return SDTGPU_EINVAL;
+	CK (h, cudaSetDevice (h->device));
+	int rc = flush_epoch (h);
+	if (rc)
+		return rc;
+	std::vector<u64> last;
+	rc = set_last_ordinals (h, thrd_num, last);
+	if (rc)
+		return rc;
+	for (int t = 0; t < thrd_num; t++)
+		out[t] = last[t] ? last[t] - 1 : 0;
+	return h->have_last ? SDTGPU_OK : SDTGPU_ESTATE;
+}
+
 int sdtgpu_table_checksum (sdtgpu_t *h, uint64_t out[4])
 {
 	if (!h || !out)

@@ -25,8 +25,12 @@
  *   4. sdtgpu_finalize = deLowCov + Mark1in1outNode + the kmerFreq histogram (prlHashReads.c:689-699);
  *      this file writes <outfile>.kmerFreq in freqStat's format (:994-1023);
  *   5. sdtgpu_export_kmersets fills the global KmerSets.
- * Knobs that the reference CLI does not have come from the environment: SDTGPU_DEVICE,
- * SDTGPU_CAPACITY_HINT (expected distinct k-mers; 0 = grow on the device), SDTGPU_BATCH_READS.
+ * Knobs that the reference CLI does not have come from the environment: SDTGPU_DEVICES (comma
+ * separated CUDA ordinals; with more than one, every GPU receives every batch and inserts the k-mers
+ * it owns — the reference's own "each worker scans the batch and keeps hash % thrd_num == id",
+ * prlHashReads.c:79-88 — and the nodes of all GPUs are merged at hand-back), SDTGPU_DEVICE (one
+ * ordinal), SDTGPU_CAPACITY_HINT (expected distinct k-mers in total; 0 = grow on the device),
+ * SDTGPU_BATCH_READS.
  * BAM libraries (b=) are not supported by this path.
  */
 #include "stdinc.h"
@@ -46,9 +50,13 @@
 #define SDT_KEY_WORDS 1
 #endif
 
+#define SDT_MAX_GPUS 16
+
 typedef struct
 {
-	sdtgpu_t *gpu;
+	sdtgpu_t *gpu;		/* gpus[0]: error reporting */
+	sdtgpu_t *gpus[SDT_MAX_GPUS];
+	int n_gpus;
 	uint8_t *packed[2], *nmask[2];	/* pinned, double buffered */
 	uint32_t *lens[2];
 	int cur;
@@ -83,8 +91,9 @@ static long long hash_file (hasher_t * hs, const char *path1, const char *path2,
 		for (t = 0; t < n; t++)
 			if ((int) lens[t] >= overlaplen + 1)	/* "kmer in reads", prlHashReads.c:516-518 */
 				hs->instances += (int) lens[t] - overlaplen + 1;
-		rc = sdtgpu_push_reads (hs->gpu, hs->packed[hs->cur], lens, N_kmer ? hs->nmask[hs->cur] : NULL,
-					(uint64_t) n, 0, hs->stride, hs->pushed_reads);
+		for (rc = 0, t = 0; t < hs->n_gpus && !rc; t++)	/* every GPU sees every batch and keeps what it owns */
+			rc = sdtgpu_push_reads (hs->gpus[t], hs->packed[hs->cur], lens, N_kmer ? hs->nmask[hs->cur] : NULL,
+						(uint64_t) n, 0, hs->stride, hs->pushed_reads);
 		if (rc)
 			die (hs, "sdtgpu_push_reads", rc);
 		hs->pushed_reads += (uint64_t) n;
@@ -114,7 +123,7 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 	time_t start_t, stop_t;
 	const char *env;
 	uint64_t hint = 0;
-	int device = 0;
+	int device = 0, devices[SDT_MAX_GPUS];
 	int64_t freq[257];
 	sdtgpu_stats st;
 	char name[256];
@@ -139,9 +148,31 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 	hs.batch_reads = 1u << 20;
 	if ((env = getenv ("SDTGPU_BATCH_READS")) && atoll (env) > 0)
 		hs.batch_reads = (uint64_t) atoll (env);
-	rc = sdtgpu_create (&hs.gpu, device, overlaplen, SDT_KEY_WORDS, maxReadLen, hint, N_kmer ? SDTGPU_F_NKMER : 0);
-	if (rc)
-		die (NULL, "sdtgpu_create", rc);
+	devices[0] = device;
+	hs.n_gpus = 1;
+	if ((env = getenv ("SDTGPU_DEVICES")) && *env)
+	{
+		char *copy = strdup (env), *tok, *save = NULL;
+		hs.n_gpus = 0;
+		for (tok = strtok_r (copy, ",", &save); tok && hs.n_gpus < SDT_MAX_GPUS; tok = strtok_r (NULL, ",", &save))
+			devices[hs.n_gpus++] = atoi (tok);
+		free (copy);
+		if (hs.n_gpus < 1)
+		{
+			devices[0] = device;
+			hs.n_gpus = 1;
+		}
+	}
+	for (b = 0; b < hs.n_gpus; b++)
+	{
+		rc = sdtgpu_create (&hs.gpus[b], devices[b], overlaplen, SDT_KEY_WORDS, maxReadLen,
+				    hint ? hint / hs.n_gpus + hint / (8 * hs.n_gpus) + 1 : 0, N_kmer ? SDTGPU_F_NKMER : 0);
+		if (rc)
+			die (NULL, "sdtgpu_create", rc);
+		if (hs.n_gpus > 1 && (rc = sdtgpu_set_owner (hs.gpus[b], b, hs.n_gpus)))
+			die (&hs, "sdtgpu_set_owner", rc);
+	}
+	hs.gpu = hs.gpus[0];
 	hs.stride = (uint32_t) (((maxReadLen + 3) / 4 + 3) / 4 * 4);
 	hs.mstride = hs.stride / 2;
 	for (b = 0; b < 2; b++)
@@ -151,7 +182,7 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 		    sdtgpu_host_alloc ((void **) &hs.nmask[b], hs.batch_reads * hs.mstride))
 			die (&hs, "sdtgpu_host_alloc", SDTGPU_ENOMEM);
 	}
-	printf ("GPU pregraph hashing on device %d, K %d, %d-word keys\n", device, overlaplen, SDT_KEY_WORDS);
+	printf ("GPU pregraph hashing on %d device(s) (first: %d), K %d, %d-word keys\n", hs.n_gpus, devices[0], overlaplen, SDT_KEY_WORDS);
 
 	time (&start_t);
 	n_solexa = readNumBack = gradsCounter = 0;
@@ -171,16 +202,28 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 			exit (-1);
 		}
 	}
-	if ((rc = sdtgpu_sync (hs.gpu)))
-		die (&hs, "sdtgpu_sync", rc);
+	for (b = 0; b < hs.n_gpus; b++)
+		if ((rc = sdtgpu_sync (hs.gpus[b])))
+			die (&hs, "sdtgpu_sync", rc);
 	time (&stop_t);
 	printf ("time spent on hash reads: %ds, %lld reads processed\n", (int) (stop_t - start_t), i);
 	free_pe_mem ();
 	free_libs ();
 
 	time (&start_t);
-	if ((rc = sdtgpu_finalize (hs.gpu, deLowKmer, freq, &st)))
-		die (&hs, "sdtgpu_finalize", rc);
+	memset (freq, 0, sizeof freq);
+	memset (&st, 0, sizeof st);
+	for (b = 0; b < hs.n_gpus; b++)
+	{	/* per-GPU post-pass; counters and the histogram add up (owners are disjoint) */
+		int64_t f1[257];
+		sdtgpu_stats s1;
+		int q;
+		if ((rc = sdtgpu_finalize (hs.gpus[b], deLowKmer, f1, &s1)))
+			die (&hs, "sdtgpu_finalize", rc);
+		for (q = 0; q < 257; q++)
+			freq[q] += f1[q];
+		st.n_nodes += s1.n_nodes; st.n_instances += s1.n_instances; st.n_removed += s1.n_removed; st.n_linear += s1.n_linear;
+	}
 	printf ("%lli nodes allocated, %lli kmer in reads, %lli kmer processed\n", (long long) st.n_nodes, hs.instances, (long long) st.n_instances);
 	if (deLowKmer)
 		printf ("%lld kmer removed\n", (long long) st.n_removed);	/* deLowCov, :908 */
@@ -195,8 +238,31 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 
 	time (&start_t);
 	sets = (sdtgpu_kmerset **) ckalloc (thrd_num * sizeof (sdtgpu_kmerset *));
-	if ((rc = sdtgpu_export_kmersets (hs.gpu, thrd_num, sets)))
-		die (&hs, "sdtgpu_export_kmersets", rc);
+	if (hs.n_gpus == 1)
+	{
+		if ((rc = sdtgpu_export_kmersets (hs.gpu, thrd_num, sets)))
+			die (&hs, "sdtgpu_export_kmersets", rc);
+	}
+	else
+	{	/* merge the GPUs' nodes, then replay them into reference KmerSets on the host */
+		sdtgpu_node *nodes = (sdtgpu_node *) malloc ((st.n_nodes ? st.n_nodes : 1) * sizeof (sdtgpu_node));
+		uint64_t *last = (uint64_t *) calloc (thrd_num, sizeof (uint64_t)), got = 0, n1;
+		if (!nodes || !last)
+			die (&hs, "malloc for the merged hand-back", SDTGPU_ENOMEM);
+		for (b = 0; b < hs.n_gpus; b++)
+		{
+			if ((rc = sdtgpu_export_nodes (hs.gpus[b], thrd_num, 0, nodes + got, st.n_nodes - got, &n1)))
+				die (&hs, "sdtgpu_export_nodes", rc);
+			got += n1;
+		}
+		rc = sdtgpu_last_ordinals (hs.gpu, thrd_num, last);	/* every GPU saw every batch: any one of them knows */
+		if (rc && rc != SDTGPU_ESTATE)
+			die (&hs, "sdtgpu_last_ordinals", rc);
+		if ((rc = sdtgpu_build_kmersets (nodes, got, SDT_KEY_WORDS, thrd_num, rc == SDTGPU_ESTATE ? NULL : last, sets)))
+			die (&hs, "sdtgpu_build_kmersets", rc);
+		free (nodes);
+		free (last);
+	}
 	KmerSets = (KmerSet **) sets;	/* sdtgpu_kmerset is layout-identical to KmerSet (newhash.h:79-88) */
 	time (&stop_t);
 	printf ("time spent on handing the k-mer table back %ds\n", (int) (stop_t - start_t));
@@ -208,6 +274,7 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 		sdtgpu_host_free (hs.lens[b]);
 		sdtgpu_host_free (hs.nmask[b]);
 	}
-	sdtgpu_destroy (hs.gpu);
+	for (b = 0; b < hs.n_gpus; b++)
+		sdtgpu_destroy (hs.gpus[b]);
 	return 1;
 }

@@ -95,6 +95,7 @@ def library() -> C.CDLL:
     L.sdtgpu_aux_stream.argtypes = [vp]
     L.sdtgpu_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)]
     L.sdtgpu_table_checksum.argtypes = [vp, vp]
+    L.sdtgpu_last_ordinals.argtypes = [vp, i32, vp]
     L.sdtgpu_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.sdtpack_open.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p, i32, i32]
     L.sdtpack_next.restype = C.c_int64

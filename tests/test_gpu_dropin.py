@@ -15,9 +15,12 @@ from conftest import make_dataset
 pytestmark = pytest.mark.gpu
 
 
-def _run(exe, cfg, prefix, K, p, d, extra=()):
+def _run(exe, cfg, prefix, K, p, d, extra=(), devices=None):
     cmd = [exe, "pregraph", "-s", cfg, "-K", str(K), "-p", str(p), "-d", str(d), "-o", prefix, *extra]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+    env = dict(os.environ)
+    if devices:
+        env["SDTGPU_DEVICES"] = devices
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     return r.stdout
 
@@ -60,3 +63,28 @@ def test_pregraph_outputs_identical(pkg, oracle, tmp_path, build, K, p, d, fastq
         la = [l for l in a.splitlines() if key in l]
         lb = [l for l in b.splitlines() if key in l]
         assert la == lb, (la, lb)
+
+
+@pytest.mark.parametrize("devices", ["0,0,0", "0,1"])
+def test_pregraph_outputs_identical_sharded(pkg, oracle, tmp_path, devices):
+    """SDTGPU_DEVICES: every table shard receives every batch and keeps the k-mers it owns; the
+    shards' nodes are merged at hand-back.  "0,0,0" runs three shards on one GPU (always possible),
+    "0,1" two GPUs.  Outputs must still equal the stock binary's byte for byte."""
+    import torch
+    if devices == "0,1" and torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    stock = os.path.join(oracle.REF_DIR, "SOAPdenovo-Trans-31mer")
+    gpu = os.path.join(oracle.REF_DIR, "SOAPdenovo-Trans-31mer-gpu")
+    if not (os.path.exists(stock) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref binaries not present")
+    tr = pkg.synth.make_transcriptome(60, 21)
+    reads, lens = make_dataset(pkg, tr, 12000, 100, 71, ragged=30)
+    cfg = pkg.synth.write_library(str(tmp_path / "in"), reads, lens, 100, paired=True)
+    a = _run(stock, cfg, str(tmp_path / "ref"), 27, 8, 1)
+    b = _run(gpu, cfg, str(tmp_path / "gpu"), 27, 8, 1, devices=devices)
+    assert f"on {len(devices.split(','))} device(s)" in b
+    ra, rb = _outputs(str(tmp_path / "ref")), _outputs(str(tmp_path / "gpu"))
+    for k in ra:
+        assert ra[k] == rb[k], f"{k} differs"
+    for key in ("nodes allocated", "linear nodes", "kmer removed"):
+        assert [l for l in a.splitlines() if key in l] == [l for l in b.splitlines() if key in l]
