@@ -34,6 +34,7 @@ BYTES_PER_INSTANCE = {1: 64, 2: 64, 4: 96}
 # upsert needs at least one load and one atomic, so a single-pass insert cannot exceed half of that.
 RANDOM_REQUESTS_PER_S = 36.65e9
 MIN_REQUESTS_PER_INSTANCE = {1: 2, 2: 2, 4: 3}
+DEFAULT_PATH = {1: "sliced", 2: "direct"}     # key: 1 GPU / more than one GPU
 METRIC = "k-mers inserted/s in pregraph hashing"
 UNIT = "k-mer instances/s"
 
@@ -127,7 +128,16 @@ def main():
     ap.add_argument("--exchange", default="reads", choices=["reads", "records"],
                     help="multi-GPU sharding: all-gather the packed reads and insert owned k-mers (default) or exchange k-mer records")
     ap.add_argument("--partitioned", action="store_true", help="experimental staged/partitioned insert path")
+    ap.add_argument("--path", default="auto", choices=["auto", "direct", "sliced", "partitioned"],
+                    help="insert path: single-pass upsert (direct), sliced build (count -> partition -> shared-memory slices), "
+                         "or the experimental staged path; auto = the fastest measured one for this GPU count")
     args = ap.parse_args()
+    if args.partitioned:
+        args.path = "partitioned"
+    if args.path == "auto":
+        args.path = DEFAULT_PATH[1 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 2]
+    args.partitioned = args.path == "partitioned"
+    sliced = args.path == "sliced"
 
     import sdt_pkg
     pkg = sdt_pkg.load()
@@ -195,7 +205,7 @@ def main():
     # distinct k-mers are dominated by error k-mers (a window is error-free with probability 0.99^K)
     slot_b = 64 if K > 63 else 32
     est_distinct = instances_rank * (1.0 - 0.99 ** K) * 1.03 + 6e7
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(est_distinct) + 1024, device=local_rank, partitioned=args.partitioned)
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(est_distinct) + 1024, device=local_rank, partitioned=args.partitioned, sliced=sliced)
     ext = torch.cuda.ExternalStream(g.stream, device=dev)
 
     exch = None
@@ -225,7 +235,7 @@ def main():
     assert (exch is not None) or st.n_instances == instances_rank, (st.n_instances, instances_rank)
     g.close()
     # the library sizes the table from the hint: load 0.5 up to 60 GiB, denser beyond
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(distinct * 1.02) + 1024, device=local_rank, partitioned=args.partitioned)
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(distinct * 1.02) + 1024, device=local_rank, partitioned=args.partitioned, sliced=sliced)
     ext = torch.cuda.ExternalStream(g.stream, device=dev)
     if exch is not None:
         exch.rebind(g)
@@ -254,6 +264,7 @@ def main():
     chk = g.stats()
     assert exch is not None or (chk.n_instances == instances_rank and chk.n_nodes == distinct), (chk.n_instances, chk.n_nodes)
     st = g.stats()
+    phases = g.phase_times(reset=False)
     cat_ms, cat_launches = g.kernel_times(reset=False)
     insert_ms, insert_launches, all_launches = g.kernel_time(reset=True)
     t = torch.tensor([ms, float(st.n_instances), float(st.n_nodes)], dtype=torch.float64, device=dev)
@@ -268,12 +279,35 @@ def main():
     ms_per_step = ms / args.steps
     value = total_instances / (ms_per_step * 1e-3)
     bpi = BYTES_PER_INSTANCE[st.device_key_words]
-    ker_ms = max(insert_ms, 1e-9) / max(insert_launches, 1)
-    inst_per_launch = st.n_instances * args.steps / max(insert_launches, 1)
+    sliced_info = None
+    if sliced:
+        # The insert is a pipeline of four streaming kernels (count, scatter level 1, scatter level 2, slice
+        # build); the SURVEY figure of 64 (96) algorithmic bytes per instance belongs to the whole insert, so
+        # `achieved` is taken over the SUM of their CUDA-event times (all on the handle's stream).  Each
+        # phase's own DRAM stream (bytes it must read + write per instance) is reported beside it.
+        rec_b = 8 * (st.device_key_words + 1)
+        read_b = stride / nwin
+        table_b = st.capacity * slot_b / max(st.n_instances, 1)
+        stream_b = {"count": read_b, "scatter1": read_b + rec_b, "scatter2": 2 * rec_b, "build": rec_b + table_b, "scan": 0.0}
+        insert_ms = sum(phases[k][0] for k in stream_b)
+        insert_launches = max(phases["build"][1], 1)
+        geo = g.slice_geometry()
+        sliced_info = {"geometry": geo, "epochs_per_step": 1, "phases": {
+            k: {"ms_per_step": phases[k][0] / args.steps, "launches_per_step": phases[k][1] / args.steps,
+                "stream_bytes_per_instance": stream_b[k],
+                "stream_gbs": (st.n_instances * args.steps * stream_b[k] / max(phases[k][0], 1e-9) / 1e6) if stream_b[k] else None}
+            for k in stream_b}}
+        dominant = max(stream_b, key=lambda k: phases[k][0])
+        sliced_info["dominant"] = "slice_" + dominant + "_kernel"
+        ker_ms = insert_ms / args.steps                      # one pipeline pass = one "launch" of the insert
+        inst_per_launch = float(st.n_instances)
+    else:
+        ker_ms = max(insert_ms, 1e-9) / max(insert_launches, 1)
+        inst_per_launch = st.n_instances * args.steps / max(insert_launches, 1)
     achieved = inst_per_launch * bpi / (ker_ms * 1e-3) / 1e9
     traffic = None      # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tp) and world == 1 and not args.partitioned:
+    if os.path.exists(tp) and world == 1 and args.path == "direct":
         with open(tp) as f:
             tj = json.load(f)
         if tj.get("key_words") == st.device_key_words:
@@ -341,9 +375,12 @@ def main():
                        "instances_per_step": total_instances, "distinct_kmers": total_nodes,
                        "table_slots_per_gpu": int(st.capacity), "slot_bytes": 64 if st.device_key_words == 4 else 32,
                        "batch_reads": batch,
-                       "l2": "table (>= 2x distinct x slot bytes) and reads are far larger than the 126 MB L2; table is reset every step"},
+                       "insert_path": args.path,
+                       "l2": "table (>= 1.6x distinct x slot bytes), k-mer records and reads are far larger than the 126 MB L2; the table is rebuilt from empty every step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": traffic, "kernel": ("insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if (world == 1 or args.exchange == "reads") else "insert_records_kernel",
+                         "traffic": traffic, "kernel": ("slice_count + slice_scatter1 + slice_scatter2 + slice_build kernels (the sliced insert pipeline; times summed)" if sliced else
+                                    "insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if (world == 1 or args.exchange == "reads") else "insert_records_kernel",
+                         "path": args.path, "sliced": sliced_info,
                          "bytes_per_instance": bpi, "kernel_ms_per_launch": ker_ms, "peak_source": peak_src,
                          "random_access": {"cold_line_requests_per_s_measured": RANDOM_REQUESTS_PER_S,
                                            "min_requests_per_instance": MIN_REQUESTS_PER_INSTANCE[st.device_key_words],

@@ -3,6 +3,7 @@
 // There is NO CPU fallback: every entry point either runs the CUDA path or returns an error.
 #include "../../include/sdtgpu.h"
 #include "sdt_kernels.cuh"
+#include "sdt_sliced.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -25,6 +26,15 @@ struct Staging
 	cudaEvent_t free_ev = nullptr;	// recorded on the compute stream after the kernel that read this buffer
 	cudaEvent_t ready_ev = nullptr;	// recorded on the copy stream after the H2D copies
 };
+
+// one pushed batch in the read log of the open epoch (sliced build); offsets into the log arenas
+struct LogSeg
+{
+	size_t off[3];	// packed, lens, mask
+	ReadBatch rb;	// pointers are resolved when the segment is used (the arenas may move)
+};
+
+static constexpr int N_CAT = 8;	// timing classes: 0 insert, 1 count, 2 scatter (level 1), 3 scatter (level 2), 4 build, 5 scan
 
 }	// namespace
 
@@ -70,10 +80,24 @@ struct sdtgpu
 	const u64 *seg_records[MAX_SEGMENTS];
 	u32 n_segments = 0;
 	double region_bytes = 16.0 * 1024 * 1024;
+	// sliced build (SDTGPU_F_SLICED): reads of the open epoch are kept in a log, counted per slice as
+	// they arrive, and turned into the table by sliced_flush (sdt_sliced.cuh)
+	bool sliced = false, table_built = false;
+	SliceGeom geom = { 0, 0, 0, 0 };
+	void *log_mem[3] = { nullptr, nullptr, nullptr };	// packed, lens, mask arenas
+	size_t log_cap[3] = { 0, 0, 0 }, log_used[3] = { 0, 0, 0 };
+	std::vector<LogSeg> log;
+	u64 log_upper = 0, epoch_budget = 0;	// instances in the log (upper bound); records an epoch may hold
+	u32 *d_hist = nullptr;
+	u64 *d_off = nullptr, *d_cur2 = nullptr, *d_seg_sum = nullptr, *d_off1 = nullptr, *d_cur1 = nullptr, *d_tpre = nullptr;
+	u64 *h_lvl1 = nullptr;	// pinned: off1[P1 + 1]
+	u64 *rec1 = nullptr, *rec2 = nullptr;
+	u64 rec1_cap = 0, rec2_cap = 0;	// records
+	u32 n_epochs = 0;
 	struct Timed { cudaEvent_t e0, e1; int cat; };
 	std::vector<Timed> timing;
-	double cat_ms[3] = { 0, 0, 0 };
-	u64 cat_launches[3] = { 0, 0, 0 };
+	double cat_ms[N_CAT] = { 0 };
+	u64 cat_launches[N_CAT] = { 0 };
 	std::vector<cudaEvent_t> ev_pool;
 	u64 all_launches = 0;
 	std::string err;
@@ -529,8 +553,12 @@ int grow_table (sdtgpu *h, u64 new_cap)
 // the epoch is unknown, so the kernel runs optimistically and stops itself when the table reaches
 // 85 % load; the table is then grown by device re-hash (the reference's encap_kmerset,
 // newhash.c:293-409, moved to the device) and the kernel resumes where it stopped.
+int sliced_flush (sdtgpu *h);
+
 int flush_epoch (sdtgpu *h)
 {
+	if (h->sliced)
+		return sliced_flush (h);
 	if (h->n_segments == 0)
 		return SDTGPU_OK;
 	int rc;
@@ -622,6 +650,331 @@ int stage_batch (sdtgpu *h, const ReadBatch &rb, u64 upper)
 	return SDTGPU_OK;
 }
 
+
+// ---- sliced build (sdt_sliced.cuh) --------------------------------------------------------------
+struct TimedLaunch
+{	// CUDA events around one launch on the handle's stream, filed under a timing class
+	sdtgpu *h;
+	cudaEvent_t e0, e1;
+	int cat;
+	TimedLaunch (sdtgpu *h_, int cat_) : h (h_), e0 (get_event (h_)), e1 (get_event (h_)), cat (cat_) { cudaEventRecord (e0, h->stream); }
+	~TimedLaunch ()
+	{
+		cudaEventRecord (e1, h->stream);
+		h->timing.push_back ({ e0, e1, cat });
+		h->all_launches++;
+	}
+};
+
+u32 env_u32 (const char *name, u32 dflt)
+{
+	const char *e = getenv (name);
+	return e && atoll (e) > 0 ? (u32) atoll (e) : dflt;
+}
+
+u32 scatter_tile_recs (int W) { return W == 4 ? SC_NT * ScatterCfg<4>::RPT : SC_NT * ScatterCfg<1>::RPT; }
+
+// geometry from the expected distinct count: slices of S slots at ~0.6 load, two partition levels
+// of about sqrt (n_slices) bins each
+int sliced_setup (sdtgpu *h, u64 hint)
+{
+	if (hint == 0)
+		return fail (h, SDTGPU_EINVAL, "the sliced build needs capacity_hint (expected distinct k-mers)");
+	const u32 S = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 4096u : (h->W == 2 ? 3072u : 2048u));
+	double load = 0.6;
+	if (const char *e = getenv ("SDTGPU_SLICE_LOAD"))
+		if (atof (e) > 0.05 && atof (e) < 0.95)
+			load = atof (e);
+	const u64 n = std::max<u64> (1, (u64) std::ceil ((double) hint / ((double) S * load)));
+	if (n > (1ull << 30))
+		return fail (h, SDTGPU_ERANGE, "capacity_hint too large for the sliced build");
+	SliceGeom g;
+	g.n_slices = (u32) n;
+	g.slice_slots = S;
+	u32 p2 = env_u32 ("SDTGPU_SLICE_P2", (u32) std::ceil (std::sqrt ((double) n)));
+	g.P2 = std::max (1u, std::min (p2, g.n_slices));
+	g.P1 = (g.n_slices + g.P2 - 1) / g.P2;
+	if (g.P1 > 32768 || g.P2 > 32768)
+		return fail (h, SDTGPU_ERANGE, "partition fan-out too large");
+	h->geom = g;
+	h->cap = (u64) g.n_slices * S;
+	return SDTGPU_OK;
+}
+
+int sliced_alloc (sdtgpu *h)
+{
+	const SliceGeom &g = h->geom;
+	const u32 nseg = (g.n_slices + SCAN_SEG - 1) / SCAN_SEG;
+	CK (h, cudaMalloc (&h->d_hist, (size_t) g.n_slices * sizeof (u32)));
+	CK (h, cudaMalloc (&h->d_off, ((size_t) g.n_slices + 1) * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_cur2, (size_t) g.n_slices * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_seg_sum, (size_t) nseg * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_off1, ((size_t) g.P1 + 1) * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_cur1, (size_t) g.P1 * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_tpre, ((size_t) g.P1 + 1) * sizeof (u64)));
+	CK (h, cudaMallocHost (&h->h_lvl1, ((size_t) g.P1 + 1) * sizeof (u64)));
+	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) g.n_slices * sizeof (u32), h->stream));
+	// records an epoch may hold: what is left of the device after the table, minus the level-2 scratch
+	size_t free_b = 0, total_b = 0;
+	CK (h, cudaMemGetInfo (&free_b, &total_b));
+	const size_t rec = 8 * (size_t) (h->W + 1);
+	double budget = 0.80 * (double) free_b - 3.0 * 1024 * 1024 * 1024;
+	if (const char *e = getenv ("SDTGPU_EPOCH_MB"))
+		if (atof (e) > 0)
+			budget = atof (e) * 1024.0 * 1024.0;
+	h->epoch_budget = (u64) std::max (budget / (double) rec, 65536.0);
+	return SDTGPU_OK;
+}
+
+ReadBatch log_batch (const sdtgpu *h, const LogSeg &s)
+{
+	ReadBatch rb = s.rb;
+	rb.packed = static_cast<const uint8_t *> (h->log_mem[0]) + s.off[0];
+	rb.lens = s.rb.lens ? reinterpret_cast<const u32 *> (static_cast<const uint8_t *> (h->log_mem[1]) + s.off[1]) : nullptr;
+	rb.nmask = s.rb.nmask ? static_cast<const uint8_t *> (h->log_mem[2]) + s.off[2] : nullptr;
+	return rb;
+}
+
+int log_reserve (sdtgpu *h, int which, size_t need)
+{
+	if (h->log_used[which] + need <= h->log_cap[which])
+		return SDTGPU_OK;
+	const size_t ncap = std::max (2 * h->log_cap[which], h->log_used[which] + need + (4u << 20));
+	void *neu = nullptr;
+	CK (h, cudaMalloc (&neu, ncap));
+	if (h->log_used[which])
+		CK (h, cudaMemcpyAsync (neu, h->log_mem[which], h->log_used[which], cudaMemcpyDeviceToDevice, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	if (h->log_mem[which])
+		CK (h, cudaFree (h->log_mem[which]));
+	h->log_mem[which] = neu;
+	h->log_cap[which] = ncap;
+	return SDTGPU_OK;
+}
+
+template <int W, bool NMODE> int launch_count_t (sdtgpu *h, const ReadBatch &rb)
+{
+	auto kern = slice_count_kernel<W, NMODE>;
+	const size_t smem = 4 * tile_words (rb, NMODE);
+	if (smem > 48 * 1024)
+		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	int occ = 0;
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, CNT_NT, smem));
+	if (occ < 1)
+		return fail (h, SDTGPU_EINVAL, "read stride too large for one shared-memory tile");
+	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
+	const unsigned grid = (unsigned) std::min<u64> (n_tiles, (u64) h->sm_count * occ);
+	{
+		TimedLaunch tl (h, 1);
+		kern<<<grid, CNT_NT, smem, h->stream>>> (rb, h->geom, h->d_hist);
+	}
+	CK (h, cudaGetLastError ());
+	return SDTGPU_OK;
+}
+
+template <int W, bool NMODE> int launch_scatter1_t (sdtgpu *h, const ReadBatch &rb)
+{
+	auto kern = slice_scatter1_kernel<W, NMODE>;
+	const size_t smem = 4 * tile_words (rb, NMODE) + scatter_smem_bytes (W, scatter_tile_recs (W), h->geom.P1);
+	if (smem > 48 * 1024)
+		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	int occ = 0;
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, SC_NT, smem));
+	if (occ < 1)
+		return fail (h, SDTGPU_EINVAL, "level-1 scatter does not fit in shared memory (stride or fan-out too large)");
+	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
+	const unsigned grid = (unsigned) std::min<u64> (n_tiles, (u64) h->sm_count * occ);
+	{
+		TimedLaunch tl (h, 2);
+		kern<<<grid, SC_NT, smem, h->stream>>> (rb, h->geom, h->d_cur1, h->rec1);
+	}
+	CK (h, cudaGetLastError ());
+	return SDTGPU_OK;
+}
+
+template <int W> int launch_group_t (sdtgpu *h, u32 q_lo, u32 q_hi, u64 tiles, u64 out_base, int merge)
+{
+	typedef typename SlotOf<W>::type S;
+	const SliceGeom &g = h->geom;
+	if (tiles)
+	{
+		auto kern = slice_scatter2_kernel<W>;
+		const size_t smem = scatter_smem_bytes (W, scatter_tile_recs (W), g.P2);
+		if (smem > 48 * 1024)
+			CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		int occ = 0;
+		CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, SC_NT, smem));
+		if (occ < 1)
+			return fail (h, SDTGPU_EINVAL, "level-2 scatter does not fit in shared memory");
+		const unsigned grid = (unsigned) std::min<u64> (tiles, (u64) h->sm_count * occ);
+		{
+			TimedLaunch tl (h, 3);
+			kern<<<grid, SC_NT, smem, h->stream>>> (h->rec1, h->d_off1, h->d_tpre, q_lo, q_hi, g, h->d_cur2, h->rec2, out_base);
+		}
+		CK (h, cudaGetLastError ());
+	}
+	{
+		auto kern = slice_build_kernel<W>;
+		const size_t smem = slice_image_bytes (W, g.slice_slots);
+		if (smem > 48 * 1024)
+			CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		int occ = 0;
+		CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, BD_NT, smem));
+		if (occ < 1)
+			return fail (h, SDTGPU_EINVAL, "slice image does not fit in shared memory (SDTGPU_SLICE_SLOTS too large)");
+		const u32 p_lo = q_lo * g.P2, p_hi = (u32) std::min<u64> ((u64) q_hi * g.P2, g.n_slices);
+		const unsigned grid = (unsigned) std::min<u64> (p_hi - p_lo, (u64) h->sm_count * occ);
+		{
+			TimedLaunch tl (h, 4);
+			kern<<<grid, BD_NT, smem, h->stream>>> (static_cast<S *> (h->table), g, h->rec2, h->d_off, out_base, p_lo, p_hi, merge, h->d_ctr);
+		}
+		CK (h, cudaGetLastError ());
+	}
+	return SDTGPU_OK;
+}
+
+int launch_count (sdtgpu *h, const ReadBatch &rb)
+{
+	const bool nmode = (h->flags & SDTGPU_F_NKMER) && rb.nmask;
+	switch (h->W)
+	{
+	case 1: return nmode ? launch_count_t<1, true> (h, rb) : launch_count_t<1, false> (h, rb);
+	case 2: return nmode ? launch_count_t<2, true> (h, rb) : launch_count_t<2, false> (h, rb);
+	default: return nmode ? launch_count_t<4, true> (h, rb) : launch_count_t<4, false> (h, rb);
+	}
+}
+
+int launch_scatter1 (sdtgpu *h, const ReadBatch &rb)
+{
+	const bool nmode = (h->flags & SDTGPU_F_NKMER) && rb.nmask;
+	switch (h->W)
+	{
+	case 1: return nmode ? launch_scatter1_t<1, true> (h, rb) : launch_scatter1_t<1, false> (h, rb);
+	case 2: return nmode ? launch_scatter1_t<2, true> (h, rb) : launch_scatter1_t<2, false> (h, rb);
+	default: return nmode ? launch_scatter1_t<4, true> (h, rb) : launch_scatter1_t<4, false> (h, rb);
+	}
+}
+
+int launch_group (sdtgpu *h, u32 q_lo, u32 q_hi, u64 tiles, u64 out_base, int merge)
+{
+	switch (h->W)
+	{
+	case 1: return launch_group_t<1> (h, q_lo, q_hi, tiles, out_base, merge);
+	case 2: return launch_group_t<2> (h, q_lo, q_hi, tiles, out_base, merge);
+	default: return launch_group_t<4> (h, q_lo, q_hi, tiles, out_base, merge);
+	}
+}
+
+// End of an epoch of the sliced build: every read in the log becomes part of the table.
+int sliced_flush (sdtgpu *h)
+{
+	int rc;
+	if (h->log.empty ())
+	{
+		if (!h->table_built)
+		{	// nothing was ever pushed: an empty table in the ordinary layout
+			if ((rc = init_table (h, h->table, h->cap)))
+				return rc;
+			h->table_built = true;
+		}
+		return SDTGPU_OK;
+	}
+	const SliceGeom g = h->geom;
+	const size_t rec = 8 * (size_t) (h->W + 1);
+	const u32 tile_recs = scatter_tile_recs (h->W);
+	const u32 nseg = (g.n_slices + SCAN_SEG - 1) / SCAN_SEG;
+	{
+		TimedLaunch tl (h, 5);
+		slice_scan_sums_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, g.n_slices, h->d_seg_sum);
+		slice_scan_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, g.n_slices, h->d_seg_sum, h->d_off, h->d_cur2);
+		slice_level1_kernel<<<1, 1024, 0, h->stream>>> (h->d_off, g, tile_recs, h->d_off1, h->d_cur1, h->d_tpre);
+		h->all_launches += 2;
+	}
+	CK (h, cudaGetLastError ());
+	CK (h, cudaMemcpyAsync (h->h_lvl1, h->d_off1, ((size_t) g.P1 + 1) * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	const u64 total = h->h_lvl1[g.P1];
+	u64 biggest = 0;
+	for (u32 q = 0; q < g.P1; q++)
+		biggest = std::max (biggest, h->h_lvl1[q + 1] - h->h_lvl1[q]);
+	if (total > h->rec1_cap)
+	{
+		if (h->rec1)
+			CK (h, cudaFree (h->rec1));
+		h->rec1 = nullptr;
+		h->rec1_cap = total + total / 64 + 1024;
+		CK (h, cudaMalloc (&h->rec1, h->rec1_cap * rec));
+	}
+	u64 group_records = (u64) env_u32 ("SDTGPU_SLICE_GROUP_MB", 2048) * 1024 * 1024 / rec;
+	group_records = std::max<u64> (std::min (group_records, std::max<u64> (total, 1)), std::max<u64> (biggest, 1));
+	if (group_records > h->rec2_cap)
+	{
+		if (h->rec2)
+			CK (h, cudaFree (h->rec2));
+		h->rec2 = nullptr;
+		h->rec2_cap = group_records;
+		CK (h, cudaMalloc (&h->rec2, h->rec2_cap * rec));
+	}
+	for (const LogSeg &s : h->log)
+		if ((rc = launch_scatter1 (h, log_batch (h, s))))
+			return rc;
+	const int merge = h->table_built ? 1 : 0;
+	for (u32 q_lo = 0; q_lo < g.P1;)
+	{
+		u32 q_hi = q_lo;
+		u64 recs = 0, tiles = 0;
+		while (q_hi < g.P1)
+		{
+			const u64 nq = h->h_lvl1[q_hi + 1] - h->h_lvl1[q_hi];
+			if (q_hi > q_lo && recs + nq > h->rec2_cap)
+				break;
+			recs += nq;
+			tiles += (nq + tile_recs - 1) / tile_recs;
+			q_hi++;
+		}
+		if ((rc = launch_group (h, q_lo, q_hi, tiles, h->h_lvl1[q_lo], merge)))
+			return rc;
+		q_lo = q_hi;
+	}
+	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) g.n_slices * sizeof (u32), h->stream));
+	h->table_built = true;
+	h->n_epochs++;
+	h->log.clear ();
+	h->log_used[0] = h->log_used[1] = h->log_used[2] = 0;
+	h->log_upper = 0;
+	return SDTGPU_OK;
+}
+
+// one batch into the read log of the open epoch + its per-slice instance counts
+int sliced_push (sdtgpu *h, const ReadBatch &rb, u64 upper)
+{
+	int rc;
+	if (h->log_upper && h->log_upper + upper > h->epoch_budget)
+		if ((rc = sliced_flush (h)))
+			return rc;
+	auto up16 = [](size_t x) { return (x + 15) & ~(size_t) 15; };
+	const size_t bytes[3] = { up16 ((size_t) rb.n_reads * rb.stride_bytes), rb.lens ? up16 ((size_t) rb.n_reads * 4) : 0,
+				  rb.nmask ? up16 ((size_t) rb.n_reads * rb.mask_stride) : 0 };
+	const void *src[3] = { rb.packed, rb.lens, rb.nmask };
+	const size_t exact[3] = { (size_t) rb.n_reads * rb.stride_bytes, (size_t) rb.n_reads * 4, (size_t) rb.n_reads * rb.mask_stride };
+	LogSeg s;
+	s.rb = rb;
+	for (int i = 0; i < 3; i++)
+	{
+		s.off[i] = h->log_used[i];
+		if (!bytes[i])
+			continue;
+		if ((rc = log_reserve (h, i, bytes[i])))
+			return rc;
+		CK (h, cudaMemcpyAsync (static_cast<uint8_t *> (h->log_mem[i]) + s.off[i], src[i], exact[i], cudaMemcpyDeviceToDevice, h->stream));
+		h->log_used[i] += bytes[i];
+	}
+	h->log.push_back (s);
+	h->log_upper += upper;
+	h->pushed_upper += upper;
+	return launch_count (h, log_batch (h, h->log.back ()));
+}
+
 }	// namespace
 
 // =================================================================================================
@@ -662,7 +1015,8 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 	sdtgpu *h = new sdtgpu ();
 	h->device = device; h->K = K; h->key_words = key_words; h->max_read_len = max_read_len; h->flags = flags;
 	h->W = K <= 31 ? 1 : (K <= 63 ? 2 : 4);
-	h->direct = (flags & SDTGPU_F_PARTITIONED) == 0;
+	h->sliced = (flags & SDTGPU_F_SLICED) != 0;
+	h->direct = (flags & (SDTGPU_F_PARTITIONED | SDTGPU_F_SLICED)) == 0;
 	h->maxwin = (u32) (max_read_len - K + 1);
 	auto bail = [&](int rc) { g_create_error = h->err; sdtgpu_destroy (h); return rc; };
 	auto body = [&]() -> int {
@@ -687,8 +1041,19 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 		CK (h, cudaMemcpyToSymbol (c_crc, h_crc, sizeof h_crc));
 		h->grow_mode = capacity_hint == 0;
 		h->cap = capacity_hint ? pick_capacity (capacity_hint, slot_bytes (h->W)) : (1ull << 20);
+		int rc;
+		if (h->sliced)
+		{	// the first build writes every slot, empty ones included: no initialisation pass
+			if ((rc = sliced_setup (h, capacity_hint)))
+				return rc;
+			CK (h, cudaMalloc (&h->table, h->cap * slot_bytes (h->W)));
+			if ((rc = sliced_alloc (h)))
+				return rc;
+			CK (h, cudaStreamSynchronize (h->stream));
+			return SDTGPU_OK;
+		}
 		CK (h, cudaMalloc (&h->table, h->cap * slot_bytes (h->W)));
-		int rc = init_table (h, h->table, h->cap);
+		rc = init_table (h, h->table, h->cap);
 		if (rc)
 			return rc;
 		CK (h, cudaStreamSynchronize (h->stream));
@@ -720,6 +1085,10 @@ void sdtgpu_destroy (sdtgpu_t *h)
 	cudaFree (h->last_packed); cudaFree (h->last_mask); cudaFree (h->last_lens);
 	cudaFree (h->staging); cudaFree (h->d_counts); cudaFree (h->d_cursors); cudaFree (h->d_seg_offsets); cudaFree (h->d_chunk_prefix); cudaFree (h->d_next_chunk);
 	for (auto e : h->ev_pool) cudaEventDestroy (e);
+	for (void *m : h->log_mem) cudaFree (m);
+	cudaFree (h->d_hist); cudaFree (h->d_off); cudaFree (h->d_cur2); cudaFree (h->d_seg_sum); cudaFree (h->d_off1); cudaFree (h->d_cur1); cudaFree (h->d_tpre);
+	cudaFree (h->rec1); cudaFree (h->rec2);
+	if (h->h_lvl1) cudaFreeHost (h->h_lvl1);
 	cudaFree (h->table);
 	cudaFree (h->d_ctr);
 	if (h->h_ctr) cudaFreeHost (h->h_ctr);
@@ -736,9 +1105,21 @@ int sdtgpu_reset (sdtgpu_t *h)
 		return SDTGPU_EINVAL;
 	CK (h, cudaSetDevice (h->device));
 	CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
-	int rc = init_table (h, h->table, h->cap);
-	if (rc)
-		return rc;
+	if (h->sliced)
+	{	// the next build rewrites the whole table; only the open epoch has to go
+		if (!h->log.empty ())
+			CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) h->geom.n_slices * sizeof (u32), h->stream));
+		h->log.clear ();
+		h->log_used[0] = h->log_used[1] = h->log_used[2] = 0;
+		h->log_upper = 0;
+		h->table_built = false;
+	}
+	else
+	{
+		int rc = init_table (h, h->table, h->cap);
+		if (rc)
+			return rc;
+	}
 	h->pushed_upper = 0; h->n_reads = 0; h->finalized = false; h->deLowKmer = 0;
 	h->n_segments = 0; h->staging_used = 0; h->staged_upper = 0;
 	if (h->snap_pending)
@@ -777,6 +1158,13 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 	h->n_reads += n_reads;
 	if ((rc = retain_last_batch (h, rb)))
 		return rc;
+	if (h->sliced)
+	{
+		u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
+		if (h->owner_ranks > 1)
+			upper = upper / h->owner_ranks + upper / (2 * h->owner_ranks) + 1024;
+		return sliced_push (h, rb, upper);
+	}
 	if (h->direct)
 	{	// single pass: every window goes straight to its (random) slot
 		u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
@@ -854,8 +1242,10 @@ int sdtgpu_set_owner (sdtgpu_t *h, int rank, int n_ranks)
 		return SDTGPU_EINVAL;
 	if (n_ranks < 1 || rank < 0 || rank >= n_ranks)
 		return fail (h, SDTGPU_EINVAL, "sdtgpu_set_owner: need 0 <= rank < n_ranks");
-	if (!h->direct && n_ranks > 1)
-		return fail (h, SDTGPU_ESTATE, "owner filtering is implemented for the single-pass insert path");
+	if (!h->direct && !h->sliced && n_ranks > 1)
+		return fail (h, SDTGPU_ESTATE, "owner filtering is not implemented for the staged (SDTGPU_F_PARTITIONED) path");
+	if (h->sliced && !h->log.empty ())
+		return fail (h, SDTGPU_ESTATE, "sdtgpu_set_owner must precede the pushes of an epoch");
 	h->owner_rank = (u32) rank;
 	h->owner_ranks = (u32) n_ranks;
 	return SDTGPU_OK;
@@ -896,6 +1286,8 @@ int sdtgpu_insert_records_device (sdtgpu_t *h, const void *d_records, uint64_t n
 		return fail (h, SDTGPU_ESTATE, "insert after finalize");
 	if (n_records == 0)
 		return SDTGPU_OK;
+	if (h->sliced)
+		return fail (h, SDTGPU_ESTATE, "insert_records_device is not available with SDTGPU_F_SLICED");
 	if (!d_records || ((uintptr_t) d_records & (h->W == 1 ? 15 : 7)))
 		return fail (h, SDTGPU_EINVAL, "records must be aligned device memory (16 bytes for 1-word keys, else 8)");
 	CK (h, cudaSetDevice (h->device));
@@ -948,7 +1340,7 @@ int sdtgpu_get_stats (sdtgpu_t *h, sdtgpu_stats *stats)
 		return rc;
 	fill_stats (h, stats);
 	if (h->h_ctr->overflow)
-		return fail (h, SDTGPU_ERANGE, "a record bin overflowed");
+		return fail (h, SDTGPU_ERANGE, h->sliced ? "a table slice overflowed: capacity_hint was too small for the sliced build" : "a record bin overflowed");
 	return SDTGPU_OK;
 }
 
@@ -979,6 +1371,8 @@ int sdtgpu_finalize (sdtgpu_t *h, int deLowKmer, int64_t kmerFreq[257], sdtgpu_s
 	int rc = read_counters (h);
 	if (rc)
 		return rc;
+	if (h->h_ctr->overflow)
+		return fail (h, SDTGPU_ERANGE, "a table slice overflowed: capacity_hint was too small for the sliced build");
 	if (kmerFreq)
 		for (int i = 0; i < 257; i++)
 			kmerFreq[i] = (int64_t) h->h_ctr->freq[i];
@@ -1166,7 +1560,7 @@ int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *ins
 	if (all_launches) *all_launches = h->all_launches;
 	if (reset)
 	{
-		for (int i = 0; i < 3; i++) { h->cat_ms[i] = 0; h->cat_launches[i] = 0; }
+		for (int i = 0; i < N_CAT; i++) { h->cat_ms[i] = 0; h->cat_launches[i] = 0; }
 		h->all_launches = 0;
 	}
 	return SDTGPU_OK;
@@ -1186,9 +1580,39 @@ int sdtgpu_kernel_times (sdtgpu_t *h, int reset, double ms[3], uint64_t launches
 	}
 	if (reset)
 	{
-		for (int i = 0; i < 3; i++) { h->cat_ms[i] = 0; h->cat_launches[i] = 0; }
+		for (int i = 0; i < N_CAT; i++) { h->cat_ms[i] = 0; h->cat_launches[i] = 0; }
 		h->all_launches = 0;
 	}
+	return SDTGPU_OK;
+}
+
+int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[8])
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	int rc = collect_times (h);
+	if (rc)
+		return rc;
+	for (int i = 0; i < N_CAT; i++)
+	{
+		if (ms) ms[i] = h->cat_ms[i];
+		if (launches) launches[i] = h->cat_launches[i];
+	}
+	if (reset)
+	{
+		for (int i = 0; i < N_CAT; i++) { h->cat_ms[i] = 0; h->cat_launches[i] = 0; }
+		h->all_launches = 0;
+	}
+	return SDTGPU_OK;
+}
+
+int sdtgpu_slice_geometry (const sdtgpu_t *h, uint32_t out[4])
+{
+	if (!h || !out)
+		return SDTGPU_EINVAL;
+	if (!h->sliced)
+		return SDTGPU_ESTATE;
+	out[0] = h->geom.n_slices; out[1] = h->geom.slice_slots; out[2] = h->geom.P1; out[3] = h->geom.P2;
 	return SDTGPU_OK;
 }
 

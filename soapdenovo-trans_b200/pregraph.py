@@ -21,6 +21,8 @@ assert NODE_DTYPE.itemsize == 56
 
 F_NKMER = 1
 F_PARTITIONED = 2
+F_SLICED = 4
+PHASES = ("insert", "count", "scatter1", "scatter2", "build", "scan", "-", "-")
 _ERR = {1: "EINVAL", 2: "ECUDA", 3: "ENOMEM", 4: "ERANGE", 5: "ESTATE"}
 
 
@@ -97,6 +99,8 @@ def library() -> C.CDLL:
     L.sdtgpu_table_checksum.argtypes = [vp, vp]
     L.sdtgpu_last_ordinals.argtypes = [vp, i32, vp]
     L.sdtgpu_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.sdtgpu_phase_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.sdtgpu_slice_geometry.argtypes = [vp, C.POINTER(u32)]
     L.sdtpack_open.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p, i32, i32]
     L.sdtpack_next.restype = C.c_int64
     L.sdtpack_next.argtypes = [vp, i32, i32, i32, vp, vp, vp, u64, u32]
@@ -170,12 +174,13 @@ class PregraphGPU:
     stage of `pregraph` (prlRead2HashTable, prlHashReads.c:338)."""
 
     def __init__(self, K: int, key_words: int, max_read_len: int, capacity_hint: int = 0, device: int = 0,
-                 n_kmer: bool = False, partitioned: bool = False):
+                 n_kmer: bool = False, partitioned: bool = False, sliced: bool = False):
         self.L = library()
         self.h = C.c_void_p()
         self.K, self.key_words, self.max_read_len, self.device = K, key_words, max_read_len, device
         rc = self.L.sdtgpu_create(C.byref(self.h), device, K, key_words, max_read_len, capacity_hint,
-                                  (F_NKMER if n_kmer else 0) | (F_PARTITIONED if partitioned else 0))
+                                  (F_NKMER if n_kmer else 0) | (F_PARTITIONED if partitioned else 0)
+                                  | (F_SLICED if sliced else 0))
         if rc:
             raise SdtGpuError(rc, self.L.sdtgpu_last_error(None).decode())
 
@@ -271,6 +276,17 @@ class PregraphGPU:
         ms, nl, al = C.c_double(), C.c_uint64(), C.c_uint64()
         self._ck(self.L.sdtgpu_kernel_time(self.h, int(reset), C.byref(ms), C.byref(nl), C.byref(al)))
         return ms.value, nl.value, al.value
+
+    def phase_times(self, reset: bool = True):
+        """{phase: (ms, launches)} per kernel class (PHASES) since the last reset."""
+        ms, nl = (C.c_double * 8)(), (C.c_uint64 * 8)()
+        self._ck(self.L.sdtgpu_phase_times(self.h, int(reset), ms, nl))
+        return {PHASES[i]: (ms[i], nl[i]) for i in range(6)}
+
+    def slice_geometry(self):
+        out = (C.c_uint32 * 4)()
+        self._ck(self.L.sdtgpu_slice_geometry(self.h, out))
+        return dict(n_slices=out[0], slice_slots=out[1], P1=out[2], P2=out[3])
 
     def kernel_times(self, reset: bool = True):
         """(ms[3], launches[3]) for insert / partition-count / partition-scatter kernels."""

@@ -10,14 +10,14 @@ from conftest import make_dataset
 pytestmark = pytest.mark.gpu
 
 
-def run_gpu(pkg, reads, lens, K, kw, d=0, batches=1, thrd_num=8, hint=0, n_kmer=False, uniform=False, max_read_len=None, partitioned=False):
+def run_gpu(pkg, reads, lens, K, kw, d=0, batches=1, thrd_num=8, hint=0, n_kmer=False, uniform=False, max_read_len=None, partitioned=False, sliced=False):
     synth = pkg.synth
     L = reads.shape[1]
     max_read_len = max_read_len or L
     stride = synth.stride_bytes(max_read_len)
     packed = synth.pack_reads(reads, lens, stride)
     nmask = synth.nmask_reads(reads, stride) if n_kmer else None
-    g = pkg.PregraphGPU(K, kw, max_read_len, capacity_hint=hint, n_kmer=n_kmer, partitioned=partitioned)
+    g = pkg.PregraphGPU(K, kw, max_read_len, capacity_hint=hint, n_kmer=n_kmer, partitioned=partitioned, sliced=sliced)
     n = len(reads)
     step = max((n + batches - 1) // batches, 1)
     for a in range(0, n, step):

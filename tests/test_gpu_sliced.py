@@ -1,0 +1,107 @@
+"""GPU parity tests of the sliced build (SDTGPU_F_SLICED, csrc/sdt_sliced.cuh): count per slice ->
+two-level record partition -> every table slice built in shared memory.  Same bar as
+test_gpu_parity.py: bit-exact multiset, counters, kmerFreq and the reference's (set, slot) layout
+against the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import make_dataset
+from test_gpu_parity import check_against_oracle, run_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("K,kw,d", [(25, 1, 0), (25, 1, 2), (31, 1, 0), (13, 1, 1), (33, 2, 0), (63, 2, 1), (63, 4, 0),
+                                    (25, 4, 2), (65, 4, 0), (95, 4, 0), (97, 4, 1), (127, 4, 0)])
+def test_sliced_parity_ragged(pkg, oracle, tiny_transcriptome, K, kw, d):
+    L = 150 if K > 63 else 100
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, L, 11 + K, ragged=40)
+    check_against_oracle(pkg, oracle, reads, lens, K, kw, d=d, batches=3, hint=400_000, sliced=True)
+
+
+@pytest.mark.parametrize("K,kw", [(31, 1), (63, 2), (127, 4)])
+def test_sliced_tiny_slices_many_epochs_and_groups(pkg, oracle, tiny_transcriptome, monkeypatch, K, kw):
+    """64-slot slices (probe wrap-around inside a slice, thousands of slices, ragged fan-out), an
+    epoch budget smaller than one push (every push is merged into the slices built before it) and a
+    level-2 scratch of 1 MB (many partition groups per build)."""
+    monkeypatch.setenv("SDTGPU_SLICE_SLOTS", "64")
+    monkeypatch.setenv("SDTGPU_SLICE_P2", "7")
+    monkeypatch.setenv("SDTGPU_EPOCH_MB", "1")
+    monkeypatch.setenv("SDTGPU_SLICE_GROUP_MB", "1")
+    L = 150 if K > 63 else 100
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 6000, L, 23, ragged=20)
+    check_against_oracle(pkg, oracle, reads, lens, K, kw, d=1, batches=5, hint=600_000, sliced=True)
+
+
+def test_sliced_uniform_and_n_kmer(pkg, oracle, tiny_transcriptome):
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 4000, 100, 5)
+    check_against_oracle(pkg, oracle, reads, lens, 25, 1, d=0, uniform=True, hint=400_000, thrd_num=5, sliced=True)
+    for K, kw in [(25, 1), (63, 4), (99, 4)]:
+        L = 150 if K > 63 else 100
+        reads, lens = make_dataset(pkg, tiny_transcriptome, 1500, L, 21, ragged=20, n_rate=0.004)
+        check_against_oracle(pkg, oracle, reads, lens, K, kw, d=0, n_kmer=True, batches=2, hint=300_000, sliced=True)
+
+
+def test_sliced_edge_cases(pkg, oracle):
+    reads = np.zeros((200, 60), dtype=np.uint8)
+    reads[100:] = 2
+    lens = np.full(200, 60, dtype=np.uint32)
+    # poly-A / poly-T: key 0 is an ordinary key; link counters saturate at 63 while count keeps going
+    check_against_oracle(pkg, oracle, reads, lens, 25, 1, d=0, hint=1000, sliced=True)
+    check_against_oracle(pkg, oracle, reads, lens, 33, 2, d=3, hint=1000, sliced=True)
+    reads[:] = 3
+    reads[::2] = 1
+    check_against_oracle(pkg, oracle, reads, lens, 31, 1, d=0, hint=1000, sliced=True)
+    # nothing to insert at all: too-short reads, an empty batch
+    lens2 = np.full(200, 25, dtype=np.uint32)
+    check_against_oracle(pkg, oracle, reads, lens2, 25, 1, d=0, hint=1000, sliced=True)
+    check_against_oracle(pkg, oracle, reads[:0], lens2[:0], 25, 1, d=0, hint=1000, sliced=True)
+
+
+def test_sliced_hot_kmers(pkg, oracle):
+    """Config-5 flavour: thousands of instances of the same k-mers land in the same slice."""
+    tr = pkg.synth.make_transcriptome(60, 13, hot=2)
+    reads, lens = make_dataset(pkg, tr, 40000, 100, 17)
+    check_against_oracle(pkg, oracle, reads, lens, 31, 1, d=2, hint=2_000_000, sliced=True)
+    check_against_oracle(pkg, oracle, reads, lens, 63, 2, d=0, hint=2_000_000, layout=False, sliced=True)
+    check_against_oracle(pkg, oracle, reads, lens, 99, 4, d=0, hint=2_000_000, layout=False, sliced=True)
+
+
+def test_sliced_equals_single_pass_fingerprint(pkg, tiny_transcriptome):
+    """The order-independent table fingerprint of the sliced build equals the single-pass insert's."""
+    reads, lens = make_dataset(pkg, pkg.synth.make_transcriptome(300, 3), 30000, 100, 9)
+    sums = []
+    for sliced in (False, True):
+        g, freq, st = run_gpu(pkg, reads, lens, 31, 1, batches=4, hint=3_000_000, sliced=sliced)
+        sums.append((g.table_checksum().tolist(), st.n_nodes, st.n_instances, freq.tolist()))
+        g.close()
+    assert sums[0] == sums[1]
+
+
+def test_sliced_reset_and_reuse(pkg, oracle, tiny_transcriptome):
+    """bench.py's step: reset, push, sync — repeated on one handle; the table is rebuilt each time."""
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 2000, 100, 3)
+    synth = pkg.synth
+    stride = synth.stride_bytes(100)
+    packed = synth.pack_reads(reads, lens, stride)
+    ref = oracle.run_hashing(reads, lens, 31, 1, 8, 0)
+    with pkg.PregraphGPU(31, 1, 100, capacity_hint=300_000, sliced=True) as g:
+        geo = g.slice_geometry()
+        assert geo["n_slices"] * geo["slice_slots"] == g.stats().capacity
+        for it in range(3):
+            g.reset()
+            g.push_reads(packed, lens, None, n_reads=len(reads), stride_bytes=stride)
+            g.sync()
+            st = g.stats()
+            assert (st.n_instances, st.n_nodes) == (ref.instances, ref.nodes)
+        assert np.array_equal(pkg.nodes_to_records(g.export_nodes(8)), oracle.sorted_multiset(ref.records))
+
+
+def test_sliced_errors(pkg, tiny_transcriptome):
+    with pytest.raises(pkg.SdtGpuError):
+        pkg.PregraphGPU(31, 1, 100, capacity_hint=0, sliced=True)      # the sliced build needs a hint
+    # a hint far too small: a slice fills up and the build reports it instead of dropping k-mers
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, 100, 1)
+    with pytest.raises(pkg.SdtGpuError) as e:
+        run_gpu(pkg, reads, lens, 31, 1, hint=1000, sliced=True)
+    assert e.value.code == 4
