@@ -40,7 +40,7 @@ __device__ __forceinline__ u32 home_of (u64 h, u32 S) { return __umulhi ((u32) h
 
 static constexpr int CNT_NT = 256;	// slice_count_kernel
 static constexpr int SC_NT = 512;	// scatter kernels
-static constexpr int BD_NT = 512;	// slice_build_kernel
+static constexpr int BD_NT = 1024;	// slice_build_kernel
 template <int W> struct ScatterCfg { static constexpr int RPT = W == 4 ? 4 : 8; };	// records per thread and tile
 static constexpr u32 NO_BIN = 0xFFFFFFFFu;
 
@@ -586,19 +586,26 @@ slice_scatter2_kernel (const u64 *rec1, const u64 *off1, const u64 *tpre, u32 q_
 }
 
 // ------------------------------------------------------------------------------------------------
-// the slice's table image in shared memory
+// The slice's table image in shared memory.  Shared-memory atomics are the scarce resource here
+// (2 cycles per lane on this part, 20x the cost of a load), so an instance costs exactly ONE of
+// them: every slot has a 5 x 5 matrix of plain 32-bit cells indexed by (left, right) with 4 = "no
+// neighbour" — the reference's update_kmer (newhash.c:71-96) touches count, one left and one right
+// counter per instance, and all three are sums over that matrix:
+//     count = sum of all cells (mod 2^32),  L[b] = min (63, sum of row b),  R[b] = min (63, sum of column b).
+// The ordinal minimum needs an atomic only when it improves (a load otherwise).
+static constexpr int CELLS = 25;
+
 template <int W> struct SliceImage
 {
 	u64 *key;	// [S * W]
 	u64 *ord;	// [S]
-	u32 *cnt;	// [S]
-	u32 *lnk;	// [S * 8]: left counters 0..3, right counters 4..7 (plain 32-bit, clamped to 63 on the way out)
+	u32 *cell;	// [CELLS * S], cell c of slot i at c * S + i
 	u32 *state;	// [S] (W > 1): 0 empty, 1 key being written, 2 occupied
 };
 
 __host__ __device__ inline size_t slice_image_bytes (int W, u32 S)
 {
-	return (size_t) S * (8 * W + 8 + 4 + 32 + (W > 1 ? 4 : 0));
+	return (size_t) S * (8 * W + 8 + 4 * CELLS + (W > 1 ? 4 : 0));
 }
 
 // find or claim the slot of `key` inside the slice; returns the slot, or S if the slice is full
@@ -658,7 +665,8 @@ __device__ __forceinline__ u32 image_find (const SliceImage<W> &im, u32 S, const
 }
 
 // One CTA per slice: build (or, with merge != 0, update) the slice's table image in shared memory
-// from its run of records and stream it to the table.
+// from its run of records and stream it to the table.  The image is empty when a slice starts (the
+// write-out of the previous slice cleans up behind itself).
 template <int W>
 __global__ void __launch_bounds__ (BD_NT)
 slice_build_kernel (typename SlotOf<W>::type *table, SliceGeom g, const u64 *rec2, const u64 *off, u64 out_base,
@@ -672,42 +680,39 @@ slice_build_kernel (typename SlotOf<W>::type *table, SliceGeom g, const u64 *rec
 	SliceImage<W> im;
 	im.key = reinterpret_cast<u64 *> (smem);
 	im.ord = im.key + (size_t) S * W;
-	im.cnt = reinterpret_cast<u32 *> (im.ord + S);
-	im.lnk = im.cnt + S;
-	im.state = im.lnk + (size_t) S * 8;
+	im.cell = reinterpret_cast<u32 *> (im.ord + S);
+	im.state = im.cell + (size_t) S * CELLS;
 	u64 instances = 0, nodes = 0;	// thread 0 only
 	if (tid == 0)
 		s_created = s_full = 0;
+	for (u32 i = tid; i < S; i += BD_NT)
+	{
+#pragma unroll
+		for (int q = 0; q < W; q++)
+			im.key[(size_t) i * W + q] = EMPTY64;
+		im.ord[i] = ORD40_NONE;
+		if constexpr (W > 1)
+			im.state[i] = 0u;
+	}
+	for (u32 i = tid; i < S * CELLS; i += BD_NT)
+		im.cell[i] = 0u;
+	__syncthreads ();
 	for (u32 p = p_lo + blockIdx.x; p < p_hi; p += gridDim.x)
 	{
 		S_t *slice = table + (u64) p * S;
-		for (u32 i = tid; i < S; i += BD_NT)
-		{
-			Key<W> k;
-			u32 L = 0, R = 0, count = 0;
-			u64 ord = ORD40_NONE;
-			bool occ = false;
-			if (merge)
-			{
-				occ = SlotIO<W>::occupied (slice + i);
-				if (occ)
-					SlotIO<W>::get (slice + i, k, L, R, count, ord);
-			}
+		if (merge)
+		{	// the keys this slice already holds, at their slots (their payload is added at write-out)
+			for (u32 i = tid; i < S; i += BD_NT)
+				if (SlotIO<W>::occupied (slice + i))
+				{
 #pragma unroll
-			for (int q = 0; q < W; q++)
-				im.key[(size_t) i * W + q] = occ ? k.w[q] : EMPTY64;
-			im.ord[i] = ord;
-			im.cnt[i] = count;
-#pragma unroll
-			for (int b = 0; b < 4; b++)
-			{
-				im.lnk[i * 8 + b] = (L >> (6 * b)) & 63u;
-				im.lnk[i * 8 + 4 + b] = (R >> (6 * b)) & 63u;
-			}
-			if constexpr (W > 1)
-				im.state[i] = occ ? 2u : 0u;
+					for (int q = 0; q < W; q++)
+						im.key[(size_t) i * W + q] = SlotIO<W>::keyp (slice + i)[q];
+					if constexpr (W > 1)
+						im.state[i] = 2u;
+				}
+			__syncthreads ();
 		}
-		__syncthreads ();
 		const u64 r0 = off[p] - out_base, r1 = off[p + 1] - out_base;
 		u32 created = 0;
 		bool full = false;
@@ -736,21 +741,9 @@ slice_build_kernel (typename SlotOf<W>::type *table, SliceGeom g, const u64 *rec
 					full = true;
 					continue;
 				}
-				const u32 left = (u32) (meta[u] >> 4) & 15u, right = (u32) meta[u] & 15u;
+				const u32 left = (u32) (meta[u] >> 4) & 15u, right = (u32) meta[u] & 15u;	// 0..4
 				const u64 ord = meta[u] >> 8;
-				atomicAdd (im.cnt + idx, 1u);	// wraps like the reference's u32 count (newhash.c:75)
-				if (left < 4)
-				{	// once a counter has reached the reference's saturation value its exact value is irrelevant
-					u32 *c = im.lnk + idx * 8 + left;
-					if (*reinterpret_cast<volatile u32 *> (c) < LINK_SAT)
-						atomicAdd (c, 1u);
-				}
-				if (right < 4)
-				{
-					u32 *c = im.lnk + idx * 8 + 4 + right;
-					if (*reinterpret_cast<volatile u32 *> (c) < LINK_SAT)
-						atomicAdd (c, 1u);
-				}
+				atomicAdd (im.cell + (left * 5 + right) * S + idx, 1u);
 				if (ord < *reinterpret_cast<volatile u64 *> (im.ord + idx))
 					atomicMin (im.ord + idx, ord);
 			}
@@ -760,7 +753,7 @@ slice_build_kernel (typename SlotOf<W>::type *table, SliceGeom g, const u64 *rec
 		if (full)
 			s_full = 1;
 		__syncthreads ();
-		// ---- stream the image out in the table's slot layout (empty slots too)
+		// ---- stream the image out in the table's slot layout (empty slots too) and clean it
 		for (u32 i = tid; i < S; i += BD_NT)
 		{
 			bool occ;
@@ -769,36 +762,73 @@ slice_build_kernel (typename SlotOf<W>::type *table, SliceGeom g, const u64 *rec
 			else
 				occ = im.state[i] == 2u;
 			u64 w0 = PAYLOAD0_INIT, w1 = 0;
+			Key<W> k;
+#pragma unroll
+			for (int q = 0; q < W; q++)
+				k.w[q] = EMPTY64;
 			if (occ)
 			{
+				u32 row[4] = { 0, 0, 0, 0 }, col[4] = { 0, 0, 0, 0 }, count = 0;
+#pragma unroll
+				for (int l = 0; l < 5; l++)
+#pragma unroll
+					for (int r = 0; r < 5; r++)
+					{
+						const u32 c = im.cell[(l * 5 + r) * S + i];
+						im.cell[(l * 5 + r) * S + i] = 0u;
+						count += c;
+						if (l < 4)
+							row[l] += min (c, LINK_SAT);	// clamped terms: no 32-bit wrap, same min (63, sum)
+						if (r < 4)
+							col[r] += min (c, LINK_SAT);
+					}
+				u64 ord = im.ord[i];
+				u32 oL = 0, oR = 0;
+				if (merge && SlotIO<W>::occupied (slice + i))
+				{	// same key (slots never move): add what the table already holds
+					Key<W> ok;
+					u32 ocount;
+					u64 oord;
+					SlotIO<W>::get (slice + i, ok, oL, oR, ocount, oord);
+					count += ocount;
+					ord = min (ord, oord);
+				}
 				u32 L = 0, R = 0;
 #pragma unroll
 				for (int b = 0; b < 4; b++)
 				{
-					L |= min (im.lnk[i * 8 + b], LINK_SAT) << (6 * b);
-					R |= min (im.lnk[i * 8 + 4 + b], LINK_SAT) << (6 * b);
+					L |= min (row[b] + ((oL >> (6 * b)) & 63u), LINK_SAT) << (6 * b);
+					R |= min (col[b] + ((oR >> (6 * b)) & 63u), LINK_SAT) << (6 * b);
 				}
-				w0 = (im.ord[i] << 24) | L;
-				w1 = ((u64) im.cnt[i] << 32) | R;
+				w0 = (ord << 24) | L;
+				w1 = ((u64) count << 32) | R;
+#pragma unroll
+				for (int q = 0; q < W; q++)
+				{
+					k.w[q] = im.key[(size_t) i * W + q];
+					im.key[(size_t) i * W + q] = EMPTY64;
+				}
+				im.ord[i] = ORD40_NONE;
+				if constexpr (W > 1)
+					im.state[i] = 0u;
 			}
 			if constexpr (W == 1)
-				st256 (slice + i, occ ? im.key[i] : EMPTY64, occ ? 0ull : EMPTY64, w0, w1);
+				st256 (slice + i, k.w[0], occ ? 0ull : EMPTY64, w0, w1);
 			else if constexpr (W == 2)
-				st256 (slice + i, occ ? im.key[2 * i] : EMPTY64, occ ? im.key[2 * i + 1] : EMPTY64, w0, w1);
+				st256 (slice + i, k.w[0], k.w[1], w0, w1);
 			else
 			{
-				st256 (slice + i, occ ? im.key[4 * i] : EMPTY64, occ ? im.key[4 * i + 1] : EMPTY64,
-				       occ ? im.key[4 * i + 2] : EMPTY64, occ ? im.key[4 * i + 3] : EMPTY64);
+				st256 (slice + i, k.w[0], k.w[1], k.w[2], k.w[3]);
 				st256 (reinterpret_cast<u64 *> (slice + i) + 4, w0, w1, 0ull, 0ull);
 			}
 		}
-		__syncthreads ();	// the image is re-initialised by the next iteration
 		if (tid == 0)
-		{
+		{	// between the two barriers nobody adds to s_created
 			instances += r1 - r0;
 			nodes += s_created;
 			s_created = 0;
 		}
+		__syncthreads ();
 	}
 	if (tid == 0)
 	{

@@ -680,7 +680,7 @@ int sliced_setup (sdtgpu *h, u64 hint)
 {
 	if (hint == 0)
 		return fail (h, SDTGPU_EINVAL, "the sliced build needs capacity_hint (expected distinct k-mers)");
-	const u32 S = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 4096u : (h->W == 2 ? 3072u : 2048u));
+	const u32 S = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 1920u : (h->W == 2 ? 1792u : 1600u));
 	double load = 0.6;
 	if (const char *e = getenv ("SDTGPU_SLICE_LOAD"))
 		if (atof (e) > 0.05 && atof (e) < 0.95)
