@@ -129,7 +129,7 @@ def main():
                     help="multi-GPU sharding: all-gather the packed reads and insert owned k-mers (default) or exchange k-mer records")
     ap.add_argument("--partitioned", action="store_true", help="experimental staged/partitioned insert path")
     ap.add_argument("--path", default="auto", choices=["auto", "direct", "sliced", "partitioned"],
-                    help="insert path: single-pass upsert (direct), sliced build (count -> partition -> shared-memory slices), "
+                    help="insert path: single-pass upsert (direct), sliced build (super-k-mer records -> slices built in shared memory), "
                          "or the experimental staged path; auto = the fastest measured one for this GPU count")
     args = ap.parse_args()
     if args.partitioned:
@@ -281,24 +281,24 @@ def main():
     bpi = BYTES_PER_INSTANCE[st.device_key_words]
     sliced_info = None
     if sliced:
-        # The insert is a pipeline of four streaming kernels (count, scatter level 1, scatter level 2, slice
+        # The insert is a pipeline of three streaming kernels (super-k-mer emit, scatter by slice, slice
         # build); the SURVEY figure of 64 (96) algorithmic bytes per instance belongs to the whole insert, so
         # `achieved` is taken over the SUM of their CUDA-event times (all on the handle's stream).  Each
         # phase's own DRAM stream (bytes it must read + write per instance) is reported beside it.
-        rec_b = 8 * (st.device_key_words + 1)
+        geo = g.slice_geometry()
+        rec_b = geo["record_bytes"] * geo["n_records"] / max(st.n_instances, 1)      # record bytes per instance
         read_b = stride / nwin
-        table_b = st.capacity * slot_b / max(st.n_instances, 1)
-        stream_b = {"count": read_b, "scatter1": read_b + rec_b, "scatter2": 2 * rec_b, "build": rec_b + table_b, "scan": 0.0}
+        node_b = st.n_nodes * slot_b / max(st.n_instances, 1)
+        stream_b = {"emit": read_b + rec_b, "scatter": 2 * rec_b, "build": rec_b + node_b, "scan": 0.0}
         insert_ms = sum(phases[k][0] for k in stream_b)
         insert_launches = max(phases["build"][1], 1)
-        geo = g.slice_geometry()
-        sliced_info = {"geometry": geo, "epochs_per_step": 1, "phases": {
+        sliced_info = {"geometry": geo, "windows_per_record": st.n_instances / max(geo["n_records"], 1), "phases": {
             k: {"ms_per_step": phases[k][0] / args.steps, "launches_per_step": phases[k][1] / args.steps,
                 "stream_bytes_per_instance": stream_b[k],
                 "stream_gbs": (st.n_instances * args.steps * stream_b[k] / max(phases[k][0], 1e-9) / 1e6) if stream_b[k] else None}
             for k in stream_b}}
         dominant = max(stream_b, key=lambda k: phases[k][0])
-        sliced_info["dominant"] = "slice_" + dominant + "_kernel"
+        sliced_info["dominant"] = "skm_" + dominant + "_kernel"
         ker_ms = insert_ms / args.steps                      # one pipeline pass = one "launch" of the insert
         inst_per_launch = float(st.n_instances)
     else:
@@ -378,7 +378,7 @@ def main():
                        "insert_path": args.path,
                        "l2": "table (>= 1.6x distinct x slot bytes), k-mer records and reads are far larger than the 126 MB L2; the table is rebuilt from empty every step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": traffic, "kernel": ("slice_count + slice_scatter1 + slice_scatter2 + slice_build kernels (the sliced insert pipeline; times summed)" if sliced else
+                         "traffic": traffic, "kernel": ("skm_emit + skm_scatter + skm_build kernels (the sliced insert pipeline; times summed)" if sliced else
                                     "insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if (world == 1 or args.exchange == "reads") else "insert_records_kernel",
                          "path": args.path, "sliced": sliced_info,
                          "bytes_per_instance": bpi, "kernel_ms_per_launch": ker_ms, "peak_source": peak_src,

@@ -81,10 +81,11 @@ typedef struct sdtgpu_stats {
 #define SDTGPU_F_PARTITIONED 2u	/* experimental: stage records, radix-partition them by table slot range and
 				 * insert bucket by bucket (L2-resident table regions) instead of the default
 				 * single-pass insert; measured slower on B200 */
-#define SDTGPU_F_SLICED    4u	/* sliced build: the reads of an epoch are logged and counted per table slice as
-				 * they arrive; sdtgpu_sync / finalize / export partition their k-mer instances by
-				 * slice (two streaming passes) and build every slice of the table in shared memory.
-				 * No random DRAM access at all; needs capacity_hint.  Same results, same layout. */
+#define SDTGPU_F_SLICED    4u	/* sliced build: pushes turn reads into super-k-mer records (runs of windows that share
+				 * a minimizer, bases included) and count them per table slice; sdtgpu_sync / finalize /
+				 * export move every record to its slice and build each slice in shared memory, one
+				 * CTA per slice, into a compact node store.  No random DRAM access; needs
+				 * capacity_hint.  Same multiset, same hand-back layout as the single-pass insert. */
 int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_read_len,
 		   uint64_t capacity_hint, unsigned flags);
 void sdtgpu_destroy (sdtgpu_t *h);
@@ -184,10 +185,11 @@ int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *ins
 int sdtgpu_kernel_times (sdtgpu_t *h, int reset, double ms[3], uint64_t launches[3]);
 
 /* per kernel class since the last reset: [0] insert (single-pass, staged or records), [1] count
- * (partition / slice histogram), [2] scatter level 1, [3] scatter level 2, [4] slice build, [5] scans */
+ * (staged path) or super-k-mer emit (sliced build), [2] scatter, [3] unused, [4] slice build, [5] scans */
 int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[8]);
-/* SDTGPU_F_SLICED only: out = { n_slices, slice_slots, P1, P2 } */
-int sdtgpu_slice_geometry (const sdtgpu_t *h, uint32_t out[4]);
+/* SDTGPU_F_SLICED only: out = { slices, slots per slice image, minimizer length m, m-mers per window,
+ * bytes per super-k-mer record, records held, nodes in the store, work items retried by the last build } */
+int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[8]);
 
 /* ---- synthetic reads on the device (bench/test utility; bit-identical to synth.py).
  * d_tr_bases: uint8 codes of all transcripts; d_starts u64[T]; d_lengths u32[T]; d_cum u64[T]. */

@@ -1,0 +1,704 @@
+// sdt_skm.cuh — the sliced build over super-k-mers: put_kmerset (newhash.c:411-462) without random
+// DRAM access and with one tenth of the k-mer records.
+//
+// Why.  A random-access insert is capped by the rate at which B200 completes requests to cold lines
+// (36.65 G/s, one load + one atomic per instance: 18.3 G instances/s, profiles/r1_random_access_findings.md),
+// and a pipeline that moves one 16-byte record per instance through shared-memory counting sorts is
+// capped by shared-memory atomics (2 cycles per lane: count + two scatter levels + build measured
+// 18.5 G/s).  So instances must not travel one by one.  Consecutive windows of a read share their
+// minimizer (the smallest hashed canonical m-mer inside the window) about eight at a time; a run of
+// windows with the same minimizer — a super-k-mer — travels as ONE record that holds the run's
+// bases, and the table is cut into slices by minimizer, so every instance of a k-mer, from either
+// strand, meets in the same slice:
+//
+//   skm_emit_kernel     reads -> super-k-mer records (unordered stream) + records per slice (REDG);
+//                       m-mer hashes and window minima live in shared memory, one pass over the reads;
+//   slice_scan_*        exclusive scan of the per-slice record counts (sdt_sliced.cuh);
+//   skm_scatter_kernel  every record to its slice's run (one L2-resident cursor atomic per record);
+//   skm_build_kernel    one CTA per slice: the records are chopped (chop_window, the same code the
+//                       single-pass path uses: prlHashReads.c:164-310) and upserted into the slice's
+//                       table image in shared memory — one shared-memory atomic per instance — and the
+//                       image is compacted into the node store in the ordinary slot layout, so
+//                       finalize / export / checksum run unchanged over [0, n_nodes).
+//
+// A slice whose distinct k-mers do not fit its image writes nothing and is retried split by k-mer
+// hash (work items (slice, r, R): keys with hash % R == r), so no input can break it.
+// All updates commute: the result is bit-identical to the reference's sequential put_kmerset.
+#pragma once
+#include "sdt_sliced.cuh"
+
+namespace sdt {
+
+struct SkmGeom
+{
+	u32 n_slices;		// slices of the key space (by minimizer)
+	u32 slice_slots;	// S: slots of a slice's shared-memory image
+	u32 m, w;		// minimizer length, m-mers per window (K - m + 1)
+	u32 nmax;		// windows per record at most (32 for 1-word keys, else 64)
+	u32 recw;		// u32 words per record (8, 12, 16)
+	u32 slice_a;		// slice of the all-A k-mer (key 0): where the -n N-windows go
+	u32 tile_reads;		// reads per shared-memory tile of skm_emit_kernel
+	u32 npos;		// m-mer positions per read at most (max_read_len - m + 1)
+	u32 chunk;		// records per shared-memory chunk of skm_build_kernel
+};
+
+static constexpr u32 SKM_HDR = 3;		// header words: ord low | ord high, n-1, flags, bases | slice
+static constexpr u32 SKM_NFLAG = 0x80000000u;	// in the per-window slice array: window contains an N (-n)
+static constexpr int EMIT_NT = 256;
+static constexpr int SCAT_NT = 256;
+
+__host__ __device__ __forceinline__ u32 fmix32 (u32 h)
+{
+	h ^= h >> 16; h *= 0x85ebca6bu;
+	h ^= h >> 13; h *= 0xc2b2ae35u;
+	h ^= h >> 16;
+	return h;
+}
+// hash of a canonical m-mer code; the window's minimizer value is the minimum of these
+__host__ __device__ __forceinline__ u32 mmer_hash (u32 code) { return fmix32 (code ^ 0x5bd1e995u); }
+#ifdef __CUDACC__
+__device__ __forceinline__ u32 slice_of_min (u32 minval, u32 n_slices) { return __umulhi (fmix32 (minval + 0x9E3779B9u), n_slices); }
+#endif
+inline u32 slice_of_min_host (u32 minval, u32 n_slices) { return (u32) (((u64) fmix32 (minval + 0x9E3779B9u) * n_slices) >> 32); }
+
+// window w of the tile -> read, offset, read length (the decode half of tile_chop)
+template <bool NMODE>
+__device__ __forceinline__ void tile_locate (const ReadTile<NMODE> &rt, int K, u32 w, u32 &r, u32 &j, u32 &len)
+{
+	if (rt.uniform)
+	{
+		r = w / rt.nwin_u;
+		j = w - r * rt.nwin_u;
+		len = rt.nwin_u + K - 1;
+	}
+	else
+	{
+		u32 lo = 0, hi = rt.nr - 1;
+		while (lo < hi)
+		{
+			const u32 mid = (lo + hi + 1) >> 1;
+			if (rt.prefix[mid] <= w)
+				lo = mid;
+			else
+				hi = mid - 1;
+		}
+		r = lo;
+		j = w - rt.prefix[r];
+		len = rt.prefix[r + 1] - rt.prefix[r] + K - 1;
+	}
+}
+
+// the same with the division of the uniform case done by multiplication (mw = floor (2^32 / nwin_u) + 1, w < 65536)
+template <bool NMODE>
+__device__ __forceinline__ void skm_locate (const ReadTile<NMODE> &rt, int K, u32 mw, u32 w, u32 &r, u32 &j, u32 &len)
+{
+	if (rt.uniform)
+	{
+		r = __umulhi (w, mw);
+		j = w - r * rt.nwin_u;
+		len = rt.nwin_u + K - 1;
+	}
+	else
+		tile_locate<NMODE> (rt, K, w, r, j, len);
+}
+
+// any N among bases [a, b) of a read (mask words: bit 31 of word 0 = base 0)
+__device__ __forceinline__ bool mask_any (const u32 *mk, u32 a, u32 b)
+{
+	bool bad = false;
+	for (u32 q = a >> 5; q <= (b - 1) >> 5; q++)
+	{
+		u32 x = mk[q];
+		const u32 lo = q << 5;
+		if (a > lo)
+			x &= 0xFFFFFFFFu >> (a - lo);
+		if (b < lo + 32)
+			x &= 0xFFFFFFFFu << (lo + 32 - b);
+		bad |= (x != 0);
+	}
+	return bad;
+}
+__device__ __forceinline__ bool mask_at (const u32 *mk, u32 b) { return (mk[b >> 5] >> (31 - (b & 31))) & 1u; }
+
+// ------------------------------------------------------------------------------------------------
+// reads -> super-k-mer records.  Record (recw u32 words, 16-byte aligned):
+//   word 0  instance ordinal of the first window, low 32 bits
+//   word 1  ordinal bits 32..39 | (n - 1) << 8 | has_left << 14 | n_run << 15 | n_bases << 16
+//   word 2  slice
+//   word 3.. bases, 16 per word, first base in the top bits (the layout of the read tile), starting
+//           with the base before the first window if there is one (has_left): a miniature read on
+//           which chop_window yields exactly the windows, keys and link bases of the original read.
+//   n_run: n instances of key 0 without links (the -n N-windows, prlHashReads.c:193-196); no bases.
+template <int W> struct SkmRec { static constexpr u32 WORDS = W == 1 ? 8u : (W == 2 ? 12u : 16u), NMAX = W == 1 ? 32u : 64u; };
+
+template <int W, bool NMODE>
+__global__ void __launch_bounds__ (EMIT_NT)
+skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, unsigned long long *rec_cursor, Counters *ctr)
+{
+	constexpr u32 RECW = SkmRec<W>::WORDS, NMAX = SkmRec<W>::NMAX;
+	extern __shared__ __align__(16) u32 smem[];
+	__shared__ u32 warp_sums[EMIT_NT / 32];
+	__shared__ u32 s_count;
+	__shared__ unsigned long long s_base;
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int K = rb.K;
+	ReadTile<NMODE> rt;
+	tile_setup<NMODE> (rt, smem, rb);
+	u32 *mhs = smem + tile_words (rb, NMODE);	// [tile_reads * npos]: m-mer hashes, later (offset | n << 16) of run starts
+	u32 *sls = mhs + (size_t) rb.tile_reads * g.npos;	// [tile_reads * npos]: slice of every window (| SKM_NFLAG)
+	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
+	for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		tile_stage<NMODE, EMIT_NT> (rt, rb, t, warp_sums);
+		if (tid == 0)
+			s_count = 0;
+		// x / d for x < 65536 without a division: (x * m) >> 32 with m = floor (2^32 / d) + 1
+		const u32 m_npos = 0xFFFFFFFFu / g.npos + 1, m_nwin = rt.nwin_u ? 0xFFFFFFFFu / rt.nwin_u + 1 : 0;
+		// ---- 1. hash of the canonical m-mer at every position of every read
+		for (u32 x = tid; x < rt.nr * g.npos; x += EMIT_NT)
+		{
+			const u32 r = __umulhi (x, m_npos), i = x - r * g.npos;
+			Key<1> f, rc;
+			extract_fwd<1> (rt.tile + r * rt.sw, (int) (i + g.m), (int) g.m, f);
+			revcomp<1> (f, (int) g.m, rc);
+			mhs[x] = mmer_hash ((u32) min (f.w[0], rc.w[0]));
+		}
+		__syncthreads ();
+		// ---- 2. slice of every window = slice of its minimizer value
+		for (u32 x = tid; x < rt.total; x += EMIT_NT)
+		{
+			u32 r, j, len;
+			skm_locate<NMODE> (rt, K, m_nwin, x, r, j, len);
+			const u32 *mh = mhs + r * g.npos + j;
+			u32 mv = mh[0];
+			for (u32 i = 1; i < g.w; i++)
+				mv = min (mv, mh[i]);
+			u32 sl = slice_of_min (mv, g.n_slices);
+			if constexpr (NMODE)
+				if (mask_any (rt.mtile + r * rt.mw, j, j + K))
+					sl = g.slice_a | SKM_NFLAG;
+			sls[r * g.npos + j] = sl;
+		}
+		__syncthreads ();
+		// ---- 3. runs of windows with the same slice -> record descriptors (read | first window << 8 |
+		// (windows - 1) << 24) in mhs[], which is free now.  Every warp walks the windows of its own
+		// reads 32 at a time; the window that ENDS a run knows where the run started from a running
+		// maximum over "start" positions (shuffles, no loop over the run).
+		{
+			const u32 rpw = (rb.tile_reads + EMIT_NT / 32 - 1) / (EMIT_NT / 32);
+			const u32 r_lo = min (rt.nr, wid * rpw), r_hi = min (rt.nr, r_lo + rpw);
+			const u32 x_lo = rt.uniform ? r_lo * rt.nwin_u : rt.prefix[r_lo], x_hi = rt.uniform ? r_hi * rt.nwin_u : rt.prefix[r_hi];
+			u32 carry = 0;
+			for (u32 xb = x_lo; xb < x_hi; xb += 32)
+			{
+				const u32 x = xb + lane;
+				const bool act = x < x_hi;
+				u32 r = 0, j = 0, len = 0, s = 0;
+				bool is_start = false, is_end = false;
+				if (act)
+				{
+					skm_locate<NMODE> (rt, K, m_nwin, x, r, j, len);
+					const u32 *sl = sls + r * g.npos;
+					s = sl[j];
+					is_start = j == 0 || sl[j - 1] != s;
+					is_end = j + 1 == len - K + 1 || sl[j + 1] != s;
+				}
+				u32 v = is_start ? x + 1 : 0;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1)
+				{
+					const u32 y = __shfl_up_sync (0xFFFFFFFFu, v, d);
+					if (lane >= (u32) d)
+						v = max (v, y);
+				}
+				v = max (v, carry);
+				carry = __shfl_sync (0xFFFFFFFFu, v, 31);
+				if (is_end && (rb.owner_ranks <= 1 || (s & ~SKM_NFLAG) % rb.owner_ranks == rb.owner_rank))
+				{
+					const u32 n = x - (v - 1) + 1, j0 = j + 1 - n;
+					const u32 nrec = (n + NMAX - 1) / NMAX;
+					const u32 pos = atomicAdd (&s_count, nrec);
+					for (u32 c = 0; c < nrec; c++)
+						mhs[pos + c] = r | ((j0 + c * NMAX) << 8) | ((min (NMAX, n - c * NMAX) - 1) << 24);
+				}
+			}
+		}
+		__syncthreads ();
+		if (tid == 0)
+			s_base = s_count ? atomicAdd (rec_cursor, (unsigned long long) s_count) : 0ull;
+		__syncthreads ();
+		const u64 base = s_base;
+		const u32 n_out = s_count;
+		if (base + n_out > rec_cap)
+		{	// the host re-emits the whole read log into a larger area (sdtgpu.cu)
+			if (tid == 0)
+				atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 2ull);
+			__syncthreads ();
+			continue;
+		}
+		// ---- 4. one thread per record: consecutive threads write consecutive records
+		for (u32 rid = tid; rid < n_out; rid += EMIT_NT)
+		{
+			const u32 d = mhs[rid];
+			const u32 r = d & 0xFFu, j0 = (d >> 8) & 0xFFFFu, n = (d >> 24) + 1;
+			const u32 len = (rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r]) + K - 1;
+			const u32 s = sls[r * g.npos + j0];
+			const u32 *rd = rt.tile + r * rt.sw;
+			u32 *rec = rec0 + (base + rid) * RECW;
+			const u64 ord = (rb.first_read_ordinal + rt.r0 + r) * rb.maxwin + j0;
+			const bool nrun = NMODE && (s & SKM_NFLAG);
+			u32 has_left = j0 > 0, has_right = j0 + n - 1 + K < len;
+			if constexpr (NMODE)
+			{
+				const u32 *mk = rt.mtile + r * rt.mw;
+				if (has_left && mask_at (mk, j0 - 1))
+					has_left = 0;
+				if (has_right && mask_at (mk, j0 + n - 1 + K))
+					has_right = 0;
+			}
+			const u32 nb = nrun ? 0 : has_left + K + n - 1 + has_right;
+			const u32 first = j0 - has_left;
+			u32 wd[4];
+			wd[0] = (u32) ord;
+			wd[1] = (u32) (ord >> 32) | ((n - 1) << 8) | (has_left << 14) | ((nrun ? 1u : 0u) << 15) | (nb << 16);
+			wd[2] = s & ~SKM_NFLAG;
+			const u32 nbw = (nb + 15) >> 4;
+#pragma unroll
+			for (u32 q = 0; q < RECW - SKM_HDR; q++)
+			{
+				u32 v = 0;
+				if (q < nbw)
+				{
+					const u32 b = first + 16 * q, wq = b >> 4, sh = 2 * (b & 15);
+					v = __funnelshift_l (rd[wq + 1], rd[wq], sh);
+					if (q == nbw - 1 && (nb & 15))
+						v &= 0xFFFFFFFFu << (32 - 2 * (nb & 15));	// nothing of the read beyond the record's bases
+				}
+				const u32 o = SKM_HDR + q;
+				wd[o & 3] = v;
+				if ((o & 3) == 3)
+					*reinterpret_cast<uint4 *> (rec + (o & ~3u)) = make_uint4 (wd[0], wd[1], wd[2], wd[3]);
+			}
+			atomicAdd (hist + (s & ~SKM_NFLAG), 1u);	// RED
+		}
+		__syncthreads ();	// tile, descriptors and slices are overwritten by the next iteration
+	}
+}
+
+// every record to its slice's run: cur[p] starts at off[p]
+__global__ void __launch_bounds__ (SCAT_NT)
+skm_scatter_kernel (const u32 *rec0, const unsigned long long *rec_count, u32 recw, unsigned long long *cur, u32 *rec2)
+{
+	const u64 n = *rec_count;
+	const u32 vec = recw >> 2;
+	for (u64 i = blockIdx.x * (u64) SCAT_NT + threadIdx.x; i < n; i += (u64) gridDim.x * SCAT_NT)
+	{
+		const uint4 *src = reinterpret_cast<const uint4 *> (rec0 + i * recw);
+		const uint4 h = ldg_stream (src);
+		const u64 pos = atomicAdd (cur + h.z, 1ull);
+		uint4 *dst = reinterpret_cast<uint4 *> (rec2 + pos * recw);
+		dst[0] = h;
+		for (u32 q = 1; q < vec; q++)
+			dst[q] = ldg_stream (src + q);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// The slice's table image in shared memory.  Shared-memory atomics are the scarce resource (2 cycles
+// per lane, 20x a load), so an instance costs exactly ONE: every slot has a 5 x 5 matrix of 16-bit
+// cells indexed by (left, right), 4 = "no neighbour".  The reference's update_kmer (newhash.c:71-96)
+// touches count, one left and one right counter per instance; all three are sums over that matrix:
+//     count = sum of all cells + extra (mod 2^32),  L[b] = min (63, row b),  R[b] = min (63, column b).
+// A cell that gets near 16 bits stops counting and the slot's 32-bit `extra` takes over (it only
+// feeds count: a saturated cell already pins its row and column at 63).
+static constexpr int CELL_WORDS = 13;	// 25 16-bit cells, two per word
+static constexpr u32 CELL_STOP = 0xF000u;	// + one in-flight increment per thread of the CTA stays below 2^16
+
+template <int W> struct SkmImage
+{
+	u64 *key;	// [S * W]
+	u64 *ord;	// [S]
+	u32 *cell;	// [CELL_WORDS * S]: word q of slot i at q * S + i
+	u32 *extra;	// [S]
+	u32 *state;	// [S] (W > 1): 0 empty, 1 key being written, 2 occupied
+};
+
+__host__ __device__ inline size_t skm_image_bytes (int W, u32 S)
+{
+	return (size_t) S * (8 * W + 8 + 4 * CELL_WORDS + 4 + (W > 1 ? 4 : 0));
+}
+__host__ __device__ inline size_t skm_build_smem (int W, const SkmGeom &g)
+{	// image + window prefix of a chunk + list of occupied slots
+	return skm_image_bytes (W, g.slice_slots) + 4 * ((size_t) g.chunk + 4) + 2 * (size_t) g.slice_slots + 16;
+}
+
+template <int W>
+__device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key<W> &key, u32 idx, u32 &created)
+{
+	for (u32 tries = 0; tries < S;)
+	{
+		if constexpr (W == 1)
+		{
+			u64 k = *reinterpret_cast<volatile u64 *> (im.key + idx);
+			if (k == key.w[0])
+				return idx;
+			if (k == EMPTY64)
+			{
+				k = atomicCAS (im.key + idx, EMPTY64, key.w[0]);
+				if (k == EMPTY64)
+				{
+					created++;
+					return idx;
+				}
+				if (k == key.w[0])
+					return idx;
+			}
+		}
+		else
+		{
+			const u32 st = *reinterpret_cast<volatile u32 *> (im.state + idx);
+			if (st == 0u)
+			{
+				if (atomicCAS (im.state + idx, 0u, 1u) == 0u)
+				{	// claimed: publish the key, then open the slot (no waiting inside this branch)
+#pragma unroll
+					for (int q = 0; q < W; q++)
+						*reinterpret_cast<volatile u64 *> (im.key + (size_t) idx * W + q) = key.w[q];
+					__threadfence_block ();
+					*reinterpret_cast<volatile u32 *> (im.state + idx) = 2u;
+					created++;
+					return idx;
+				}
+				continue;	// lost the race: look at the same slot again
+			}
+			if (st == 1u)
+				continue;	// its key is being written
+			bool eq = true;
+#pragma unroll
+			for (int q = 0; q < W; q++)
+				eq &= (*reinterpret_cast<volatile u64 *> (im.key + (size_t) idx * W + q) == key.w[q]);
+			if (eq)
+				return idx;
+		}
+		if (++idx == S)
+			idx = 0;
+		tries++;
+	}
+	return S;
+}
+
+struct SkmWork { u32 slice, r, R; };	// keys of `slice` with sub-hash % R == r
+
+// One CTA per work item.  items == nullptr: item i is (slice i, 0, 1).
+static constexpr u32 MAX_SWEEPS = 4;	// slice_slots <= MAX_SWEEPS * BD_NT
+
+template <int W>
+__global__ void __launch_bounds__ (BD_NT, 1)
+skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long long *node_cursor, SkmGeom g, int K,
+		  const u32 *rec2, const u64 *off, const SkmWork *items, u32 n_items,
+		  SkmWork *failed, u32 *n_failed, u32 max_failed, Counters *ctr)
+{
+	typedef typename SlotOf<W>::type S_t;
+	extern __shared__ __align__(16) u32 smem[];
+	__shared__ u32 s_full, s_tot, s_warp[BD_NT / 32], s_wcnt[MAX_SWEEPS * (BD_NT / 32)];
+	__shared__ unsigned long long s_base;
+	const u32 S = g.slice_slots, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const u32 n_sweeps = (S + BD_NT - 1) / BD_NT;
+	SkmImage<W> im;
+	im.key = reinterpret_cast<u64 *> (smem);
+	im.ord = im.key + (size_t) S * W;
+	im.cell = reinterpret_cast<u32 *> (im.ord + S);
+	im.extra = im.cell + (size_t) S * CELL_WORDS;
+	im.state = im.extra + S;
+	u32 *pre = im.extra + S + (W > 1 ? S : 0);	// [chunk + 1]: exclusive prefix of the windows of a chunk's records
+	unsigned short *list = reinterpret_cast<unsigned short *> (pre + g.chunk + 2);	// [S]: occupied slots in rank order
+	u64 nodes = 0;	// thread 0 only
+	if (tid == 0)
+		s_full = 0;
+	for (u32 i = tid; i < S; i += BD_NT)
+	{
+#pragma unroll
+		for (int q = 0; q < W; q++)
+			im.key[(size_t) i * W + q] = EMPTY64;
+		im.ord[i] = ORD40_NONE;
+		im.extra[i] = 0u;
+		if constexpr (W > 1)
+			im.state[i] = 0u;
+	}
+	for (u32 i = tid; i < S * CELL_WORDS; i += BD_NT)
+		im.cell[i] = 0u;
+	__syncthreads ();
+	for (u32 it = blockIdx.x; it < n_items; it += gridDim.x)
+	{
+		SkmWork wk;
+		if (items)
+			wk = items[it];
+		else
+		{
+			wk.slice = it;
+			wk.r = 0;
+			wk.R = 1;
+		}
+		const u64 r0 = off[wk.slice], r1 = off[wk.slice + 1];
+		u32 created = 0;
+		u64 mine = 0;	// instances this thread applied
+		for (u64 c0 = r0; c0 < r1; c0 += g.chunk)
+		{	// g.chunk <= BD_NT records at a time: flatten their windows over the whole block
+			const u32 nrec = (u32) min ((u64) g.chunk, r1 - c0);
+			const u32 *recs = rec2 + c0 * g.recw;
+			u32 nwin = 0;
+			if (tid < nrec)
+			{
+				const u32 h1 = __ldg (recs + (size_t) tid * g.recw + 1);
+				nwin = ((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1;	// an N-run is applied in one go
+			}
+			u32 incl = nwin;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const u32 y = __shfl_up_sync (0xFFFFFFFFu, incl, d);
+				if (lane >= (u32) d)
+					incl += y;
+			}
+			if (lane == 31)
+				s_warp[wid] = incl;
+			__syncthreads ();
+			u32 lower = 0, total = 0;
+			for (u32 q = 0; q < BD_NT / 32; q++)
+			{
+				const u32 v = s_warp[q];
+				if (q < wid)
+					lower += v;
+				total += v;
+			}
+			if (tid < nrec)
+				pre[tid] = lower + incl - nwin;
+			if (tid == 0)
+				pre[nrec] = total;
+			__syncthreads ();
+			// same trip count for every lane and a warp barrier per trip: lanes that finish a probe
+			// sequence early must not run ahead into the next window on their own
+			for (u32 w0 = 0; w0 < total; w0 += BD_NT)
+			{
+				const u32 wi = w0 + tid;
+				if (wi < total && !*reinterpret_cast<volatile u32 *> (&s_full))
+				{
+					u32 lo = 0, hi = nrec - 1;	// largest x with pre[x] <= wi
+					while (lo < hi)
+					{
+						const u32 mid = (lo + hi + 1) >> 1;
+						if (pre[mid] <= wi)
+							lo = mid;
+						else
+							hi = mid - 1;
+					}
+					const u32 tw = wi - pre[lo];
+					const u32 *rec = recs + (size_t) lo * g.recw;
+					const u32 h1 = __ldg (rec + 1);
+					const u64 ord0 = (u64) __ldg (rec) | ((u64) (h1 & 0xFFu) << 32);
+					const u32 n = ((h1 >> 8) & 63u) + 1, has_left = (h1 >> 14) & 1u, nrun = (h1 >> 15) & 1u, nb = h1 >> 16;
+					Key<W> key;
+					u32 left = 4, right = 4, add = 1;
+					if (nrun)
+					{	// n instances of key 0 without links: they only feed count (and the ordinal)
+#pragma unroll
+						for (int q = 0; q < W; q++)
+							key.w[q] = 0;
+						add = n;
+					}
+					else
+						chop_window<W, false> (rec + SKM_HDR, nullptr, (int) nb, (int) (has_left + tw), K, key, left, right);
+					const u64 h = key_hash<W> (key);
+					if (wk.R == 1 || (u32) (h >> 32) % wk.R == wk.r)
+					{
+						const u32 idx = skm_find<W> (im, S, key, home_of (h, S), created);
+						if (idx == S)
+							s_full = 1;
+						else
+						{
+							const u32 c = left * 5 + right;
+							u32 *cw = im.cell + (c >> 1) * S + idx;
+							const u32 sh = 16 * (c & 1);
+							if (nrun || ((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
+								atomicAdd (im.extra + idx, add);
+							else
+								atomicAdd (cw, 1u << sh);
+							const u64 ord = ord0 + tw;
+							if (ord < *reinterpret_cast<volatile u64 *> (im.ord + idx))
+								atomicMin (im.ord + idx, ord);
+							mine += add;
+						}
+					}
+				}
+				__syncwarp ();
+			}
+			__syncthreads ();	// pre[] and s_warp[] are rewritten by the next chunk
+		}
+		// ---- nodes of this item: rank the occupied slots, reserve space in the store, compact, clean
+		const bool full = s_full != 0;
+		for (u32 sw = 0; sw < n_sweeps; sw++)
+		{
+			const u32 i = sw * BD_NT + tid;
+			bool occ = false;
+			if (i < S)
+			{
+				if constexpr (W == 1)
+					occ = im.key[i] != EMPTY64;
+				else
+					occ = im.state[i] == 2u;
+			}
+			const u32 bal = __ballot_sync (0xFFFFFFFFu, occ);
+			if (lane == 0)
+				s_wcnt[sw * (BD_NT / 32) + wid] = __popc (bal);
+		}
+		__syncthreads ();
+		if (wid == 0)
+		{	// exclusive scan of the (sweep, warp) counts; thread 0 reserves the item's space in the store
+			const u32 e_n = n_sweeps * (BD_NT / 32);	// <= 128: four entries per lane
+			u32 c[4], sum = 0;
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				c[q] = 4 * lane + q < e_n ? s_wcnt[4 * lane + q] : 0;
+				sum += c[q];
+			}
+			u32 incl = sum;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const u32 y = __shfl_up_sync (0xFFFFFFFFu, incl, d);
+				if (lane >= (u32) d)
+					incl += y;
+			}
+			u32 run = incl - sum;
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				if (4 * lane + q < e_n)
+					s_wcnt[4 * lane + q] = run;
+				run += c[q];
+			}
+			const u32 tot = __shfl_sync (0xFFFFFFFFu, incl, 31);
+			if (lane == 0)
+			{
+				unsigned long long b = 0;
+				bool fail = full;
+				if (!fail && tot)
+				{
+					b = atomicAdd (node_cursor, (unsigned long long) tot);
+					if (b + tot > store_cap)
+					{
+						fail = true;
+						atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 4ull);	// node store exhausted
+					}
+				}
+				if (full)
+				{	// retried later, split by k-mer hash
+					const u32 f = atomicAdd (n_failed, 1u);
+					if (f < max_failed)
+						failed[f] = wk;
+					else
+						atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 8ull);
+				}
+				s_base = fail ? ~0ull : b;
+				s_tot = tot;
+				if (!fail)
+					nodes += tot;
+			}
+		}
+		__syncthreads ();
+		for (u32 sw = 0; sw < n_sweeps; sw++)
+		{
+			const u32 i = sw * BD_NT + tid;
+			bool occ = false;
+			if (i < S)
+			{
+				if constexpr (W == 1)
+					occ = im.key[i] != EMPTY64;
+				else
+					occ = im.state[i] == 2u;
+			}
+			const u32 bal = __ballot_sync (0xFFFFFFFFu, occ);
+			if (occ)
+				list[s_wcnt[sw * (BD_NT / 32) + wid] + __popc (bal & ((1u << lane) - 1u))] = (unsigned short) i;
+		}
+		__syncthreads ();
+		const u64 nbase = s_base;
+		const bool write = nbase != ~0ull;
+		const u32 tot = s_tot;
+		for (u32 rank = tid; rank < tot; rank += BD_NT)
+		{	// one thread per node: consecutive threads write consecutive slots of the store
+			const u32 i = list[rank];
+			u32 row[4] = { 0, 0, 0, 0 }, col[4] = { 0, 0, 0, 0 }, count = im.extra[i];
+#pragma unroll
+			for (int q = 0; q < CELL_WORDS; q++)
+			{
+				const u32 v = im.cell[q * S + i];
+				im.cell[q * S + i] = 0u;
+#pragma unroll
+				for (int hlf = 0; hlf < 2; hlf++)
+				{
+					const int c = 2 * q + hlf;
+					if (c < 25)
+					{
+						const u32 x = (v >> (16 * hlf)) & 0xFFFFu;
+						count += x;
+						if (c / 5 < 4)
+							row[c / 5] += min (x, LINK_SAT);	// clamped terms: same min (63, sum), no overflow
+						if (c % 5 < 4)
+							col[c % 5] += min (x, LINK_SAT);
+					}
+				}
+			}
+			u32 L = 0, R = 0;
+#pragma unroll
+			for (int b = 0; b < 4; b++)
+			{
+				L |= min (row[b], LINK_SAT) << (6 * b);
+				R |= min (col[b], LINK_SAT) << (6 * b);
+			}
+			const u64 w0 = (im.ord[i] << 24) | L, w1 = ((u64) count << 32) | R;
+			Key<W> k;
+#pragma unroll
+			for (int q = 0; q < W; q++)
+			{
+				k.w[q] = im.key[(size_t) i * W + q];
+				im.key[(size_t) i * W + q] = EMPTY64;
+			}
+			im.ord[i] = ORD40_NONE;
+			im.extra[i] = 0u;
+			if constexpr (W > 1)
+				im.state[i] = 0u;
+			if (write)
+			{
+				S_t *dst = store + nbase + rank;
+				if constexpr (W == 1)
+					st256 (dst, k.w[0], 0ull, w0, w1);
+				else if constexpr (W == 2)
+					st256 (dst, k.w[0], k.w[1], w0, w1);
+				else
+				{
+					st256 (dst, k.w[0], k.w[1], k.w[2], k.w[3]);
+					st256 (reinterpret_cast<u64 *> (dst) + 4, w0, w1, 0ull, 0ull);
+				}
+			}
+		}
+		// instances applied by a work item that is going to be retried are not counted
+		{
+			u64 v = write ? mine : 0;
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1)
+				v += __shfl_down_sync (0xFFFFFFFFu, v, d);
+			if (lane == 0 && v)
+				atomicAdd (&ctr->n_instances, v);
+		}
+		__syncthreads ();
+		if (tid == 0)
+			s_full = 0;
+		__syncthreads ();
+	}
+	if (tid == 0 && nodes)
+		atomicAdd (&ctr->n_nodes, nodes);
+}
+
+}	// namespace sdt

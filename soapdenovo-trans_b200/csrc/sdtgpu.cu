@@ -3,7 +3,7 @@
 // There is NO CPU fallback: every entry point either runs the CUDA path or returns an error.
 #include "../../include/sdtgpu.h"
 #include "sdt_kernels.cuh"
-#include "sdt_sliced.cuh"
+#include "sdt_skm.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -83,16 +83,18 @@ struct sdtgpu
 	// sliced build (SDTGPU_F_SLICED): reads of the open epoch are kept in a log, counted per slice as
 	// they arrive, and turned into the table by sliced_flush (sdt_sliced.cuh)
 	bool sliced = false, table_built = false;
-	SliceGeom geom = { 0, 0, 0, 0 };
+	SkmGeom geom = {};
 	void *log_mem[3] = { nullptr, nullptr, nullptr };	// packed, lens, mask arenas
 	size_t log_cap[3] = { 0, 0, 0 }, log_used[3] = { 0, 0, 0 };
 	std::vector<LogSeg> log;
-	u64 log_upper = 0, epoch_budget = 0;	// instances in the log (upper bound); records an epoch may hold
 	u32 *d_hist = nullptr;
-	u64 *d_off = nullptr, *d_cur2 = nullptr, *d_seg_sum = nullptr, *d_off1 = nullptr, *d_cur1 = nullptr, *d_tpre = nullptr;
-	u64 *h_lvl1 = nullptr;	// pinned: off1[P1 + 1]
-	u64 *rec1 = nullptr, *rec2 = nullptr;
-	u64 rec1_cap = 0, rec2_cap = 0;	// records
+	u64 *d_off = nullptr, *d_cur2 = nullptr, *d_seg_sum = nullptr;
+	u64 *d_small = nullptr, *h_small = nullptr;	// [0] record cursor, [1] node cursor, [2] failed work items; pinned mirror
+	void *d_failed = nullptr, *d_items = nullptr;	// SkmWork lists
+	u32 *rec0 = nullptr, *rec2 = nullptr;	// super-k-mer records: as emitted, grouped by slice
+	u64 rec0_cap = 0, rec2_cap = 0, rec_upper = 0;	// records
+	u64 n_store = 0, n_records = 0, n_retried = 0;	// nodes in the store after the last build
+	bool dirty = false;	// records were emitted since the last build
 	u32 n_epochs = 0;
 	struct Timed { cudaEvent_t e0, e1; int cat; };
 	std::vector<Timed> timing;
@@ -651,7 +653,7 @@ int stage_batch (sdtgpu *h, const ReadBatch &rb, u64 upper)
 }
 
 
-// ---- sliced build (sdt_sliced.cuh) --------------------------------------------------------------
+// ---- sliced build over super-k-mers (sdt_skm.cuh) ------------------------------------------------
 struct TimedLaunch
 {	// CUDA events around one launch on the handle's stream, filed under a timing class
 	sdtgpu *h;
@@ -672,57 +674,58 @@ u32 env_u32 (const char *name, u32 dflt)
 	return e && atoll (e) > 0 ? (u32) atoll (e) : dflt;
 }
 
-u32 scatter_tile_recs (int W) { return W == 4 ? SC_NT * ScatterCfg<4>::RPT : SC_NT * ScatterCfg<1>::RPT; }
-
-// geometry from the expected distinct count: slices of S slots at ~0.6 load, two partition levels
-// of about sqrt (n_slices) bins each
-int sliced_setup (sdtgpu *h, u64 hint)
+// Geometry from the expected distinct count: slices whose images run at ~half load on average
+// (minimizer slices are lumpier than hashed k-mers: sd ~14 % of the mean at 1150 keys per slice)
+int skm_setup (sdtgpu *h, u64 hint)
 {
 	if (hint == 0)
 		return fail (h, SDTGPU_EINVAL, "the sliced build needs capacity_hint (expected distinct k-mers)");
-	const u32 S = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 1920u : (h->W == 2 ? 1792u : 1600u));
-	double load = 0.6;
+	SkmGeom g;
+	// default: what fits one CTA per SM (227 KB): 74 / 86 / 102 bytes per slot for 1- / 2- / 4-word keys
+	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 2976u : (h->W == 2 ? 2560u : 2176u)) & ~1u;
+	if (g.slice_slots < 32 || g.slice_slots > MAX_SWEEPS * BD_NT)
+		return fail (h, SDTGPU_EINVAL, "SDTGPU_SLICE_SLOTS out of range");
+	double load = 0.5;
 	if (const char *e = getenv ("SDTGPU_SLICE_LOAD"))
 		if (atof (e) > 0.05 && atof (e) < 0.95)
 			load = atof (e);
-	const u64 n = std::max<u64> (1, (u64) std::ceil ((double) hint / ((double) S * load)));
+	const u64 n = std::max<u64> (1, (u64) std::ceil ((double) hint / ((double) g.slice_slots * load)));
 	if (n > (1ull << 30))
 		return fail (h, SDTGPU_ERANGE, "capacity_hint too large for the sliced build");
-	SliceGeom g;
 	g.n_slices = (u32) n;
-	g.slice_slots = S;
-	u32 p2 = env_u32 ("SDTGPU_SLICE_P2", (u32) std::ceil (std::sqrt ((double) n)));
-	g.P2 = std::max (1u, std::min (p2, g.n_slices));
-	g.P1 = (g.n_slices + g.P2 - 1) / g.P2;
-	if (g.P1 > 32768 || g.P2 > 32768)
-		return fail (h, SDTGPU_ERANGE, "partition fan-out too large");
+	g.m = env_u32 ("SDTGPU_MINIMIZER", h->K >= 21 ? 15u : (u32) std::max (7, h->K - 6));
+	if (g.m > 15 || (int) g.m > h->K - 2 || g.m < 5)
+		return fail (h, SDTGPU_EINVAL, "SDTGPU_MINIMIZER out of range");
+	g.w = (u32) h->K - g.m + 1;
+	g.nmax = h->W == 1 ? 32 : 64;
+	g.recw = h->W == 1 ? 8 : (h->W == 2 ? 12 : 16);
+	g.npos = (u32) h->max_read_len - g.m + 1;
+	g.tile_reads = std::max (4u, std::min (64u, (8192u / g.npos) & ~3u));
+	g.chunk = std::min<u32> (env_u32 ("SDTGPU_SLICE_CHUNK", BD_NT), BD_NT);
+	g.slice_a = slice_of_min_host (mmer_hash (0), g.n_slices);
+	if (g.npos * g.tile_reads > 60000 || h->max_read_len > 60000)
+		return fail (h, SDTGPU_ERANGE, "max_read_len too large for the sliced build");
 	h->geom = g;
-	h->cap = (u64) g.n_slices * S;
+	h->cap = hint + hint / 8 + 65536;	// node store: compact, one slot per distinct k-mer
 	return SDTGPU_OK;
 }
 
-int sliced_alloc (sdtgpu *h)
+static constexpr u32 MAX_FAILED = 1u << 16;
+
+int skm_alloc (sdtgpu *h)
 {
-	const SliceGeom &g = h->geom;
+	const SkmGeom &g = h->geom;
 	const u32 nseg = (g.n_slices + SCAN_SEG - 1) / SCAN_SEG;
 	CK (h, cudaMalloc (&h->d_hist, (size_t) g.n_slices * sizeof (u32)));
 	CK (h, cudaMalloc (&h->d_off, ((size_t) g.n_slices + 1) * sizeof (u64)));
 	CK (h, cudaMalloc (&h->d_cur2, (size_t) g.n_slices * sizeof (u64)));
 	CK (h, cudaMalloc (&h->d_seg_sum, (size_t) nseg * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_off1, ((size_t) g.P1 + 1) * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_cur1, (size_t) g.P1 * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_tpre, ((size_t) g.P1 + 1) * sizeof (u64)));
-	CK (h, cudaMallocHost (&h->h_lvl1, ((size_t) g.P1 + 1) * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_small, 8 * sizeof (u64)));	// [0] record cursor, [1] node cursor, [2] failed items
+	CK (h, cudaMalloc (&h->d_failed, (size_t) MAX_FAILED * sizeof (SkmWork)));
+	CK (h, cudaMalloc (&h->d_items, (size_t) MAX_FAILED * sizeof (SkmWork)));
+	CK (h, cudaMallocHost (&h->h_small, 8 * sizeof (u64)));
 	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) g.n_slices * sizeof (u32), h->stream));
-	// records an epoch may hold: what is left of the device after the table, minus the level-2 scratch
-	size_t free_b = 0, total_b = 0;
-	CK (h, cudaMemGetInfo (&free_b, &total_b));
-	const size_t rec = 8 * (size_t) (h->W + 1);
-	double budget = 0.80 * (double) free_b - 3.0 * 1024 * 1024 * 1024;
-	if (const char *e = getenv ("SDTGPU_EPOCH_MB"))
-		if (atof (e) > 0)
-			budget = atof (e) * 1024.0 * 1024.0;
-	h->epoch_budget = (u64) std::max (budget / (double) rec, 65536.0);
+	CK (h, cudaMemsetAsync (h->d_small, 0, 8 * sizeof (u64), h->stream));
 	return SDTGPU_OK;
 }
 
@@ -735,223 +738,206 @@ ReadBatch log_batch (const sdtgpu *h, const LogSeg &s)
 	return rb;
 }
 
-int log_reserve (sdtgpu *h, int which, size_t need)
-{
-	if (h->log_used[which] + need <= h->log_cap[which])
+int grow_device (sdtgpu *h, void **mem, size_t *cap, size_t keep, size_t need)
+{	// *mem holds `keep` live bytes; make room for `need`
+	if (need <= *cap)
 		return SDTGPU_OK;
-	const size_t ncap = std::max (2 * h->log_cap[which], h->log_used[which] + need + (4u << 20));
+	const size_t ncap = std::max (*cap + *cap / 2, need + (4u << 20));
 	void *neu = nullptr;
 	CK (h, cudaMalloc (&neu, ncap));
-	if (h->log_used[which])
-		CK (h, cudaMemcpyAsync (neu, h->log_mem[which], h->log_used[which], cudaMemcpyDeviceToDevice, h->stream));
+	if (keep)
+		CK (h, cudaMemcpyAsync (neu, *mem, keep, cudaMemcpyDeviceToDevice, h->stream));
 	CK (h, cudaStreamSynchronize (h->stream));
-	if (h->log_mem[which])
-		CK (h, cudaFree (h->log_mem[which]));
-	h->log_mem[which] = neu;
-	h->log_cap[which] = ncap;
+	if (*mem)
+		CK (h, cudaFree (*mem));
+	*mem = neu;
+	*cap = ncap;
 	return SDTGPU_OK;
 }
 
-template <int W, bool NMODE> int launch_count_t (sdtgpu *h, const ReadBatch &rb)
+template <int W, bool NMODE> int launch_emit_t (sdtgpu *h, ReadBatch rb)
 {
-	auto kern = slice_count_kernel<W, NMODE>;
-	const size_t smem = 4 * tile_words (rb, NMODE);
+	const SkmGeom &g = h->geom;
+	rb.tile_reads = g.tile_reads;
+	auto kern = skm_emit_kernel<W, NMODE>;
+	const size_t smem = 4 * (tile_words (rb, NMODE) + 2 * (size_t) g.tile_reads * g.npos);
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
-	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, CNT_NT, smem));
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, EMIT_NT, smem));
 	if (occ < 1)
 		return fail (h, SDTGPU_EINVAL, "read stride too large for one shared-memory tile");
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
 	const unsigned grid = (unsigned) std::min<u64> (n_tiles, (u64) h->sm_count * occ);
 	{
 		TimedLaunch tl (h, 1);
-		kern<<<grid, CNT_NT, smem, h->stream>>> (rb, h->geom, h->d_hist);
+		kern<<<grid, EMIT_NT, smem, h->stream>>> (rb, g, h->d_hist, h->rec0, h->rec0_cap, reinterpret_cast<unsigned long long *> (h->d_small), h->d_ctr);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
 }
 
-template <int W, bool NMODE> int launch_scatter1_t (sdtgpu *h, const ReadBatch &rb)
+int launch_emit (sdtgpu *h, const ReadBatch &rb)
 {
-	auto kern = slice_scatter1_kernel<W, NMODE>;
-	const size_t smem = 4 * tile_words (rb, NMODE) + scatter_smem_bytes (W, scatter_tile_recs (W), h->geom.P1);
+	const bool nmode = (h->flags & SDTGPU_F_NKMER) && rb.nmask;
+	switch (h->W)
+	{
+	case 1: return nmode ? launch_emit_t<1, true> (h, rb) : launch_emit_t<1, false> (h, rb);
+	case 2: return nmode ? launch_emit_t<2, true> (h, rb) : launch_emit_t<2, false> (h, rb);
+	default: return nmode ? launch_emit_t<4, true> (h, rb) : launch_emit_t<4, false> (h, rb);
+	}
+}
+
+template <int W> int launch_build_t (sdtgpu *h, const SkmWork *items, u32 n_items)
+{
+	typedef typename SlotOf<W>::type S;
+	const SkmGeom &g = h->geom;
+	auto kern = skm_build_kernel<W>;
+	const size_t smem = skm_build_smem (W, g);
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
-	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, SC_NT, smem));
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, BD_NT, smem));
 	if (occ < 1)
-		return fail (h, SDTGPU_EINVAL, "level-1 scatter does not fit in shared memory (stride or fan-out too large)");
-	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
-	const unsigned grid = (unsigned) std::min<u64> (n_tiles, (u64) h->sm_count * occ);
+		return fail (h, SDTGPU_EINVAL, "slice image does not fit in shared memory (SDTGPU_SLICE_SLOTS too large)");
+	const unsigned grid = (unsigned) std::min<u64> (n_items, (u64) h->sm_count * occ);
+	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	{
-		TimedLaunch tl (h, 2);
-		kern<<<grid, SC_NT, smem, h->stream>>> (rb, h->geom, h->d_cur1, h->rec1);
+		TimedLaunch tl (h, 4);
+		kern<<<grid, BD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, h->rec2, h->d_off, items, n_items,
+							 static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
 }
 
-template <int W> int launch_group_t (sdtgpu *h, u32 q_lo, u32 q_hi, u64 tiles, u64 out_base, int merge)
+int launch_build (sdtgpu *h, const SkmWork *items, u32 n_items)
 {
-	typedef typename SlotOf<W>::type S;
-	const SliceGeom &g = h->geom;
-	if (tiles)
+	switch (h->W)
 	{
-		auto kern = slice_scatter2_kernel<W>;
-		const size_t smem = scatter_smem_bytes (W, scatter_tile_recs (W), g.P2);
-		if (smem > 48 * 1024)
-			CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		int occ = 0;
-		CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, SC_NT, smem));
-		if (occ < 1)
-			return fail (h, SDTGPU_EINVAL, "level-2 scatter does not fit in shared memory");
-		const unsigned grid = (unsigned) std::min<u64> (tiles, (u64) h->sm_count * occ);
-		{
-			TimedLaunch tl (h, 3);
-			kern<<<grid, SC_NT, smem, h->stream>>> (h->rec1, h->d_off1, h->d_tpre, q_lo, q_hi, g, h->d_cur2, h->rec2, out_base);
-		}
-		CK (h, cudaGetLastError ());
+	case 1: return launch_build_t<1> (h, items, n_items);
+	case 2: return launch_build_t<2> (h, items, n_items);
+	default: return launch_build_t<4> (h, items, n_items);
 	}
-	{
-		auto kern = slice_build_kernel<W>;
-		const size_t smem = slice_image_bytes (W, g.slice_slots);
-		if (smem > 48 * 1024)
-			CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		int occ = 0;
-		CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, BD_NT, smem));
-		if (occ < 1)
-			return fail (h, SDTGPU_EINVAL, "slice image does not fit in shared memory (SDTGPU_SLICE_SLOTS too large)");
-		const u32 p_lo = q_lo * g.P2, p_hi = (u32) std::min<u64> ((u64) q_hi * g.P2, g.n_slices);
-		const unsigned grid = (unsigned) std::min<u64> (p_hi - p_lo, (u64) h->sm_count * occ);
-		{
-			TimedLaunch tl (h, 4);
-			kern<<<grid, BD_NT, smem, h->stream>>> (static_cast<S *> (h->table), g, h->rec2, h->d_off, out_base, p_lo, p_hi, merge, h->d_ctr);
-		}
-		CK (h, cudaGetLastError ());
-	}
+}
+
+int skm_emit_all (sdtgpu *h)
+{	// slow path: the record area was too small for what the reads produced; the cursor has counted
+	// every record, so the area is resized to fit and the whole read log is emitted again
+	int rc;
+	const u64 need = h->h_small[0] + h->h_small[0] / 16 + 4096;
+	const size_t rec = 4 * (size_t) h->geom.recw;
+	size_t cap_b = h->rec0_cap * rec;
+	if ((rc = grow_device (h, (void **) &h->rec0, &cap_b, 0, need * rec)))
+		return rc;
+	h->rec0_cap = cap_b / rec;
+	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) h->geom.n_slices * sizeof (u32), h->stream));
+	CK (h, cudaMemsetAsync (h->d_small, 0, sizeof (u64), h->stream));
+	CK (h, cudaMemsetAsync (&h->d_ctr->overflow, 0, sizeof (u64), h->stream));
+	for (const LogSeg &s : h->log)
+		if ((rc = launch_emit (h, log_batch (h, s))))
+			return rc;
+	h->rec_upper = std::max (h->rec_upper, need);
 	return SDTGPU_OK;
 }
 
-int launch_count (sdtgpu *h, const ReadBatch &rb)
-{
-	const bool nmode = (h->flags & SDTGPU_F_NKMER) && rb.nmask;
-	switch (h->W)
-	{
-	case 1: return nmode ? launch_count_t<1, true> (h, rb) : launch_count_t<1, false> (h, rb);
-	case 2: return nmode ? launch_count_t<2, true> (h, rb) : launch_count_t<2, false> (h, rb);
-	default: return nmode ? launch_count_t<4, true> (h, rb) : launch_count_t<4, false> (h, rb);
-	}
-}
-
-int launch_scatter1 (sdtgpu *h, const ReadBatch &rb)
-{
-	const bool nmode = (h->flags & SDTGPU_F_NKMER) && rb.nmask;
-	switch (h->W)
-	{
-	case 1: return nmode ? launch_scatter1_t<1, true> (h, rb) : launch_scatter1_t<1, false> (h, rb);
-	case 2: return nmode ? launch_scatter1_t<2, true> (h, rb) : launch_scatter1_t<2, false> (h, rb);
-	default: return nmode ? launch_scatter1_t<4, true> (h, rb) : launch_scatter1_t<4, false> (h, rb);
-	}
-}
-
-int launch_group (sdtgpu *h, u32 q_lo, u32 q_hi, u64 tiles, u64 out_base, int merge)
-{
-	switch (h->W)
-	{
-	case 1: return launch_group_t<1> (h, q_lo, q_hi, tiles, out_base, merge);
-	case 2: return launch_group_t<2> (h, q_lo, q_hi, tiles, out_base, merge);
-	default: return launch_group_t<4> (h, q_lo, q_hi, tiles, out_base, merge);
-	}
-}
-
-// End of an epoch of the sliced build: every read in the log becomes part of the table.
+// Everything pushed since the last reset becomes the node store: scan the per-slice record counts,
+// move every record to its slice's run, build the slices.  Records persist until sdtgpu_reset, so a
+// later push followed by another flush rebuilds the store from all of them.
 int sliced_flush (sdtgpu *h)
 {
 	int rc;
+	if (h->table_built && !h->dirty)
+		return SDTGPU_OK;
+	const SkmGeom g = h->geom;
+	const size_t rec = 4 * (size_t) g.recw;
+	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
+	h->n_store = 0;
 	if (h->log.empty ())
 	{
-		if (!h->table_built)
-		{	// nothing was ever pushed: an empty table in the ordinary layout
-			if ((rc = init_table (h, h->table, h->cap)))
-				return rc;
-			h->table_built = true;
-		}
+		h->table_built = true;
+		h->dirty = false;
 		return SDTGPU_OK;
 	}
-	const SliceGeom g = h->geom;
-	const size_t rec = 8 * (size_t) (h->W + 1);
-	const u32 tile_recs = scatter_tile_recs (h->W);
+	for (int attempt = 0;; attempt++)
+	{
+		CK (h, cudaMemcpyAsync (h->h_small, h->d_small, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaStreamSynchronize (h->stream));
+		if (!(h->h_small[3] & 2))
+			break;
+		if (attempt == 2)
+			return fail (h, SDTGPU_ERANGE, "record area overflow persists");
+		if ((rc = skm_emit_all (h)))
+			return rc;
+	}
+	const u64 n_rec = h->h_small[0];
+	h->n_records = n_rec;
+	{
+		size_t cap_b = h->rec2_cap * rec;
+		if ((rc = grow_device (h, (void **) &h->rec2, &cap_b, 0, std::max<u64> (n_rec, 1) * rec)))
+			return rc;
+		h->rec2_cap = cap_b / rec;
+	}
 	const u32 nseg = (g.n_slices + SCAN_SEG - 1) / SCAN_SEG;
 	{
 		TimedLaunch tl (h, 5);
 		slice_scan_sums_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, g.n_slices, h->d_seg_sum);
 		slice_scan_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, g.n_slices, h->d_seg_sum, h->d_off, h->d_cur2);
-		slice_level1_kernel<<<1, 1024, 0, h->stream>>> (h->d_off, g, tile_recs, h->d_off1, h->d_cur1, h->d_tpre);
-		h->all_launches += 2;
+		h->all_launches++;
 	}
 	CK (h, cudaGetLastError ());
-	CK (h, cudaMemcpyAsync (h->h_lvl1, h->d_off1, ((size_t) g.P1 + 1) * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-	CK (h, cudaStreamSynchronize (h->stream));
-	const u64 total = h->h_lvl1[g.P1];
-	u64 biggest = 0;
-	for (u32 q = 0; q < g.P1; q++)
-		biggest = std::max (biggest, h->h_lvl1[q + 1] - h->h_lvl1[q]);
-	if (total > h->rec1_cap)
+	if (n_rec)
 	{
-		if (h->rec1)
-			CK (h, cudaFree (h->rec1));
-		h->rec1 = nullptr;
-		h->rec1_cap = total + total / 64 + 1024;
-		CK (h, cudaMalloc (&h->rec1, h->rec1_cap * rec));
+		const unsigned grid = (unsigned) std::min<u64> ((n_rec + SCAT_NT - 1) / SCAT_NT, (u64) h->sm_count * 8);
+		TimedLaunch tl (h, 2);
+		skm_scatter_kernel<<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, g.recw, reinterpret_cast<unsigned long long *> (h->d_cur2), h->rec2);
 	}
-	u64 group_records = (u64) env_u32 ("SDTGPU_SLICE_GROUP_MB", 2048) * 1024 * 1024 / rec;
-	group_records = std::max<u64> (std::min (group_records, std::max<u64> (total, 1)), std::max<u64> (biggest, 1));
-	if (group_records > h->rec2_cap)
+	CK (h, cudaGetLastError ());
+	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over
+	CK (h, cudaMemsetAsync (small + 1, 0, 2 * sizeof (u64), h->stream));
+	CK (h, cudaMemsetAsync (&h->d_ctr->n_nodes, 0, 2 * sizeof (u64), h->stream));	// n_nodes, n_instances
+	if ((rc = launch_build (h, nullptr, g.n_slices)))
+		return rc;
+	h->n_retried = 0;
+	std::vector<SkmWork> items, failed;
+	for (u32 depth = 0;; depth++)
 	{
-		if (h->rec2)
-			CK (h, cudaFree (h->rec2));
-		h->rec2 = nullptr;
-		h->rec2_cap = group_records;
-		CK (h, cudaMalloc (&h->rec2, h->rec2_cap * rec));
-	}
-	for (const LogSeg &s : h->log)
-		if ((rc = launch_scatter1 (h, log_batch (h, s))))
+		CK (h, cudaMemcpyAsync (h->h_small + 1, small + 1, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaStreamSynchronize (h->stream));
+		if (h->h_small[3] & 4)
+			return fail (h, SDTGPU_ERANGE, "node store exhausted: capacity_hint was too small for the sliced build");
+		const u32 n_failed = (u32) h->h_small[2];
+		if (n_failed == 0)
+			break;
+		if ((h->h_small[3] & 8) || n_failed > MAX_FAILED / 8 || depth == 6)
+			return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
+		// split every failed item eight ways by k-mer hash and run the pieces
+		failed.resize (n_failed);
+		CK (h, cudaMemcpy (failed.data (), h->d_failed, n_failed * sizeof (SkmWork), cudaMemcpyDeviceToHost));
+		items.clear ();
+		for (const SkmWork &f : failed)
+			for (u32 q = 0; q < 8; q++)
+				items.push_back ({ f.slice, f.r + f.R * q, f.R * 8 });
+		h->n_retried += n_failed;
+		CK (h, cudaMemcpyAsync (h->d_items, items.data (), items.size () * sizeof (SkmWork), cudaMemcpyHostToDevice, h->stream));
+		CK (h, cudaMemsetAsync (small + 2, 0, sizeof (u64), h->stream));
+		if ((rc = launch_build (h, static_cast<const SkmWork *> (h->d_items), (u32) items.size ())))
 			return rc;
-	const int merge = h->table_built ? 1 : 0;
-	for (u32 q_lo = 0; q_lo < g.P1;)
-	{
-		u32 q_hi = q_lo;
-		u64 recs = 0, tiles = 0;
-		while (q_hi < g.P1)
-		{
-			const u64 nq = h->h_lvl1[q_hi + 1] - h->h_lvl1[q_hi];
-			if (q_hi > q_lo && recs + nq > h->rec2_cap)
-				break;
-			recs += nq;
-			tiles += (nq + tile_recs - 1) / tile_recs;
-			q_hi++;
-		}
-		if ((rc = launch_group (h, q_lo, q_hi, tiles, h->h_lvl1[q_lo], merge)))
-			return rc;
-		q_lo = q_hi;
+		CK (h, cudaStreamSynchronize (h->stream));	// `items` is pageable host memory
 	}
-	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) g.n_slices * sizeof (u32), h->stream));
+	h->n_store = h->h_small[1];
 	h->table_built = true;
+	h->dirty = false;
 	h->n_epochs++;
-	h->log.clear ();
-	h->log_used[0] = h->log_used[1] = h->log_used[2] = 0;
-	h->log_upper = 0;
 	return SDTGPU_OK;
 }
 
-// one batch into the read log of the open epoch + its per-slice instance counts
+// one batch: into the read log (kept for the slow path above) and through skm_emit_kernel
 int sliced_push (sdtgpu *h, const ReadBatch &rb, u64 upper)
 {
 	int rc;
-	if (h->log_upper && h->log_upper + upper > h->epoch_budget)
-		if ((rc = sliced_flush (h)))
-			return rc;
 	auto up16 = [](size_t x) { return (x + 15) & ~(size_t) 15; };
 	const size_t bytes[3] = { up16 ((size_t) rb.n_reads * rb.stride_bytes), rb.lens ? up16 ((size_t) rb.n_reads * 4) : 0,
 				  rb.nmask ? up16 ((size_t) rb.n_reads * rb.mask_stride) : 0 };
@@ -964,16 +950,27 @@ int sliced_push (sdtgpu *h, const ReadBatch &rb, u64 upper)
 		s.off[i] = h->log_used[i];
 		if (!bytes[i])
 			continue;
-		if ((rc = log_reserve (h, i, bytes[i])))
+		if ((rc = grow_device (h, &h->log_mem[i], &h->log_cap[i], h->log_used[i], h->log_used[i] + bytes[i])))
 			return rc;
 		CK (h, cudaMemcpyAsync (static_cast<uint8_t *> (h->log_mem[i]) + s.off[i], src[i], exact[i], cudaMemcpyDeviceToDevice, h->stream));
 		h->log_used[i] += bytes[i];
 	}
 	h->log.push_back (s);
-	h->log_upper += upper;
 	h->pushed_upper += upper;
-	return launch_count (h, log_batch (h, h->log.back ()));
+	// record area: a third of a record per window is ~2.5x what reads produce (about one per eight
+	// windows at K = 31); if a batch needs more the emit kernel says so and sliced_flush re-emits
+	const size_t rec = 4 * (size_t) h->geom.recw;
+	const u64 want = h->rec_upper + upper / env_u32 ("SDTGPU_REC_DIV", 3) + rb.n_reads / 8 + 4096;
+	size_t cap_b = h->rec0_cap * rec;
+	if ((rc = grow_device (h, (void **) &h->rec0, &cap_b, cap_b, want * rec)))
+		return rc;
+	h->rec0_cap = cap_b / rec;
+	h->rec_upper = want;
+	h->dirty = true;
+	return launch_emit (h, log_batch (h, h->log.back ()));
 }
+
+u64 iter_slots (const sdtgpu *h) { return h->sliced ? h->n_store : h->cap; }
 
 }	// namespace
 
@@ -1044,10 +1041,10 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 		int rc;
 		if (h->sliced)
 		{	// the first build writes every slot, empty ones included: no initialisation pass
-			if ((rc = sliced_setup (h, capacity_hint)))
+			if ((rc = skm_setup (h, capacity_hint)))
 				return rc;
 			CK (h, cudaMalloc (&h->table, h->cap * slot_bytes (h->W)));
-			if ((rc = sliced_alloc (h)))
+			if ((rc = skm_alloc (h)))
 				return rc;
 			CK (h, cudaStreamSynchronize (h->stream));
 			return SDTGPU_OK;
@@ -1086,9 +1083,9 @@ void sdtgpu_destroy (sdtgpu_t *h)
 	cudaFree (h->staging); cudaFree (h->d_counts); cudaFree (h->d_cursors); cudaFree (h->d_seg_offsets); cudaFree (h->d_chunk_prefix); cudaFree (h->d_next_chunk);
 	for (auto e : h->ev_pool) cudaEventDestroy (e);
 	for (void *m : h->log_mem) cudaFree (m);
-	cudaFree (h->d_hist); cudaFree (h->d_off); cudaFree (h->d_cur2); cudaFree (h->d_seg_sum); cudaFree (h->d_off1); cudaFree (h->d_cur1); cudaFree (h->d_tpre);
-	cudaFree (h->rec1); cudaFree (h->rec2);
-	if (h->h_lvl1) cudaFreeHost (h->h_lvl1);
+	cudaFree (h->d_hist); cudaFree (h->d_off); cudaFree (h->d_cur2); cudaFree (h->d_seg_sum); cudaFree (h->d_small);
+	cudaFree (h->d_failed); cudaFree (h->d_items); cudaFree (h->rec0); cudaFree (h->rec2);
+	if (h->h_small) cudaFreeHost (h->h_small);
 	cudaFree (h->table);
 	cudaFree (h->d_ctr);
 	if (h->h_ctr) cudaFreeHost (h->h_ctr);
@@ -1106,13 +1103,18 @@ int sdtgpu_reset (sdtgpu_t *h)
 	CK (h, cudaSetDevice (h->device));
 	CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
 	if (h->sliced)
-	{	// the next build rewrites the whole table; only the open epoch has to go
+	{	// records, their per-slice counts and the read log go; the store is rewritten by the next build
 		if (!h->log.empty ())
+		{
 			CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) h->geom.n_slices * sizeof (u32), h->stream));
+			CK (h, cudaMemsetAsync (h->d_small, 0, 8 * sizeof (u64), h->stream));
+		}
 		h->log.clear ();
 		h->log_used[0] = h->log_used[1] = h->log_used[2] = 0;
-		h->log_upper = 0;
+		h->rec_upper = 0;
+		h->n_store = 0;
 		h->table_built = false;
+		h->dirty = false;
 	}
 	else
 	{
@@ -1163,7 +1165,7 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 		u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
 		if (h->owner_ranks > 1)
 			upper = upper / h->owner_ranks + upper / (2 * h->owner_ranks) + 1024;
-		return sliced_push (h, rb, upper);
+		return sliced_push (h, rb, upper);	// (with owner filtering the record area is simply sized generously)
 	}
 	if (h->direct)
 	{	// single pass: every window goes straight to its (random) slot
@@ -1339,8 +1341,8 @@ int sdtgpu_get_stats (sdtgpu_t *h, sdtgpu_stats *stats)
 	if (rc)
 		return rc;
 	fill_stats (h, stats);
-	if (h->h_ctr->overflow)
-		return fail (h, SDTGPU_ERANGE, h->sliced ? "a table slice overflowed: capacity_hint was too small for the sliced build" : "a record bin overflowed");
+	if (h->h_ctr->overflow && !h->sliced)
+		return fail (h, SDTGPU_ERANGE, "a record bin overflowed");
 	return SDTGPU_OK;
 }
 
@@ -1357,13 +1359,15 @@ int sdtgpu_finalize (sdtgpu_t *h, int deLowKmer, int64_t kmerFreq[257], sdtgpu_s
 	int frc = flush_epoch (h);
 	if (frc)
 		return frc;
-	const unsigned grid = (unsigned) std::min<u64> ((h->cap + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
-	switch (h->W)
-	{
-	case 1: finalize_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot1 *> (h->table), h->cap, deLowKmer, h->d_ctr); break;
-	case 2: finalize_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot2 *> (h->table), h->cap, deLowKmer, h->d_ctr); break;
-	default: finalize_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot4 *> (h->table), h->cap, deLowKmer, h->d_ctr); break;
-	}
+	const u64 slots = iter_slots (h);	// the whole table, or the node store of the sliced build
+	const unsigned grid = (unsigned) std::min<u64> ((slots + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
+	if (grid)
+		switch (h->W)
+		{
+		case 1: finalize_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot1 *> (h->table), slots, deLowKmer, h->d_ctr); break;
+		case 2: finalize_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot2 *> (h->table), slots, deLowKmer, h->d_ctr); break;
+		default: finalize_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<Slot4 *> (h->table), slots, deLowKmer, h->d_ctr); break;
+		}
 	CK (h, cudaGetLastError ());
 	h->all_launches++;
 	h->finalized = true;
@@ -1371,8 +1375,8 @@ int sdtgpu_finalize (sdtgpu_t *h, int deLowKmer, int64_t kmerFreq[257], sdtgpu_s
 	int rc = read_counters (h);
 	if (rc)
 		return rc;
-	if (h->h_ctr->overflow)
-		return fail (h, SDTGPU_ERANGE, "a table slice overflowed: capacity_hint was too small for the sliced build");
+	if (h->h_ctr->overflow && !h->sliced)
+		return fail (h, SDTGPU_ERANGE, "a record bin overflowed");
 	if (kmerFreq)
 		for (int i = 0; i < 257; i++)
 			kmerFreq[i] = (int64_t) h->h_ctr->freq[i];
@@ -1416,12 +1420,13 @@ int sdtgpu_export_nodes (sdtgpu_t *h, int thrd_num, int sort_by_ordinal, sdtgpu_
 	sdtgpu_node *d_out = nullptr;
 	CK (h, cudaMalloc (&d_out, n * sizeof (sdtgpu_node)));
 	CK (h, cudaMemsetAsync (&h->d_ctr->export_cursor, 0, sizeof (u64), h->stream));
-	const unsigned grid = (unsigned) std::min<u64> ((h->cap + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
+	const u64 slots = iter_slots (h);
+	const unsigned grid = (unsigned) std::min<u64> ((slots + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
 	switch (h->W)
 	{
-	case 1: export_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot1 *> (h->table), h->cap, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
-	case 2: export_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot2 *> (h->table), h->cap, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
-	default: export_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot4 *> (h->table), h->cap, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
+	case 1: export_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot1 *> (h->table), slots, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
+	case 2: export_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot2 *> (h->table), slots, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
+	default: export_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot4 *> (h->table), slots, h->key_words, thrd_num, h->deLowKmer, d_out, n, h->d_ctr); break;
 	}
 	h->all_launches++;
 	cudaError_t e = cudaGetLastError ();
@@ -1498,13 +1503,15 @@ int sdtgpu_table_checksum (sdtgpu_t *h, uint64_t out[4])
 	u64 *d = nullptr;
 	CK (h, cudaMalloc (&d, 4 * sizeof (u64)));
 	CK (h, cudaMemsetAsync (d, 0, 4 * sizeof (u64), h->stream));
-	const unsigned grid = (unsigned) std::min<u64> ((h->cap + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
-	switch (h->W)
-	{
-	case 1: checksum_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot1 *> (h->table), h->cap, d); break;
-	case 2: checksum_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot2 *> (h->table), h->cap, d); break;
-	default: checksum_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot4 *> (h->table), h->cap, d); break;
-	}
+	const u64 slots = iter_slots (h);
+	const unsigned grid = (unsigned) std::min<u64> ((slots + BLOCK - 1) / BLOCK, (u64) h->sm_count * 8);
+	if (grid)
+		switch (h->W)
+		{
+		case 1: checksum_kernel<1><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot1 *> (h->table), slots, d); break;
+		case 2: checksum_kernel<2><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot2 *> (h->table), slots, d); break;
+		default: checksum_kernel<4><<<grid, BLOCK, 0, h->stream>>> (static_cast<const Slot4 *> (h->table), slots, d); break;
+		}
 	h->all_launches++;
 	cudaError_t e = cudaGetLastError ();
 	if (e == cudaSuccess)
@@ -1606,13 +1613,14 @@ int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[
 	return SDTGPU_OK;
 }
 
-int sdtgpu_slice_geometry (const sdtgpu_t *h, uint32_t out[4])
+int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[8])
 {
 	if (!h || !out)
 		return SDTGPU_EINVAL;
 	if (!h->sliced)
 		return SDTGPU_ESTATE;
-	out[0] = h->geom.n_slices; out[1] = h->geom.slice_slots; out[2] = h->geom.P1; out[3] = h->geom.P2;
+	out[0] = h->geom.n_slices; out[1] = h->geom.slice_slots; out[2] = h->geom.m; out[3] = h->geom.w;
+	out[4] = 4 * (uint64_t) h->geom.recw; out[5] = h->n_records; out[6] = h->n_store; out[7] = h->n_retried;
 	return SDTGPU_OK;
 }
 

@@ -22,7 +22,7 @@ assert NODE_DTYPE.itemsize == 56
 F_NKMER = 1
 F_PARTITIONED = 2
 F_SLICED = 4
-PHASES = ("insert", "count", "scatter1", "scatter2", "build", "scan", "-", "-")
+PHASES = ("insert", "emit", "scatter", "-", "build", "scan", "-", "-")
 _ERR = {1: "EINVAL", 2: "ECUDA", 3: "ENOMEM", 4: "ERANGE", 5: "ESTATE"}
 
 
@@ -100,7 +100,7 @@ def library() -> C.CDLL:
     L.sdtgpu_last_ordinals.argtypes = [vp, i32, vp]
     L.sdtgpu_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.sdtgpu_phase_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
-    L.sdtgpu_slice_geometry.argtypes = [vp, C.POINTER(u32)]
+    L.sdtgpu_slice_geometry.argtypes = [vp, C.POINTER(u64)]
     L.sdtpack_open.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p, i32, i32]
     L.sdtpack_next.restype = C.c_int64
     L.sdtpack_next.argtypes = [vp, i32, i32, i32, vp, vp, vp, u64, u32]
@@ -284,9 +284,10 @@ class PregraphGPU:
         return {PHASES[i]: (ms[i], nl[i]) for i in range(6)}
 
     def slice_geometry(self):
-        out = (C.c_uint32 * 4)()
+        out = (C.c_uint64 * 8)()
         self._ck(self.L.sdtgpu_slice_geometry(self.h, out))
-        return dict(n_slices=out[0], slice_slots=out[1], P1=out[2], P2=out[3])
+        return dict(n_slices=out[0], slice_slots=out[1], m=out[2], mmers_per_window=out[3], record_bytes=out[4],
+                    n_records=out[5], n_nodes=out[6], retried_items=out[7])
 
     def kernel_times(self, reset: bool = True):
         """(ms[3], launches[3]) for insert / partition-count / partition-scatter kernels."""

@@ -1,5 +1,5 @@
-"""GPU parity tests of the sliced build (SDTGPU_F_SLICED, csrc/sdt_sliced.cuh): count per slice ->
-two-level record partition -> every table slice built in shared memory.  Same bar as
+"""GPU parity tests of the sliced build (SDTGPU_F_SLICED, csrc/sdt_skm.cuh): reads -> super-k-mer
+records -> one scatter by minimizer slice -> every slice built in shared memory -> compact node store.  Same bar as
 test_gpu_parity.py: bit-exact multiset, counters, kmerFreq and the reference's (set, slot) layout
 against the oracle, through the C ABI."""
 import numpy as np
@@ -20,17 +20,58 @@ def test_sliced_parity_ragged(pkg, oracle, tiny_transcriptome, K, kw, d):
 
 
 @pytest.mark.parametrize("K,kw", [(31, 1), (63, 2), (127, 4)])
-def test_sliced_tiny_slices_many_epochs_and_groups(pkg, oracle, tiny_transcriptome, monkeypatch, K, kw):
-    """64-slot slices (probe wrap-around inside a slice, thousands of slices, ragged fan-out), an
-    epoch budget smaller than one push (every push is merged into the slices built before it) and a
-    level-2 scratch of 1 MB (many partition groups per build)."""
+def test_sliced_tiny_slices_retries_and_record_overflow(pkg, oracle, tiny_transcriptome, monkeypatch, K, kw):
+    """64-slot slice images: tens of thousands of slices, many of which overflow and are retried split
+    by k-mer hash; a record area sized for 1/64 record per window, so the emit kernel runs out of room
+    and the whole read log is emitted again; 8-record chunks in the build kernel."""
     monkeypatch.setenv("SDTGPU_SLICE_SLOTS", "64")
-    monkeypatch.setenv("SDTGPU_SLICE_P2", "7")
-    monkeypatch.setenv("SDTGPU_EPOCH_MB", "1")
-    monkeypatch.setenv("SDTGPU_SLICE_GROUP_MB", "1")
+    monkeypatch.setenv("SDTGPU_SLICE_LOAD", "0.7")
+    monkeypatch.setenv("SDTGPU_SLICE_CHUNK", "8")
+    monkeypatch.setenv("SDTGPU_REC_DIV", "64")
     L = 150 if K > 63 else 100
     reads, lens = make_dataset(pkg, tiny_transcriptome, 6000, L, 23, ragged=20)
-    check_against_oracle(pkg, oracle, reads, lens, K, kw, d=1, batches=5, hint=600_000, sliced=True)
+    ref = oracle.run_hashing(reads, lens, K, kw, 8, 1)
+    g, freq, st = run_gpu(pkg, reads, lens, K, kw, d=1, batches=5, hint=int(ref.nodes * 1.05), sliced=True)
+    try:
+        geo = g.slice_geometry()
+        assert geo["retried_items"] > 0 and geo["n_nodes"] == ref.nodes
+        assert (st.n_instances, st.n_nodes, st.n_removed, st.n_linear) == (ref.instances, ref.nodes, ref.removed, ref.linear)
+        assert np.array_equal(freq, ref.kmerfreq)
+        assert np.array_equal(pkg.nodes_to_records(g.export_nodes(8)), oracle.sorted_multiset(ref.records))
+        rec, info = g.export_kmersets(8)
+        assert np.array_equal(info, ref.set_info) and np.array_equal(rec, ref.records)
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("K,kw,m", [(13, 1, 0), (15, 1, 0), (21, 1, 9), (31, 1, 5), (33, 2, 15), (127, 4, 11)])
+def test_sliced_minimizer_lengths(pkg, oracle, tiny_transcriptome, monkeypatch, K, kw, m):
+    """Short K (few m-mers per window) and explicit minimizer lengths; runs longer than a record holds
+    (m = 5 at K = 31: 27 m-mers per window, long runs; K = 127 on 150-bp reads)."""
+    if m:
+        monkeypatch.setenv("SDTGPU_MINIMIZER", str(m))
+    L = 150 if K > 63 else 100
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 2500, L, 7 + K, ragged=30)
+    check_against_oracle(pkg, oracle, reads, lens, K, kw, d=0, batches=2, hint=400_000, sliced=True)
+
+
+def test_sliced_interleaved_stats_and_pushes(pkg, oracle, tiny_transcriptome):
+    """stats() between pushes builds the store early; later pushes rebuild it from all records."""
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, 100, 41, ragged=10)
+    synth = pkg.synth
+    stride = synth.stride_bytes(100)
+    packed = synth.pack_reads(reads, lens, stride)
+    ref = oracle.run_hashing(reads, lens, 31, 1, 8, 0)
+    half = len(reads) // 2
+    with pkg.PregraphGPU(31, 1, 100, capacity_hint=300_000, sliced=True) as g:
+        g.push_reads(packed[:half], lens[:half], None, n_reads=half, stride_bytes=stride, first_read_ordinal=0)
+        st = g.stats()
+        assert 0 < st.n_nodes < ref.nodes
+        g.push_reads(packed[half:], lens[half:], None, n_reads=len(reads) - half, stride_bytes=stride, first_read_ordinal=half)
+        freq, st = g.finalize(0)
+        assert (st.n_instances, st.n_nodes, st.n_linear) == (ref.instances, ref.nodes, ref.linear)
+        rec, info = g.export_kmersets(8)
+        assert np.array_equal(rec, ref.records)
 
 
 def test_sliced_uniform_and_n_kmer(pkg, oracle, tiny_transcriptome):
@@ -86,8 +127,6 @@ def test_sliced_reset_and_reuse(pkg, oracle, tiny_transcriptome):
     packed = synth.pack_reads(reads, lens, stride)
     ref = oracle.run_hashing(reads, lens, 31, 1, 8, 0)
     with pkg.PregraphGPU(31, 1, 100, capacity_hint=300_000, sliced=True) as g:
-        geo = g.slice_geometry()
-        assert geo["n_slices"] * geo["slice_slots"] == g.stats().capacity
         for it in range(3):
             g.reset()
             g.push_reads(packed, lens, None, n_reads=len(reads), stride_bytes=stride)
