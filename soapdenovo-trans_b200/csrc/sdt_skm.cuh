@@ -218,7 +218,8 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 					const u32 n = x - (v - 1) + 1, j0 = j + 1 - n;
 					const u32 nrec = (n + NMAX - 1) / NMAX;
 					const u32 pos = atomicAdd (&s_count, nrec);
-					for (u32 c = 0; c < nrec; c++)
+					mhs[pos] = r | (j0 << 8) | ((min (NMAX, n) - 1) << 24);
+					for (u32 c = 1; c < nrec; c++)	// runs longer than a record holds: rare
 						mhs[pos + c] = r | ((j0 + c * NMAX) << 8) | ((min (NMAX, n - c * NMAX) - 1) << 24);
 				}
 			}
@@ -400,7 +401,7 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 {
 	typedef typename SlotOf<W>::type S_t;
 	extern __shared__ __align__(16) u32 smem[];
-	__shared__ u32 s_full, s_tot, s_warp[BD_NT / 32], s_wcnt[MAX_SWEEPS * (BD_NT / 32)];
+	__shared__ u32 s_full, s_tot, s_next, s_warp[BD_NT / 32], s_wcnt[MAX_SWEEPS * (BD_NT / 32)];
 	__shared__ unsigned long long s_base;
 	const u32 S = g.slice_slots, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const u32 n_sweeps = (S + BD_NT - 1) / BD_NT;
@@ -443,16 +444,19 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 		u32 created = 0;
 		u64 mine = 0;	// instances this thread applied
 		for (u64 c0 = r0; c0 < r1; c0 += g.chunk)
-		{	// g.chunk <= BD_NT records at a time: flatten their windows over the whole block
+		{	// g.chunk <= 2 * BD_NT records at a time; their windows are flattened and handed out to the
+			// warps 32 at a time from a shared counter
 			const u32 nrec = (u32) min ((u64) g.chunk, r1 - c0);
 			const u32 *recs = rec2 + c0 * g.recw;
-			u32 nwin = 0;
-			if (tid < nrec)
-			{
-				const u32 h1 = __ldg (recs + (size_t) tid * g.recw + 1);
-				nwin = ((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1;	// an N-run is applied in one go
-			}
-			u32 incl = nwin;
+			u32 nw[2] = { 0, 0 };
+#pragma unroll
+			for (int q = 0; q < 2; q++)
+				if (2 * tid + q < nrec)
+				{
+					const u32 h1 = __ldg (recs + (size_t) (2 * tid + q) * g.recw + 1);
+					nw[q] = ((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1;	// an N-run is applied in one go
+				}
+			u32 incl = nw[0] + nw[1];
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1)
 			{
@@ -462,6 +466,8 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 			}
 			if (lane == 31)
 				s_warp[wid] = incl;
+			if (tid == 0)
+				s_next = 0;
 			__syncthreads ();
 			u32 lower = 0, total = 0;
 			for (u32 q = 0; q < BD_NT / 32; q++)
@@ -471,34 +477,51 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 					lower += v;
 				total += v;
 			}
-			if (tid < nrec)
-				pre[tid] = lower + incl - nwin;
+			const u32 excl = lower + incl - nw[0] - nw[1];
+			if (2 * tid < nrec)
+				pre[2 * tid] = excl;
+			if (2 * tid + 1 < nrec)
+				pre[2 * tid + 1] = excl + nw[0];
 			if (tid == 0)
 				pre[nrec] = total;
 			__syncthreads ();
-			// same trip count for every lane and a warp barrier per trip: lanes that finish a probe
-			// sequence early must not run ahead into the next window on their own
-			for (u32 w0 = 0; w0 < total; w0 += BD_NT)
+			const u32 nblk = (total + 31) >> 5;
+			for (;;)
 			{
-				const u32 wi = w0 + tid;
-				if (wi < total && !*reinterpret_cast<volatile u32 *> (&s_full))
+				u32 blk = 0;
+				if (lane == 0)
+					blk = atomicAdd (&s_next, 1u);
+				blk = __shfl_sync (0xFFFFFFFFu, blk, 0);
+				if (blk >= nblk)
+					break;
+				const u32 wb = blk << 5;
+				u32 lo = 0, hi = nrec - 1;	// record of window wb: largest x with pre[x] <= wb (the same for every lane)
+				while (lo < hi)
 				{
-					u32 lo = 0, hi = nrec - 1;	// largest x with pre[x] <= wi
-					while (lo < hi)
-					{
-						const u32 mid = (lo + hi + 1) >> 1;
-						if (pre[mid] <= wi)
-							lo = mid;
-						else
-							hi = mid - 1;
-					}
-					const u32 tw = wi - pre[lo];
-					const u32 *rec = recs + (size_t) lo * g.recw;
+					const u32 mid = (lo + hi + 1) >> 1;
+					if (pre[mid] <= wb)
+						lo = mid;
+					else
+						hi = mid - 1;
+				}
+				// record boundaries inside the block as a bit mask: lane l looks at the end of record lo + l
+				const u32 e = lo + 1 + lane <= nrec ? pre[lo + 1 + lane] : 0xFFFFFFFFu;
+				const u32 B = __reduce_or_sync (0xFFFFFFFFu, e - wb < 32u ? 1u << (e - wb) : 0u);
+				const u32 wi = wb + lane;
+				const bool valid = wi < total && !*reinterpret_cast<volatile u32 *> (&s_full);
+				Key<W> key;
+				u32 left = 4, right = 4, add = 1, nrun = 0, idx = S;
+				u64 ord = 0, h = 0;
+				bool wanted = false;
+				if (valid)
+				{
+					const u32 x = lo + __popc (B & ((2u << lane) - 1u));
+					const u32 tw = wi - pre[x];
+					const u32 *rec = recs + (size_t) x * g.recw;
 					const u32 h1 = __ldg (rec + 1);
-					const u64 ord0 = (u64) __ldg (rec) | ((u64) (h1 & 0xFFu) << 32);
-					const u32 n = ((h1 >> 8) & 63u) + 1, has_left = (h1 >> 14) & 1u, nrun = (h1 >> 15) & 1u, nb = h1 >> 16;
-					Key<W> key;
-					u32 left = 4, right = 4, add = 1;
+					ord = ((u64) __ldg (rec) | ((u64) (h1 & 0xFFu) << 32)) + tw;
+					const u32 n = ((h1 >> 8) & 63u) + 1, has_left = (h1 >> 14) & 1u, nb = h1 >> 16;
+					nrun = (h1 >> 15) & 1u;
 					if (nrun)
 					{	// n instances of key 0 without links: they only feed count (and the ordinal)
 #pragma unroll
@@ -508,31 +531,29 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 					}
 					else
 						chop_window<W, false> (rec + SKM_HDR, nullptr, (int) nb, (int) (has_left + tw), K, key, left, right);
-					const u64 h = key_hash<W> (key);
-					if (wk.R == 1 || (u32) (h >> 32) % wk.R == wk.r)
-					{
-						const u32 idx = skm_find<W> (im, S, key, home_of (h, S), created);
-						if (idx == S)
-							s_full = 1;
-						else
-						{
-							const u32 c = left * 5 + right;
-							u32 *cw = im.cell + (c >> 1) * S + idx;
-							const u32 sh = 16 * (c & 1);
-							if (nrun || ((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
-								atomicAdd (im.extra + idx, add);
-							else
-								atomicAdd (cw, 1u << sh);
-							const u64 ord = ord0 + tw;
-							if (ord < *reinterpret_cast<volatile u64 *> (im.ord + idx))
-								atomicMin (im.ord + idx, ord);
-							mine += add;
-						}
-					}
+					h = key_hash<W> (key);
+					wanted = wk.R == 1 || (u32) (h >> 32) % wk.R == wk.r;
+					if (wanted)
+						idx = skm_find<W> (im, S, key, home_of (h, S), created);
 				}
-				__syncwarp ();
+				__syncwarp ();	// probe sequences differ in length: meet again before the update
+				if (idx < S)
+				{
+					const u32 c = left * 5 + right;
+					u32 *cw = im.cell + (c >> 1) * S + idx;
+					const u32 sh = 16 * (c & 1);
+					if (nrun || ((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
+						atomicAdd (im.extra + idx, add);
+					else
+						atomicAdd (cw, 1u << sh);
+					if (ord < *reinterpret_cast<volatile u64 *> (im.ord + idx))
+						atomicMin (im.ord + idx, ord);
+					mine += add;
+				}
+				else if (wanted)
+					s_full = 1;
 			}
-			__syncthreads ();	// pre[] and s_warp[] are rewritten by the next chunk
+			__syncthreads ();	// pre[], s_warp[] and s_next are rewritten by the next chunk
 		}
 		// ---- nodes of this item: rank the occupied slots, reserve space in the store, compact, clean
 		const bool full = s_full != 0;

@@ -682,7 +682,7 @@ int skm_setup (sdtgpu *h, u64 hint)
 		return fail (h, SDTGPU_EINVAL, "the sliced build needs capacity_hint (expected distinct k-mers)");
 	SkmGeom g;
 	// default: what fits one CTA per SM (227 KB): 74 / 86 / 102 bytes per slot for 1- / 2- / 4-word keys
-	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 2976u : (h->W == 2 ? 2560u : 2176u)) & ~1u;
+	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 2912u : (h->W == 2 ? 2528u : 2144u)) & ~1u;
 	if (g.slice_slots < 32 || g.slice_slots > MAX_SWEEPS * BD_NT)
 		return fail (h, SDTGPU_EINVAL, "SDTGPU_SLICE_SLOTS out of range");
 	double load = 0.5;
@@ -701,7 +701,7 @@ int skm_setup (sdtgpu *h, u64 hint)
 	g.recw = h->W == 1 ? 8 : (h->W == 2 ? 12 : 16);
 	g.npos = (u32) h->max_read_len - g.m + 1;
 	g.tile_reads = std::max (4u, std::min (64u, (8192u / g.npos) & ~3u));
-	g.chunk = std::min<u32> (env_u32 ("SDTGPU_SLICE_CHUNK", BD_NT), BD_NT);
+	g.chunk = std::min<u32> (env_u32 ("SDTGPU_SLICE_CHUNK", 2 * BD_NT), 2 * BD_NT);
 	g.slice_a = slice_of_min_host (mmer_hash (0), g.n_slices);
 	if (g.npos * g.tile_reads > 60000 || h->max_read_len > 60000)
 		return fail (h, SDTGPU_ERANGE, "max_read_len too large for the sliced build");

@@ -21,7 +21,7 @@ f = lambda d, k: float(d.get(k) or 0)
 tot = sum(f(d, "Instructions Executed") for d in data) or 1
 tots = sum(f(d, "# Samples") for d in data) or 1
 print("total warp instructions %.4g, samples %d" % (tot, tots))
-for d in sorted(data, key=lambda d: -f(d, "# Samples"))[:n]:
+for d in sorted(data, key=lambda d: -f(d, sys.argv[5] if len(sys.argv) > 5 else "# Samples"))[:n]:
     ie = f(d, "Instructions Executed") or 1
     print("%5.1f%% smp %5.1f%% inst  thr %4.1f | %s:%s %s" % (100 * f(d, "# Samples") / tots, 100 * f(d, "Instructions Executed") / tot,
           f(d, "Thread Instructions Executed") / ie, d["file"], d["Line No"], d["Source"].strip()[:95]))
