@@ -121,6 +121,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--pairs", type=int, default=0, help="override the config's read-pair count (testing)")
+    ap.add_argument("--transcripts", type=int, default=0, help="override the config's transcript count (testing: keeps the coverage of the full workload at a smaller size)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -145,6 +146,8 @@ def main():
     cfg_d = dict(synth.CONFIGS[args.config])
     if args.pairs:
         cfg_d["n_pairs"] = args.pairs
+    if args.transcripts:
+        cfg_d["n_transcripts"] = args.transcripts
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

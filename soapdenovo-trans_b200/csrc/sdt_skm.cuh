@@ -39,13 +39,13 @@ struct SkmGeom
 	u32 slice_a;		// slice of the all-A k-mer (key 0): where the -n N-windows go
 	u32 tile_reads;		// reads per shared-memory tile of skm_emit_kernel
 	u32 npos;		// m-mer positions per read at most (max_read_len - m + 1)
-	u32 chunk;		// records per shared-memory chunk of skm_build_kernel
 };
 
 static constexpr u32 SKM_HDR = 3;		// header words: ord low | ord high, n-1, flags, bases | slice
 static constexpr u32 SKM_NFLAG = 0x80000000u;	// in the per-window slice array: window contains an N (-n)
 static constexpr int EMIT_NT = 256;
 static constexpr int SCAT_NT = 256;
+static constexpr u32 BD_CHUNK = 2 * BD_NT;	// records per pass of skm_build_kernel
 
 __host__ __device__ __forceinline__ u32 fmix32 (u32 h)
 {
@@ -313,6 +313,7 @@ skm_scatter_kernel (const u32 *rec0, const unsigned long long *rec_count, u32 re
 // A cell that gets near 16 bits stops counting and the slot's 32-bit `extra` takes over (it only
 // feeds count: a saturated cell already pins its row and column at 63).
 static constexpr int CELL_WORDS = 13;	// 25 16-bit cells, two per word
+static constexpr u32 SKM_MAX_TRIES = 128;
 static constexpr u32 CELL_STOP = 0xF000u;	// + one in-flight increment per thread of the CTA stays below 2^16
 
 template <int W> struct SkmImage
@@ -329,14 +330,19 @@ __host__ __device__ inline size_t skm_image_bytes (int W, u32 S)
 	return (size_t) S * (8 * W + 8 + 4 * CELL_WORDS + 4 + (W > 1 ? 4 : 0));
 }
 __host__ __device__ inline size_t skm_build_smem (int W, const SkmGeom &g)
-{	// image + window prefix of a chunk + list of occupied slots
-	return skm_image_bytes (W, g.slice_slots) + 4 * ((size_t) g.chunk + 4) + 2 * (size_t) g.slice_slots + 16;
+{	// image + window prefix of a chunk of records
+	return skm_image_bytes (W, g.slice_slots) + 4 * ((size_t) BD_CHUNK + 4);
 }
 
+// Double hashing (S is prime, 1 <= step < S): in shared memory a probe costs the same wherever it
+// lands, and a warp step lasts as long as its longest probe sequence — at half load the longest of a
+// few unsuccessful searches is ~4 probes here against ~13 with linear probing.
 template <int W>
-__device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key<W> &key, u32 idx, u32 &created)
+__device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key<W> &key, u32 idx, u32 step)
 {
-	for (u32 tries = 0; tries < S;)
+	// a probe sequence that finds SKM_MAX_TRIES slots taken gives up: the image is as good as full
+	// (0.9^128 = 1e-6), and the caller has the work item retried split by k-mer hash
+	for (u32 tries = 0; tries < min (S, SKM_MAX_TRIES);)
 	{
 		if constexpr (W == 1)
 		{
@@ -347,10 +353,7 @@ __device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key
 			{
 				k = atomicCAS (im.key + idx, EMPTY64, key.w[0]);
 				if (k == EMPTY64)
-				{
-					created++;
 					return idx;
-				}
 				if (k == key.w[0])
 					return idx;
 			}
@@ -367,7 +370,6 @@ __device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key
 						*reinterpret_cast<volatile u64 *> (im.key + (size_t) idx * W + q) = key.w[q];
 					__threadfence_block ();
 					*reinterpret_cast<volatile u32 *> (im.state + idx) = 2u;
-					created++;
 					return idx;
 				}
 				continue;	// lost the race: look at the same slot again
@@ -381,8 +383,9 @@ __device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key
 			if (eq)
 				return idx;
 		}
-		if (++idx == S)
-			idx = 0;
+		idx += step;
+		if (idx >= S)
+			idx -= S;
 		tries++;
 	}
 	return S;
@@ -390,32 +393,171 @@ __device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key
 
 struct SkmWork { u32 slice, r, R; };	// keys of `slice` with sub-hash % R == r
 
-// One CTA per work item.  items == nullptr: item i is (slice i, 0, 1).
 static constexpr u32 MAX_SWEEPS = 4;	// slice_slots <= MAX_SWEEPS * BD_NT
 
+// Rolling state of one record: what nextKmer / reverseComplement (kmer.c:209, 653) compute per base,
+// kept incrementally — the forward k-mer takes the next base at the bottom, its reverse complement
+// takes the complement at the top — so a window costs a handful of shifts instead of an extraction.
+template <int W> struct SkmRoll
+{
+	static constexpr int PW = W == 1 ? 1 : 2;	// 64-bit words of bases still to come (NMAX bases at most)
+	Key<W> f, rc;
+	u64 pend[PW];	// the bases after the current window, first one in the top bits
+	u64 ord;	// instance ordinal of the current window
+	u32 left;	// base before the current window (4: none)
+	u32 n, t;	// windows of the record, current window
+	u32 has_right;	// the last window has a base after it
+	u32 add;	// instances per step (an N-run applies all of its windows at once)
+};
+
+// bits [2 * b, 2 * b + 64) of the record's bases (words rd[0 .. last], first base in the top bits);
+// words past `last` hold nothing a window can ask for and are not read
+__device__ __forceinline__ u64 bases64 (const u32 *rd, u32 b, u32 last)
+{
+	const u32 q = b >> 4, r = 2 * (b & 15);
+	const u32 w0 = rd[min (q, last)], w1 = rd[min (q + 1, last)], w2 = rd[min (q + 2, last)];
+	return ((u64) __funnelshift_l (w1, w0, r) << 32) | __funnelshift_l (w2, w1, r);
+}
+
+// rolling state at window tw of a record
+template <int W>
+__device__ __forceinline__ void skm_roll_init (SkmRoll<W> &s, const u32 *rec, int K, u32 tw)
+{
+	constexpr u32 LAST = SkmRec<W>::WORDS - SKM_HDR - 1;
+	const uint4 hd = __ldg (reinterpret_cast<const uint4 *> (rec));	// ord low | header | slice | first bases
+	const u32 h1 = hd.y;
+	const u32 n = ((h1 >> 8) & 63u) + 1, has_left = (h1 >> 14) & 1u, nrun = (h1 >> 15) & 1u, nb = h1 >> 16;
+	s.ord = ((u64) hd.x | ((u64) (h1 & 0xFFu) << 32)) + tw;
+	s.t = tw;
+	if (nrun)
+	{	// n instances of key 0 without links: they only feed count (and the ordinal); one step (tw = 0)
+#pragma unroll
+		for (int q = 0; q < W; q++)
+		{
+			s.f.w[q] = 0;
+			s.rc.w[q] = ~0ull;
+		}
+#pragma unroll
+		for (int q = 0; q < SkmRoll<W>::PW; q++)
+			s.pend[q] = 0;
+		s.left = 4;
+		s.n = 1;
+		s.has_right = 0;
+		s.add = n;
+		return;
+	}
+	const u32 *rd = rec + SKM_HDR;
+	const u32 j = has_left + tw;	// first base of the window
+	const u32 p0 = j + (u32) K;	// first base after it
+	extract_fwd<W> (rd, (int) p0, K, s.f);
+	revcomp<W> (s.f, K, s.rc);
+	s.left = j ? base_at (rd, (int) j - 1) : 4u;
+	s.pend[0] = bases64 (rd, p0, LAST);
+	if constexpr (W > 1)
+		s.pend[1] = n - tw > 32 ? bases64 (rd, p0 + 32, LAST) : 0ull;	// only long records reach into the second word
+	s.n = n;
+	s.has_right = nb - has_left - (u32) K - (n - 1);
+	s.add = 1;
+}
+
+// the window's canonical key and its links in the stored orientation (chopKmer4read, prlHashReads.c:215-230, 275-308)
+template <int W>
+__device__ __forceinline__ void skm_roll_window (const SkmRoll<W> &s, Key<W> &key, u32 &left, u32 &right)
+{
+	const u32 nb = (u32) (s.pend[0] >> 62);
+	const u32 next = (s.t + 1 == s.n && !s.has_right) ? 4u : nb;
+	if (key_less<W> (s.f, s.rc))
+	{
+		key = s.f;
+		left = s.left;
+		right = next;
+	}
+	else
+	{
+		key = s.rc;
+		left = next < 4 ? (next ^ 2u) : 4u;
+		right = s.left < 4 ? (s.left ^ 2u) : 4u;
+	}
+}
+
+// one base forward.  top = 2 * (K - 1): bit position of the k-mer's first base
+template <int W>
+__device__ __forceinline__ void skm_roll_step (SkmRoll<W> &s, const Key<W> &mask, int top)
+{
+	const u64 nb = s.pend[0] >> 62;
+	const int tw = W - 1 - (top >> 6), ts = top & 63;	// word and shift of the first base
+#pragma unroll
+	for (int q = 0; q < W; q++)
+		if (q == tw)
+			s.left = (u32) (s.f.w[q] >> ts) & 3u;
+#pragma unroll
+	for (int q = 0; q < W; q++)
+		s.f.w[q] = ((s.f.w[q] << 2) | (q + 1 < W ? s.f.w[q + 1] >> 62 : nb)) & mask.w[q];
+#pragma unroll
+	for (int q = W - 1; q >= 0; q--)
+	{
+		u64 v = s.rc.w[q] >> 2;
+		if (q > 0)
+			v |= s.rc.w[q - 1] << 62;
+		if (q == tw)
+			v |= (nb ^ 2ull) << ts;
+		s.rc.w[q] = v;
+	}
+	if constexpr (W == 1)
+		s.pend[0] <<= 2;
+	else
+	{
+		s.pend[0] = (s.pend[0] << 2) | (s.pend[1] >> 62);
+		s.pend[1] <<= 2;
+	}
+	s.t++;
+	s.ord++;
+}
+
+// One CTA per work item, items handed out through *item_cursor.  items == nullptr: item i is (slice i, 0, 1).
+//
+// Records -> image: the windows of up to BD_CHUNK records are flattened and cut into BD_NT equal runs,
+// one per thread (a slice holds about one record per thread, of 1 to 32 windows: whole records per
+// lane leave most lanes waiting for the longest).  A thread finds the record of its first window
+// (binary search in the window prefix), sets up the rolling state there (one 16-byte header load +
+// one extraction) and rolls on, re-seating itself when it crosses into the next record.  Instances
+// that meet in the same (slot, cell) within a warp step are added by one lane for all.
+// Image -> node store: every warp owns a contiguous range of slots; occupied slots are ranked by
+// ballot + a scan of the 32 warp totals, thread 0 reserves the item's space in the store, and the
+// nodes go out in slot order, 32 bytes per lane, consecutive lanes to consecutive nodes.
 template <int W>
 __global__ void __launch_bounds__ (BD_NT, 1)
 skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long long *node_cursor, SkmGeom g, int K,
-		  const u32 *rec2, const u64 *off, const SkmWork *items, u32 n_items,
+		  const u32 *rec2, const u64 *off, const SkmWork *items, u32 n_items, unsigned long long *item_cursor,
 		  SkmWork *failed, u32 *n_failed, u32 max_failed, Counters *ctr)
 {
 	typedef typename SlotOf<W>::type S_t;
 	extern __shared__ __align__(16) u32 smem[];
-	__shared__ u32 s_full, s_tot, s_next, s_warp[BD_NT / 32], s_wcnt[MAX_SWEEPS * (BD_NT / 32)];
+	__shared__ u32 s_full, s_item[2], s_warp[BD_NT / 32];
 	__shared__ unsigned long long s_base;
 	const u32 S = g.slice_slots, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const u32 n_sweeps = (S + BD_NT - 1) / BD_NT;
+	const u32 spw = ((S + BD_NT - 1) / BD_NT) * 32;	// slots per warp in the compaction (a multiple of 32)
 	SkmImage<W> im;
 	im.key = reinterpret_cast<u64 *> (smem);
 	im.ord = im.key + (size_t) S * W;
 	im.cell = reinterpret_cast<u32 *> (im.ord + S);
 	im.extra = im.cell + (size_t) S * CELL_WORDS;
 	im.state = im.extra + S;
-	u32 *pre = im.extra + S + (W > 1 ? S : 0);	// [chunk + 1]: exclusive prefix of the windows of a chunk's records
-	unsigned short *list = reinterpret_cast<unsigned short *> (pre + g.chunk + 2);	// [S]: occupied slots in rank order
-	u64 nodes = 0;	// thread 0 only
+	u32 *pre = im.extra + S + (W > 1 ? S : 0);	// [BD_CHUNK + 1]: exclusive prefix of the windows of a chunk's records
+	Key<W> kmask;	// the low 2K bits
+#pragma unroll
+	for (int q = 0; q < W; q++)
+	{
+		const int bits = 2 * K - 64 * (W - 1 - q);
+		kmask.w[q] = bits >= 64 ? ~0ull : (bits > 0 ? (1ull << bits) - 1 : 0ull);
+	}
+	const int top = 2 * (K - 1);
+	u64 nodes = 0, inst = 0;	// nodes: thread 0 only; inst: instances this thread applied (items that were written)
 	if (tid == 0)
+	{
 		s_full = 0;
+		s_item[0] = (u32) atomicAdd (item_cursor, 1ull);
+	}
 	for (u32 i = tid; i < S; i += BD_NT)
 	{
 #pragma unroll
@@ -429,8 +571,14 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 	for (u32 i = tid; i < S * CELL_WORDS; i += BD_NT)
 		im.cell[i] = 0u;
 	__syncthreads ();
-	for (u32 it = blockIdx.x; it < n_items; it += gridDim.x)
+	for (u32 round = 0;; round++)
 	{
+		const u32 it = s_item[round & 1];
+		if (it >= n_items)
+			break;
+		u32 next_item = 0;
+		if (tid == 0)	// the next item is asked for now and looked at after this one: the round trip is hidden
+			next_item = (u32) atomicAdd (item_cursor, 1ull);
 		SkmWork wk;
 		if (items)
 			wk = items[it];
@@ -441,12 +589,11 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 			wk.R = 1;
 		}
 		const u64 r0 = off[wk.slice], r1 = off[wk.slice + 1];
-		u32 created = 0;
-		u64 mine = 0;	// instances this thread applied
-		for (u64 c0 = r0; c0 < r1; c0 += g.chunk)
-		{	// g.chunk <= 2 * BD_NT records at a time; their windows are flattened and handed out to the
-			// warps 32 at a time from a shared counter
-			const u32 nrec = (u32) min ((u64) g.chunk, r1 - c0);
+		u64 mine = 0;
+		for (u64 c0 = r0; c0 < r1 && !*reinterpret_cast<volatile u32 *> (&s_full); c0 += BD_CHUNK)
+		{	// up to BD_CHUNK records at a time: their windows are flattened (exclusive prefix in pre[]) and
+			// cut into BD_NT equal runs, one per thread
+			const u32 nrec = (u32) min ((u64) BD_CHUNK, r1 - c0);
 			const u32 *recs = rec2 + c0 * g.recw;
 			u32 nw[2] = { 0, 0 };
 #pragma unroll
@@ -466,124 +613,125 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 			}
 			if (lane == 31)
 				s_warp[wid] = incl;
-			if (tid == 0)
-				s_next = 0;
 			__syncthreads ();
-			u32 lower = 0, total = 0;
-			for (u32 q = 0; q < BD_NT / 32; q++)
+			u32 total;
 			{
-				const u32 v = s_warp[q];
-				if (q < wid)
-					lower += v;
-				total += v;
+				const u32 c = s_warp[lane];
+				u32 in2 = c;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1)
+				{
+					const u32 y = __shfl_up_sync (0xFFFFFFFFu, in2, d);
+					if (lane >= (u32) d)
+						in2 += y;
+				}
+				const u32 lower = __shfl_sync (0xFFFFFFFFu, in2 - c, wid);
+				total = __shfl_sync (0xFFFFFFFFu, in2, 31);
+				const u32 excl = lower + incl - nw[0] - nw[1];
+				if (2 * tid < nrec)
+					pre[2 * tid] = excl;
+				if (2 * tid + 1 < nrec)
+					pre[2 * tid + 1] = excl + nw[0];
+				if (tid == 0)
+					pre[nrec] = total;
 			}
-			const u32 excl = lower + incl - nw[0] - nw[1];
-			if (2 * tid < nrec)
-				pre[2 * tid] = excl;
-			if (2 * tid + 1 < nrec)
-				pre[2 * tid + 1] = excl + nw[0];
-			if (tid == 0)
-				pre[nrec] = total;
 			__syncthreads ();
-			const u32 nblk = (total + 31) >> 5;
-			for (;;)
+			const u32 per = (total + BD_NT - 1) / BD_NT;	// windows per thread
+			const u32 w0 = tid * per, w1 = min (total, w0 + per);
+			SkmRoll<W> st;
+			st.n = st.t = 0;
+			u32 x = 0;
+			if (w0 < w1)
 			{
-				u32 blk = 0;
-				if (lane == 0)
-					blk = atomicAdd (&s_next, 1u);
-				blk = __shfl_sync (0xFFFFFFFFu, blk, 0);
-				if (blk >= nblk)
-					break;
-				const u32 wb = blk << 5;
-				u32 lo = 0, hi = nrec - 1;	// record of window wb: largest x with pre[x] <= wb (the same for every lane)
+				u32 lo = 0, hi = nrec - 1;	// record of window w0: largest x with pre[x] <= w0
 				while (lo < hi)
 				{
 					const u32 mid = (lo + hi + 1) >> 1;
-					if (pre[mid] <= wb)
+					if (pre[mid] <= w0)
 						lo = mid;
 					else
 						hi = mid - 1;
 				}
-				// record boundaries inside the block as a bit mask: lane l looks at the end of record lo + l
-				const u32 e = lo + 1 + lane <= nrec ? pre[lo + 1 + lane] : 0xFFFFFFFFu;
-				const u32 B = __reduce_or_sync (0xFFFFFFFFu, e - wb < 32u ? 1u << (e - wb) : 0u);
-				const u32 wi = wb + lane;
-				const bool valid = wi < total && !*reinterpret_cast<volatile u32 *> (&s_full);
-				Key<W> key;
-				u32 left = 4, right = 4, add = 1, nrun = 0, idx = S;
-				u64 ord = 0, h = 0;
+				x = lo;
+				skm_roll_init<W> (st, recs + (size_t) x * g.recw, K, w0 - pre[x]);
+			}
+			for (u32 t = 0; t < per && !*reinterpret_cast<volatile u32 *> (&s_full); t++)
+			{
+				const bool act = w0 + t < w1;
+				if (act && st.t == st.n)	// on to the next record
+					skm_roll_init<W> (st, recs + (size_t) ++x * g.recw, K, 0);
+				u32 idx = S, cellid = 0;
 				bool wanted = false;
-				if (valid)
+				if (act)
 				{
-					const u32 x = lo + __popc (B & ((2u << lane) - 1u));
-					const u32 tw = wi - pre[x];
-					const u32 *rec = recs + (size_t) x * g.recw;
-					const u32 h1 = __ldg (rec + 1);
-					ord = ((u64) __ldg (rec) | ((u64) (h1 & 0xFFu) << 32)) + tw;
-					const u32 n = ((h1 >> 8) & 63u) + 1, has_left = (h1 >> 14) & 1u, nb = h1 >> 16;
-					nrun = (h1 >> 15) & 1u;
-					if (nrun)
-					{	// n instances of key 0 without links: they only feed count (and the ordinal)
-#pragma unroll
-						for (int q = 0; q < W; q++)
-							key.w[q] = 0;
-						add = n;
-					}
-					else
-						chop_window<W, false> (rec + SKM_HDR, nullptr, (int) nb, (int) (has_left + tw), K, key, left, right);
-					h = key_hash<W> (key);
+					Key<W> key;
+					u32 left, right;
+					skm_roll_window<W> (st, key, left, right);
+					const u64 h = key_hash<W> (key);
 					wanted = wk.R == 1 || (u32) (h >> 32) % wk.R == wk.r;
 					if (wanted)
-						idx = skm_find<W> (im, S, key, home_of (h, S), created);
+						idx = skm_find<W> (im, S, key, home_of (h, S), 1u + __umulhi ((u32) (h >> 32), S - 1));
+					cellid = left * 5 + right;
 				}
 				__syncwarp ();	// probe sequences differ in length: meet again before the update
-				if (idx < S)
+				const bool hit = idx < S;
+				// lanes of this step that meet in the same (slot, cell): the lowest one adds for all
+				const bool one = hit && st.add == 1;
+				const u32 peers = __match_any_sync (0xFFFFFFFFu, one ? idx * 32 + cellid : 0xFFFFFFFFu - lane);
+				if (hit)
 				{
-					const u32 c = left * 5 + right;
-					u32 *cw = im.cell + (c >> 1) * S + idx;
-					const u32 sh = 16 * (c & 1);
-					if (nrun || ((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
-						atomicAdd (im.extra + idx, add);
-					else
-						atomicAdd (cw, 1u << sh);
-					if (ord < *reinterpret_cast<volatile u64 *> (im.ord + idx))
-						atomicMin (im.ord + idx, ord);
-					mine += add;
+					if (!one)
+						atomicAdd (im.extra + idx, st.add);	// an N-run: all of its windows at once
+					else if ((u32) (__ffs (peers) - 1) == lane)
+					{
+						const u32 cnt = __popc (peers);
+						u32 *cw = im.cell + (cellid >> 1) * S + idx;
+						const u32 sh = 16 * (cellid & 1);
+						if (((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
+							atomicAdd (im.extra + idx, cnt);
+						else
+							atomicAdd (cw, cnt << sh);
+					}
+					if (st.ord < *reinterpret_cast<volatile u64 *> (im.ord + idx))
+						atomicMin (im.ord + idx, st.ord);
+					mine += st.add;
 				}
 				else if (wanted)
 					s_full = 1;
+				if (act)
+					skm_roll_step<W> (st, kmask, top);
 			}
-			__syncthreads ();	// pre[], s_warp[] and s_next are rewritten by the next chunk
+			__syncthreads ();	// pre[] and s_warp[] are rewritten by the next chunk
 		}
-		// ---- nodes of this item: rank the occupied slots, reserve space in the store, compact, clean
+		// ---- image -> node store
 		const bool full = s_full != 0;
-		for (u32 sw = 0; sw < n_sweeps; sw++)
-		{
-			const u32 i = sw * BD_NT + tid;
-			bool occ = false;
-			if (i < S)
-			{
-				if constexpr (W == 1)
-					occ = im.key[i] != EMPTY64;
-				else
-					occ = im.state[i] == 2u;
-			}
-			const u32 bal = __ballot_sync (0xFFFFFFFFu, occ);
-			if (lane == 0)
-				s_wcnt[sw * (BD_NT / 32) + wid] = __popc (bal);
-		}
-		__syncthreads ();
-		if (wid == 0)
-		{	// exclusive scan of the (sweep, warp) counts; thread 0 reserves the item's space in the store
-			const u32 e_n = n_sweeps * (BD_NT / 32);	// <= 128: four entries per lane
-			u32 c[4], sum = 0;
+		u32 bal[MAX_SWEEPS], cnt = 0;
 #pragma unroll
-			for (int q = 0; q < 4; q++)
+		for (u32 sw = 0; sw < MAX_SWEEPS; sw++)
+		{
+			bal[sw] = 0;
+			if (sw * 32 < spw)
 			{
-				c[q] = 4 * lane + q < e_n ? s_wcnt[4 * lane + q] : 0;
-				sum += c[q];
+				const u32 i = wid * spw + sw * 32 + lane;
+				bool occ = false;
+				if (i < S)
+				{
+					if constexpr (W == 1)
+						occ = im.key[i] != EMPTY64;
+					else
+						occ = im.state[i] == 2u;
+				}
+				bal[sw] = __ballot_sync (0xFFFFFFFFu, occ);
+				cnt += __popc (bal[sw]);
 			}
-			u32 incl = sum;
+		}
+		if (lane == 0)
+			s_warp[wid] = cnt;
+		__syncthreads ();
+		u32 run, tot;
+		{	// every warp scans the 32 warp totals
+			const u32 c = s_warp[lane];
+			u32 incl = c;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1)
 			{
@@ -591,132 +739,118 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 				if (lane >= (u32) d)
 					incl += y;
 			}
-			u32 run = incl - sum;
-#pragma unroll
-			for (int q = 0; q < 4; q++)
-			{
-				if (4 * lane + q < e_n)
-					s_wcnt[4 * lane + q] = run;
-				run += c[q];
-			}
-			const u32 tot = __shfl_sync (0xFFFFFFFFu, incl, 31);
-			if (lane == 0)
-			{
-				unsigned long long b = 0;
-				bool fail = full;
-				if (!fail && tot)
-				{
-					b = atomicAdd (node_cursor, (unsigned long long) tot);
-					if (b + tot > store_cap)
-					{
-						fail = true;
-						atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 4ull);	// node store exhausted
-					}
-				}
-				if (full)
-				{	// retried later, split by k-mer hash
-					const u32 f = atomicAdd (n_failed, 1u);
-					if (f < max_failed)
-						failed[f] = wk;
-					else
-						atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 8ull);
-				}
-				s_base = fail ? ~0ull : b;
-				s_tot = tot;
-				if (!fail)
-					nodes += tot;
-			}
+			run = __shfl_sync (0xFFFFFFFFu, incl - c, wid);
+			tot = __shfl_sync (0xFFFFFFFFu, incl, 31);
 		}
-		__syncthreads ();
-		for (u32 sw = 0; sw < n_sweeps; sw++)
+		if (tid == 0)
 		{
-			const u32 i = sw * BD_NT + tid;
-			bool occ = false;
-			if (i < S)
+			unsigned long long b = 0;
+			bool fail = full;
+			if (!fail && tot)
 			{
-				if constexpr (W == 1)
-					occ = im.key[i] != EMPTY64;
-				else
-					occ = im.state[i] == 2u;
+				b = atomicAdd (node_cursor, (unsigned long long) tot);
+				if (b + tot > store_cap)
+				{
+					fail = true;
+					atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 4ull);	// node store exhausted
+				}
 			}
-			const u32 bal = __ballot_sync (0xFFFFFFFFu, occ);
-			if (occ)
-				list[s_wcnt[sw * (BD_NT / 32) + wid] + __popc (bal & ((1u << lane) - 1u))] = (unsigned short) i;
+			if (full)
+			{	// retried later, split by k-mer hash
+				const u32 f = atomicAdd (n_failed, 1u);
+				if (f < max_failed)
+					failed[f] = wk;
+				else
+					atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 8ull);
+			}
+			s_base = fail ? ~0ull : b;
+			if (!fail)
+				nodes += tot;
 		}
 		__syncthreads ();
 		const u64 nbase = s_base;
 		const bool write = nbase != ~0ull;
-		const u32 tot = s_tot;
-		for (u32 rank = tid; rank < tot; rank += BD_NT)
-		{	// one thread per node: consecutive threads write consecutive slots of the store
-			const u32 i = list[rank];
-			u32 row[4] = { 0, 0, 0, 0 }, col[4] = { 0, 0, 0, 0 }, count = im.extra[i];
 #pragma unroll
-			for (int q = 0; q < CELL_WORDS; q++)
+		for (u32 sw = 0; sw < MAX_SWEEPS; sw++)
+		{
+			if (sw * 32 < spw)
 			{
-				const u32 v = im.cell[q * S + i];
-				im.cell[q * S + i] = 0u;
-#pragma unroll
-				for (int hlf = 0; hlf < 2; hlf++)
+				if ((bal[sw] >> lane) & 1u)
 				{
-					const int c = 2 * q + hlf;
-					if (c < 25)
+					const u32 i = wid * spw + sw * 32 + lane;
+					const u32 rank = run + __popc (bal[sw] & ((1u << lane) - 1u));
+					u32 row[4] = { 0, 0, 0, 0 }, col[4] = { 0, 0, 0, 0 }, count = im.extra[i];
+#pragma unroll
+					for (int q = 0; q < CELL_WORDS; q++)
 					{
-						const u32 x = (v >> (16 * hlf)) & 0xFFFFu;
-						count += x;
-						if (c / 5 < 4)
-							row[c / 5] += min (x, LINK_SAT);	// clamped terms: same min (63, sum), no overflow
-						if (c % 5 < 4)
-							col[c % 5] += min (x, LINK_SAT);
+						const u32 v = im.cell[q * S + i];
+						im.cell[q * S + i] = 0u;
+#pragma unroll
+						for (int hlf = 0; hlf < 2; hlf++)
+						{
+							const int c = 2 * q + hlf;
+							if (c < 25)
+							{
+								const u32 x = (v >> (16 * hlf)) & 0xFFFFu;
+								count += x;
+								if (c / 5 < 4)
+									row[c / 5] += min (x, LINK_SAT);	// clamped terms: same min (63, sum), no overflow
+								if (c % 5 < 4)
+									col[c % 5] += min (x, LINK_SAT);
+							}
+						}
+					}
+					u32 L = 0, R = 0;
+#pragma unroll
+					for (int b = 0; b < 4; b++)
+					{
+						L |= min (row[b], LINK_SAT) << (6 * b);
+						R |= min (col[b], LINK_SAT) << (6 * b);
+					}
+					const u64 w0 = (im.ord[i] << 24) | L, w1 = ((u64) count << 32) | R;
+					Key<W> k;
+#pragma unroll
+					for (int q = 0; q < W; q++)
+					{
+						k.w[q] = im.key[(size_t) i * W + q];
+						im.key[(size_t) i * W + q] = EMPTY64;
+					}
+					im.ord[i] = ORD40_NONE;
+					im.extra[i] = 0u;
+					if constexpr (W > 1)
+						im.state[i] = 0u;
+					if (write)
+					{
+						S_t *dst = store + nbase + rank;
+						if constexpr (W == 1)
+							st256 (dst, k.w[0], 0ull, w0, w1);
+						else if constexpr (W == 2)
+							st256 (dst, k.w[0], k.w[1], w0, w1);
+						else
+						{
+							st256 (dst, k.w[0], k.w[1], k.w[2], k.w[3]);
+							st256 (reinterpret_cast<u64 *> (dst) + 4, w0, w1, 0ull, 0ull);
+						}
 					}
 				}
-			}
-			u32 L = 0, R = 0;
-#pragma unroll
-			for (int b = 0; b < 4; b++)
-			{
-				L |= min (row[b], LINK_SAT) << (6 * b);
-				R |= min (col[b], LINK_SAT) << (6 * b);
-			}
-			const u64 w0 = (im.ord[i] << 24) | L, w1 = ((u64) count << 32) | R;
-			Key<W> k;
-#pragma unroll
-			for (int q = 0; q < W; q++)
-			{
-				k.w[q] = im.key[(size_t) i * W + q];
-				im.key[(size_t) i * W + q] = EMPTY64;
-			}
-			im.ord[i] = ORD40_NONE;
-			im.extra[i] = 0u;
-			if constexpr (W > 1)
-				im.state[i] = 0u;
-			if (write)
-			{
-				S_t *dst = store + nbase + rank;
-				if constexpr (W == 1)
-					st256 (dst, k.w[0], 0ull, w0, w1);
-				else if constexpr (W == 2)
-					st256 (dst, k.w[0], k.w[1], w0, w1);
-				else
-				{
-					st256 (dst, k.w[0], k.w[1], k.w[2], k.w[3]);
-					st256 (reinterpret_cast<u64 *> (dst) + 4, w0, w1, 0ull, 0ull);
-				}
+				run += __popc (bal[sw]);
 			}
 		}
-		// instances applied by a work item that is going to be retried are not counted
-		{
-			u64 v = write ? mine : 0;
-#pragma unroll
-			for (int d = 16; d > 0; d >>= 1)
-				v += __shfl_down_sync (0xFFFFFFFFu, v, d);
-			if (lane == 0 && v)
-				atomicAdd (&ctr->n_instances, v);
-		}
-		__syncthreads ();
+		if (write)	// instances applied by a work item that is going to be retried are not counted
+			inst += mine;
 		if (tid == 0)
+		{
 			s_full = 0;
-		__syncthreads ();
+			s_item[(round + 1) & 1] = next_item;
+		}
+		__syncthreads ();	// the image is clean; s_item[] of the next round is in place
+	}
+	{
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1)
+			inst += __shfl_down_sync (0xFFFFFFFFu, inst, d);
+		if (lane == 0 && inst)
+			atomicAdd (&ctr->n_instances, inst);
 	}
 	if (tid == 0 && nodes)
 		atomicAdd (&ctr->n_nodes, nodes);

@@ -89,7 +89,7 @@ struct sdtgpu
 	std::vector<LogSeg> log;
 	u32 *d_hist = nullptr;
 	u64 *d_off = nullptr, *d_cur2 = nullptr, *d_seg_sum = nullptr;
-	u64 *d_small = nullptr, *h_small = nullptr;	// [0] record cursor, [1] node cursor, [2] failed work items; pinned mirror
+	u64 *d_small = nullptr, *h_small = nullptr;	// [0] record cursor, [1] node cursor, [2] failed work items, [3] work-item cursor; pinned mirror
 	void *d_failed = nullptr, *d_items = nullptr;	// SkmWork lists
 	u32 *rec0 = nullptr, *rec2 = nullptr;	// super-k-mer records: as emitted, grouped by slice
 	u64 rec0_cap = 0, rec2_cap = 0, rec_upper = 0;	// records
@@ -681,10 +681,18 @@ int skm_setup (sdtgpu *h, u64 hint)
 	if (hint == 0)
 		return fail (h, SDTGPU_EINVAL, "the sliced build needs capacity_hint (expected distinct k-mers)");
 	SkmGeom g;
-	// default: what fits one CTA per SM (227 KB): 74 / 86 / 102 bytes per slot for 1- / 2- / 4-word keys
-	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 2912u : (h->W == 2 ? 2528u : 2144u)) & ~1u;
+	// default: what fits one CTA per SM (227 KB): 72 / 84 / 100 bytes per slot for 1- / 2- / 4-word keys
+	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 3104u : (h->W == 2 ? 2656u : 2240u));
 	if (g.slice_slots < 32 || g.slice_slots > MAX_SWEEPS * BD_NT)
 		return fail (h, SDTGPU_EINVAL, "SDTGPU_SLICE_SLOTS out of range");
+	for (;; g.slice_slots--)
+	{	// the largest prime below: the image is probed by double hashing (skm_find)
+		bool prime = true;
+		for (u32 d = 2; d * d <= g.slice_slots && prime; d++)
+			prime = g.slice_slots % d != 0;
+		if (prime)
+			break;
+	}
 	double load = 0.5;
 	if (const char *e = getenv ("SDTGPU_SLICE_LOAD"))
 		if (atof (e) > 0.05 && atof (e) < 0.95)
@@ -701,7 +709,6 @@ int skm_setup (sdtgpu *h, u64 hint)
 	g.recw = h->W == 1 ? 8 : (h->W == 2 ? 12 : 16);
 	g.npos = (u32) h->max_read_len - g.m + 1;
 	g.tile_reads = std::max (4u, std::min (64u, (8192u / g.npos) & ~3u));
-	g.chunk = std::min<u32> (env_u32 ("SDTGPU_SLICE_CHUNK", 2 * BD_NT), 2 * BD_NT);
 	g.slice_a = slice_of_min_host (mmer_hash (0), g.n_slices);
 	if (g.npos * g.tile_reads > 60000 || h->max_read_len > 60000)
 		return fail (h, SDTGPU_ERANGE, "max_read_len too large for the sliced build");
@@ -802,9 +809,10 @@ template <int W> int launch_build_t (sdtgpu *h, const SkmWork *items, u32 n_item
 		return fail (h, SDTGPU_EINVAL, "slice image does not fit in shared memory (SDTGPU_SLICE_SLOTS too large)");
 	const unsigned grid = (unsigned) std::min<u64> (n_items, (u64) h->sm_count * occ);
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
+	CK (h, cudaMemsetAsync (small + 3, 0, sizeof (u64), h->stream));	// work-item cursor
 	{
 		TimedLaunch tl (h, 4);
-		kern<<<grid, BD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, h->rec2, h->d_off, items, n_items,
+		kern<<<grid, BD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, h->rec2, h->d_off, items, n_items, small + 3,
 							 static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
 	}
 	CK (h, cudaGetLastError ());

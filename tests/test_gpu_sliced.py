@@ -23,10 +23,9 @@ def test_sliced_parity_ragged(pkg, oracle, tiny_transcriptome, K, kw, d):
 def test_sliced_tiny_slices_retries_and_record_overflow(pkg, oracle, tiny_transcriptome, monkeypatch, K, kw):
     """64-slot slice images: tens of thousands of slices, many of which overflow and are retried split
     by k-mer hash; a record area sized for 1/64 record per window, so the emit kernel runs out of room
-    and the whole read log is emitted again; 8-record chunks in the build kernel."""
+    and the whole read log is emitted again."""
     monkeypatch.setenv("SDTGPU_SLICE_SLOTS", "64")
     monkeypatch.setenv("SDTGPU_SLICE_LOAD", "0.7")
-    monkeypatch.setenv("SDTGPU_SLICE_CHUNK", "8")
     monkeypatch.setenv("SDTGPU_REC_DIV", "64")
     L = 150 if K > 63 else 100
     reads, lens = make_dataset(pkg, tiny_transcriptome, 6000, L, 23, ragged=20)
