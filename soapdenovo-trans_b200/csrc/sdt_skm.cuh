@@ -39,13 +39,13 @@ struct SkmGeom
 	u32 slice_a;		// slice of the all-A k-mer (key 0): where the -n N-windows go
 	u32 tile_reads;		// reads per shared-memory tile of skm_emit_kernel
 	u32 npos;		// m-mer positions per read at most (max_read_len - m + 1)
+	u32 build_nt;		// threads per CTA of skm_build_kernel: 1024 (one CTA per SM) or 512 (two)
 };
 
 static constexpr u32 SKM_HDR = 3;		// header words: ord low | ord high, n-1, flags, bases | slice
 static constexpr u32 SKM_NFLAG = 0x80000000u;	// in the per-window slice array: window contains an N (-n)
 static constexpr int EMIT_NT = 256;
 static constexpr int SCAT_NT = 256;
-static constexpr u32 BD_CHUNK = 2 * BD_NT;	// records per pass of skm_build_kernel
 
 __host__ __device__ __forceinline__ u32 fmix32 (u32 h)
 {
@@ -331,7 +331,7 @@ __host__ __device__ inline size_t skm_image_bytes (int W, u32 S)
 }
 __host__ __device__ inline size_t skm_build_smem (int W, const SkmGeom &g)
 {	// image + window prefix of a chunk of records
-	return skm_image_bytes (W, g.slice_slots) + 4 * ((size_t) BD_CHUNK + 4);
+	return skm_image_bytes (W, g.slice_slots) + 4 * (2 * (size_t) g.build_nt + 4);
 }
 
 // Double hashing (S is prime, 1 <= step < S): in shared memory a probe costs the same wherever it
@@ -391,9 +391,9 @@ __device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key
 	return S;
 }
 
-struct SkmWork { u32 slice, r, R; };	// keys of `slice` with sub-hash % R == r
+struct SkmWork { u32 slice, r, R, nrec; };	// keys of `slice` with sub-hash % R == r; nrec: records of the slice (set when an item fails)
 
-static constexpr u32 MAX_SWEEPS = 4;	// slice_slots <= MAX_SWEEPS * BD_NT
+static constexpr u32 MAX_SWEEPS = 4;	// slice_slots <= MAX_SWEEPS * threads per CTA
 
 // Rolling state of one record: what nextKmer / reverseComplement (kmer.c:209, 653) compute per base,
 // kept incrementally — the forward k-mer takes the next base at the bottom, its reverse complement
@@ -446,6 +446,26 @@ __device__ __forceinline__ void skm_roll_init (SkmRoll<W> &s, const u32 *rec, in
 		s.add = n;
 		return;
 	}
+	if constexpr (W == 1)
+		if (tw == 0)
+		{	// start of a record (the common re-seat): the record's 160 bits of bases, two 16-byte loads
+			const uint4 h2 = __ldg (reinterpret_cast<const uint4 *> (rec) + 1);
+			u64 hi = ((u64) hd.w << 32) | h2.x, mid = ((u64) h2.y << 32) | h2.z;
+			if (has_left)
+			{
+				hi = (hi << 2) | (mid >> 62);
+				mid = (mid << 2) | ((u64) h2.w >> 30);
+			}
+			const int sh = 64 - 2 * K;	// 2 <= sh
+			s.f.w[0] = hi >> sh;
+			s.rc.w[0] = revcomp64 (s.f.w[0]) >> sh;
+			s.pend[0] = (hi << (64 - sh)) | (mid >> sh);
+			s.left = has_left ? hd.w >> 30 : 4u;
+			s.n = n;
+			s.has_right = nb - has_left - (u32) K - (n - 1);
+			s.add = 1;
+			return;
+		}
 	const u32 *rd = rec + SKM_HDR;
 	const u32 j = has_left + tw;	// first base of the window
 	const u32 p0 = j + (u32) K;	// first base after it
@@ -516,7 +536,7 @@ __device__ __forceinline__ void skm_roll_step (SkmRoll<W> &s, const Key<W> &mask
 
 // One CTA per work item, items handed out through *item_cursor.  items == nullptr: item i is (slice i, 0, 1).
 //
-// Records -> image: the windows of up to BD_CHUNK records are flattened and cut into BD_NT equal runs,
+// Records -> image: the windows of up to 2 NT records are flattened and cut into NT equal runs,
 // one per thread (a slice holds about one record per thread, of 1 to 32 windows: whole records per
 // lane leave most lanes waiting for the longest).  A thread finds the record of its first window
 // (binary search in the window prefix), sets up the rolling state there (one 16-byte header load +
@@ -525,25 +545,25 @@ __device__ __forceinline__ void skm_roll_step (SkmRoll<W> &s, const Key<W> &mask
 // Image -> node store: every warp owns a contiguous range of slots; occupied slots are ranked by
 // ballot + a scan of the 32 warp totals, thread 0 reserves the item's space in the store, and the
 // nodes go out in slot order, 32 bytes per lane, consecutive lanes to consecutive nodes.
-template <int W>
-__global__ void __launch_bounds__ (BD_NT, 1)
+template <int W, int NT>
+__global__ void __launch_bounds__ (NT, 1024 / NT)
 skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long long *node_cursor, SkmGeom g, int K,
 		  const u32 *rec2, const u64 *off, const SkmWork *items, u32 n_items, unsigned long long *item_cursor,
 		  SkmWork *failed, u32 *n_failed, u32 max_failed, Counters *ctr)
 {
 	typedef typename SlotOf<W>::type S_t;
 	extern __shared__ __align__(16) u32 smem[];
-	__shared__ u32 s_full, s_item[2], s_warp[BD_NT / 32];
+	__shared__ u32 s_full, s_item[2], s_warp[NT / 32];
 	__shared__ unsigned long long s_base;
 	const u32 S = g.slice_slots, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const u32 spw = ((S + BD_NT - 1) / BD_NT) * 32;	// slots per warp in the compaction (a multiple of 32)
+	const u32 spw = ((S + NT - 1) / NT) * 32;	// slots per warp in the compaction (a multiple of 32)
 	SkmImage<W> im;
 	im.key = reinterpret_cast<u64 *> (smem);
 	im.ord = im.key + (size_t) S * W;
 	im.cell = reinterpret_cast<u32 *> (im.ord + S);
 	im.extra = im.cell + (size_t) S * CELL_WORDS;
 	im.state = im.extra + S;
-	u32 *pre = im.extra + S + (W > 1 ? S : 0);	// [BD_CHUNK + 1]: exclusive prefix of the windows of a chunk's records
+	u32 *pre = im.extra + S + (W > 1 ? S : 0);	// [2 NT + 1]: exclusive prefix of the windows of a chunk's records
 	Key<W> kmask;	// the low 2K bits
 #pragma unroll
 	for (int q = 0; q < W; q++)
@@ -558,7 +578,7 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 		s_full = 0;
 		s_item[0] = (u32) atomicAdd (item_cursor, 1ull);
 	}
-	for (u32 i = tid; i < S; i += BD_NT)
+	for (u32 i = tid; i < S; i += NT)
 	{
 #pragma unroll
 		for (int q = 0; q < W; q++)
@@ -568,7 +588,7 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 		if constexpr (W > 1)
 			im.state[i] = 0u;
 	}
-	for (u32 i = tid; i < S * CELL_WORDS; i += BD_NT)
+	for (u32 i = tid; i < S * CELL_WORDS; i += NT)
 		im.cell[i] = 0u;
 	__syncthreads ();
 	for (u32 round = 0;; round++)
@@ -587,13 +607,14 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 			wk.slice = it;
 			wk.r = 0;
 			wk.R = 1;
+			wk.nrec = 0;
 		}
 		const u64 r0 = off[wk.slice], r1 = off[wk.slice + 1];
 		u64 mine = 0;
-		for (u64 c0 = r0; c0 < r1 && !*reinterpret_cast<volatile u32 *> (&s_full); c0 += BD_CHUNK)
-		{	// up to BD_CHUNK records at a time: their windows are flattened (exclusive prefix in pre[]) and
-			// cut into BD_NT equal runs, one per thread
-			const u32 nrec = (u32) min ((u64) BD_CHUNK, r1 - c0);
+		for (u64 c0 = r0; c0 < r1 && !*reinterpret_cast<volatile u32 *> (&s_full); c0 += 2 * NT)
+		{	// up to 2 NT records at a time: their windows are flattened (exclusive prefix in pre[]) and
+			// cut into NT equal runs, one per thread
+			const u32 nrec = (u32) min ((u64) (2 * NT), r1 - c0);
 			const u32 *recs = rec2 + c0 * g.recw;
 			u32 nw[2] = { 0, 0 };
 #pragma unroll
@@ -616,7 +637,7 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 			__syncthreads ();
 			u32 total;
 			{
-				const u32 c = s_warp[lane];
+				const u32 c = lane < NT / 32 ? s_warp[lane] : 0u;
 				u32 in2 = c;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1)
@@ -636,7 +657,7 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 					pre[nrec] = total;
 			}
 			__syncthreads ();
-			const u32 per = (total + BD_NT - 1) / BD_NT;	// windows per thread
+			const u32 per = (total + NT - 1) / NT;	// windows per thread
 			const u32 w0 = tid * per, w1 = min (total, w0 + per);
 			SkmRoll<W> st;
 			st.n = st.t = 0;
@@ -705,11 +726,11 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 		}
 		// ---- image -> node store
 		const bool full = s_full != 0;
-		u32 bal[MAX_SWEEPS], cnt = 0;
+		// every warp lists the occupied slots of its range (pre[] is free now) and counts them
+		unsigned short *wl = reinterpret_cast<unsigned short *> (pre) + wid * spw;
+		u32 cnt = 0;
 #pragma unroll
 		for (u32 sw = 0; sw < MAX_SWEEPS; sw++)
-		{
-			bal[sw] = 0;
 			if (sw * 32 < spw)
 			{
 				const u32 i = wid * spw + sw * 32 + lane;
@@ -721,16 +742,17 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 					else
 						occ = im.state[i] == 2u;
 				}
-				bal[sw] = __ballot_sync (0xFFFFFFFFu, occ);
-				cnt += __popc (bal[sw]);
+				const u32 bal = __ballot_sync (0xFFFFFFFFu, occ);
+				if (occ)
+					wl[cnt + __popc (bal & ((1u << lane) - 1u))] = (unsigned short) i;
+				cnt += __popc (bal);
 			}
-		}
 		if (lane == 0)
 			s_warp[wid] = cnt;
 		__syncthreads ();
 		u32 run, tot;
 		{	// every warp scans the 32 warp totals
-			const u32 c = s_warp[lane];
+			const u32 c = lane < NT / 32 ? s_warp[lane] : 0u;
 			u32 incl = c;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1)
@@ -758,6 +780,7 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 			if (full)
 			{	// retried later, split by k-mer hash
 				const u32 f = atomicAdd (n_failed, 1u);
+				wk.nrec = (u32) min (r1 - r0, (u64) 0xFFFFFFFFu);
 				if (f < max_failed)
 					failed[f] = wk;
 				else
@@ -770,70 +793,61 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 		__syncthreads ();
 		const u64 nbase = s_base;
 		const bool write = nbase != ~0ull;
+		for (u32 k = lane; k < cnt; k += 32)
+		{	// one lane per node: consecutive lanes write consecutive slots of the store
+			const u32 i = wl[k];
+			u32 row[4] = { 0, 0, 0, 0 }, col[4] = { 0, 0, 0, 0 }, count = im.extra[i];
 #pragma unroll
-		for (u32 sw = 0; sw < MAX_SWEEPS; sw++)
-		{
-			if (sw * 32 < spw)
+			for (int q = 0; q < CELL_WORDS; q++)
 			{
-				if ((bal[sw] >> lane) & 1u)
+				const u32 v = im.cell[q * S + i];
+				im.cell[q * S + i] = 0u;
+#pragma unroll
+				for (int hlf = 0; hlf < 2; hlf++)
 				{
-					const u32 i = wid * spw + sw * 32 + lane;
-					const u32 rank = run + __popc (bal[sw] & ((1u << lane) - 1u));
-					u32 row[4] = { 0, 0, 0, 0 }, col[4] = { 0, 0, 0, 0 }, count = im.extra[i];
-#pragma unroll
-					for (int q = 0; q < CELL_WORDS; q++)
+					const int c = 2 * q + hlf;
+					if (c < 25)
 					{
-						const u32 v = im.cell[q * S + i];
-						im.cell[q * S + i] = 0u;
-#pragma unroll
-						for (int hlf = 0; hlf < 2; hlf++)
-						{
-							const int c = 2 * q + hlf;
-							if (c < 25)
-							{
-								const u32 x = (v >> (16 * hlf)) & 0xFFFFu;
-								count += x;
-								if (c / 5 < 4)
-									row[c / 5] += min (x, LINK_SAT);	// clamped terms: same min (63, sum), no overflow
-								if (c % 5 < 4)
-									col[c % 5] += min (x, LINK_SAT);
-							}
-						}
-					}
-					u32 L = 0, R = 0;
-#pragma unroll
-					for (int b = 0; b < 4; b++)
-					{
-						L |= min (row[b], LINK_SAT) << (6 * b);
-						R |= min (col[b], LINK_SAT) << (6 * b);
-					}
-					const u64 w0 = (im.ord[i] << 24) | L, w1 = ((u64) count << 32) | R;
-					Key<W> k;
-#pragma unroll
-					for (int q = 0; q < W; q++)
-					{
-						k.w[q] = im.key[(size_t) i * W + q];
-						im.key[(size_t) i * W + q] = EMPTY64;
-					}
-					im.ord[i] = ORD40_NONE;
-					im.extra[i] = 0u;
-					if constexpr (W > 1)
-						im.state[i] = 0u;
-					if (write)
-					{
-						S_t *dst = store + nbase + rank;
-						if constexpr (W == 1)
-							st256 (dst, k.w[0], 0ull, w0, w1);
-						else if constexpr (W == 2)
-							st256 (dst, k.w[0], k.w[1], w0, w1);
-						else
-						{
-							st256 (dst, k.w[0], k.w[1], k.w[2], k.w[3]);
-							st256 (reinterpret_cast<u64 *> (dst) + 4, w0, w1, 0ull, 0ull);
-						}
+						const u32 x = hlf ? v >> 16 : v & 0xFFFFu;
+						count += x;
+						if (c / 5 < 4)
+							row[c / 5] += x;	// five 16-bit terms: no overflow
+						if (c % 5 < 4)
+							col[c % 5] += x;
 					}
 				}
-				run += __popc (bal[sw]);
+			}
+			u32 L = 0, R = 0;
+#pragma unroll
+			for (int b = 0; b < 4; b++)
+			{
+				L |= min (row[b], LINK_SAT) << (6 * b);
+				R |= min (col[b], LINK_SAT) << (6 * b);
+			}
+			const u64 w0 = (im.ord[i] << 24) | L, w1 = ((u64) count << 32) | R;
+			Key<W> k2;
+#pragma unroll
+			for (int q = 0; q < W; q++)
+			{
+				k2.w[q] = im.key[(size_t) i * W + q];
+				im.key[(size_t) i * W + q] = EMPTY64;
+			}
+			im.ord[i] = ORD40_NONE;
+			im.extra[i] = 0u;
+			if constexpr (W > 1)
+				im.state[i] = 0u;
+			if (write)
+			{
+				S_t *dst = store + nbase + run + k;
+				if constexpr (W == 1)
+					st256 (dst, k2.w[0], 0ull, w0, w1);
+				else if constexpr (W == 2)
+					st256 (dst, k2.w[0], k2.w[1], w0, w1);
+				else
+				{
+					st256 (dst, k2.w[0], k2.w[1], k2.w[2], k2.w[3]);
+					st256 (reinterpret_cast<u64 *> (dst) + 4, w0, w1, 0ull, 0ull);
+				}
 			}
 		}
 		if (write)	// instances applied by a work item that is going to be retried are not counted

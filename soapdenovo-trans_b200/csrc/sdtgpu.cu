@@ -34,7 +34,7 @@ struct LogSeg
 	ReadBatch rb;	// pointers are resolved when the segment is used (the arenas may move)
 };
 
-static constexpr int N_CAT = 8;	// timing classes: 0 insert, 1 count, 2 scatter (level 1), 3 scatter (level 2), 4 build, 5 scan
+static constexpr int N_CAT = 8;	// timing classes: 0 insert, 1 count, 2 scatter (level 1), 3 scatter (level 2), 4 build, 5 scan, 6 build retries
 
 }	// namespace
 
@@ -681,9 +681,11 @@ int skm_setup (sdtgpu *h, u64 hint)
 	if (hint == 0)
 		return fail (h, SDTGPU_EINVAL, "the sliced build needs capacity_hint (expected distinct k-mers)");
 	SkmGeom g;
-	// default: what fits one CTA per SM (227 KB): 72 / 84 / 100 bytes per slot for 1- / 2- / 4-word keys
-	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", h->W == 1 ? 3104u : (h->W == 2 ? 2656u : 2240u));
-	if (g.slice_slots < 32 || g.slice_slots > MAX_SWEEPS * BD_NT)
+	g.build_nt = env_u32 ("SDTGPU_BUILD_NT", 1024) == 512 ? 512 : 1024;
+	// default: what fits one CTA per SM (227 KB): 72 / 84 / 100 bytes per slot for 1- / 2- / 4-word keys; half of it for two CTAs
+	const u32 dflt = g.build_nt == 1024 ? (h->W == 1 ? 3104u : (h->W == 2 ? 2656u : 2240u)) : (h->W == 1 ? 1552u : (h->W == 2 ? 1330u : 1118u));
+	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", dflt);
+	if (g.slice_slots < 32 || g.slice_slots > MAX_SWEEPS * g.build_nt)
 		return fail (h, SDTGPU_EINVAL, "SDTGPU_SLICE_SLOTS out of range");
 	for (;; g.slice_slots--)
 	{	// the largest prime below: the image is probed by double hashing (skm_find)
@@ -717,7 +719,7 @@ int skm_setup (sdtgpu *h, u64 hint)
 	return SDTGPU_OK;
 }
 
-static constexpr u32 MAX_FAILED = 1u << 16;
+static constexpr u32 MAX_FAILED = 1u << 18;
 
 int skm_alloc (sdtgpu *h)
 {
@@ -795,37 +797,37 @@ int launch_emit (sdtgpu *h, const ReadBatch &rb)
 	}
 }
 
-template <int W> int launch_build_t (sdtgpu *h, const SkmWork *items, u32 n_items)
+template <int W, int NT> int launch_build_t (sdtgpu *h, const SkmWork *items, u32 n_items, int cat)
 {
 	typedef typename SlotOf<W>::type S;
 	const SkmGeom &g = h->geom;
-	auto kern = skm_build_kernel<W>;
+	auto kern = skm_build_kernel<W, NT>;
 	const size_t smem = skm_build_smem (W, g);
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
-	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, BD_NT, smem));
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, NT, smem));
 	if (occ < 1)
 		return fail (h, SDTGPU_EINVAL, "slice image does not fit in shared memory (SDTGPU_SLICE_SLOTS too large)");
 	const unsigned grid = (unsigned) std::min<u64> (n_items, (u64) h->sm_count * occ);
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	CK (h, cudaMemsetAsync (small + 3, 0, sizeof (u64), h->stream));	// work-item cursor
 	{
-		TimedLaunch tl (h, 4);
-		kern<<<grid, BD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, h->rec2, h->d_off, items, n_items, small + 3,
+		TimedLaunch tl (h, cat);
+		kern<<<grid, NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, h->rec2, h->d_off, items, n_items, small + 3,
 							 static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
 }
 
-int launch_build (sdtgpu *h, const SkmWork *items, u32 n_items)
+int launch_build (sdtgpu *h, const SkmWork *items, u32 n_items, int cat)
 {
 	switch (h->W)
 	{
-	case 1: return launch_build_t<1> (h, items, n_items);
-	case 2: return launch_build_t<2> (h, items, n_items);
-	default: return launch_build_t<4> (h, items, n_items);
+	case 1: return h->geom.build_nt == 512 ? launch_build_t<1, 512> (h, items, n_items, cat) : launch_build_t<1, 1024> (h, items, n_items, cat);
+	case 2: return h->geom.build_nt == 512 ? launch_build_t<2, 512> (h, items, n_items, cat) : launch_build_t<2, 1024> (h, items, n_items, cat);
+	default: return h->geom.build_nt == 512 ? launch_build_t<4, 512> (h, items, n_items, cat) : launch_build_t<4, 1024> (h, items, n_items, cat);
 	}
 }
 
@@ -905,7 +907,7 @@ int sliced_flush (sdtgpu *h)
 	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over
 	CK (h, cudaMemsetAsync (small + 1, 0, 2 * sizeof (u64), h->stream));
 	CK (h, cudaMemsetAsync (&h->d_ctr->n_nodes, 0, 2 * sizeof (u64), h->stream));	// n_nodes, n_instances
-	if ((rc = launch_build (h, nullptr, g.n_slices)))
+	if ((rc = launch_build (h, nullptr, g.n_slices, 4)))
 		return rc;
 	h->n_retried = 0;
 	std::vector<SkmWork> items, failed;
@@ -919,19 +921,31 @@ int sliced_flush (sdtgpu *h)
 		const u32 n_failed = (u32) h->h_small[2];
 		if (n_failed == 0)
 			break;
-		if ((h->h_small[3] & 8) || n_failed > MAX_FAILED / 8 || depth == 6)
+		if ((h->h_small[3] & 8) || n_failed > MAX_FAILED || depth == 6)
 			return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
-		// split every failed item eight ways by k-mer hash and run the pieces
+		// A failed item is split by k-mer hash into pieces.  Every piece scans all records of the slice
+		// again (a window that is not the piece's costs a roll and a hash, about a third of an insert),
+		// so the factor is sized to what the slice holds rather than fixed: slices overflow because they
+		// hold a few more distinct k-mers than the image does (two pieces do), or because a highly
+		// expressed locus piles the error k-mers of thousands of reads on one minimizer — about one new
+		// k-mer per eight windows on top of the image's usual half load.
 		failed.resize (n_failed);
 		CK (h, cudaMemcpy (failed.data (), h->d_failed, n_failed * sizeof (SkmWork), cudaMemcpyDeviceToHost));
 		items.clear ();
+		const double wpr = 0.5 * g.w + 1.0;	// windows per record, about
 		for (const SkmWork &f : failed)
-			for (u32 q = 0; q < 8; q++)
-				items.push_back ({ f.slice, f.r + f.R * q, f.R * 8 });
+		{
+			const double est = (0.5 * g.slice_slots + 0.12 * (double) f.nrec * wpr) / f.R;
+			const u32 q = (u32) std::min (4096.0, std::max (2.0, std::ceil (est / (0.7 * g.slice_slots))));
+			for (u32 i = 0; i < q; i++)
+				items.push_back ({ f.slice, f.r + f.R * i, f.R * q, f.nrec });
+		}
+		if (items.size () > MAX_FAILED)
+			return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
 		h->n_retried += n_failed;
 		CK (h, cudaMemcpyAsync (h->d_items, items.data (), items.size () * sizeof (SkmWork), cudaMemcpyHostToDevice, h->stream));
 		CK (h, cudaMemsetAsync (small + 2, 0, sizeof (u64), h->stream));
-		if ((rc = launch_build (h, static_cast<const SkmWork *> (h->d_items), (u32) items.size ())))
+		if ((rc = launch_build (h, static_cast<const SkmWork *> (h->d_items), (u32) items.size (), 6)))
 			return rc;
 		CK (h, cudaStreamSynchronize (h->stream));	// `items` is pageable host memory
 	}

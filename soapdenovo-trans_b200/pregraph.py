@@ -22,7 +22,7 @@ assert NODE_DTYPE.itemsize == 56
 F_NKMER = 1
 F_PARTITIONED = 2
 F_SLICED = 4
-PHASES = ("insert", "emit", "scatter", "-", "build", "scan", "-", "-")
+PHASES = ("insert", "emit", "scatter", "-", "build", "scan", "retry", "-")
 _ERR = {1: "EINVAL", 2: "ECUDA", 3: "ENOMEM", 4: "ERANGE", 5: "ESTATE"}
 
 
@@ -281,7 +281,7 @@ class PregraphGPU:
         """{phase: (ms, launches)} per kernel class (PHASES) since the last reset."""
         ms, nl = (C.c_double * 8)(), (C.c_uint64 * 8)()
         self._ck(self.L.sdtgpu_phase_times(self.h, int(reset), ms, nl))
-        return {PHASES[i]: (ms[i], nl[i]) for i in range(6)}
+        return {PHASES[i]: (ms[i], nl[i]) for i in range(7)}
 
     def slice_geometry(self):
         out = (C.c_uint64 * 8)()

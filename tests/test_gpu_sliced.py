@@ -54,6 +54,15 @@ def test_sliced_minimizer_lengths(pkg, oracle, tiny_transcriptome, monkeypatch, 
     check_against_oracle(pkg, oracle, reads, lens, K, kw, d=0, batches=2, hint=400_000, sliced=True)
 
 
+@pytest.mark.parametrize("K,kw", [(31, 1), (25, 1), (63, 2), (127, 4)])
+def test_sliced_two_ctas_per_sm(pkg, oracle, tiny_transcriptome, monkeypatch, K, kw):
+    """SDTGPU_BUILD_NT=512: half-size slice images, two build CTAs of 512 threads per SM."""
+    monkeypatch.setenv("SDTGPU_BUILD_NT", "512")
+    L = 150 if K > 63 else 100
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, L, 3 + K, ragged=30)
+    check_against_oracle(pkg, oracle, reads, lens, K, kw, d=1, batches=2, hint=400_000, sliced=True)
+
+
 def test_sliced_interleaved_stats_and_pushes(pkg, oracle, tiny_transcriptome):
     """stats() between pushes builds the store early; later pushes rebuild it from all records."""
     reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, 100, 41, ragged=10)
