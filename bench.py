@@ -292,7 +292,7 @@ def main():
         rec_b = geo["record_bytes"] * geo["n_records"] / max(st.n_instances, 1)      # record bytes per instance
         read_b = stride / nwin
         node_b = st.n_nodes * slot_b / max(st.n_instances, 1)
-        stream_b = {"emit": read_b + rec_b, "scatter": 2 * rec_b, "build": rec_b + node_b, "scan": 0.0, "retry": 0.0}
+        stream_b = {"emit": read_b + rec_b, "scatter": 2 * rec_b, "dedupe": 2 * rec_b, "build": rec_b + node_b, "scan": 0.0, "retry": 0.0}
         insert_ms = sum(phases[k][0] for k in stream_b)
         insert_launches = max(phases["build"][1] + phases["retry"][1], 1)
         sliced_info = {"geometry": geo, "windows_per_record": st.n_instances / max(geo["n_records"], 1), "phases": {

@@ -305,6 +305,126 @@ skm_scatter_kernel (const u32 *rec0, const unsigned long long *rec_count, u32 re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Copies of the same super-k-mer collapse into one record before the build.  At the coverage of a
+// transcriptome most records of a slice are byte-identical copies (every error-free read that spans
+// a super-k-mer emits the same bases, neighbours and window count; only the ordinal differs), and a
+// window costs the build ~400 instructions while finding a copy costs ~100 per record.  A surviving
+// record carries its multiplicity in word 2 (the slice number is no longer needed once the record
+// sits in its slice's run) and the smallest ordinal of its copies: window t of every copy is the
+// same (key, left, right) instance with ordinal ord0 + t, so count and link counters take the
+// multiplicity (update_kmer, newhash.c:71-96, is a sum) and the node's first ordinal the minimum.
+//
+// One CTA per slice, DD_CHUNK records at a time staged in shared memory; a table of record indices
+// keyed by the record's content finds the copies; survivors go back to the front of the run.
+// end[slice] = one past the last surviving record.
+static constexpr int DD_NT = 256;
+template <int W> struct DedupeCfg { static constexpr u32 CHUNK = W == 1 ? 2048u : 1024u, TABLE = 2 * CHUNK; };
+template <int W> __host__ __device__ inline size_t skm_dedupe_smem () { return (size_t) DedupeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) DedupeCfg<W>::TABLE * 4; }
+
+template <int W>
+__global__ void __launch_bounds__ (DD_NT)
+skm_dedupe_kernel (u32 *rec2, const u64 *off, u32 n_slices, unsigned long long *end, unsigned long long *n_kept)
+{
+	constexpr u32 RECW = SkmRec<W>::WORDS, CH = DedupeCfg<W>::CHUNK, TS = DedupeCfg<W>::TABLE, VEC = RECW / 4;
+	extern __shared__ __align__(16) u32 smem[];
+	__shared__ u32 s_out;
+	u32 *st = smem;			// [CH * RECW]: the chunk's records
+	u32 *tab = smem + CH * RECW;	// [TS]: record index + 1, 0 = free
+	const u32 tid = threadIdx.x, lane = tid & 31;
+	u64 kept_total = 0;	// thread 0
+	for (u32 sl = blockIdx.x; sl < n_slices; sl += gridDim.x)
+	{
+		const u64 r0 = off[sl], r1 = off[sl + 1];
+		u64 out = r0;	// next free position of the run
+		for (u64 c0 = r0; c0 < r1; c0 += CH)
+		{
+			const u32 nrec = (u32) min ((u64) CH, r1 - c0);
+			{	// stage (coalesced 16-byte loads); word 2 becomes the multiplicity
+				const uint4 *src = reinterpret_cast<const uint4 *> (rec2 + c0 * RECW);
+				uint4 *dst = reinterpret_cast<uint4 *> (st);
+				for (u32 v = tid; v < nrec * VEC; v += DD_NT)
+				{
+					uint4 x = ldg_stream (src + v);
+					if (v % VEC == 0)
+						x.z = 1u;
+					dst[v] = x;
+				}
+				for (u32 v = tid; v < TS; v += DD_NT)
+					tab[v] = 0u;
+				if (tid == 0)
+					s_out = 0;
+			}
+			__syncthreads ();
+			for (u32 i = tid; i < nrec; i += DD_NT)
+			{
+				u32 *me = st + i * RECW;
+				const u32 h1 = me[1];
+				if ((h1 >> 15) & 1u)
+					continue;	// an N-run stays as it is
+				u32 hsh = h1 & ~0xFFu;
+#pragma unroll
+				for (u32 q = SKM_HDR; q < RECW; q++)
+					hsh = (hsh ^ me[q]) * 0x9E3779B1u + (hsh >> 15);
+				u32 slot = fmix32 (hsh) & (TS - 1);
+				for (;;)
+				{
+					u32 e = tab[slot];
+					if (e == 0u)
+						e = atomicCAS (tab + slot, 0u, i + 1);
+					if (e == 0u)
+						break;	// first of its kind
+					u32 *rep = st + (e - 1) * RECW;
+					bool same = ((*reinterpret_cast<volatile u32 *> (rep + 1) ^ h1) & ~0xFFu) == 0u;	// the low 8 bits are ordinal bits and change
+#pragma unroll
+					for (u32 q = SKM_HDR; q < RECW; q++)
+						same &= rep[q] == me[q];
+					if (same)
+					{	// words 0-1 as one 64-bit number: the header bits above the ordinal are equal, so the minimum is the ordinal's
+						atomicAdd (rep + 2, 1u);
+						const u64 mine = *reinterpret_cast<const u64 *> (me);
+						if (mine < *reinterpret_cast<volatile u64 *> (rep))
+							atomicMin (reinterpret_cast<unsigned long long *> (rep), mine);
+						me[2] = 0u;	// dropped
+						break;
+					}
+					slot = (slot + 1) & (TS - 1);
+				}
+			}
+			__syncthreads ();
+			// survivors back to the run, in any order: a warp reserves its share with one atomic
+			for (u32 b = 0; b < nrec; b += DD_NT)
+			{
+				const u32 i = b + tid;
+				const bool keep = i < nrec && st[i * RECW + 2] != 0u;
+				const u32 bal = __ballot_sync (0xFFFFFFFFu, keep);
+				u32 base = 0;
+				if (lane == 0 && bal)
+					base = atomicAdd (&s_out, (u32) __popc (bal));
+				base = __shfl_sync (0xFFFFFFFFu, base, 0);
+				if (keep)
+				{
+					const uint4 *src = reinterpret_cast<const uint4 *> (st + i * RECW);
+					uint4 *dst = reinterpret_cast<uint4 *> (rec2 + (out + base + __popc (bal & ((1u << lane) - 1u))) * RECW);
+#pragma unroll
+					for (u32 q = 0; q < VEC; q++)
+						dst[q] = src[q];
+				}
+			}
+			__syncthreads ();
+			out += s_out;
+			__syncthreads ();	// s_out, the chunk and the table are rewritten by the next pass
+		}
+		if (tid == 0)
+		{
+			end[sl] = out;
+			kept_total += out - r0;
+		}
+	}
+	if (tid == 0 && kept_total)
+		atomicAdd (n_kept, kept_total);
+}
+
+// ------------------------------------------------------------------------------------------------
 // The slice's table image in shared memory.  Shared-memory atomics are the scarce resource (2 cycles
 // per lane, 20x a load), so an instance costs exactly ONE: every slot has a 5 x 5 matrix of 16-bit
 // cells indexed by (left, right), 4 = "no neighbour".  The reference's update_kmer (newhash.c:71-96)
@@ -407,7 +527,7 @@ template <int W> struct SkmRoll
 	u32 left;	// base before the current window (4: none)
 	u32 n, t;	// windows of the record, current window
 	u32 has_right;	// the last window has a base after it
-	u32 add;	// instances per step (an N-run applies all of its windows at once)
+	u32 add;	// instances per step: the record's multiplicity (skm_dedupe_kernel); an N-run applies all of its windows at once
 };
 
 // bits [2 * b, 2 * b + 64) of the record's bases (words rd[0 .. last], first base in the top bits);
@@ -443,7 +563,7 @@ __device__ __forceinline__ void skm_roll_init (SkmRoll<W> &s, const u32 *rec, in
 		s.left = 4;
 		s.n = 1;
 		s.has_right = 0;
-		s.add = n;
+		s.add = n * hd.z;
 		return;
 	}
 	if constexpr (W == 1)
@@ -463,7 +583,7 @@ __device__ __forceinline__ void skm_roll_init (SkmRoll<W> &s, const u32 *rec, in
 			s.left = has_left ? hd.w >> 30 : 4u;
 			s.n = n;
 			s.has_right = nb - has_left - (u32) K - (n - 1);
-			s.add = 1;
+			s.add = hd.z;
 			return;
 		}
 	const u32 *rd = rec + SKM_HDR;
@@ -477,7 +597,7 @@ __device__ __forceinline__ void skm_roll_init (SkmRoll<W> &s, const u32 *rec, in
 		s.pend[1] = n - tw > 32 ? bases64 (rd, p0 + 32, LAST) : 0ull;	// only long records reach into the second word
 	s.n = n;
 	s.has_right = nb - has_left - (u32) K - (n - 1);
-	s.add = 1;
+	s.add = hd.z;
 }
 
 // the window's canonical key and its links in the stored orientation (chopKmer4read, prlHashReads.c:215-230, 275-308)
@@ -548,7 +668,7 @@ __device__ __forceinline__ void skm_roll_step (SkmRoll<W> &s, const Key<W> &mask
 template <int W, int NT>
 __global__ void __launch_bounds__ (NT, 1024 / NT)
 skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long long *node_cursor, SkmGeom g, int K,
-		  const u32 *rec2, const u64 *off, const SkmWork *items, u32 n_items, unsigned long long *item_cursor,
+		  const u32 *rec2, const u64 *off, const u64 *end, const SkmWork *items, u32 n_items, unsigned long long *item_cursor,
 		  SkmWork *failed, u32 *n_failed, u32 max_failed, Counters *ctr)
 {
 	typedef typename SlotOf<W>::type S_t;
@@ -609,7 +729,7 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 			wk.R = 1;
 			wk.nrec = 0;
 		}
-		const u64 r0 = off[wk.slice], r1 = off[wk.slice + 1];
+		const u64 r0 = off[wk.slice], r1 = end[wk.slice];	// the run's surviving records (skm_dedupe_kernel)
 		u64 mine = 0;
 		for (u64 c0 = r0; c0 < r1 && !*reinterpret_cast<volatile u32 *> (&s_full); c0 += 2 * NT)
 		{	// up to 2 NT records at a time: their windows are flattened (exclusive prefix in pre[]) and
@@ -696,22 +816,32 @@ skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long 
 				}
 				__syncwarp ();	// probe sequences differ in length: meet again before the update
 				const bool hit = idx < S;
-				// lanes of this step that meet in the same (slot, cell): the lowest one adds for all
+				// lanes of this step that meet in the same (slot, cell) with one instance each: the lowest one adds for all
 				const bool one = hit && st.add == 1;
 				const u32 peers = __match_any_sync (0xFFFFFFFFu, one ? idx * 32 + cellid : 0xFFFFFFFFu - lane);
 				if (hit)
 				{
-					if (!one)
-						atomicAdd (im.extra + idx, st.add);	// an N-run: all of its windows at once
-					else if ((u32) (__ffs (peers) - 1) == lane)
+					u32 *cw = im.cell + (cellid >> 1) * S + idx;
+					const u32 sh = 16 * (cellid & 1);
+					if (one)
 					{
-						const u32 cnt = __popc (peers);
-						u32 *cw = im.cell + (cellid >> 1) * S + idx;
-						const u32 sh = 16 * (cellid & 1);
-						if (((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
-							atomicAdd (im.extra + idx, cnt);
-						else
-							atomicAdd (cw, cnt << sh);
+						if ((u32) (__ffs (peers) - 1) == lane)
+						{
+							const u32 cnt = __popc (peers);
+							if (((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
+								atomicAdd (im.extra + idx, cnt);
+							else
+								atomicAdd (cw, cnt << sh);
+						}
+					}
+					else
+					{	// a multiplicity: the cell takes what can still matter to a 6-bit link counter, `extra` the rest
+						// (in flight at most 63 per thread of the CTA on top of 62: below 2^16)
+						const u32 inc = ((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= LINK_SAT ? 0u : min (st.add, LINK_SAT);
+						if (inc)
+							atomicAdd (cw, inc << sh);
+						if (st.add > inc)
+							atomicAdd (im.extra + idx, st.add - inc);
 					}
 					if (st.ord < *reinterpret_cast<volatile u64 *> (im.ord + idx))
 						atomicMin (im.ord + idx, st.ord);

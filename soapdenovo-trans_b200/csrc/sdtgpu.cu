@@ -34,7 +34,7 @@ struct LogSeg
 	ReadBatch rb;	// pointers are resolved when the segment is used (the arenas may move)
 };
 
-static constexpr int N_CAT = 8;	// timing classes: 0 insert, 1 count, 2 scatter (level 1), 3 scatter (level 2), 4 build, 5 scan, 6 build retries
+static constexpr int N_CAT = 8;	// timing classes: 0 insert, 1 count / emit, 2 scatter, 3 dedupe, 4 build, 5 scan, 6 build retries
 
 }	// namespace
 
@@ -89,7 +89,7 @@ struct sdtgpu
 	std::vector<LogSeg> log;
 	u32 *d_hist = nullptr;
 	u64 *d_off = nullptr, *d_cur2 = nullptr, *d_seg_sum = nullptr;
-	u64 *d_small = nullptr, *h_small = nullptr;	// [0] record cursor, [1] node cursor, [2] failed work items, [3] work-item cursor; pinned mirror
+	u64 *d_small = nullptr, *h_small = nullptr;	// [0] record cursor, [1] node cursor, [2] failed work items, [3] work-item cursor, [4] records after dedupe; pinned mirror
 	void *d_failed = nullptr, *d_items = nullptr;	// SkmWork lists
 	u32 *rec0 = nullptr, *rec2 = nullptr;	// super-k-mer records: as emitted, grouped by slice
 	u64 rec0_cap = 0, rec2_cap = 0, rec_upper = 0;	// records
@@ -814,11 +814,41 @@ template <int W, int NT> int launch_build_t (sdtgpu *h, const SkmWork *items, u3
 	CK (h, cudaMemsetAsync (small + 3, 0, sizeof (u64), h->stream));	// work-item cursor
 	{
 		TimedLaunch tl (h, cat);
-		kern<<<grid, NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, h->rec2, h->d_off, items, n_items, small + 3,
+		kern<<<grid, NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, h->rec2, h->d_off, h->d_cur2, items, n_items, small + 3,
 							 static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
+}
+
+template <int W> int launch_dedupe_t (sdtgpu *h)
+{
+	auto kern = skm_dedupe_kernel<W>;
+	const size_t smem = skm_dedupe_smem<W> ();
+	CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	int occ = 0;
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, DD_NT, smem));
+	if (occ < 1)
+		return fail (h, SDTGPU_ECUDA, "skm_dedupe_kernel does not fit");
+	const unsigned grid = (unsigned) std::min<u64> (h->geom.n_slices, (u64) h->sm_count * occ);
+	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
+	CK (h, cudaMemsetAsync (small + 4, 0, sizeof (u64), h->stream));	// surviving records
+	{
+		TimedLaunch tl (h, 3);
+		kern<<<grid, DD_NT, smem, h->stream>>> (h->rec2, h->d_off, h->geom.n_slices, reinterpret_cast<unsigned long long *> (h->d_cur2), small + 4);
+	}
+	CK (h, cudaGetLastError ());
+	return SDTGPU_OK;
+}
+
+int launch_dedupe (sdtgpu *h)
+{
+	switch (h->W)
+	{
+	case 1: return launch_dedupe_t<1> (h);
+	case 2: return launch_dedupe_t<2> (h);
+	default: return launch_dedupe_t<4> (h);
+	}
 }
 
 int launch_build (sdtgpu *h, const SkmWork *items, u32 n_items, int cat)
@@ -904,6 +934,11 @@ int sliced_flush (sdtgpu *h)
 		skm_scatter_kernel<<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, g.recw, reinterpret_cast<unsigned long long *> (h->d_cur2), h->rec2);
 	}
 	CK (h, cudaGetLastError ());
+	if (n_rec)
+	{	// copies of a super-k-mer collapse into one record with a multiplicity; d_cur2[slice] becomes the end of what is left
+		if (int rc2 = launch_dedupe (h))
+			return rc2;
+	}
 	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over
 	CK (h, cudaMemsetAsync (small + 1, 0, 2 * sizeof (u64), h->stream));
 	CK (h, cudaMemsetAsync (&h->d_ctr->n_nodes, 0, 2 * sizeof (u64), h->stream));	// n_nodes, n_instances
@@ -935,7 +970,7 @@ int sliced_flush (sdtgpu *h)
 		const double wpr = 0.5 * g.w + 1.0;	// windows per record, about
 		for (const SkmWork &f : failed)
 		{
-			const double est = (0.5 * g.slice_slots + 0.12 * (double) f.nrec * wpr) / f.R;
+			const double est = (0.5 * g.slice_slots + 0.2 * (double) f.nrec * wpr) / f.R;
 			const u32 q = (u32) std::min (4096.0, std::max (2.0, std::ceil (est / (0.7 * g.slice_slots))));
 			for (u32 i = 0; i < q; i++)
 				items.push_back ({ f.slice, f.r + f.R * i, f.R * q, f.nrec });

@@ -22,7 +22,7 @@ assert NODE_DTYPE.itemsize == 56
 F_NKMER = 1
 F_PARTITIONED = 2
 F_SLICED = 4
-PHASES = ("insert", "emit", "scatter", "-", "build", "scan", "retry", "-")
+PHASES = ("insert", "emit", "scatter", "dedupe", "build", "scan", "retry", "-")
 _ERR = {1: "EINVAL", 2: "ECUDA", 3: "ENOMEM", 4: "ERANGE", 5: "ESTATE"}
 
 
