@@ -39,12 +39,14 @@ struct SkmGeom
 	u32 slice_a;		// slice of the all-A k-mer (key 0): where the -n N-windows go
 	u32 tile_reads;		// reads per shared-memory tile of skm_emit_kernel
 	u32 npos;		// m-mer positions per read at most (max_read_len - m + 1)
+	u32 npad;		// row stride of the per-read arrays of skm_emit_kernel (a multiple of 4, >= npos)
 	u32 build_nt;		// threads per CTA of skm_build_kernel: 1024 (one CTA per SM) or 512 (two)
 };
 
 static constexpr u32 SKM_HDR = 3;		// header words: ord low | ord high, n-1, flags, bases | slice
 static constexpr u32 SKM_NFLAG = 0x80000000u;	// in the per-window slice array: window contains an N (-n)
 static constexpr int EMIT_NT = 256;
+static constexpr u32 EMIT_SEG = 16;	// windows per thread in the run detection of skm_emit_kernel
 static constexpr int SCAT_NT = 256;
 
 __host__ __device__ __forceinline__ u32 fmix32 (u32 h)
@@ -144,83 +146,122 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 	const int K = rb.K;
 	ReadTile<NMODE> rt;
 	tile_setup<NMODE> (rt, smem, rb);
-	u32 *mhs = smem + tile_words (rb, NMODE);	// [tile_reads * npos]: m-mer hashes, later (offset | n << 16) of run starts
-	u32 *sls = mhs + (size_t) rb.tile_reads * g.npos;	// [tile_reads * npos]: slice of every window (| SKM_NFLAG)
+	u32 *mhs = smem + tile_words (rb, NMODE);	// [tile_reads * npad + 16]: m-mer hashes, later descriptors (read | first window << 8 | (n - 1) << 24) of the records
+	u32 *sls = mhs + (size_t) rb.tile_reads * g.npad + 16;	// [tile_reads * npad]: slice of every window (| SKM_NFLAG)
+	const u32 maxwin = g.npos - g.w + 1;	// windows of the longest read
+	const u32 gpr = (maxwin + 3) >> 2, spr = (maxwin + EMIT_SEG - 1) / EMIT_SEG;	// groups of 4 windows, segments of EMIT_SEG windows per read
+	const u32 m_npos = 0xFFFFFFFFu / g.npos + 1, m_gpr = 0xFFFFFFFFu / gpr + 1, m_spr = 0xFFFFFFFFu / spr + 1;	// x / d = (x * m) >> 32 for x < 65536
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
 	for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x)
 	{
 		tile_stage<NMODE, EMIT_NT> (rt, rb, t, warp_sums);
 		if (tid == 0)
 			s_count = 0;
-		// x / d for x < 65536 without a division: (x * m) >> 32 with m = floor (2^32 / d) + 1
-		const u32 m_npos = 0xFFFFFFFFu / g.npos + 1, m_nwin = rt.nwin_u ? 0xFFFFFFFFu / rt.nwin_u + 1 : 0;
-		// ---- 1. hash of the canonical m-mer at every position of every read
-		for (u32 x = tid; x < rt.nr * g.npos; x += EMIT_NT)
+		// ---- 1. hash of the canonical m-mer at every position of every read (m <= 15: 32-bit arithmetic)
 		{
-			const u32 r = __umulhi (x, m_npos), i = x - r * g.npos;
-			Key<1> f, rc;
-			extract_fwd<1> (rt.tile + r * rt.sw, (int) (i + g.m), (int) g.m, f);
-			revcomp<1> (f, (int) g.m, rc);
-			mhs[x] = mmer_hash ((u32) min (f.w[0], rc.w[0]));
-		}
-		__syncthreads ();
-		// ---- 2. slice of every window = slice of its minimizer value
-		for (u32 x = tid; x < rt.total; x += EMIT_NT)
-		{
-			u32 r, j, len;
-			skm_locate<NMODE> (rt, K, m_nwin, x, r, j, len);
-			const u32 *mh = mhs + r * g.npos + j;
-			u32 mv = mh[0];
-			for (u32 i = 1; i < g.w; i++)
-				mv = min (mv, mh[i]);
-			u32 sl = slice_of_min (mv, g.n_slices);
-			if constexpr (NMODE)
-				if (mask_any (rt.mtile + r * rt.mw, j, j + K))
-					sl = g.slice_a | SKM_NFLAG;
-			sls[r * g.npos + j] = sl;
-		}
-		__syncthreads ();
-		// ---- 3. runs of windows with the same slice -> record descriptors (read | first window << 8 |
-		// (windows - 1) << 24) in mhs[], which is free now.  Every warp walks the windows of its own
-		// reads 32 at a time; the window that ENDS a run knows where the run started from a running
-		// maximum over "start" positions (shuffles, no loop over the run).
-		{
-			const u32 rpw = (rb.tile_reads + EMIT_NT / 32 - 1) / (EMIT_NT / 32);
-			const u32 r_lo = min (rt.nr, wid * rpw), r_hi = min (rt.nr, r_lo + rpw);
-			const u32 x_lo = rt.uniform ? r_lo * rt.nwin_u : rt.prefix[r_lo], x_hi = rt.uniform ? r_hi * rt.nwin_u : rt.prefix[r_hi];
-			u32 carry = 0;
-			for (u32 xb = x_lo; xb < x_hi; xb += 32)
+			const u32 msh = 32 - 2 * g.m;
+			for (u32 x = tid; x < rt.nr * g.npos; x += EMIT_NT)
 			{
-				const u32 x = xb + lane;
-				const bool act = x < x_hi;
-				u32 r = 0, j = 0, len = 0, s = 0;
-				bool is_start = false, is_end = false;
-				if (act)
-				{
-					skm_locate<NMODE> (rt, K, m_nwin, x, r, j, len);
-					const u32 *sl = sls + r * g.npos;
-					s = sl[j];
-					is_start = j == 0 || sl[j - 1] != s;
-					is_end = j + 1 == len - K + 1 || sl[j + 1] != s;
-				}
-				u32 v = is_start ? x + 1 : 0;
+				const u32 r = __umulhi (x, m_npos), i = x - r * g.npos;
+				const u32 *rd = rt.tile + r * rt.sw + (i >> 4);
+				const u32 f = __funnelshift_l (rd[1], rd[0], 2 * (i & 15)) >> msh;
+				u32 c = __brev (f ^ 0xAAAAAAAAu);	// complement (x ^ 2 per base, inc/def.h:42), then reverse the 2-bit groups
+				c = (((c >> 1) & 0x55555555u) | ((c & 0x55555555u) << 1)) >> msh;
+				mhs[r * g.npad + i] = mmer_hash (min (f, c));
+			}
+		}
+		__syncthreads ();
+		// ---- 2. slice of every window = slice of its minimizer value (the smallest of its w m-mer hashes).
+		// One thread per four consecutive windows j0 .. j0+3: they share the hashes j0+3 .. j0+w-1, so the
+		// sliding minimum costs ~(w + 9) / 4 comparisons per window instead of w; 16-byte loads keep the
+		// stride-4 access free of bank conflicts.
+		for (u32 x = tid; x < rt.nr * gpr; x += EMIT_NT)
+		{
+			const u32 r = gpr == 1 ? x : __umulhi (x, m_gpr), j0 = 4 * (x - r * gpr);	// (the multiplier of 1 does not fit 32 bits)
+			const u32 nwin = rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r];
+			if (j0 >= nwin)
+				continue;
+			const uint4 *mh = reinterpret_cast<const uint4 *> (mhs + r * g.npad + j0);
+			const uint4 c0 = mh[0];
+			const u32 a2 = c0.z, a1 = min (c0.y, a2), a0 = min (c0.x, a1);	// hashes 0..2 belong to the first windows only
+			u32 common = g.w > 3 ? c0.w : 0xFFFFFFFFu;	// hashes 3 .. w-1: in all four windows
+			u32 b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;	// running minima of hashes w, w..w+1, w..w+2
+			if (g.w == 3)
+				b0 = b1 = b2 = c0.w;
+			const u32 nv = (g.w + 6) >> 2;	// 16-byte chunks that hold hashes 0 .. w+2
+			for (u32 k = 1; k < nv; k++)
+			{
+				const uint4 c = mh[k];
+				const u32 e = 4 * k;
+				if (e + 3 < g.w)
+					common = min (common, min (min (c.x, c.y), min (c.z, c.w)));
+				else
+				{	// the chunk reaches past hash w-1
+					const u32 v[4] = { c.x, c.y, c.z, c.w };
 #pragma unroll
-				for (int d = 1; d < 32; d <<= 1)
-				{
-					const u32 y = __shfl_up_sync (0xFFFFFFFFu, v, d);
-					if (lane >= (u32) d)
-						v = max (v, y);
+					for (u32 q = 0; q < 4; q++)
+					{
+						const u32 idx = e + q;
+						if (idx < g.w)
+							common = min (common, v[q]);
+						else
+						{
+							if (idx == g.w)
+								b0 = v[q];
+							if (idx <= g.w + 1)
+								b1 = min (b1, v[q]);
+							if (idx <= g.w + 2)
+								b2 = min (b2, v[q]);
+						}
+					}
 				}
-				v = max (v, carry);
-				carry = __shfl_sync (0xFFFFFFFFu, v, 31);
-				if (is_end && (rb.owner_ranks <= 1 || (s & ~SKM_NFLAG) % rb.owner_ranks == rb.owner_rank))
+			}
+			b1 = min (b1, b0);
+			b2 = min (b2, b1);
+			const u32 mv[4] = { min (common, a0), min (min (common, a1), b0), min (min (common, a2), b1), min (common, b2) };
+			u32 *sl = sls + r * g.npad + j0;
+#pragma unroll
+			for (u32 q = 0; q < 4; q++)
+				if (j0 + q < nwin)
 				{
-					const u32 n = x - (v - 1) + 1, j0 = j + 1 - n;
-					const u32 nrec = (n + NMAX - 1) / NMAX;
-					const u32 pos = atomicAdd (&s_count, nrec);
-					mhs[pos] = r | (j0 << 8) | ((min (NMAX, n) - 1) << 24);
-					for (u32 c = 1; c < nrec; c++)	// runs longer than a record holds: rare
-						mhs[pos + c] = r | ((j0 + c * NMAX) << 8) | ((min (NMAX, n - c * NMAX) - 1) << 24);
+					u32 v = slice_of_min (mv[q], g.n_slices);
+					if constexpr (NMODE)
+						if (mask_any (rt.mtile + r * rt.mw, j0 + q, j0 + q + K))
+							v = g.slice_a | SKM_NFLAG;
+					sl[q] = v;
+				}
+		}
+		__syncthreads ();
+		// ---- 3. runs of windows with the same slice -> record descriptors in mhs[], which is free now.
+		// One thread per segment of EMIT_SEG windows of a read walks them in order and reports the runs
+		// that END in its segment (a run that started before the segment is traced back to its start).
+		for (u32 x = tid; x < rt.nr * spr; x += EMIT_NT)
+		{
+			const u32 r = spr == 1 ? x : __umulhi (x, m_spr), js = EMIT_SEG * (x - r * spr);
+			const u32 nwin = rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r];
+			if (js >= nwin)
+				continue;
+			const u32 je = min (js + EMIT_SEG, nwin);
+			const u32 *sl = sls + r * g.npad;
+			u32 s = sl[js], start = js;
+			while (start > 0 && sl[start - 1] == s)
+				start--;
+			for (u32 j = js; j < je; j++)
+			{
+				const u32 nxt = j + 1 < nwin ? sl[j + 1] : 0xFFFFFFFFu;	// no slice has this number (bit 31 is the N flag, 30 bits of slice)
+				if (nxt != s)
+				{	// windows start .. j are a run
+					if (rb.owner_ranks <= 1 || (s & ~SKM_NFLAG) % rb.owner_ranks == rb.owner_rank)
+					{
+						const u32 n = j - start + 1;
+						const u32 nrec = (n + NMAX - 1) / NMAX;
+						const u32 pos = atomicAdd (&s_count, nrec);
+						mhs[pos] = r | (start << 8) | ((min (NMAX, n) - 1) << 24);
+						for (u32 c = 1; c < nrec; c++)	// runs longer than a record holds: rare
+							mhs[pos + c] = r | ((start + c * NMAX) << 8) | ((min (NMAX, n - c * NMAX) - 1) << 24);
+					}
+					start = j + 1;
+					s = nxt;
 				}
 			}
 		}
@@ -243,7 +284,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 			const u32 d = mhs[rid];
 			const u32 r = d & 0xFFu, j0 = (d >> 8) & 0xFFFFu, n = (d >> 24) + 1;
 			const u32 len = (rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r]) + K - 1;
-			const u32 s = sls[r * g.npos + j0];
+			const u32 s = sls[r * g.npad + j0];
 			const u32 *rd = rt.tile + r * rt.sw;
 			u32 *rec = rec0 + (base + rid) * RECW;
 			const u64 ord = (rb.first_read_ordinal + rt.r0 + r) * rb.maxwin + j0;
@@ -286,7 +327,9 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 	}
 }
 
-// every record to its slice's run: cur[p] starts at off[p]
+// every record to its slice's run: cur[p] starts at off[p].  (Bound by the scattered 32-byte writes:
+// loading the whole record ahead of the cursor atomic, or keeping four records in flight per thread,
+// measured slower — 25.5 against 22.7 ms on C2.)
 __global__ void __launch_bounds__ (SCAT_NT)
 skm_scatter_kernel (const u32 *rec0, const unsigned long long *rec_count, u32 recw, unsigned long long *cur, u32 *rec2)
 {

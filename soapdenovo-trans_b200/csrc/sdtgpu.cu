@@ -710,9 +710,10 @@ int skm_setup (sdtgpu *h, u64 hint)
 	g.nmax = h->W == 1 ? 32 : 64;
 	g.recw = h->W == 1 ? 8 : (h->W == 2 ? 12 : 16);
 	g.npos = (u32) h->max_read_len - g.m + 1;
-	g.tile_reads = std::max (4u, std::min (64u, (8192u / g.npos) & ~3u));
+	g.npad = (std::max (g.npos, g.npos - g.w + 1 + 6) + 3) & ~3u;
+	g.tile_reads = std::max (4u, std::min (64u, (8192u / g.npad) & ~3u));
 	g.slice_a = slice_of_min_host (mmer_hash (0), g.n_slices);
-	if (g.npos * g.tile_reads > 60000 || h->max_read_len > 60000)
+	if (g.npad * g.tile_reads > 60000 || h->max_read_len > 60000)
 		return fail (h, SDTGPU_ERANGE, "max_read_len too large for the sliced build");
 	h->geom = g;
 	h->cap = hint + hint / 8 + 65536;	// node store: compact, one slot per distinct k-mer
@@ -769,7 +770,7 @@ template <int W, bool NMODE> int launch_emit_t (sdtgpu *h, ReadBatch rb)
 	const SkmGeom &g = h->geom;
 	rb.tile_reads = g.tile_reads;
 	auto kern = skm_emit_kernel<W, NMODE>;
-	const size_t smem = 4 * (tile_words (rb, NMODE) + 2 * (size_t) g.tile_reads * g.npos);
+	const size_t smem = 4 * (tile_words (rb, NMODE) + 2 * (size_t) g.tile_reads * g.npad + 16);
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
