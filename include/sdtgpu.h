@@ -185,11 +185,13 @@ int sdtgpu_kernel_time (sdtgpu_t *h, int reset, double *insert_ms, uint64_t *ins
 int sdtgpu_kernel_times (sdtgpu_t *h, int reset, double ms[3], uint64_t launches[3]);
 
 /* per kernel class since the last reset: [0] insert (single-pass, staged or records), [1] count
- * (staged path) or super-k-mer emit (sliced build), [2] scatter, [3] unused, [4] slice build, [5] scans */
+ * (staged path) or super-k-mer emit (sliced build), [2] scatter, [3] record dedupe (sliced build),
+ * [4] slice build, [5] scans, [6] slice build, retried work items */
 int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[8]);
 /* SDTGPU_F_SLICED only: out = { slices, slots per slice image, minimizer length m, m-mers per window,
- * bytes per super-k-mer record, records held, nodes in the store, work items retried by the last build } */
-int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[8]);
+ * bytes per super-k-mer record, records held, nodes in the store, work items retried by the last build,
+ * records left after identical ones were merged (last build), 0, 0, 0 } */
+int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[12]);
 
 /* ---- synthetic reads on the device (bench/test utility; bit-identical to synth.py).
  * d_tr_bases: uint8 codes of all transcripts; d_starts u64[T]; d_lengths u32[T]; d_cum u64[T]. */

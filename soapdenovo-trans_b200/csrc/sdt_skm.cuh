@@ -327,23 +327,47 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 	}
 }
 
-// every record to its slice's run: cur[p] starts at off[p].  (Bound by the scattered 32-byte writes:
-// loading the whole record ahead of the cursor atomic, or keeping four records in flight per thread,
-// measured slower — 25.5 against 22.7 ms on C2.)
+// every record to its slice's run: cur[p] starts at off[p].  The kernel is bound by the rate at which
+// the memory system takes requests to cold lines (profiles/r1_random_access_findings.md), so a record
+// goes out in as few stores as its size allows: one 32-byte store for 1-word keys, two for 4-word keys.
+__device__ __forceinline__ void ld256_stream (const void *p, u64 &a, u64 &b, u64 &c, u64 &d)
+{
+	asm volatile ("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
+template <int RECW>
 __global__ void __launch_bounds__ (SCAT_NT)
-skm_scatter_kernel (const u32 *rec0, const unsigned long long *rec_count, u32 recw, unsigned long long *cur, u32 *rec2)
+skm_scatter_kernel (const u32 *rec0, const unsigned long long *rec_count, unsigned long long *cur, u32 *rec2)
 {
 	const u64 n = *rec_count;
-	const u32 vec = recw >> 2;
 	for (u64 i = blockIdx.x * (u64) SCAT_NT + threadIdx.x; i < n; i += (u64) gridDim.x * SCAT_NT)
 	{
-		const uint4 *src = reinterpret_cast<const uint4 *> (rec0 + i * recw);
-		const uint4 h = ldg_stream (src);
-		const u64 pos = atomicAdd (cur + h.z, 1ull);
-		uint4 *dst = reinterpret_cast<uint4 *> (rec2 + pos * recw);
-		dst[0] = h;
-		for (u32 q = 1; q < vec; q++)
-			dst[q] = ldg_stream (src + q);
+		const u32 *src = rec0 + i * RECW;
+		if constexpr (RECW % 8 == 0)
+		{
+			u64 a, b, c, d;
+			ld256_stream (src, a, b, c, d);
+			const u64 pos = atomicAdd (cur + (u32) b, 1ull);	// word 2: the slice
+			u32 *dst = rec2 + pos * RECW;
+			st256 (dst, a, b, c, d);
+#pragma unroll
+			for (int q = 1; q < RECW / 8; q++)
+			{
+				ld256_stream (src + 8 * q, a, b, c, d);
+				st256 (dst + 8 * q, a, b, c, d);
+			}
+		}
+		else
+		{
+			const uint4 *s4 = reinterpret_cast<const uint4 *> (src);
+			const uint4 h = ldg_stream (s4);
+			const u64 pos = atomicAdd (cur + h.z, 1ull);
+			uint4 *dst = reinterpret_cast<uint4 *> (rec2 + pos * RECW);
+			dst[0] = h;
+#pragma unroll
+			for (int q = 1; q < RECW / 4; q++)
+				dst[q] = ldg_stream (s4 + q);
+		}
 	}
 }
 

@@ -93,7 +93,7 @@ struct sdtgpu
 	void *d_failed = nullptr, *d_items = nullptr;	// SkmWork lists
 	u32 *rec0 = nullptr, *rec2 = nullptr;	// super-k-mer records: as emitted, grouped by slice
 	u64 rec0_cap = 0, rec2_cap = 0, rec_upper = 0;	// records
-	u64 n_store = 0, n_records = 0, n_retried = 0;	// nodes in the store after the last build
+	u64 n_store = 0, n_records = 0, n_retried = 0, n_merged = 0;	// nodes in the store after the last build
 	bool dirty = false;	// records were emitted since the last build
 	u32 n_epochs = 0;
 	struct Timed { cudaEvent_t e0, e1; int cat; };
@@ -695,7 +695,7 @@ int skm_setup (sdtgpu *h, u64 hint)
 		if (prime)
 			break;
 	}
-	double load = 0.5;
+	double load = 0.45;
 	if (const char *e = getenv ("SDTGPU_SLICE_LOAD"))
 		if (atof (e) > 0.05 && atof (e) < 0.95)
 			load = atof (e);
@@ -932,7 +932,13 @@ int sliced_flush (sdtgpu *h)
 	{
 		const unsigned grid = (unsigned) std::min<u64> ((n_rec + SCAT_NT - 1) / SCAT_NT, (u64) h->sm_count * 8);
 		TimedLaunch tl (h, 2);
-		skm_scatter_kernel<<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, g.recw, reinterpret_cast<unsigned long long *> (h->d_cur2), h->rec2);
+		unsigned long long *cur = reinterpret_cast<unsigned long long *> (h->d_cur2);
+		if (g.recw == 8)
+			skm_scatter_kernel<8><<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, cur, h->rec2);
+		else if (g.recw == 12)
+			skm_scatter_kernel<12><<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, cur, h->rec2);
+		else
+			skm_scatter_kernel<16><<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, cur, h->rec2);
 	}
 	CK (h, cudaGetLastError ());
 	if (n_rec)
@@ -950,6 +956,7 @@ int sliced_flush (sdtgpu *h)
 	for (u32 depth = 0;; depth++)
 	{
 		CK (h, cudaMemcpyAsync (h->h_small + 1, small + 1, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (h->h_small + 4, small + 4, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaStreamSynchronize (h->stream));
 		if (h->h_small[3] & 4)
@@ -986,6 +993,7 @@ int sliced_flush (sdtgpu *h)
 		CK (h, cudaStreamSynchronize (h->stream));	// `items` is pageable host memory
 	}
 	h->n_store = h->h_small[1];
+	h->n_merged = n_rec ? h->h_small[4] : 0;
 	h->table_built = true;
 	h->dirty = false;
 	h->n_epochs++;
@@ -1671,7 +1679,7 @@ int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[
 	return SDTGPU_OK;
 }
 
-int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[8])
+int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[12])
 {
 	if (!h || !out)
 		return SDTGPU_EINVAL;
@@ -1679,6 +1687,7 @@ int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[8])
 		return SDTGPU_ESTATE;
 	out[0] = h->geom.n_slices; out[1] = h->geom.slice_slots; out[2] = h->geom.m; out[3] = h->geom.w;
 	out[4] = 4 * (uint64_t) h->geom.recw; out[5] = h->n_records; out[6] = h->n_store; out[7] = h->n_retried;
+	out[8] = h->n_merged; out[9] = out[10] = out[11] = 0;
 	return SDTGPU_OK;
 }
 

@@ -284,10 +284,10 @@ class PregraphGPU:
         return {PHASES[i]: (ms[i], nl[i]) for i in range(7)}
 
     def slice_geometry(self):
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 12)()
         self._ck(self.L.sdtgpu_slice_geometry(self.h, out))
         return dict(n_slices=out[0], slice_slots=out[1], m=out[2], mmers_per_window=out[3], record_bytes=out[4],
-                    n_records=out[5], n_nodes=out[6], retried_items=out[7])
+                    n_records=out[5], n_nodes=out[6], retried_items=out[7], n_records_merged=out[8])
 
     def kernel_times(self, reset: bool = True):
         """(ms[3], launches[3]) for insert / partition-count / partition-scatter kernels."""
