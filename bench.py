@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--batch-reads", type=int, default=1 << 22)
-    ap.add_argument("--exchange", default="reads", choices=["reads", "records"],
+    ap.add_argument("--exchange", default="reads", choices=["reads", "records", "reads-replicated"],
                     help="multi-GPU sharding: all-gather the packed reads and insert owned k-mers (default) or exchange k-mer records")
     ap.add_argument("--partitioned", action="store_true", help="experimental staged/partitioned insert path")
     ap.add_argument("--path", default="auto", choices=["auto", "direct", "sliced", "partitioned"],
@@ -211,10 +211,12 @@ def main():
     g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(est_distinct) + 1024, device=local_rank, partitioned=args.partitioned, sliced=sliced)
     ext = torch.cuda.ExternalStream(g.stream, device=dev)
 
-    exch = None
+    exch, exch_kind = None, None
     if world > 1:
-        from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads
-        if args.exchange == "records":
+        from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads, SkmExchange
+        if sliced and args.exchange != "reads-replicated":
+            exch, exch_kind = SkmExchange(pkg, g, world, rank, dev), "skm"
+        elif args.exchange == "records":
             exch = Exchange(pkg, g, world, rank, dev, max_round_instances=min(batch, n_reads) * nwin)
         else:
             exch = ReplicatedReads(pkg, g, world, rank, dev, max_round_reads=min(batch, n_reads), stride=stride)
@@ -236,6 +238,10 @@ def main():
     st = g.stats()
     distinct = st.n_nodes
     assert (exch is not None) or st.n_instances == instances_rank, (st.n_instances, instances_rank)
+    if world > 1:       # one geometry on all ranks (the super-k-mer exchange cuts the minimizer space by it)
+        dmax = torch.tensor([distinct], dtype=torch.int64, device=dev)
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        distinct = int(dmax.item())
     g.close()
     # the library sizes the table from the hint: load 0.5 up to 60 GiB, denser beyond
     g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(distinct * 1.02) + 1024, device=local_rank, partitioned=args.partitioned, sliced=sliced)
@@ -339,6 +345,8 @@ def main():
                         exch.aux.wait_event(exch.inserted[exch.r & 1])      # same buffer parity as the exchange
                         buf[: b - a].copy_(h_packed[a:b], non_blocking=True)
                     exch.round(g, buf, b - a, L, stride, 2 * first_pair + a)
+            if exch is not None:
+                exch.flush(g)
             g.sync()
             return g.stats()
         e2e_step()
@@ -374,7 +382,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers sharded by owner ({'packed reads all-gathered over NCCL, every rank inserts the k-mers it owns' if args.exchange == 'reads' else 'k-mer records exchanged over NCCL'})" if world > 1 else ""),
+            "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers sharded by owner ({'super-k-mer records of the sliced build exchanged over NCCL, one all-to-all per step' if exch_kind == 'skm' else ('packed reads all-gathered over NCCL, every rank inserts the k-mers it owns' if args.exchange != 'records' else 'k-mer records exchanged over NCCL')})" if world > 1 else ""),
                        "instances_per_step": total_instances, "distinct_kmers": total_nodes,
                        "table_slots_per_gpu": int(st.capacity), "slot_bytes": 64 if st.device_key_words == 4 else 32,
                        "batch_reads": batch,

@@ -193,6 +193,24 @@ int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[
  * records left after identical ones were merged (last build), 0, 0, 0 } */
 int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[12]);
 
+/* ---- super-k-mer exchange: the sliced build on several GPUs, one process per GPU (SDTGPU_F_SLICED).
+ * The reference shards k-mers over its threads by hash (prlHashReads.c:79-88); here the table slices
+ * (ranges of minimizers) are dealt to the ranks in contiguous ranges, so whole super-k-mer records
+ * travel — 4 bytes per k-mer instance instead of a 16-byte record each.  Per epoch, on every rank:
+ *   sdtgpu_skm_set_world   once, before the first push: rank and number of ranks;
+ *   sdtgpu_push_reads*     this rank's own reads (global first_read_ordinal);
+ *   sdtgpu_skm_stage       groups the records by slice: *d_records = device address of the records,
+ *                          offsets[r] .. offsets[r + 1] = the records (units: records of
+ *                          sdtgpu_slice_geometry()[4] bytes) that belong to rank r, r < world;
+ *   (caller)               all-to-all of counts and records (NCCL) into the buffer that
+ *   sdtgpu_skm_import_buffer  returns for the total it is going to receive;
+ *   sdtgpu_skm_import      builds this rank's slices from the n_records received.
+ * Afterwards finalize / export / stats see this rank's share of the table. */
+int sdtgpu_skm_set_world (sdtgpu_t *h, int rank, int world);
+int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *offsets /* world + 1 */);
+int sdtgpu_skm_import_buffer (sdtgpu_t *h, uint64_t n_records, void **d_buffer);
+int sdtgpu_skm_import (sdtgpu_t *h, uint64_t n_records);
+
 /* ---- synthetic reads on the device (bench/test utility; bit-identical to synth.py).
  * d_tr_bases: uint8 codes of all transcripts; d_starts u64[T]; d_lengths u32[T]; d_cum u64[T]. */
 int sdtgpu_synth_reads_device (int device, void *stream, const uint8_t *d_tr_bases, const uint64_t *d_starts,

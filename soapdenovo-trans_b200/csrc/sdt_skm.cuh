@@ -371,6 +371,25 @@ skm_scatter_kernel (const u32 *rec0, const unsigned long long *rec_count, unsign
 	}
 }
 
+// super-k-mer exchange, receiving side: records that arrived from all ranks carry global slice
+// numbers; this rank owns slices [lo, lo + n_local).  Re-base them and count records per slice.
+__global__ void __launch_bounds__ (SCAT_NT)
+skm_recount_kernel (u32 *rec, u64 n, u32 recw, u32 lo, u32 n_local, u32 *hist, Counters *ctr)
+{
+	for (u64 i = blockIdx.x * (u64) SCAT_NT + threadIdx.x; i < n; i += (u64) gridDim.x * SCAT_NT)
+	{
+		u32 *w2 = rec + i * recw + 2;
+		const u32 s = *w2 - lo;
+		if (s >= n_local)
+		{	// not this rank's: the exchange went wrong
+			atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 16ull);
+			continue;
+		}
+		*w2 = s;
+		atomicAdd (hist + s, 1u);	// RED
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // Copies of the same super-k-mer collapse into one record before the build.  At the coverage of a
 // transcriptome most records of a slice are byte-identical copies (every error-free read that spans

@@ -93,6 +93,8 @@ struct sdtgpu
 	void *d_failed = nullptr, *d_items = nullptr;	// SkmWork lists
 	u32 *rec0 = nullptr, *rec2 = nullptr;	// super-k-mer records: as emitted, grouped by slice
 	u64 rec0_cap = 0, rec2_cap = 0, rec_upper = 0;	// records
+	u32 n_local_or_all () const { return n_local ? n_local : geom.n_slices; }
+	u32 skm_world = 1, skm_rank = 0, n_local = 0;	// super-k-mer exchange (sdtgpu_skm_set_world): slices per rank; geom.n_slices = n_local * skm_world
 	u64 n_store = 0, n_records = 0, n_retried = 0, n_merged = 0;	// nodes in the store after the last build
 	bool dirty = false;	// records were emitted since the last build
 	u32 n_epochs = 0;
@@ -822,7 +824,7 @@ template <int W, int NT> int launch_build_t (sdtgpu *h, const SkmWork *items, u3
 	return SDTGPU_OK;
 }
 
-template <int W> int launch_dedupe_t (sdtgpu *h)
+template <int W> int launch_dedupe_t (sdtgpu *h, u32 n_slices)
 {
 	auto kern = skm_dedupe_kernel<W>;
 	const size_t smem = skm_dedupe_smem<W> ();
@@ -831,24 +833,24 @@ template <int W> int launch_dedupe_t (sdtgpu *h)
 	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, DD_NT, smem));
 	if (occ < 1)
 		return fail (h, SDTGPU_ECUDA, "skm_dedupe_kernel does not fit");
-	const unsigned grid = (unsigned) std::min<u64> (h->geom.n_slices, (u64) h->sm_count * occ);
+	const unsigned grid = (unsigned) std::min<u64> (n_slices, (u64) h->sm_count * occ);
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	CK (h, cudaMemsetAsync (small + 4, 0, sizeof (u64), h->stream));	// surviving records
 	{
 		TimedLaunch tl (h, 3);
-		kern<<<grid, DD_NT, smem, h->stream>>> (h->rec2, h->d_off, h->geom.n_slices, reinterpret_cast<unsigned long long *> (h->d_cur2), small + 4);
+		kern<<<grid, DD_NT, smem, h->stream>>> (h->rec2, h->d_off, n_slices, reinterpret_cast<unsigned long long *> (h->d_cur2), small + 4);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
 }
 
-int launch_dedupe (sdtgpu *h)
+int launch_dedupe (sdtgpu *h, u32 n_slices)
 {
 	switch (h->W)
 	{
-	case 1: return launch_dedupe_t<1> (h);
-	case 2: return launch_dedupe_t<2> (h);
-	default: return launch_dedupe_t<4> (h);
+	case 1: return launch_dedupe_t<1> (h, n_slices);
+	case 2: return launch_dedupe_t<2> (h, n_slices);
+	default: return launch_dedupe_t<4> (h, n_slices);
 	}
 }
 
@@ -882,24 +884,10 @@ int skm_emit_all (sdtgpu *h)
 	return SDTGPU_OK;
 }
 
-// Everything pushed since the last reset becomes the node store: scan the per-slice record counts,
-// move every record to its slice's run, build the slices.  Records persist until sdtgpu_reset, so a
-// later push followed by another flush rebuilds the store from all of them.
-int sliced_flush (sdtgpu *h)
+// part 1 of a flush: how many records the pushes produced (re-emitting the read log if the record area ran out)
+int skm_collect (sdtgpu *h, u64 *n_rec)
 {
 	int rc;
-	if (h->table_built && !h->dirty)
-		return SDTGPU_OK;
-	const SkmGeom g = h->geom;
-	const size_t rec = 4 * (size_t) g.recw;
-	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
-	h->n_store = 0;
-	if (h->log.empty ())
-	{
-		h->table_built = true;
-		h->dirty = false;
-		return SDTGPU_OK;
-	}
 	for (int attempt = 0;; attempt++)
 	{
 		CK (h, cudaMemcpyAsync (h->h_small, h->d_small, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
@@ -912,19 +900,29 @@ int sliced_flush (sdtgpu *h)
 		if ((rc = skm_emit_all (h)))
 			return rc;
 	}
-	const u64 n_rec = h->h_small[0];
-	h->n_records = n_rec;
+	*n_rec = h->h_small[0];
+	return SDTGPU_OK;
+}
+
+// part 2: the n_rec records of rec0 (their count is also in d_small[0]) go to rec2, grouped by slice:
+// scan of d_hist[0 .. n_slices) -> d_off, d_cur2; scatter
+int skm_group (sdtgpu *h, u64 n_rec, u32 n_slices)
+{
+	int rc;
+	const SkmGeom &g = h->geom;
+	const size_t rec = 4 * (size_t) g.recw;
+	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	{
 		size_t cap_b = h->rec2_cap * rec;
 		if ((rc = grow_device (h, (void **) &h->rec2, &cap_b, 0, std::max<u64> (n_rec, 1) * rec)))
 			return rc;
 		h->rec2_cap = cap_b / rec;
 	}
-	const u32 nseg = (g.n_slices + SCAN_SEG - 1) / SCAN_SEG;
+	const u32 nseg = (n_slices + SCAN_SEG - 1) / SCAN_SEG;
 	{
 		TimedLaunch tl (h, 5);
-		slice_scan_sums_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, g.n_slices, h->d_seg_sum);
-		slice_scan_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, g.n_slices, h->d_seg_sum, h->d_off, h->d_cur2);
+		slice_scan_sums_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, n_slices, h->d_seg_sum);
+		slice_scan_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, n_slices, h->d_seg_sum, h->d_off, h->d_cur2);
 		h->all_launches++;
 	}
 	CK (h, cudaGetLastError ());
@@ -941,15 +939,52 @@ int sliced_flush (sdtgpu *h)
 			skm_scatter_kernel<16><<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, cur, h->rec2);
 	}
 	CK (h, cudaGetLastError ());
+	return SDTGPU_OK;
+}
+
+int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices);
+
+// Everything pushed since the last reset becomes the node store: scan the per-slice record counts,
+// move every record to its slice's run, build the slices.  Records persist until sdtgpu_reset, so a
+// later push followed by another flush rebuilds the store from all of them.
+int sliced_flush (sdtgpu *h)
+{
+	int rc;
+	if (h->table_built && !h->dirty)
+		return SDTGPU_OK;
+	h->n_store = 0;
+	if (h->log.empty ())
+	{
+		h->table_built = true;
+		h->dirty = false;
+		return SDTGPU_OK;
+	}
+	if (h->skm_world > 1)
+		return fail (h, SDTGPU_ESTATE, "super-k-mer exchange: reads were pushed but sdtgpu_skm_stage / sdtgpu_skm_import have not run");
+	u64 n_rec = 0;
+	if ((rc = skm_collect (h, &n_rec)))
+		return rc;
+	h->n_records = n_rec;
+	if ((rc = skm_group (h, n_rec, h->geom.n_slices)))
+		return rc;
+	return skm_build_all (h, n_rec, h->geom.n_slices);
+}
+
+// part 3: rec2 (grouped by slice, n_slices slices) -> node store
+int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
+{
+	int rc;
+	const SkmGeom g = h->geom;
+	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	if (n_rec)
 	{	// copies of a super-k-mer collapse into one record with a multiplicity; d_cur2[slice] becomes the end of what is left
-		if (int rc2 = launch_dedupe (h))
+		if (int rc2 = launch_dedupe (h, n_slices))
 			return rc2;
 	}
 	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over
 	CK (h, cudaMemsetAsync (small + 1, 0, 2 * sizeof (u64), h->stream));
 	CK (h, cudaMemsetAsync (&h->d_ctr->n_nodes, 0, 2 * sizeof (u64), h->stream));	// n_nodes, n_instances
-	if ((rc = launch_build (h, nullptr, g.n_slices, 4)))
+	if ((rc = launch_build (h, nullptr, n_slices, 4)))
 		return rc;
 	h->n_retried = 0;
 	std::vector<SkmWork> items, failed;
@@ -961,6 +996,8 @@ int sliced_flush (sdtgpu *h)
 		CK (h, cudaStreamSynchronize (h->stream));
 		if (h->h_small[3] & 4)
 			return fail (h, SDTGPU_ERANGE, "node store exhausted: capacity_hint was too small for the sliced build");
+		if (h->h_small[3] & 16)
+			return fail (h, SDTGPU_EINVAL, "super-k-mer exchange: a received record belongs to another rank's slices");
 		const u32 n_failed = (u32) h->h_small[2];
 		if (n_failed == 0)
 			break;
@@ -1317,6 +1354,108 @@ int sdtgpu_set_owner (sdtgpu_t *h, int rank, int n_ranks)
 	h->owner_rank = (u32) rank;
 	h->owner_ranks = (u32) n_ranks;
 	return SDTGPU_OK;
+}
+
+// ---- super-k-mer exchange (multi-GPU sliced build): the slices are dealt to the ranks in contiguous
+// ranges; a rank turns ITS reads into records, groups them by (global) slice — which groups them by
+// owner — hands the runs to the caller's all-to-all, and builds its own slices from what it receives.
+int sdtgpu_skm_set_world (sdtgpu_t *h, int rank, int world)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	if (!h->sliced)
+		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_set_world needs SDTGPU_F_SLICED");
+	if (world < 1 || rank < 0 || rank >= world)
+		return fail (h, SDTGPU_EINVAL, "sdtgpu_skm_set_world: need 0 <= rank < world");
+	if (!h->log.empty ())
+		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_set_world must precede the pushes of an epoch");
+	CK (h, cudaSetDevice (h->device));
+	if (h->n_local == 0)
+		h->n_local = h->geom.n_slices;	// from capacity_hint = the distinct k-mers expected on THIS rank
+	if ((u64) h->n_local * (u64) world > (1ull << 30))
+		return fail (h, SDTGPU_ERANGE, "too many slices");
+	CK (h, cudaStreamSynchronize (h->stream));
+	cudaFree (h->d_hist); cudaFree (h->d_off); cudaFree (h->d_cur2); cudaFree (h->d_seg_sum);
+	h->d_hist = nullptr; h->d_off = h->d_cur2 = h->d_seg_sum = nullptr;
+	h->skm_world = (u32) world;
+	h->skm_rank = (u32) rank;
+	SkmGeom &g = h->geom;
+	g.n_slices = h->n_local * (u32) world;
+	g.slice_a = slice_of_min_host (mmer_hash (0), g.n_slices);
+	const u32 nseg = (g.n_slices + SCAN_SEG - 1) / SCAN_SEG;
+	CK (h, cudaMalloc (&h->d_hist, (size_t) g.n_slices * sizeof (u32)));
+	CK (h, cudaMalloc (&h->d_off, ((size_t) g.n_slices + 1) * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_cur2, (size_t) g.n_slices * sizeof (u64)));
+	CK (h, cudaMalloc (&h->d_seg_sum, (size_t) nseg * sizeof (u64)));
+	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) g.n_slices * sizeof (u32), h->stream));
+	return SDTGPU_OK;
+}
+
+int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *offsets)
+{
+	int rc;
+	if (!h || !d_records || !offsets)
+		return SDTGPU_EINVAL;
+	if (!h->sliced)
+		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_stage needs SDTGPU_F_SLICED");
+	CK (h, cudaSetDevice (h->device));
+	u64 n_rec = 0;
+	if (h->log.empty ())
+		CK (h, cudaMemsetAsync (h->d_small, 0, sizeof (u64), h->stream));
+	if ((rc = skm_collect (h, &n_rec)))
+		return rc;
+	h->n_records = n_rec;
+	if ((rc = skm_group (h, n_rec, h->geom.n_slices)))
+		return rc;
+	for (u32 r = 0; r <= h->skm_world; r++)	// first record of every rank's slice range
+		CK (h, cudaMemcpyAsync (offsets + r, h->d_off + (size_t) r * h->n_local_or_all (), sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	*d_records = h->rec2;
+	return SDTGPU_OK;
+}
+
+int sdtgpu_skm_import_buffer (sdtgpu_t *h, uint64_t n_records, void **d_buffer)
+{
+	int rc;
+	if (!h || !d_buffer)
+		return SDTGPU_EINVAL;
+	if (!h->sliced)
+		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_import_buffer needs SDTGPU_F_SLICED");
+	CK (h, cudaSetDevice (h->device));
+	const size_t rec = 4 * (size_t) h->geom.recw;
+	size_t cap_b = h->rec0_cap * rec;
+	if ((rc = grow_device (h, (void **) &h->rec0, &cap_b, 0, std::max<u64> (n_records, 1) * rec)))
+		return rc;
+	h->rec0_cap = cap_b / rec;
+	*d_buffer = h->rec0;
+	return SDTGPU_OK;
+}
+
+int sdtgpu_skm_import (sdtgpu_t *h, uint64_t n_records)
+{
+	int rc;
+	if (!h)
+		return SDTGPU_EINVAL;
+	if (!h->sliced)
+		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_import needs SDTGPU_F_SLICED");
+	if (n_records > h->rec0_cap)
+		return fail (h, SDTGPU_EINVAL, "sdtgpu_skm_import: more records than sdtgpu_skm_import_buffer made room for");
+	CK (h, cudaSetDevice (h->device));
+	const u32 n_local = h->n_local_or_all ();
+	h->h_small[5] = n_records;
+	CK (h, cudaMemcpyAsync (h->d_small, h->h_small + 5, sizeof (u64), cudaMemcpyHostToDevice, h->stream));
+	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) n_local * sizeof (u32), h->stream));
+	if (n_records)
+	{
+		const unsigned grid = (unsigned) std::min<u64> ((n_records + SCAT_NT - 1) / SCAT_NT, (u64) h->sm_count * 8);
+		TimedLaunch tl (h, 1);
+		skm_recount_kernel<<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, n_records, h->geom.recw, h->skm_rank * n_local, n_local, h->d_hist, h->d_ctr);
+	}
+	CK (h, cudaGetLastError ());
+	h->n_store = 0;
+	if ((rc = skm_group (h, n_records, n_local)))
+		return rc;
+	return skm_build_all (h, n_records, n_local);
 }
 
 size_t sdtgpu_record_bytes (const sdtgpu_t *h) { return h ? 8 * (size_t) (h->W + 1) : 0; }

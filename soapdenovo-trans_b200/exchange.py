@@ -11,6 +11,12 @@ owns (:79-88).  Two ways to stretch that over GPUs live here:
   (sdtgpu_bucket_reads_device), the bins cross NVLink with one grouped NCCL send/recv per round and
   each rank upserts what it received (sdtgpu_insert_records_device).
 
+* `SkmExchange` (sliced build, `PregraphGPU(..., sliced=True)`): each rank turns only its own reads
+  into super-k-mer records (one record per ~8 consecutive windows, 4 bytes per instance), the table
+  slices are dealt to the ranks in contiguous ranges, the records are grouped by slice — hence by
+  owner — and cross NVLink in ONE variable-size all-to-all per epoch; every rank then builds its own
+  slices in shared memory (sdtgpu_skm_stage / sdtgpu_skm_import).
+
 Updates are commutative, so arrival order is free and the union of the ranks' tables is the
 reference's multiset either way.
 
@@ -157,3 +163,70 @@ class ReplicatedReads:
 
     def flush(self, g):
         pass
+
+
+class _DevMem:
+    """A device allocation owned by the library, seen by torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (max(nbytes // 8, 1),), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def _wrap(ptr: int, nbytes: int, dev) -> torch.Tensor:
+    if nbytes == 0 or ptr == 0:
+        return torch.empty(0, dtype=torch.int64, device=dev)
+    return torch.as_tensor(_DevMem(ptr, nbytes), device=dev)[: nbytes // 8]
+
+
+class SkmExchange:
+    """Round driver of the super-k-mer exchange (sliced build on several GPUs).  `round` only pushes this
+    rank's reads (the emit kernel runs, nothing crosses the fabric yet); `flush` groups the records by
+    slice, exchanges counts and records with two all-to-alls and builds this rank's slices."""
+
+    def __init__(self, pkg, g, world: int, rank: int, dev, group=None):
+        self.world, self.rank, self.dev, self.group = world, rank, dev, group
+        self.nvlink_bytes = 0
+        self.rebind(g)
+
+    def rebind(self, g):
+        g.skm_set_world(self.rank, self.world)
+        geo = g.slice_geometry()
+        self.rec_bytes = int(geo["record_bytes"])
+        self.main = torch.cuda.ExternalStream(g.stream, device=self.dev)
+        self.aux = torch.cuda.ExternalStream(g.aux_stream, device=self.dev)     # the caller may stage a round's reads on it
+        self.inserted = [torch.cuda.Event() for _ in range(2)]
+        self.r = 0
+        # every rank must cut the minimizer space the same way: same capacity_hint, K and minimizer length
+        mine = torch.tensor([geo["n_slices"], geo["m"], geo["slice_slots"]], dtype=torch.int64, device=self.dev)
+        seen = torch.empty((self.world, 3), dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(seen.view(-1), mine, group=self.group)
+        if not bool((seen == mine).all()):
+            raise ValueError(f"SkmExchange: ranks disagree on the slice geometry (pass the same capacity_hint everywhere): {seen.tolist()}")
+
+    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None):
+        b = self.r & 1
+        self.r += 1
+        staged = torch.cuda.Event()
+        staged.record(self.aux)                     # whatever the caller queued on the auxiliary stream (an H2D copy of the round)
+        self.main.wait_event(staged)
+        g.push_reads(d_packed, d_lens, None, n_reads=int(n_reads), uniform_len=uniform_len, stride_bytes=stride,
+                     first_read_ordinal=int(first_read_ordinal), device=True)
+        self.inserted[b].record(self.main)          # the round's buffer is free again (the library keeps its own copy of the reads)
+
+    def flush(self, g):
+        ptr, offs = g.skm_stage()                   # synchronises the handle's stream
+        rb, w8 = self.rec_bytes, self.rec_bytes // 8
+        send_counts = [offs[r + 1] - offs[r] for r in range(self.world)]
+        with torch.cuda.stream(self.main):
+            sc = torch.tensor(send_counts, dtype=torch.int64, device=self.dev)
+            rc = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+            dist.all_to_all_single(rc, sc, group=self.group)
+            recv_counts = [int(x) for x in rc.tolist()]
+            total = sum(recv_counts)
+            send = _wrap(ptr + offs[0] * rb, (offs[-1] - offs[0]) * rb, self.dev)
+            recv = _wrap(g.skm_import_buffer(total), total * rb, self.dev)
+            dist.all_to_all_single(recv, send, output_split_sizes=[n * w8 for n in recv_counts],
+                                   input_split_sizes=[n * w8 for n in send_counts], group=self.group)
+            self.nvlink_bytes += (sum(send_counts) - send_counts[self.rank]) * rb
+        g.skm_import(total)                         # on the handle's stream, after the all-to-all
+        return total

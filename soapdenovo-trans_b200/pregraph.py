@@ -79,6 +79,10 @@ def library() -> C.CDLL:
     L.sdtgpu_push_reads.argtypes = [vp, vp, vp, vp, u64, u32, u32, u64]
     L.sdtgpu_push_reads_device.argtypes = [vp, vp, vp, vp, u64, u32, u32, u64]
     L.sdtgpu_set_owner.argtypes = [vp, i32, i32]
+    L.sdtgpu_skm_set_world.argtypes = [vp, i32, i32]
+    L.sdtgpu_skm_stage.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.sdtgpu_skm_import_buffer.argtypes = [vp, u64, C.POINTER(vp)]
+    L.sdtgpu_skm_import.argtypes = [vp, u64]
     L.sdtgpu_record_bytes.restype = C.c_size_t
     L.sdtgpu_record_bytes.argtypes = [vp]
     L.sdtgpu_bucket_reads_device.argtypes = [vp, vp, vp, vp, u64, u32, u32, u64, i32, vp, u64, vp]
@@ -227,6 +231,26 @@ class PregraphGPU:
 
     def set_owner(self, rank: int, n_ranks: int):
         self._ck(self.L.sdtgpu_set_owner(self.h, rank, n_ranks))
+
+    # ---- super-k-mer exchange (multi-GPU sliced build; include/sdtgpu.h)
+    def skm_set_world(self, rank: int, world: int):
+        self._ck(self.L.sdtgpu_skm_set_world(self.h, rank, world))
+        self._skm_world = world
+
+    def skm_stage(self):
+        """-> (device address of the records grouped by slice, offsets[world + 1] in records)."""
+        world = getattr(self, "_skm_world", 1)
+        ptr, offs = C.c_void_p(), (C.c_uint64 * (world + 1))()
+        self._ck(self.L.sdtgpu_skm_stage(self.h, C.byref(ptr), offs))
+        return int(ptr.value or 0), [int(x) for x in offs]
+
+    def skm_import_buffer(self, n_records: int) -> int:
+        ptr = C.c_void_p()
+        self._ck(self.L.sdtgpu_skm_import_buffer(self.h, n_records, C.byref(ptr)))
+        return int(ptr.value or 0)
+
+    def skm_import(self, n_records: int):
+        self._ck(self.L.sdtgpu_skm_import(self.h, n_records))
 
     def record_bytes(self) -> int:
         return int(self.L.sdtgpu_record_bytes(self.h))

@@ -26,7 +26,7 @@ def _worker(rank, world, port, K, kw, L, d, out_dir, mode):
     import torch.distributed as dist
     import sdt_pkg
     pkg = sdt_pkg.load()
-    from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads
+    from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads, SkmExchange
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -39,14 +39,17 @@ def _worker(rank, world, port, K, kw, L, d, out_dir, mode):
     stride = synth.stride_bytes(L)
     d_packed = torch.from_numpy(synth.pack_reads(reads[lo:hi], lens[lo:hi], stride)).to(dev)
     d_lens = torch.from_numpy(lens[lo:hi].astype(np.int32)).to(dev)
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=1_500_000, device=rank)
-    if mode == "records":
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=1_500_000, device=rank, sliced=(mode == "skm"))
+    if mode == "skm":
+        ex = SkmExchange(pkg, g, world, rank, dev)
+    elif mode == "records":
         ex = Exchange(pkg, g, world, rank, dev, max_round_instances=2048 * (L - K + 1))
     else:
         ex = ReplicatedReads(pkg, g, world, rank, dev, max_round_reads=2048, stride=stride)
     for a in range(0, hi - lo, 2048):                            # several rounds, exercises the double buffering
         b = min(a + 2048, hi - lo)
         ex.round(g, d_packed[a:b], b - a, 0, stride, lo + a, d_lens=d_lens[a:b])
+    ex.flush(g)
     g.sync()
     freq, st = g.finalize(d)
     nodes = g.export_nodes(8)
@@ -58,7 +61,7 @@ def _worker(rank, world, port, K, kw, L, d, out_dir, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["reads", "records"])
+@pytest.mark.parametrize("mode", ["reads", "records", "skm"])
 @pytest.mark.parametrize("K,kw,L,d", [(25, 1, 100, 0), (63, 4, 100, 1), (127, 4, 150, 0)])
 def test_two_gpu_union_matches_oracle(pkg, oracle, tmp_path, K, kw, L, d, mode):
     import torch

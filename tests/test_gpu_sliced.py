@@ -63,6 +63,39 @@ def test_sliced_two_ctas_per_sm(pkg, oracle, tiny_transcriptome, monkeypatch, K,
     check_against_oracle(pkg, oracle, reads, lens, K, kw, d=1, batches=2, hint=400_000, sliced=True)
 
 
+@pytest.mark.parametrize("K,kw", [(31, 1), (63, 2), (127, 4)])
+def test_skm_stage_import_one_rank(pkg, oracle, tiny_transcriptome, K, kw):
+    """The two halves of the multi-GPU super-k-mer exchange on one GPU: stage (records grouped by slice),
+    a device copy standing in for the all-to-all, import (re-base, count, group, build)."""
+    import torch
+    from soapdenovo_trans_b200.exchange import _wrap
+    L = 150 if K > 63 else 100
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, L, 5 + K, ragged=30)
+    synth = pkg.synth
+    stride = synth.stride_bytes(L)
+    packed = synth.pack_reads(reads, lens, stride)
+    ref = oracle.run_hashing(reads, lens, K, kw, 8, 1)
+    dev = torch.device("cuda", 0)
+    with pkg.PregraphGPU(K, kw, L, capacity_hint=400_000, sliced=True) as g:
+        g.skm_set_world(0, 1)
+        g.push_reads(packed, lens, None, n_reads=len(reads), stride_bytes=stride)
+        ptr, offs = g.skm_stage()
+        n = offs[1] - offs[0]
+        rb = g.slice_geometry()["record_bytes"]
+        assert offs[0] == 0 and n == g.slice_geometry()["n_records"] > 0
+        src = _wrap(ptr, n * rb, dev).clone()
+        torch.cuda.synchronize()
+        dst = _wrap(g.skm_import_buffer(n), n * rb, dev)
+        dst.copy_(src)
+        torch.cuda.synchronize()
+        g.skm_import(n)
+        freq, st = g.finalize(1)
+        assert (st.n_instances, st.n_nodes, st.n_removed, st.n_linear) == (ref.instances, ref.nodes, ref.removed, ref.linear)
+        assert np.array_equal(freq, ref.kmerfreq)
+        rec, info = g.export_kmersets(8)
+        assert np.array_equal(info, ref.set_info) and np.array_equal(rec, ref.records)
+
+
 def test_sliced_interleaved_stats_and_pushes(pkg, oracle, tiny_transcriptome):
     """stats() between pushes builds the store early; later pushes rebuild it from all records."""
     reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, 100, 41, ragged=10)
