@@ -34,7 +34,7 @@ BYTES_PER_INSTANCE = {1: 64, 2: 64, 4: 96}
 # upsert needs at least one load and one atomic, so a single-pass insert cannot exceed half of that.
 RANDOM_REQUESTS_PER_S = 36.65e9
 MIN_REQUESTS_PER_INSTANCE = {1: 2, 2: 2, 4: 3}
-DEFAULT_PATH = {1: "sliced", 2: "direct"}     # key: 1 GPU / more than one GPU
+DEFAULT_PATH = {1: "sliced", 2: "sliced"}     # key: 1 GPU / more than one GPU (super-k-mer exchange)
 METRIC = "k-mers inserted/s in pregraph hashing"
 UNIT = "k-mer instances/s"
 
