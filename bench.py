@@ -315,8 +315,8 @@ def main():
         inst_per_launch = st.n_instances * args.steps / max(insert_launches, 1)
     achieved = inst_per_launch * bpi / (ker_ms * 1e-3) / 1e9
     traffic = None      # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tp) and world == 1 and args.path == "direct":
+    tp = os.path.join(ROOT, "profiles", "r1_traffic_sliced.json" if sliced else "r1_traffic.json")
+    if os.path.exists(tp) and world == 1 and args.path in ("direct", "sliced"):
         with open(tp) as f:
             tj = json.load(f)
         if tj.get("key_words") == st.device_key_words:
