@@ -135,15 +135,16 @@ def main():
     args = ap.parse_args()
     if args.partitioned:
         args.path = "partitioned"
-    if args.path == "auto":
-        args.path = DEFAULT_PATH[1 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 2]
-    args.partitioned = args.path == "partitioned"
-    sliced = args.path == "sliced"
-
     import sdt_pkg
     pkg = sdt_pkg.load()
     synth = pkg.synth
     cfg_d = dict(synth.CONFIGS[args.config])
+    if args.path == "auto":
+        # the sliced build is tuned for 1-word keys (K <= 31, the metric's config); at K = 63 / 127 super-k-mers are
+        # 2-4x longer, the slices lumpier (11 % of them overflow on C3) and the single-pass insert is faster
+        args.path = DEFAULT_PATH[1 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 2] if cfg_d["key_words"] == 1 and cfg_d["K"] <= 31 and not cfg_d["hot"] else "direct"
+    args.partitioned = args.path == "partitioned"
+    sliced = args.path == "sliced"
     if args.pairs:
         cfg_d["n_pairs"] = args.pairs
     if args.transcripts:
@@ -389,7 +390,7 @@ def main():
                        "insert_path": args.path,
                        "l2": "table (>= 1.6x distinct x slot bytes), k-mer records and reads are far larger than the 126 MB L2; the table is rebuilt from empty every step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": traffic, "kernel": ("skm_emit + skm_scatter + skm_build kernels (the sliced insert pipeline; times summed)" if sliced else
+                         "traffic": traffic, "kernel": ("skm_emit + skm_scatter + skm_dedupe + skm_build kernels (the sliced insert pipeline; times summed)" if sliced else
                                     "insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if (world == 1 or args.exchange == "reads") else "insert_records_kernel",
                          "path": args.path, "sliced": sliced_info,
                          "bytes_per_instance": bpi, "kernel_ms_per_launch": ker_ms, "peak_source": peak_src,

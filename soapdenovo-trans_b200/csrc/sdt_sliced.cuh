@@ -1,28 +1,13 @@
-// sdt_sliced.cuh — the sliced build: put_kmerset (newhash.c:411-462) without random DRAM access.
+// sdt_sliced.cuh — shared pieces of the sliced build (sdt_skm.cuh): the shared-memory read tile
+// (stage, flatten, locate a window) and the exclusive scan of records per slice.
 //
-// Why: on B200 a request to a cold line of a larger-than-L2 table completes at 36.65 G/s whatever
-// its width (profiles/r1_random_access_findings.md), so a single-pass insert (one load + one atomic
-// per instance) cannot exceed 18.3 G instances/s.  Streaming traffic has no such limit.  The sliced
-// build therefore turns every table access into shared-memory traffic plus sequential DRAM streams:
-//
-//   the table is n_slices x slice_slots slots; a key lives in slice  mulhi64(mix(key), n_slices),
-//   probing stays inside the slice (home = mulhi32(low32(mix), slice_slots), +1 with wrap);
-//
-//   slice_count_kernel     chop (prlHashReads.c:164-310) every window, histogram of instances per
-//                          slice (RED into an L2-resident array) — sizes every stream exactly;
-//   slice_scan_*           exclusive scan -> record offset of every slice and level-1 partition;
-//   slice_scatter1_kernel  chop again, (key, meta) records into P1 level-1 partitions (P2 slices
-//                          each); a tile of records is ordered by partition in shared memory first,
-//                          so the global stores are runs of consecutive records;
-//   slice_scatter2_kernel  one level-1 partition at a time: records into their slice's run;
-//   slice_build_kernel     one CTA per slice: the slice's table image is built in shared memory
-//                          (key claim by 64-bit CAS or a per-slot lock word, 32-bit counters and the
-//                          ordinal minimum with shared-memory atomics, link counters clamped to the
-//                          reference's 6-bit saturation when written out) and streamed to the table
-//                          in the ordinary slot layout, empty slots included — so finalize / export /
-//                          checksum run unchanged and no table initialisation pass is needed.
-//
-// All updates commute, so the result is bit-identical to the reference's sequential put_kmerset.
+// Why a sliced build at all: on B200 a request to a cold line of a larger-than-L2 table completes at
+// 36.65 G/s whatever its width (profiles/r1_random_access_findings.md), so a single-pass insert (one
+// load + one atomic per instance) cannot exceed 18.3 G instances/s.  Streaming traffic has no such
+// limit: the sliced build turns every table access into shared-memory traffic plus sequential DRAM
+// streams.  (The first version of it, which moved one 16-byte (key, meta) record per instance
+// through two levels of shared-memory counting sorts, lived in this file; it reached 18.5 G/s and
+// was replaced by the super-k-mer pipeline of sdt_skm.cuh.)
 #pragma once
 #include "sdt_kernels.cuh"
 

@@ -722,7 +722,7 @@ int skm_setup (sdtgpu *h, u64 hint)
 	return SDTGPU_OK;
 }
 
-static constexpr u32 MAX_FAILED = 1u << 18;
+static constexpr u32 MAX_FAILED = 1u << 21;
 
 int skm_alloc (sdtgpu *h)
 {
@@ -1060,10 +1060,13 @@ int sliced_push (sdtgpu *h, const ReadBatch &rb, u64 upper)
 	}
 	h->log.push_back (s);
 	h->pushed_upper += upper;
-	// record area: a third of a record per window is ~2.5x what reads produce (about one per eight
-	// windows at K = 31); if a batch needs more the emit kernel says so and sliced_flush re-emits
+	// record area: random minimizers start a new run every (w + 1) / 2 windows and every read ends one
+	// (C2: 0.124 records per window measured, 0.139 reserved; K = 63: 0.076; K = 127 on 150 bp: 0.069);
+	// if a batch needs more the emit kernel says so and sliced_flush re-emits into a larger area
 	const size_t rec = 4 * (size_t) h->geom.recw;
-	const u64 want = h->rec_upper + upper / env_u32 ("SDTGPU_REC_DIV", 3) + rb.n_reads / 8 + 4096;
+	u64 want = h->rec_upper + (u64) ((double) upper * 2.2 / (h->geom.w + 1.0)) + rb.n_reads + rb.n_reads / 5 + 4096;
+	if (getenv ("SDTGPU_REC_DIV"))	// tests: an area that is too small
+		want = h->rec_upper + upper / env_u32 ("SDTGPU_REC_DIV", 3) + rb.n_reads / 8 + 4096;
 	size_t cap_b = h->rec0_cap * rec;
 	if ((rc = grow_device (h, (void **) &h->rec0, &cap_b, cap_b, want * rec)))
 		return rc;
