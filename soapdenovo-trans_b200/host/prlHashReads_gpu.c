@@ -123,6 +123,7 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 	time_t start_t, stop_t;
 	const char *env;
 	uint64_t hint = 0;
+	uint32_t flags = N_kmer ? SDTGPU_F_NKMER : 0;
 	int device = 0, devices[SDT_MAX_GPUS];
 	int64_t freq[257];
 	sdtgpu_stats st;
@@ -163,10 +164,13 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 			hs.n_gpus = 1;
 		}
 	}
+	/* SDTGPU_SLICED=1 (needs SDTGPU_CAPACITY_HINT): the sliced build instead of the single-pass insert */
+	if ((env = getenv ("SDTGPU_SLICED")) && atoi (env) > 0 && hint)
+		flags |= SDTGPU_F_SLICED;
 	for (b = 0; b < hs.n_gpus; b++)
 	{
 		rc = sdtgpu_create (&hs.gpus[b], devices[b], overlaplen, SDT_KEY_WORDS, maxReadLen,
-				    hint ? hint / hs.n_gpus + hint / (8 * hs.n_gpus) + 1 : 0, N_kmer ? SDTGPU_F_NKMER : 0);
+				    hint ? hint / hs.n_gpus + hint / (8 * hs.n_gpus) + 1 : 0, flags);
 		if (rc)
 			die (NULL, "sdtgpu_create", rc);
 		if (hs.n_gpus > 1 && (rc = sdtgpu_set_owner (hs.gpus[b], b, hs.n_gpus)))

@@ -15,11 +15,13 @@ from conftest import make_dataset
 pytestmark = pytest.mark.gpu
 
 
-def _run(exe, cfg, prefix, K, p, d, extra=(), devices=None):
+def _run(exe, cfg, prefix, K, p, d, extra=(), devices=None, sliced_hint=0):
     cmd = [exe, "pregraph", "-s", cfg, "-K", str(K), "-p", str(p), "-d", str(d), "-o", prefix, *extra]
     env = dict(os.environ)
     if devices:
         env["SDTGPU_DEVICES"] = devices
+    if sliced_hint:
+        env["SDTGPU_SLICED"], env["SDTGPU_CAPACITY_HINT"] = "1", str(sliced_hint)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     return r.stdout
@@ -63,6 +65,26 @@ def test_pregraph_outputs_identical(pkg, oracle, tmp_path, build, K, p, d, fastq
         la = [l for l in a.splitlines() if key in l]
         lb = [l for l in b.splitlines() if key in l]
         assert la == lb, (la, lb)
+
+
+@pytest.mark.parametrize("build,K,p,d", [("31mer", 31, 8, 1), ("127mer", 63, 5, 0)])
+def test_pregraph_outputs_identical_sliced_build(pkg, oracle, tmp_path, build, K, p, d):
+    """SDTGPU_SLICED=1: the drop-in runs the sliced build (super-k-mer records, slices built in shared
+    memory) instead of the single-pass insert; the hand-back and every pregraph output stay byte-identical."""
+    stock = os.path.join(oracle.REF_DIR, f"SOAPdenovo-Trans-{build}")
+    gpu = os.path.join(oracle.REF_DIR, f"SOAPdenovo-Trans-{build}-gpu")
+    if not (os.path.exists(stock) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref binaries not present")
+    tr = pkg.synth.make_transcriptome(60, 21)
+    reads, lens = make_dataset(pkg, tr, 12000, 100, 5 + K, ragged=30)
+    cfg = pkg.synth.write_library(str(tmp_path / "in"), reads, lens, 100, paired=True)
+    a = _run(stock, cfg, str(tmp_path / "ref"), K, p, d)
+    b = _run(gpu, cfg, str(tmp_path / "gpu"), K, p, d, sliced_hint=4_000_000)
+    ra, rb = _outputs(str(tmp_path / "ref")), _outputs(str(tmp_path / "gpu"))
+    for k in ra:
+        assert ra[k] == rb[k], f"{k} differs ({len(ra[k])} vs {len(rb[k])} bytes)"
+    for key in ("nodes allocated", "linear nodes", "kmer removed"):
+        assert [l for l in a.splitlines() if key in l] == [l for l in b.splitlines() if key in l]
 
 
 @pytest.mark.parametrize("devices", ["0,0,0", "0,1"])
