@@ -407,7 +407,8 @@ static constexpr int DD_NT = 256;
 template <int W> struct DedupeCfg { static constexpr u32 CHUNK = W == 1 ? 2048u : 1024u, TABLE = 2 * CHUNK; };
 template <int W> __host__ __device__ inline size_t skm_dedupe_smem () { return (size_t) DedupeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) DedupeCfg<W>::TABLE * 4; }
 
-template <int W>
+// HAS_MULT: word 2 of the incoming records already is a multiplicity (the sub-records of skm_resplit_kernel)
+template <int W, bool HAS_MULT>
 __global__ void __launch_bounds__ (DD_NT)
 skm_dedupe_kernel (u32 *rec2, const u64 *off, u32 n_slices, unsigned long long *end, unsigned long long *n_kept)
 {
@@ -431,7 +432,7 @@ skm_dedupe_kernel (u32 *rec2, const u64 *off, u32 n_slices, unsigned long long *
 				for (u32 v = tid; v < nrec * VEC; v += DD_NT)
 				{
 					uint4 x = ldg_stream (src + v);
-					if (v % VEC == 0)
+					if (!HAS_MULT && v % VEC == 0)
 						x.z = 1u;
 					dst[v] = x;
 				}
@@ -466,7 +467,7 @@ skm_dedupe_kernel (u32 *rec2, const u64 *off, u32 n_slices, unsigned long long *
 						same &= rep[q] == me[q];
 					if (same)
 					{	// words 0-1 as one 64-bit number: the header bits above the ordinal are equal, so the minimum is the ordinal's
-						atomicAdd (rep + 2, 1u);
+						atomicAdd (rep + 2, HAS_MULT ? me[2] : 1u);
 						const u64 mine = *reinterpret_cast<const u64 *> (me);
 						if (mine < *reinterpret_cast<volatile u64 *> (rep))
 							atomicMin (reinterpret_cast<unsigned long long *> (rep), mine);
@@ -738,6 +739,132 @@ __device__ __forceinline__ void skm_roll_step (SkmRoll<W> &s, const Key<W> &mask
 	}
 	s.t++;
 	s.ord++;
+}
+
+// A slice that overflowed its image is cut into q sub-slices by k-mer hash in ONE pass over its
+// records: every window becomes a one-window sub-record (the window's K bases and its neighbours,
+// the record's multiplicity, the window's ordinal) in the run of sub-slice qbase + bucket.  The
+// sub-slices then go through skm_dedupe_kernel and skm_build_kernel like any slice.  (Retrying a
+// slice as q work items that each filter the windows by hash scans its records q times; the slices
+// that overflow are the highly expressed loci — most of the reads of a skewed data set.)
+// PASS 0 counts sub-records per sub-slice (hist2), PASS 1 writes them (cur2 starts at the scanned offsets).
+struct SkmSplit { u32 slice, q, qbase, rlo, rhi, pad[3]; };	// records [rlo, rhi) of the slice's run -> sub-slices qbase .. qbase + q
+static constexpr int RS_NT = 256;
+
+__device__ __forceinline__ u32 skm_bucket (u64 h, u32 q) { return __umulhi ((u32) (h >> 32) * 0x9E3779B1u, q); }
+
+template <int W, int PASS>
+__global__ void __launch_bounds__ (RS_NT)
+skm_resplit_kernel (const u32 *rec2, const u64 *off, const u64 *end, const SkmSplit *splits, u32 n_splits, int K,
+		    u32 *hist2, unsigned long long *cur2, u32 *rec3)
+{
+	constexpr u32 RECW = SkmRec<W>::WORDS, LAST = RECW - SKM_HDR - 1;
+	Key<W> kmask;
+#pragma unroll
+	for (int q = 0; q < W; q++)
+	{
+		const int bits = 2 * K - 64 * (W - 1 - q);
+		kmask.w[q] = bits >= 64 ? ~0ull : (bits > 0 ? (1ull << bits) - 1 : 0ull);
+	}
+	const int top = 2 * (K - 1);
+	// one CTA per chunk of a failed slice's records (the host cuts big slices into chunks so that a
+	// huge slice does not sit on one CTA)
+	for (u32 sp = blockIdx.x; sp < n_splits; sp += gridDim.x)
+	{
+		const SkmSplit S = splits[sp];
+		const u64 r0 = off[S.slice], r1 = min (end[S.slice], r0 + S.rhi);
+		for (u64 i = r0 + S.rlo + threadIdx.x; i < r1; i += RS_NT)
+		{
+			const u32 *rec = rec2 + i * RECW;
+			SkmRoll<W> st;
+			skm_roll_init<W> (st, rec, K, 0);
+			const u32 h1 = __ldg (rec + 1);
+			const u32 phl = (h1 >> 14) & 1u, nrun = (h1 >> 15) & 1u, pnb = h1 >> 16;
+			const u32 phr = nrun ? 0u : pnb - phl - (u32) K - (st.n - 1);
+			for (u32 t = 0; t < st.n; t++)
+			{
+				Key<W> key;
+				u32 left, right;
+				skm_roll_window<W> (st, key, left, right);
+				const u32 g = S.qbase + skm_bucket (key_hash<W> (key), S.q);
+				if (PASS == 0)
+				{
+					atomicAdd (hist2 + g, 1u);
+					if (cur2)
+					{
+						atomicAdd (cur2, (unsigned long long) st.add);	// debug: instances that enter the split
+						atomicAdd (cur2 + 1, key_hash<W> (key) >> 20);	// debug: checksum of the keys
+						atomicAdd (cur2 + 2, (unsigned long long) g);	// debug: checksum of the buckets
+						atomicAdd (cur2 + 3, (unsigned long long) S.q * 1000003ull + S.qbase);
+					}
+				}
+				else
+				{
+					const u64 pos = atomicAdd (cur2 + g, 1ull);
+					u32 *dst = rec3 + pos * RECW;
+					if (hist2)
+					{
+						atomicAdd (reinterpret_cast<unsigned long long *> (hist2), (unsigned long long) st.add);	// debug
+						atomicAdd (reinterpret_cast<unsigned long long *> (hist2) + 1, 1ull);
+						atomicAdd (reinterpret_cast<unsigned long long *> (hist2) + 2, (unsigned long long) g);
+						atomicAdd (reinterpret_cast<unsigned long long *> (hist2) + 3, key_hash<W> (key) >> 20);
+						if (pos >= 251710ull)
+							atomicAdd (reinterpret_cast<unsigned long long *> (hist2) + 4, 1ull);
+					}
+					const u32 hl = nrun ? 0u : (t > 0 || phl), hr = nrun ? 0u : (t + 1 < st.n || phr);
+					const u32 nb = nrun ? 0u : hl + (u32) K + hr, first = nrun ? 0u : phl + t - hl;
+					u32 wd[4];
+					wd[0] = (u32) st.ord;
+					wd[1] = (u32) (st.ord >> 32) | (hl << 14) | (nrun << 15) | (nb << 16);	// one window: n - 1 = 0
+					wd[2] = st.add;	// multiplicity (an N-run: all of its windows)
+					const u32 nbw = (nb + 15) >> 4;
+					const u32 *rd = rec + SKM_HDR;
+#pragma unroll
+					for (u32 q = 0; q < RECW - SKM_HDR; q++)
+					{
+						u32 v = 0;
+						if (q < nbw)
+						{
+							const u32 b = first + 16 * q, wq = b >> 4, sh = 2 * (b & 15);
+							v = __funnelshift_l (__ldg (rd + min (wq + 1, LAST)), __ldg (rd + min (wq, LAST)), sh);
+							if (q == nbw - 1 && (nb & 15))
+								v &= 0xFFFFFFFFu << (32 - 2 * (nb & 15));
+						}
+						const u32 o = SKM_HDR + q;
+						wd[o & 3] = v;
+						if ((o & 3) == 3)
+							*reinterpret_cast<uint4 *> (dst + (o & ~3u)) = make_uint4 (wd[0], wd[1], wd[2], wd[3]);
+					}
+				}
+				skm_roll_step<W> (st, kmask, top);
+			}
+		}
+	}
+}
+
+__global__ void skm_debug_cmp_kernel (const u32 *a, const u32 *b, u32 n, unsigned long long *bad)
+{
+	for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
+		if (a[g] != b[g])
+			atomicAdd (bad, 1ull);
+}
+
+__global__ void skm_debug_cur_kernel (const u64 *off, const u64 *cur, u32 n, unsigned long long *bad)
+{
+	for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
+		if (cur[g] != off[g + 1])
+			atomicAdd (bad, 1ull);
+}
+
+__global__ void skm_debug_sum_kernel (const u32 *rec, const u64 *off, const u64 *end, u32 n, u32 recw, unsigned long long *sum)
+{
+	for (u32 sl = blockIdx.x; sl < n; sl += gridDim.x)
+		for (u64 i = off[sl] + threadIdx.x; i < end[sl]; i += blockDim.x)
+		{
+			const u32 h1 = rec[i * recw + 1];
+			const u32 nwin = ((h1 >> 8) & 63u) + 1;
+			atomicAdd (sum, (unsigned long long) rec[i * recw + 2] * nwin);
+		}
 }
 
 // One CTA per work item, items handed out through *item_cursor.  items == nullptr: item i is (slice i, 0, 1).

@@ -92,6 +92,9 @@ struct sdtgpu
 	u64 *d_small = nullptr, *h_small = nullptr;	// [0] record cursor, [1] node cursor, [2] failed work items, [3] work-item cursor, [4] records after dedupe; pinned mirror
 	void *d_failed = nullptr, *d_items = nullptr;	// SkmWork lists
 	u32 *rec0 = nullptr, *rec2 = nullptr;	// super-k-mer records: as emitted, grouped by slice
+	u32 *rec3 = nullptr;			// sub-records of the slices that overflowed (skm_resplit_kernel), grouped by sub-slice
+	size_t rec3_cap_b = 0, sub_cap = 0;
+	void *sub_mem = nullptr;		// run offsets, cursors, scan sums and counts of the sub-slices
 	u64 rec0_cap = 0, rec2_cap = 0, rec_upper = 0;	// records
 	u32 n_local_or_all () const { return n_local ? n_local : geom.n_slices; }
 	u32 skm_world = 1, skm_rank = 0, n_local = 0;	// super-k-mer exchange (sdtgpu_skm_set_world): slices per rank; geom.n_slices = n_local * skm_world
@@ -800,7 +803,9 @@ int launch_emit (sdtgpu *h, const ReadBatch &rb)
 	}
 }
 
-template <int W, int NT> int launch_build_t (sdtgpu *h, const SkmWork *items, u32 n_items, int cat)
+struct SkmArrays { u32 *rec; u64 *off; u64 *end; };	// records grouped by slice, run starts, ends of what dedupe left
+
+template <int W, int NT> int launch_build_t (sdtgpu *h, const SkmArrays &ar, const SkmWork *items, u32 n_items, int cat)
 {
 	typedef typename SlotOf<W>::type S;
 	const SkmGeom &g = h->geom;
@@ -817,16 +822,16 @@ template <int W, int NT> int launch_build_t (sdtgpu *h, const SkmWork *items, u3
 	CK (h, cudaMemsetAsync (small + 3, 0, sizeof (u64), h->stream));	// work-item cursor
 	{
 		TimedLaunch tl (h, cat);
-		kern<<<grid, NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, h->rec2, h->d_off, h->d_cur2, items, n_items, small + 3,
+		kern<<<grid, NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, ar.rec, ar.off, ar.end, items, n_items, small + 3,
 							 static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
 }
 
-template <int W> int launch_dedupe_t (sdtgpu *h, u32 n_slices)
+template <int W, bool HAS_MULT> int launch_dedupe_t (sdtgpu *h, const SkmArrays &ar, u32 n_slices)
 {
-	auto kern = skm_dedupe_kernel<W>;
+	auto kern = skm_dedupe_kernel<W, HAS_MULT>;
 	const size_t smem = skm_dedupe_smem<W> ();
 	CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
@@ -835,32 +840,57 @@ template <int W> int launch_dedupe_t (sdtgpu *h, u32 n_slices)
 		return fail (h, SDTGPU_ECUDA, "skm_dedupe_kernel does not fit");
 	const unsigned grid = (unsigned) std::min<u64> (n_slices, (u64) h->sm_count * occ);
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
-	CK (h, cudaMemsetAsync (small + 4, 0, sizeof (u64), h->stream));	// surviving records
+	if (!HAS_MULT)
+		CK (h, cudaMemsetAsync (small + 4, 0, sizeof (u64), h->stream));	// surviving records
 	{
 		TimedLaunch tl (h, 3);
-		kern<<<grid, DD_NT, smem, h->stream>>> (h->rec2, h->d_off, n_slices, reinterpret_cast<unsigned long long *> (h->d_cur2), small + 4);
+		kern<<<grid, DD_NT, smem, h->stream>>> (ar.rec, ar.off, n_slices, reinterpret_cast<unsigned long long *> (ar.end), HAS_MULT ? small + 5 : small + 4);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
 }
 
-int launch_dedupe (sdtgpu *h, u32 n_slices)
+int launch_dedupe (sdtgpu *h, const SkmArrays &ar, u32 n_slices, bool has_mult)
 {
 	switch (h->W)
 	{
-	case 1: return launch_dedupe_t<1> (h, n_slices);
-	case 2: return launch_dedupe_t<2> (h, n_slices);
-	default: return launch_dedupe_t<4> (h, n_slices);
+	case 1: return has_mult ? launch_dedupe_t<1, true> (h, ar, n_slices) : launch_dedupe_t<1, false> (h, ar, n_slices);
+	case 2: return has_mult ? launch_dedupe_t<2, true> (h, ar, n_slices) : launch_dedupe_t<2, false> (h, ar, n_slices);
+	default: return has_mult ? launch_dedupe_t<4, true> (h, ar, n_slices) : launch_dedupe_t<4, false> (h, ar, n_slices);
 	}
 }
 
-int launch_build (sdtgpu *h, const SkmWork *items, u32 n_items, int cat)
+template <int W> int launch_resplit_t (sdtgpu *h, const SkmArrays &ar, const SkmSplit *chunks, u32 n_chunks, int pass, u32 *hist2, u64 *cur2, u32 *rec3)
+{
+	const unsigned grid = (unsigned) std::min<u64> (n_chunks, (u64) h->sm_count * 8);
+	TimedLaunch tl (h, 6);
+	if (pass == 0)
+		skm_resplit_kernel<W, 0><<<grid, RS_NT, 0, h->stream>>> (ar.rec, ar.off, ar.end, chunks, n_chunks, h->K, hist2, reinterpret_cast<unsigned long long *> (cur2), nullptr);
+	else
+		skm_resplit_kernel<W, 1><<<grid, RS_NT, 0, h->stream>>> (ar.rec, ar.off, ar.end, chunks, n_chunks, h->K, hist2, reinterpret_cast<unsigned long long *> (cur2), rec3);
+	return SDTGPU_OK;
+}
+
+int launch_resplit (sdtgpu *h, const SkmArrays &ar, const SkmSplit *chunks, u32 n_chunks, int pass, u32 *hist2, u64 *cur2, u32 *rec3)
+{
+	int rc;
+	switch (h->W)
+	{
+	case 1: rc = launch_resplit_t<1> (h, ar, chunks, n_chunks, pass, hist2, cur2, rec3); break;
+	case 2: rc = launch_resplit_t<2> (h, ar, chunks, n_chunks, pass, hist2, cur2, rec3); break;
+	default: rc = launch_resplit_t<4> (h, ar, chunks, n_chunks, pass, hist2, cur2, rec3); break;
+	}
+	CK (h, cudaGetLastError ());
+	return rc;
+}
+
+int launch_build (sdtgpu *h, const SkmArrays &ar, const SkmWork *items, u32 n_items, int cat)
 {
 	switch (h->W)
 	{
-	case 1: return h->geom.build_nt == 512 ? launch_build_t<1, 512> (h, items, n_items, cat) : launch_build_t<1, 1024> (h, items, n_items, cat);
-	case 2: return h->geom.build_nt == 512 ? launch_build_t<2, 512> (h, items, n_items, cat) : launch_build_t<2, 1024> (h, items, n_items, cat);
-	default: return h->geom.build_nt == 512 ? launch_build_t<4, 512> (h, items, n_items, cat) : launch_build_t<4, 1024> (h, items, n_items, cat);
+	case 1: return h->geom.build_nt == 512 ? launch_build_t<1, 512> (h, ar, items, n_items, cat) : launch_build_t<1, 1024> (h, ar, items, n_items, cat);
+	case 2: return h->geom.build_nt == 512 ? launch_build_t<2, 512> (h, ar, items, n_items, cat) : launch_build_t<2, 1024> (h, ar, items, n_items, cat);
+	default: return h->geom.build_nt == 512 ? launch_build_t<4, 512> (h, ar, items, n_items, cat) : launch_build_t<4, 1024> (h, ar, items, n_items, cat);
 	}
 }
 
@@ -976,24 +1006,28 @@ int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
 	int rc;
 	const SkmGeom g = h->geom;
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
+	SkmArrays ar = { h->rec2, h->d_off, h->d_cur2 };
 	if (n_rec)
 	{	// copies of a super-k-mer collapse into one record with a multiplicity; d_cur2[slice] becomes the end of what is left
-		if (int rc2 = launch_dedupe (h, n_slices))
-			return rc2;
+		if ((rc = launch_dedupe (h, ar, n_slices, false)))
+			return rc;
 	}
 	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over
 	CK (h, cudaMemsetAsync (small + 1, 0, 2 * sizeof (u64), h->stream));
 	CK (h, cudaMemsetAsync (&h->d_ctr->n_nodes, 0, 2 * sizeof (u64), h->stream));	// n_nodes, n_instances
-	if ((rc = launch_build (h, nullptr, n_slices, 4)))
+	if ((rc = launch_build (h, ar, nullptr, n_slices, 4)))
 		return rc;
 	h->n_retried = 0;
 	std::vector<SkmWork> items, failed;
+	const double wpr = 0.5 * g.w + 1.0;	// windows per record, about
 	for (u32 depth = 0;; depth++)
 	{
 		CK (h, cudaMemcpyAsync (h->h_small + 1, small + 1, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaMemcpyAsync (h->h_small + 4, small + 4, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaStreamSynchronize (h->stream));
+		if (depth == 0)
+			h->n_merged = n_rec ? h->h_small[4] : 0;
 		if (h->h_small[3] & 4)
 			return fail (h, SDTGPU_ERANGE, "node store exhausted: capacity_hint was too small for the sliced build");
 		if (h->h_small[3] & 16)
@@ -1001,18 +1035,130 @@ int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
 		const u32 n_failed = (u32) h->h_small[2];
 		if (n_failed == 0)
 			break;
-		if ((h->h_small[3] & 8) || n_failed > MAX_FAILED || depth == 6)
+		if ((h->h_small[3] & 8) || n_failed > MAX_FAILED || depth == 8)
 			return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
-		// A failed item is split by k-mer hash into pieces.  Every piece scans all records of the slice
-		// again (a window that is not the piece's costs a roll and a hash, about a third of an insert),
-		// so the factor is sized to what the slice holds rather than fixed: slices overflow because they
-		// hold a few more distinct k-mers than the image does (two pieces do), or because a highly
-		// expressed locus piles the error k-mers of thousands of reads on one minimizer — about one new
-		// k-mer per eight windows on top of the image's usual half load.
 		failed.resize (n_failed);
 		CK (h, cudaMemcpy (failed.data (), h->d_failed, n_failed * sizeof (SkmWork), cudaMemcpyDeviceToHost));
+		h->n_retried += n_failed;
+		CK (h, cudaMemsetAsync (small + 2, 0, sizeof (u64), h->stream));
+		if (depth == 0 && env_u32 ("SDTGPU_RESPLIT", 0))
+		{	// EXPERIMENTAL, off by default.  Slices that overflowed their image are cut into sub-slices by
+			// k-mer hash in one pass over their records (skm_resplit_kernel): sub-records are counted,
+			// scanned, written, merged and built like slices.  It removes the quadratic cost of retrying a
+			// hot slice as q filtered scans (C5: retries 51 -> ~5 ms), but the per-sub-slice counts of its
+			// two passes disagree in some runs (1-word keys, K = 31) and instances are lost; SDTGPU_DEBUG_SPLIT=1
+			// prints the checksums that show it.  Until that is understood the hash-split retry below is the default.
+			std::vector<SkmSplit> chunks;
+			u64 Q = 0;
+			for (const SkmWork &f : failed)
+			{
+				const double est = 0.5 * g.slice_slots + 0.5 * (double) f.nrec * wpr;
+				const u32 q = (u32) std::min (65536.0, std::max (2.0, std::ceil (est / (0.6 * g.slice_slots))));
+				for (u64 lo = 0; lo < std::max<u64> (f.nrec, 1); lo += 32768)
+					chunks.push_back ({ f.slice, q, (u32) Q, (u32) lo, (u32) std::min<u64> (f.nrec, lo + 32768), { 0, 0, 0 } });
+				Q += q;
+			}
+			if (Q > (1ull << 28) || chunks.size () * sizeof (SkmSplit) > (size_t) MAX_FAILED * sizeof (SkmWork))
+				return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
+			const u32 nq = (u32) Q, nseg2 = (nq + SCAN_SEG - 1) / SCAN_SEG;
+			size_t need = (size_t) nq * 4 + ((size_t) nq + 1) * 8 + (size_t) nq * 8 + (size_t) nseg2 * 8 + 64;
+			if ((rc = grow_device (h, &h->sub_mem, &h->sub_cap, 0, need)))
+				return rc;
+			u64 *off2 = static_cast<u64 *> (h->sub_mem), *cur2 = off2 + nq + 1, *seg2 = cur2 + nq;
+			u32 *hist2 = reinterpret_cast<u32 *> (seg2 + nseg2);
+			CK (h, cudaMemsetAsync (hist2, 0, (size_t) nq * 4, h->stream));
+			CK (h, cudaStreamSynchronize (h->stream));
+			CK (h, cudaMemcpy (h->d_items, chunks.data (), chunks.size () * sizeof (SkmSplit), cudaMemcpyHostToDevice));	// blocking: pageable source
+			const SkmSplit *d_chunks = static_cast<const SkmSplit *> (h->d_items);
+			const bool dbg = getenv ("SDTGPU_DEBUG_SPLIT") != nullptr;
+			CK (h, cudaMemsetAsync (small + 6, 0, 2 * sizeof (u64), h->stream));
+			if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 0, hist2, dbg ? reinterpret_cast<u64 *> (small + 6) : nullptr, nullptr)))
+				return rc;
+			if (dbg)
+			{	// is the count pass reproducible?
+				u32 *hist3 = nullptr;
+				u64 *acc = nullptr, hacc[8];
+				CK (h, cudaMalloc (&hist3, (size_t) nq * 4));
+				CK (h, cudaMalloc (&acc, 64));
+				CK (h, cudaMemsetAsync (hist3, 0, (size_t) nq * 4, h->stream));
+				for (int rep = 0; rep < 2; rep++)
+				{
+					CK (h, cudaMemsetAsync (hist3, 0, (size_t) nq * 4, h->stream));
+					CK (h, cudaMemsetAsync (acc, 0, 64, h->stream));
+					if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 0, hist3, acc, nullptr)))
+						return rc;
+					CK (h, cudaMemcpyAsync (hacc, acc, 64, cudaMemcpyDeviceToHost, h->stream));
+					CK (h, cudaStreamSynchronize (h->stream));
+					fprintf (stderr, "[split] count pass %d: instances %llu keysum %llu bucketsum %llu splitsum %llu\n", rep, (unsigned long long) hacc[0], (unsigned long long) hacc[1], (unsigned long long) hacc[2], (unsigned long long) hacc[3]);
+				}
+				cudaFree (acc);
+				CK (h, cudaMemsetAsync (small + 5, 0, sizeof (u64), h->stream));
+				skm_debug_cmp_kernel<<<64, 256, 0, h->stream>>> (hist2, hist3, nq, small + 5);
+				u64 bad = 0;
+				CK (h, cudaMemcpyAsync (&bad, small + 5, 8, cudaMemcpyDeviceToHost, h->stream));
+				CK (h, cudaStreamSynchronize (h->stream));
+				fprintf (stderr, "[split] count pass run twice: %llu of %u buckets differ\n", (unsigned long long) bad, nq);
+				cudaFree (hist3);
+			}
+			{
+				TimedLaunch tl (h, 5);
+				slice_scan_sums_kernel<<<nseg2, SCAN_NT, 0, h->stream>>> (hist2, nq, seg2);
+				slice_scan_kernel<<<nseg2, SCAN_NT, 0, h->stream>>> (hist2, nq, seg2, off2, cur2);
+			}
+			CK (h, cudaGetLastError ());
+			u64 n_sub = 0;
+			CK (h, cudaMemcpyAsync (&n_sub, off2 + nq, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+			CK (h, cudaStreamSynchronize (h->stream));	// also: `chunks` is pageable host memory
+			const size_t rec = 4 * (size_t) g.recw;
+			if ((rc = grow_device (h, (void **) &h->rec3, &h->rec3_cap_b, 0, std::max<u64> (n_sub, 1) * rec)))
+				return rc;
+			if (dbg)
+				CK (h, cudaMemsetAsync (h->d_failed, 0, 64, h->stream));
+			if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 1, dbg ? static_cast<u32 *> (h->d_failed) : nullptr, cur2, h->rec3)))
+				return rc;
+			if (dbg)
+			{
+				u64 d3[8];
+				CK (h, cudaMemcpyAsync (d3, h->d_failed, 64, cudaMemcpyDeviceToHost, h->stream));
+				CK (h, cudaStreamSynchronize (h->stream));
+				fprintf (stderr, "[split] pass 1: instances %llu windows %llu bucketsum %llu keysum %llu pos>=n_sub %llu\n", (unsigned long long) d3[0], (unsigned long long) d3[1], (unsigned long long) d3[2], (unsigned long long) d3[3], (unsigned long long) d3[4]);
+			}
+			ar = SkmArrays { h->rec3, off2, cur2 };	// from here on the work items are sub-slices
+			CK (h, cudaMemsetAsync (small + 5, 0, sizeof (u64), h->stream));
+			if (dbg)
+			{
+				skm_debug_cur_kernel<<<64, 256, 0, h->stream>>> (ar.off, ar.end, nq, small + 5);
+				u64 bad = 0;
+				CK (h, cudaMemcpyAsync (&bad, small + 5, 8, cudaMemcpyDeviceToHost, h->stream));
+				CK (h, cudaStreamSynchronize (h->stream));
+				fprintf (stderr, "[split] buckets whose cursor != next offset: %llu\n", (unsigned long long) bad);
+				CK (h, cudaMemsetAsync (small + 5, 0, sizeof (u64), h->stream));
+				skm_debug_sum_kernel<<<1024, 256, 0, h->stream>>> (ar.rec, ar.off, ar.off + 1, nq, g.recw, small + 7);
+				u64 d2[2];
+				CK (h, cudaMemcpyAsync (d2, small + 6, 16, cudaMemcpyDeviceToHost, h->stream));
+				CK (h, cudaStreamSynchronize (h->stream));
+				fprintf (stderr, "[split] failed %u Q %u n_sub %llu  in %llu  written %llu", n_failed, nq, (unsigned long long) n_sub, (unsigned long long) d2[0], (unsigned long long) d2[1]);
+				CK (h, cudaMemsetAsync (small + 7, 0, sizeof (u64), h->stream));
+			}
+			if (n_sub && (rc = launch_dedupe (h, ar, nq, true)))
+				return rc;
+			if (dbg)
+			{
+				skm_debug_sum_kernel<<<1024, 256, 0, h->stream>>> (ar.rec, ar.off, ar.end, nq, g.recw, small + 7);
+				u64 d2 = 0;
+				CK (h, cudaMemcpyAsync (&d2, small + 7, 8, cudaMemcpyDeviceToHost, h->stream));
+				CK (h, cudaStreamSynchronize (h->stream));
+				fprintf (stderr, "  after dedupe %llu\n", (unsigned long long) d2);
+			}
+			CK (h, cudaStreamSynchronize (h->stream));	// d_items is about to be reused
+			if ((rc = launch_build (h, ar, nullptr, nq, 6)))
+				return rc;
+			continue;
+		}
+		// A failed item is split by k-mer hash into pieces (keys with hash % R == r).  Every piece scans
+		// all records of the (sub-)slice again — a window that is not the piece's costs a roll and a hash,
+		// about a third of an insert — so the factor is sized to what the slice holds.
 		items.clear ();
-		const double wpr = 0.5 * g.w + 1.0;	// windows per record, about
 		for (const SkmWork &f : failed)
 		{
 			const double est = (0.5 * g.slice_slots + 0.2 * (double) f.nrec * wpr) / f.R;
@@ -1022,15 +1168,12 @@ int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
 		}
 		if (items.size () > MAX_FAILED)
 			return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
-		h->n_retried += n_failed;
 		CK (h, cudaMemcpyAsync (h->d_items, items.data (), items.size () * sizeof (SkmWork), cudaMemcpyHostToDevice, h->stream));
-		CK (h, cudaMemsetAsync (small + 2, 0, sizeof (u64), h->stream));
-		if ((rc = launch_build (h, static_cast<const SkmWork *> (h->d_items), (u32) items.size (), 6)))
+		if ((rc = launch_build (h, ar, static_cast<const SkmWork *> (h->d_items), (u32) items.size (), 6)))
 			return rc;
 		CK (h, cudaStreamSynchronize (h->stream));	// `items` is pageable host memory
 	}
 	h->n_store = h->h_small[1];
-	h->n_merged = n_rec ? h->h_small[4] : 0;
 	h->table_built = true;
 	h->dirty = false;
 	h->n_epochs++;
@@ -1190,6 +1333,7 @@ void sdtgpu_destroy (sdtgpu_t *h)
 	for (auto e : h->ev_pool) cudaEventDestroy (e);
 	for (void *m : h->log_mem) cudaFree (m);
 	cudaFree (h->d_hist); cudaFree (h->d_off); cudaFree (h->d_cur2); cudaFree (h->d_seg_sum); cudaFree (h->d_small);
+	cudaFree (h->rec3); cudaFree (h->sub_mem);
 	cudaFree (h->d_failed); cudaFree (h->d_items); cudaFree (h->rec0); cudaFree (h->rec2);
 	if (h->h_small) cudaFreeHost (h->h_small);
 	cudaFree (h->table);
