@@ -627,7 +627,7 @@ __device__ __forceinline__ u64 bases64 (const u32 *rd, u32 b, u32 last)
 }
 
 // rolling state at window tw of a record
-template <int W>
+template <int W, bool FAST = true>
 __device__ __forceinline__ void skm_roll_init (SkmRoll<W> &s, const u32 *rec, int K, u32 tw)
 {
 	constexpr u32 LAST = SkmRec<W>::WORDS - SKM_HDR - 1;
@@ -653,7 +653,7 @@ __device__ __forceinline__ void skm_roll_init (SkmRoll<W> &s, const u32 *rec, in
 		s.add = n * hd.z;
 		return;
 	}
-	if constexpr (W == 1)
+	if constexpr (W == 1 && FAST)
 		if (tw == 0)
 		{	// start of a record (the common re-seat): the record's 160 bits of bases, two 16-byte loads
 			const uint4 h2 = __ldg (reinterpret_cast<const uint4 *> (rec) + 1);
@@ -777,10 +777,11 @@ skm_resplit_kernel (const u32 *rec2, const u64 *off, const u64 *end, const SkmSp
 		{
 			const u32 *rec = rec2 + i * RECW;
 			SkmRoll<W> st;
-			skm_roll_init<W> (st, rec, K, 0);
+			skm_roll_init<W, false> (st, rec, K, 0);
 			const u32 h1 = __ldg (rec + 1);
 			const u32 phl = (h1 >> 14) & 1u, nrun = (h1 >> 15) & 1u, pnb = h1 >> 16;
 			const u32 phr = nrun ? 0u : pnb - phl - (u32) K - (st.n - 1);
+#pragma unroll 1
 			for (u32 t = 0; t < st.n; t++)
 			{
 				Key<W> key;
