@@ -246,23 +246,30 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 			u32 s = sl[js], start = js;
 			while (start > 0 && sl[start - 1] == s)
 				start--;
+			// first mark where runs end (a tight, convergent loop), then report them: reporting inside the
+			// walk made every step of the warp pay for the few lanes that had a run to report
+			u32 ends = 0;
 			for (u32 j = js; j < je; j++)
 			{
 				const u32 nxt = j + 1 < nwin ? sl[j + 1] : 0xFFFFFFFFu;	// no slice has this number (bit 31 is the N flag, 30 bits of slice)
-				if (nxt != s)
-				{	// windows start .. j are a run
-					if (rb.owner_ranks <= 1 || (s & ~SKM_NFLAG) % rb.owner_ranks == rb.owner_rank)
-					{
-						const u32 n = j - start + 1;
-						const u32 nrec = (n + NMAX - 1) / NMAX;
-						const u32 pos = atomicAdd (&s_count, nrec);
-						mhs[pos] = r | (start << 8) | ((min (NMAX, n) - 1) << 24);
-						for (u32 c = 1; c < nrec; c++)	// runs longer than a record holds: rare
-							mhs[pos + c] = r | ((start + c * NMAX) << 8) | ((min (NMAX, n - c * NMAX) - 1) << 24);
-					}
-					start = j + 1;
-					s = nxt;
+				ends |= (nxt != s ? 1u : 0u) << (j - js);
+				s = nxt;
+			}
+			while (ends)
+			{
+				const u32 j = js + (u32) __ffs (ends) - 1;	// windows start .. j are a run
+				ends &= ends - 1;
+				const u32 rs = sl[j];
+				if (rb.owner_ranks <= 1 || (rs & ~SKM_NFLAG) % rb.owner_ranks == rb.owner_rank)
+				{
+					const u32 n = j - start + 1;
+					const u32 nrec = (n + NMAX - 1) / NMAX;
+					const u32 pos = atomicAdd (&s_count, nrec);
+					mhs[pos] = r | (start << 8) | ((min (NMAX, n) - 1) << 24);
+					for (u32 c = 1; c < nrec; c++)	// runs longer than a record holds: rare
+						mhs[pos + c] = r | ((start + c * NMAX) << 8) | ((min (NMAX, n - c * NMAX) - 1) << 24);
 				}
+				start = j + 1;
 			}
 		}
 		__syncthreads ();
@@ -403,7 +410,7 @@ skm_recount_kernel (u32 *rec, u64 n, u32 recw, u32 lo, u32 n_local, u32 *hist, C
 // One CTA per slice, DD_CHUNK records at a time staged in shared memory; a table of record indices
 // keyed by the record's content finds the copies; survivors go back to the front of the run.
 // end[slice] = one past the last surviving record.
-static constexpr int DD_NT = 256;
+static constexpr int DD_NT = 512;	// 2 CTAs of 80-96 KB per SM: 32 warps to hide the staging loads (256 threads: 11.2 ms on C2)
 template <int W> struct DedupeCfg { static constexpr u32 CHUNK = W == 1 ? 2048u : 1024u, TABLE = 2 * CHUNK; };
 template <int W> __host__ __device__ inline size_t skm_dedupe_smem () { return (size_t) DedupeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) DedupeCfg<W>::TABLE * 4; }
 
