@@ -165,6 +165,24 @@ class ReplicatedReads:
         pass
 
 
+def exchange_runs(send: torch.Tensor, send_counts, words: int, make_recv, group=None):
+    """The super-k-mer exchange's plumbing, backend-agnostic (NCCL on the GPUs, gloo in tests/test_exchange_cpu.py).
+    send: flat int64 tensor holding, back to back, the records for rank 0, 1, ... (`send_counts[r]` records of
+    `words` int64 each — the runs sdtgpu_skm_stage hands out are already in this order, so nothing is packed).
+    make_recv(total_records) -> flat int64 tensor to receive into (sdtgpu_skm_import_buffer).
+    Two collectives: the counts, then the records.  Returns (total_records, recv_counts)."""
+    world = dist.get_world_size(group)
+    sc = torch.tensor([int(x) for x in send_counts], dtype=torch.int64, device=send.device)
+    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.tolist()]
+    total = sum(recv_counts)
+    recv = make_recv(total)
+    dist.all_to_all_single(recv, send, output_split_sizes=[n * words for n in recv_counts],
+                           input_split_sizes=[int(n) * words for n in send_counts], group=group)
+    return total, recv_counts
+
+
 class _DevMem:
     """A device allocation owned by the library, seen by torch through __cuda_array_interface__ (no copy)."""
 
@@ -218,15 +236,8 @@ class SkmExchange:
         rb, w8 = self.rec_bytes, self.rec_bytes // 8
         send_counts = [offs[r + 1] - offs[r] for r in range(self.world)]
         with torch.cuda.stream(self.main):
-            sc = torch.tensor(send_counts, dtype=torch.int64, device=self.dev)
-            rc = torch.empty(self.world, dtype=torch.int64, device=self.dev)
-            dist.all_to_all_single(rc, sc, group=self.group)
-            recv_counts = [int(x) for x in rc.tolist()]
-            total = sum(recv_counts)
             send = _wrap(ptr + offs[0] * rb, (offs[-1] - offs[0]) * rb, self.dev)
-            recv = _wrap(g.skm_import_buffer(total), total * rb, self.dev)
-            dist.all_to_all_single(recv, send, output_split_sizes=[n * w8 for n in recv_counts],
-                                   input_split_sizes=[n * w8 for n in send_counts], group=self.group)
+            total, _ = exchange_runs(send, send_counts, w8, lambda n: _wrap(g.skm_import_buffer(n), n * rb, self.dev), group=self.group)
             self.nvlink_bytes += (sum(send_counts) - send_counts[self.rank]) * rb
         g.skm_import(total)                         # on the handle's stream, after the all-to-all
         return total

@@ -77,3 +77,59 @@ def test_exchange_records_gloo(world, words):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def _worker_runs(rank, world, port, words, q):
+    sys.path.insert(0, ROOT)
+    import sdt_pkg
+    sdt_pkg.load()
+    from soapdenovo_trans_b200.exchange import exchange_runs
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for rnd in range(3):
+            rng = np.random.default_rng(7 * rnd + rank)
+            counts = rng.integers(0, 50, size=world)
+            if rnd == 1:
+                counts[:] = 0                      # an epoch without records must work
+            # the runs for rank 0, 1, ... back to back, as sdtgpu_skm_stage hands them out; a record encodes (src, dst, index)
+            recs = [torch.full((int(counts[d]), words), 0, dtype=torch.int64) + (rank * 1_000_000 + d * 10_000) +
+                    torch.arange(int(counts[d]), dtype=torch.int64)[:, None] for d in range(world)]
+            send = torch.cat(recs).reshape(-1)
+            got = {}
+
+            def make_recv(n):
+                got["buf"] = torch.full((n * words,), -1, dtype=torch.int64)
+                return got["buf"]
+            total, rc = exchange_runs(send, counts.tolist(), words, make_recv)
+            allc = [None] * world
+            dist.all_gather_object(allc, counts.tolist())
+            want = [allc[src][rank] for src in range(world)]
+            assert rc == want and total == sum(want)
+            recv = got["buf"].reshape(-1, words)
+            off = 0
+            for src in range(world):                # received runs arrive in source-rank order
+                exp = torch.arange(want[src], dtype=torch.int64) + src * 1_000_000 + rank * 10_000
+                assert torch.equal(recv[off:off + want[src]], exp[:, None].expand(-1, words)), (rank, src)
+                off += want[src]
+            assert off == recv.shape[0]
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,words", [(2, 4), (3, 6)])
+def test_exchange_runs_gloo(world, words):
+    """The super-k-mer exchange (SkmExchange.flush): counts all-to-all, then the runs in place."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_runs, args=(r, world, port, words, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
