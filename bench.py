@@ -186,7 +186,13 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    real_stdout = None
     if world > 1:
+        # stdout carries ONE JSON line; what libraries write to file descriptor 1 while the job runs (NCCL's
+        # version banner at communicator creation) goes to stderr instead
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     hbm_gbs, peak_src = load_peaks()
 
@@ -404,6 +410,9 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(all_launches),
             "clocks": sampler.summary(),
         }
+        sys.stdout.flush()
+        if real_stdout is not None:
+            os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     # orderly teardown: tensors that were used on the table's streams must go before the streams do
     torch.cuda.synchronize()
