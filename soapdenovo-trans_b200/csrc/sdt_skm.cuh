@@ -796,29 +796,11 @@ skm_resplit_kernel (const u32 *rec2, const u64 *off, const u64 *end, const SkmSp
 				skm_roll_window<W> (st, key, left, right);
 				const u32 g = S.qbase + skm_bucket (key_hash<W> (key), S.q);
 				if (PASS == 0)
-				{
 					atomicAdd (hist2 + g, 1u);
-					if (cur2)
-					{
-						atomicAdd (cur2, (unsigned long long) st.add);	// debug: instances that enter the split
-						atomicAdd (cur2 + 1, key_hash<W> (key) >> 20);	// debug: checksum of the keys
-						atomicAdd (cur2 + 2, (unsigned long long) g);	// debug: checksum of the buckets
-						atomicAdd (cur2 + 3, (unsigned long long) S.q * 1000003ull + S.qbase);
-					}
-				}
 				else
 				{
 					const u64 pos = atomicAdd (cur2 + g, 1ull);
 					u32 *dst = rec3 + pos * RECW;
-					if (hist2)
-					{
-						atomicAdd (reinterpret_cast<unsigned long long *> (hist2), (unsigned long long) st.add);	// debug
-						atomicAdd (reinterpret_cast<unsigned long long *> (hist2) + 1, 1ull);
-						atomicAdd (reinterpret_cast<unsigned long long *> (hist2) + 2, (unsigned long long) g);
-						atomicAdd (reinterpret_cast<unsigned long long *> (hist2) + 3, key_hash<W> (key) >> 20);
-						if (pos >= 251710ull)
-							atomicAdd (reinterpret_cast<unsigned long long *> (hist2) + 4, 1ull);
-					}
 					const u32 hl = nrun ? 0u : (t > 0 || phl), hr = nrun ? 0u : (t + 1 < st.n || phr);
 					const u32 nb = nrun ? 0u : hl + (u32) K + hr, first = nrun ? 0u : phl + t - hl;
 					u32 wd[4];
@@ -848,31 +830,6 @@ skm_resplit_kernel (const u32 *rec2, const u64 *off, const u64 *end, const SkmSp
 			}
 		}
 	}
-}
-
-__global__ void skm_debug_cmp_kernel (const u32 *a, const u32 *b, u32 n, unsigned long long *bad)
-{
-	for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
-		if (a[g] != b[g])
-			atomicAdd (bad, 1ull);
-}
-
-__global__ void skm_debug_cur_kernel (const u64 *off, const u64 *cur, u32 n, unsigned long long *bad)
-{
-	for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
-		if (cur[g] != off[g + 1])
-			atomicAdd (bad, 1ull);
-}
-
-__global__ void skm_debug_sum_kernel (const u32 *rec, const u64 *off, const u64 *end, u32 n, u32 recw, unsigned long long *sum)
-{
-	for (u32 sl = blockIdx.x; sl < n; sl += gridDim.x)
-		for (u64 i = off[sl] + threadIdx.x; i < end[sl]; i += blockDim.x)
-		{
-			const u32 h1 = rec[i * recw + 1];
-			const u32 nwin = ((h1 >> 8) & 63u) + 1;
-			atomicAdd (sum, (unsigned long long) rec[i * recw + 2] * nwin);
-		}
 }
 
 // One CTA per work item, items handed out through *item_cursor.  items == nullptr: item i is (slice i, 0, 1).

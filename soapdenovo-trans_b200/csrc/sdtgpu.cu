@@ -1046,8 +1046,9 @@ int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
 			// k-mer hash in one pass over their records (skm_resplit_kernel): sub-records are counted,
 			// scanned, written, merged and built like slices.  It removes the quadratic cost of retrying a
 			// hot slice as q filtered scans (C5: retries 51 -> ~5 ms), but the per-sub-slice counts of its
-			// two passes disagree in some runs (1-word keys, K = 31) and instances are lost; SDTGPU_DEBUG_SPLIT=1
-			// prints the checksums that show it.  Until that is understood the hash-split retry below is the default.
+			// two passes disagree in some runs (1-word keys, K = 31: cursors do not end at the next run's
+			// offset, sub-records overwrite each other, instances are lost) although each pass alone is
+			// reproducible.  Until that is understood the hash-split retry below is the default.
 			std::vector<SkmSplit> chunks;
 			u64 Q = 0;
 			for (const SkmWork &f : failed)
@@ -1070,36 +1071,8 @@ int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
 			CK (h, cudaStreamSynchronize (h->stream));
 			CK (h, cudaMemcpy (h->d_items, chunks.data (), chunks.size () * sizeof (SkmSplit), cudaMemcpyHostToDevice));	// blocking: pageable source
 			const SkmSplit *d_chunks = static_cast<const SkmSplit *> (h->d_items);
-			const bool dbg = getenv ("SDTGPU_DEBUG_SPLIT") != nullptr;
-			CK (h, cudaMemsetAsync (small + 6, 0, 2 * sizeof (u64), h->stream));
-			if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 0, hist2, dbg ? reinterpret_cast<u64 *> (small + 6) : nullptr, nullptr)))
+			if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 0, hist2, nullptr, nullptr)))
 				return rc;
-			if (dbg)
-			{	// is the count pass reproducible?
-				u32 *hist3 = nullptr;
-				u64 *acc = nullptr, hacc[8];
-				CK (h, cudaMalloc (&hist3, (size_t) nq * 4));
-				CK (h, cudaMalloc (&acc, 64));
-				CK (h, cudaMemsetAsync (hist3, 0, (size_t) nq * 4, h->stream));
-				for (int rep = 0; rep < 2; rep++)
-				{
-					CK (h, cudaMemsetAsync (hist3, 0, (size_t) nq * 4, h->stream));
-					CK (h, cudaMemsetAsync (acc, 0, 64, h->stream));
-					if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 0, hist3, acc, nullptr)))
-						return rc;
-					CK (h, cudaMemcpyAsync (hacc, acc, 64, cudaMemcpyDeviceToHost, h->stream));
-					CK (h, cudaStreamSynchronize (h->stream));
-					fprintf (stderr, "[split] count pass %d: instances %llu keysum %llu bucketsum %llu splitsum %llu\n", rep, (unsigned long long) hacc[0], (unsigned long long) hacc[1], (unsigned long long) hacc[2], (unsigned long long) hacc[3]);
-				}
-				cudaFree (acc);
-				CK (h, cudaMemsetAsync (small + 5, 0, sizeof (u64), h->stream));
-				skm_debug_cmp_kernel<<<64, 256, 0, h->stream>>> (hist2, hist3, nq, small + 5);
-				u64 bad = 0;
-				CK (h, cudaMemcpyAsync (&bad, small + 5, 8, cudaMemcpyDeviceToHost, h->stream));
-				CK (h, cudaStreamSynchronize (h->stream));
-				fprintf (stderr, "[split] count pass run twice: %llu of %u buckets differ\n", (unsigned long long) bad, nq);
-				cudaFree (hist3);
-			}
 			{
 				TimedLaunch tl (h, 5);
 				slice_scan_sums_kernel<<<nseg2, SCAN_NT, 0, h->stream>>> (hist2, nq, seg2);
@@ -1108,48 +1081,16 @@ int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
 			CK (h, cudaGetLastError ());
 			u64 n_sub = 0;
 			CK (h, cudaMemcpyAsync (&n_sub, off2 + nq, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-			CK (h, cudaStreamSynchronize (h->stream));	// also: `chunks` is pageable host memory
+			CK (h, cudaStreamSynchronize (h->stream));
 			const size_t rec = 4 * (size_t) g.recw;
 			if ((rc = grow_device (h, (void **) &h->rec3, &h->rec3_cap_b, 0, std::max<u64> (n_sub, 1) * rec)))
 				return rc;
-			if (dbg)
-				CK (h, cudaMemsetAsync (h->d_failed, 0, 64, h->stream));
-			if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 1, dbg ? static_cast<u32 *> (h->d_failed) : nullptr, cur2, h->rec3)))
+			if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 1, nullptr, cur2, h->rec3)))
 				return rc;
-			if (dbg)
-			{
-				u64 d3[8];
-				CK (h, cudaMemcpyAsync (d3, h->d_failed, 64, cudaMemcpyDeviceToHost, h->stream));
-				CK (h, cudaStreamSynchronize (h->stream));
-				fprintf (stderr, "[split] pass 1: instances %llu windows %llu bucketsum %llu keysum %llu pos>=n_sub %llu\n", (unsigned long long) d3[0], (unsigned long long) d3[1], (unsigned long long) d3[2], (unsigned long long) d3[3], (unsigned long long) d3[4]);
-			}
 			ar = SkmArrays { h->rec3, off2, cur2 };	// from here on the work items are sub-slices
 			CK (h, cudaMemsetAsync (small + 5, 0, sizeof (u64), h->stream));
-			if (dbg)
-			{
-				skm_debug_cur_kernel<<<64, 256, 0, h->stream>>> (ar.off, ar.end, nq, small + 5);
-				u64 bad = 0;
-				CK (h, cudaMemcpyAsync (&bad, small + 5, 8, cudaMemcpyDeviceToHost, h->stream));
-				CK (h, cudaStreamSynchronize (h->stream));
-				fprintf (stderr, "[split] buckets whose cursor != next offset: %llu\n", (unsigned long long) bad);
-				CK (h, cudaMemsetAsync (small + 5, 0, sizeof (u64), h->stream));
-				skm_debug_sum_kernel<<<1024, 256, 0, h->stream>>> (ar.rec, ar.off, ar.off + 1, nq, g.recw, small + 7);
-				u64 d2[2];
-				CK (h, cudaMemcpyAsync (d2, small + 6, 16, cudaMemcpyDeviceToHost, h->stream));
-				CK (h, cudaStreamSynchronize (h->stream));
-				fprintf (stderr, "[split] failed %u Q %u n_sub %llu  in %llu  written %llu", n_failed, nq, (unsigned long long) n_sub, (unsigned long long) d2[0], (unsigned long long) d2[1]);
-				CK (h, cudaMemsetAsync (small + 7, 0, sizeof (u64), h->stream));
-			}
 			if (n_sub && (rc = launch_dedupe (h, ar, nq, true)))
 				return rc;
-			if (dbg)
-			{
-				skm_debug_sum_kernel<<<1024, 256, 0, h->stream>>> (ar.rec, ar.off, ar.end, nq, g.recw, small + 7);
-				u64 d2 = 0;
-				CK (h, cudaMemcpyAsync (&d2, small + 7, 8, cudaMemcpyDeviceToHost, h->stream));
-				CK (h, cudaStreamSynchronize (h->stream));
-				fprintf (stderr, "  after dedupe %llu\n", (unsigned long long) d2);
-			}
 			CK (h, cudaStreamSynchronize (h->stream));	// d_items is about to be reused
 			if ((rc = launch_build (h, ar, nullptr, nq, 6)))
 				return rc;
