@@ -1295,7 +1295,7 @@ int sdtgpu_reset (sdtgpu_t *h)
 	CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
 	if (h->sliced)
 	{	// records, their per-slice counts and the read log go; the store is rewritten by the next build
-		if (!h->log.empty ())
+		if (!h->log.empty () || h->skm_world > 1)	// (exchange: sdtgpu_skm_import leaves its own counts in d_hist even if this rank pushed nothing)
 		{
 			CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) h->geom.n_slices * sizeof (u32), h->stream));
 			CK (h, cudaMemsetAsync (h->d_small, 0, 8 * sizeof (u64), h->stream));
