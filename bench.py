@@ -265,6 +265,7 @@ def main():
         one_step(g)
     barrier()
     g.kernel_time(reset=True)
+    pkg.pregraph.debug_prof(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -277,6 +278,7 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     ms = e0.elapsed_time(e1)
+    build_prof = pkg.pregraph.debug_prof(reset=True)
     chk = g.stats()
     assert exch is not None or (chk.n_instances == instances_rank and chk.n_nodes == distinct), (chk.n_instances, chk.n_nodes)
     st = g.stats()
@@ -314,6 +316,7 @@ def main():
                 "stream_gbs": (st.n_instances * args.steps * stream_b[k] / max(phases[k][0], 1e-9) / 1e6) if stream_b[k] else None}
             for k in stream_b}}
         dominant = max(stream_b, key=lambda k: phases[k][0])
+        sliced_info["build_phase_cycles"] = build_prof
         sliced_info["dominant"] = "skm_" + dominant + "_kernel"
         ker_ms = insert_ms / args.steps                      # one pipeline pass = one "launch" of the insert
         inst_per_launch = float(st.n_instances)
@@ -414,13 +417,16 @@ def main():
         if real_stdout is not None:
             os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
-    # orderly teardown: tensors that were used on the table's streams must go before the streams do
+    # orderly teardown: everything that was enqueued on the handle's streams is done, torch's views of the
+    # streams and the library's buffers go first, then the handle (which owns the streams), then NCCL
     torch.cuda.synchronize()
+    del ext
+    exch = None
+    g.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     sys.stdout.flush()
-    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -193,6 +193,10 @@ int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[
  * records left after identical ones were merged (last build), 0, 0, 0 } */
 int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[12]);
 
+/* debug (library built with -DSDT_BUILD_PROF; zeros otherwise): phase clocks of the slice build kernel,
+ * summed over thread 0 of every CTA (SM cycles): [0] prepare, [2] insert, [3] compact, [4] work items, [5] chunks */
+int sdtgpu_debug_prof (uint64_t out[8], int reset);
+
 /* ---- super-k-mer exchange: the sliced build on several GPUs, one process per GPU (SDTGPU_F_SLICED).
  * The reference shards k-mers over its threads by hash (prlHashReads.c:79-88); here the table slices
  * (ranges of minimizers) are dealt to the ranks in contiguous ranges, so whole super-k-mer records

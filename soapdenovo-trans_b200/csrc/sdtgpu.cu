@@ -4,6 +4,7 @@
 #include "../../include/sdtgpu.h"
 #include "sdt_kernels.cuh"
 #include "sdt_skm.cuh"
+#include "sdt_build.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -67,6 +68,7 @@ struct sdtgpu
 	bool snap_pending = false;
 	u64 snap_pushed = 0, known_nodes = 0, known_at = 0;
 	u64 n_reads = 0;
+	u64 ord_end = 0;	// one past the largest instance ordinal pushed since the last reset
 	u32 n_grows = 0;
 	bool finalized = false;
 	int deLowKmer = 0;
@@ -312,6 +314,7 @@ int make_batch (sdtgpu *h, ReadBatch &rb, const uint8_t *d_packed, const u32 *d_
 	const u64 ord_limit = ORD40_NONE;	// the slot keeps 40 bits of ordinal
 	if ((first_read_ordinal + n_reads) >= ord_limit / h->maxwin)
 		return fail (h, SDTGPU_ERANGE, "instance ordinal would overflow the slot's ordinal field");
+	h->ord_end = std::max<u64> (h->ord_end, (first_read_ordinal + n_reads) * h->maxwin);
 	rb.packed = d_packed;
 	rb.lens = d_lens;
 	rb.nmask = (h->flags & SDTGPU_F_NKMER) ? d_nmask : nullptr;
@@ -686,11 +689,11 @@ int skm_setup (sdtgpu *h, u64 hint)
 	if (hint == 0)
 		return fail (h, SDTGPU_EINVAL, "the sliced build needs capacity_hint (expected distinct k-mers)");
 	SkmGeom g;
-	g.build_nt = env_u32 ("SDTGPU_BUILD_NT", 1024) == 512 ? 512 : 1024;
-	// default: what fits one CTA per SM (227 KB): 72 / 84 / 100 bytes per slot for 1- / 2- / 4-word keys; half of it for two CTAs
-	const u32 dflt = g.build_nt == 1024 ? (h->W == 1 ? 3104u : (h->W == 2 ? 2656u : 2240u)) : (h->W == 1 ? 1552u : (h->W == 2 ? 1330u : 1118u));
+	g.build_nt = env_u32 ("SDTGPU_BUILD_OLD", 0) ? (env_u32 ("SDTGPU_BUILD_NT", 1024) == 512 ? 512 : 1024) : 0;	// 0: the two-group kernel (sdt_build.cuh)
+	// default: what fits one CTA per SM (227 KB) beside the staging areas: 72 / 84 / 100 bytes per slot for 1- / 2- / 4-word keys
+	const u32 dflt = g.build_nt == 0 ? skm_build2_max_slots (h->W) : g.build_nt == 1024 ? (h->W == 1 ? 3104u : (h->W == 2 ? 2656u : 2240u)) : (h->W == 1 ? 1552u : (h->W == 2 ? 1330u : 1118u));
 	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", dflt);
-	if (g.slice_slots < 32 || g.slice_slots > MAX_SWEEPS * g.build_nt)
+	if (g.slice_slots < 32 || g.slice_slots > (g.build_nt ? MAX_SWEEPS * g.build_nt : dflt))
 		return fail (h, SDTGPU_EINVAL, "SDTGPU_SLICE_SLOTS out of range");
 	for (;; g.slice_slots--)
 	{	// the largest prime below: the image is probed by double hashing (skm_find)
@@ -884,8 +887,37 @@ int launch_resplit (sdtgpu *h, const SkmArrays &ar, const SkmSplit *chunks, u32 
 	return rc;
 }
 
+template <int W, bool ORD32> int launch_build2_t (sdtgpu *h, const SkmArrays &ar, const SkmWork *items, u32 n_items, int cat)
+{
+	typedef typename SlotOf<W>::type S;
+	const SkmGeom &g = h->geom;
+	auto kern = skm_build2_kernel<W, ORD32>;
+	const size_t smem = skm_build2_smem (W, g.slice_slots, ORD32);
+	CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	const unsigned grid = (unsigned) std::min<u64> (std::max<u64> (n_items, 1), (u64) h->sm_count);
+	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
+	CK (h, cudaMemsetAsync (small + 3, 0, sizeof (u64), h->stream));	// work-item cursor
+	{
+		TimedLaunch tl (h, cat);
+		kern<<<grid, BUILD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, ar.rec, ar.off, ar.end, items, n_items, small + 3,
+							   static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
+	}
+	CK (h, cudaGetLastError ());
+	return SDTGPU_OK;
+}
+
 int launch_build (sdtgpu *h, const SkmArrays &ar, const SkmWork *items, u32 n_items, int cat)
 {
+	if (h->geom.build_nt == 0)
+	{	// 32-bit ordinals in the slice images when every instance ordinal pushed so far fits (one GPU: the records are this handle's own)
+		const bool ord32 = h->skm_world <= 1 && h->ord_end < 0xFFFFFFFFull && !getenv ("SDTGPU_ORD64");
+		switch (h->W)
+		{
+		case 1: return ord32 ? launch_build2_t<1, true> (h, ar, items, n_items, cat) : launch_build2_t<1, false> (h, ar, items, n_items, cat);
+		case 2: return ord32 ? launch_build2_t<2, true> (h, ar, items, n_items, cat) : launch_build2_t<2, false> (h, ar, items, n_items, cat);
+		default: return ord32 ? launch_build2_t<4, true> (h, ar, items, n_items, cat) : launch_build2_t<4, false> (h, ar, items, n_items, cat);
+		}
+	}
 	switch (h->W)
 	{
 	case 1: return h->geom.build_nt == 512 ? launch_build_t<1, 512> (h, ar, items, n_items, cat) : launch_build_t<1, 1024> (h, ar, items, n_items, cat);
@@ -1313,7 +1345,7 @@ int sdtgpu_reset (sdtgpu_t *h)
 		if (rc)
 			return rc;
 	}
-	h->pushed_upper = 0; h->n_reads = 0; h->finalized = false; h->deLowKmer = 0;
+	h->pushed_upper = 0; h->n_reads = 0; h->ord_end = 0; h->finalized = false; h->deLowKmer = 0;
 	h->n_segments = 0; h->staging_used = 0; h->staged_upper = 0;
 	if (h->snap_pending)
 		CK (h, cudaEventSynchronize (h->snap_ev));
@@ -1904,6 +1936,28 @@ int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[
 		h->all_launches = 0;
 	}
 	return SDTGPU_OK;
+}
+
+int sdtgpu_debug_prof (uint64_t out[8], int reset)
+{
+#ifdef SDT_BUILD_PROF
+	unsigned long long v[8];
+	if (cudaMemcpyFromSymbol (v, g_build_prof, sizeof v) != cudaSuccess)
+		return SDTGPU_ECUDA;
+	for (int i = 0; i < 8; i++)
+		out[i] = v[i];
+	if (reset)
+	{
+		memset (v, 0, sizeof v);
+		cudaMemcpyToSymbol (g_build_prof, v, sizeof v);
+	}
+	return SDTGPU_OK;
+#else
+	for (int i = 0; i < 8; i++)
+		out[i] = 0;
+	(void) reset;
+	return SDTGPU_OK;
+#endif
 }
 
 int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[12])

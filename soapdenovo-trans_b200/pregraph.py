@@ -47,7 +47,7 @@ class KmerSet(C.Structure):
 def build_library(force: bool = False) -> str:
     """Compiles csrc/ + host/ for sm_100a into libsdtgpu.so (in-tree, so it travels to the GPU box)."""
     srcs = [os.path.join(PKG_DIR, p) for p in ("csrc/sdtgpu.cu", "csrc/sdt_synth.cu", "csrc/sdt_device.cuh",
-                                               "csrc/sdt_kernels.cuh", "host/kmerset_builder.cpp", "host/sdt_readpack.c", "../include/sdtpack.h",
+                                               "csrc/sdt_kernels.cuh", "csrc/sdt_sliced.cuh", "csrc/sdt_skm.cuh", "csrc/sdt_build.cuh", "host/kmerset_builder.cpp", "host/sdt_readpack.c", "../include/sdtpack.h",
                                                "../include/sdtgpu.h")]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
@@ -105,6 +105,7 @@ def library() -> C.CDLL:
     L.sdtgpu_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.sdtgpu_phase_times.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.sdtgpu_slice_geometry.argtypes = [vp, C.POINTER(u64)]
+    L.sdtgpu_debug_prof.argtypes = [C.POINTER(u64), i32]
     L.sdtpack_open.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p, i32, i32]
     L.sdtpack_next.restype = C.c_int64
     L.sdtpack_next.argtypes = [vp, i32, i32, i32, vp, vp, vp, u64, u32]
@@ -113,6 +114,14 @@ def library() -> C.CDLL:
     L.sdtgpu_synth_reads_device.argtypes = [i32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u32, u32, vp]
     _lib = L
     return L
+
+
+def debug_prof(reset: bool = True):
+    """Phase clocks of the slice build kernel (SM cycles summed over the groups' first threads)."""
+    out = (C.c_uint64 * 8)()
+    library().sdtgpu_debug_prof(out, int(reset))
+    names = ("prepare", "wait_image", "insert", "compact", "items", "chunks")
+    return {n: int(out[i]) for i, n in enumerate(names)}
 
 
 def hash_kmer(key_words4, key_words: int) -> int:

@@ -45,7 +45,7 @@ def _insert_all(pkg, g, d_packed, L, stride, batch):
     g.sync()
 
 
-@pytest.mark.parametrize("name,n_pairs", [("C2", 25_000_000), ("C5", 5_000_000), ("C3", 50_000_000), ("C4", 50_000_000)])
+@pytest.mark.parametrize("name,n_pairs", [("C1", 500_000), ("C2", 25_000_000), ("C5", 5_000_000), ("C3", 50_000_000), ("C4", 50_000_000)])
 def test_full_size_properties(pkg, oracle, name, n_pairs):
     import torch
     cfg = dict(pkg.synth.CONFIGS[name])
@@ -83,6 +83,14 @@ def test_full_size_properties(pkg, oracle, name, n_pairs):
         fp3 = g.table_checksum()
         g.close()
         assert np.array_equal(fp1, fp3)
+    # the sliced build (bench.py's path) at full size: same fingerprint as the single-pass insert
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(st.n_nodes * 1.02) + 1024, sliced=True)
+    _insert_all(pkg, g, d_packed, L, stride, 1 << 22)
+    st_s = g.stats()
+    fp_s = g.table_checksum()
+    g.close()
+    assert (st_s.n_instances, st_s.n_nodes) == (st.n_instances, st.n_nodes)
+    assert np.array_equal(fp1, fp_s)
     # anchor to the oracle: the first 40 000 device-generated reads, bit for bit
     n_sub = 40_000
     sub = d_packed[:n_sub].cpu().numpy()
