@@ -1,14 +1,25 @@
 #!/usr/bin/env python
 """bench.py — k-mers inserted/s in pregraph hashing (BASELINE.json metric), 1..8 B200.
 
-One "step" = one pass of the hot path over the whole synthetic workload: empty the table, then
-chop + insert every window of every read (sdtgpu_push_reads_device; at N > 1 bucket by owner ->
-NCCL all-to-all -> insert).  `value` times the step with the packed reads already resident in HBM;
-`e2e` times the same job through the C ABI with HOST buffers (pinned), H2D copies and the D2H read
-of the result counters inside the timed region.  `roofline` is the insert kernel's algorithmic
-bytes (64 B per instance for K <= 63, 96 B for K <= 127) over its CUDA-event time
-against the measured HBM copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times the
-unmodified reference's prlRead2HashTable (oracle/_ref) on a bounded sample of the same reads.
+One "step" = one pass of the hot path over the whole synthetic workload: empty the handle, push every
+read (sdtgpu_push_reads_device), sdtgpu_sync — reads -> super-k-mer records in per-slice chains ->
+copies merged, chains cut into work items -> every item built in shared memory -> node store (at N > 1:
+records merged per sender, exchanged by slice owner over NCCL, built by the owner).  Nothing about
+the data is learned outside the timed region: the handle gets NO capacity hint on one GPU (the library
+sizes itself from the number of windows pushed, inside the step) and the same closed-form estimate
+on several GPUs (every rank must cut the minimizer space the same way).
+
+`value`   the step with the packed reads already resident in HBM (CUDA events on the handle's stream);
+`e2e`     the same job through the C ABI with HOST buffers (pinned): H2D copies and the D2H read of the
+          result counters inside the timed region;
+`e2e_from_files`  FASTA on disk -> sdtpack (parallel parse + 2-bit pack) -> sdtgpu_push_reads -> counters,
+          on the SAME sample of reads the reference arm hashes (like for like with `cpu_baseline`), and with
+          --files-full on the whole workload;
+`roofline`  the insert pipeline's algorithmic bytes (64 B per instance for K <= 63, 96 B for
+          K <= 127) over the summed CUDA-event times of its kernels, against the measured HBM copy bandwidth
+          in MEASURED_PEAKS.json; `traffic` = the DRAM bytes ncu measured for the same kernels on this config;
+`cpu_baseline`  the unmodified reference's prlRead2HashTable (oracle/_ref) on a bounded sample of the same reads;
+`parity_checked`  the sliced build's table fingerprint equals the single-pass insert's on this workload (untimed).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--pairs P] [--impl reference]
 """
@@ -34,7 +45,6 @@ BYTES_PER_INSTANCE = {1: 64, 2: 64, 4: 96}
 # upsert needs at least one load and one atomic, so a single-pass insert cannot exceed half of that.
 RANDOM_REQUESTS_PER_S = 36.65e9
 MIN_REQUESTS_PER_INSTANCE = {1: 2, 2: 2, 4: 3}
-DEFAULT_PATH = {1: "sliced", 2: "sliced"}     # key: 1 GPU / more than one GPU (super-k-mer exchange)
 METRIC = "k-mers inserted/s in pregraph hashing"
 UNIT = "k-mer instances/s"
 
@@ -45,6 +55,11 @@ def load_peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def estimate_distinct(instances: int, K: int) -> int:
+    """The library's own rule when it gets no hint (estimate_distinct, csrc/sdtgpu.cu)."""
+    return int(min(instances + 1024.0, instances * (1.0 - 0.99 ** K) * 1.05 + 65536.0))
 
 
 class ClockSampler(threading.Thread):
@@ -84,14 +99,40 @@ def unpack_reads(packed: np.ndarray, read_len: int) -> np.ndarray:
     return out[:, :read_len]
 
 
+def write_fasta_pair(dirpath: str, reads: np.ndarray, tag: str = "s"):
+    """reads: base codes [n, L] in arrival order (read1, read2 alternately) -> f1/f2 FASTA, one sequence line per
+    record, file sizes not a multiple of 32 768.  Vectorised: C2 in full is 5.7 GB of text."""
+    n, L = reads.shape
+    lut = np.frombuffer(b"ACTG", dtype=np.uint8)
+    paths = []
+    for mate in (0, 1):
+        r = reads[mate::2]
+        m = len(r)
+        hdr = np.frombuffer(b">" + tag.encode() + b"0000000000\n", dtype=np.uint8)
+        rec = np.empty((m, len(hdr) + L + 1), dtype=np.uint8)
+        rec[:, :len(hdr)] = hdr
+        idx = np.arange(m, dtype=np.int64)
+        for d in range(10):     # decimal read number into the header
+            rec[:, len(hdr) - 2 - d] = 48 + (idx // 10 ** d) % 10
+        rec[:, len(hdr):len(hdr) + L] = lut[r]
+        rec[:, -1] = 10
+        path = os.path.join(dirpath, f"{tag}_{mate + 1}.fa")
+        with open(path, "wb") as f:
+            f.write(rec.tobytes())
+            if (rec.size % 32768) == 0:
+                f.write(b"\n")
+        paths.append(path)
+    cfg = os.path.join(dirpath, f"{tag}.cfg")
+    with open(cfg, "w") as f:
+        f.write(f"max_rd_len={L}\n[LIB]\navg_ins=200\nreverse_seq=0\nasm_flags=3\nf1={paths[0]}\nf2={paths[1]}\n")
+    return cfg, paths
+
+
 def reference_run(cfg_d: dict, sample_reads: np.ndarray, threads: int):
     """Unmodified reference prlRead2HashTable (oracle/_ref/ref_hash_*) on `sample_reads` (base codes)."""
     from oracle import oracle as O
-    import sdt_pkg
-    synth = sdt_pkg.load().synth
-    lens = np.full(len(sample_reads), sample_reads.shape[1], dtype=np.uint32)
     with tempfile.TemporaryDirectory() as d:
-        cfg = synth.write_library(d, sample_reads, lens, sample_reads.shape[1], paired=True)
+        cfg, _ = write_fasta_pair(d, sample_reads)
         kw = 1 if cfg_d["key_words"] == 1 else 4
         info, _, _ = O.run_reference(cfg, os.path.join(d, "out"), cfg_d["K"], kw, threads, 0, dump=False)
     return info
@@ -113,6 +154,48 @@ def ref_threads() -> int:
     return max(1, min(os.cpu_count() or 8, 64))
 
 
+def files_e2e(pkg, cfg_d, reads: np.ndarray, device: int, batch_reads: int, repeats: int = 2):
+    """FASTA on disk -> sdtpack_next -> sdtgpu_push_reads (double-buffered pinned batches) -> counters.
+    The handle gets no hint.  Returns (instances/s, seconds, instances, nodes) of the fastest repeat."""
+    import ctypes as C
+    L, K, kw = cfg_d["read_len"], cfg_d["K"], cfg_d["key_words"]
+    lib = pkg.library()
+    stride = pkg.synth.stride_bytes(L)
+    best = None
+    with tempfile.TemporaryDirectory() as d:
+        _, paths = write_fasta_pair(d, reads, tag="f")
+        bufs = []
+        for _ in range(2):
+            p, l = C.c_void_p(), C.c_void_p()
+            assert lib.sdtgpu_host_alloc(C.byref(p), batch_reads * stride) == 0 and lib.sdtgpu_host_alloc(C.byref(l), batch_reads * 4) == 0
+            bufs.append((p, l))
+        try:
+            with pkg.PregraphGPU(K, kw, L, capacity_hint=0, device=device, sliced=True) as g:
+                for rep in range(repeats + 1):      # first pass: page cache + allocations
+                    t0 = time.perf_counter()
+                    g.reset()
+                    rd = pkg.ReadPacker(paths[0], paths[1], fastq=False)
+                    pushed, cur = 0, 0
+                    while True:
+                        p, l = bufs[cur]
+                        n = lib.sdtpack_next(rd.h, L, 0, 0, p, l, None, batch_reads, stride)
+                        if n <= 0:
+                            break
+                        g._ck(lib.sdtgpu_push_reads(g.h, p, l, None, n, 0, stride, pushed))
+                        pushed += n
+                        cur ^= 1
+                    rd.close()
+                    st = g.stats()
+                    dt = time.perf_counter() - t0
+                    if rep and (best is None or dt < best[1]):
+                        best = (st.n_instances / dt, dt, int(st.n_instances), int(st.n_nodes))
+        finally:
+            for p, l in bufs:
+                lib.sdtgpu_host_free(p)
+                lib.sdtgpu_host_free(l)
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -125,25 +208,22 @@ def main():
     ap.add_argument("--cpu-sample-pairs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed fingerprint check against the single-pass insert")
+    ap.add_argument("--files-full", action="store_true", help="also measure e2e_from_files on the whole workload (writes it as FASTA first)")
     ap.add_argument("--batch-reads", type=int, default=1 << 22)
     ap.add_argument("--exchange", default="reads", choices=["reads", "records", "reads-replicated"],
-                    help="multi-GPU sharding: all-gather the packed reads and insert owned k-mers (default) or exchange k-mer records")
-    ap.add_argument("--partitioned", action="store_true", help="experimental staged/partitioned insert path")
-    ap.add_argument("--path", default="auto", choices=["auto", "direct", "sliced", "partitioned"],
-                    help="insert path: single-pass upsert (direct), sliced build (super-k-mer records -> slices built in shared memory), "
-                         "or the experimental staged path; auto = the fastest measured one for this GPU count")
+                    help="multi-GPU sharding of --path direct: all-gather the packed reads and insert owned k-mers (default) or exchange k-mer records")
+    ap.add_argument("--path", default="sliced", choices=["auto", "direct", "sliced"],
+                    help="insert path: the sliced build (super-k-mer records -> chains -> work items built in shared memory; every config) "
+                         "or the single-pass upsert (direct)")
+    ap.add_argument("--hint", type=int, default=-1, help="capacity_hint for the handle (-1: none on one GPU, the closed-form estimate on several)")
     args = ap.parse_args()
-    if args.partitioned:
-        args.path = "partitioned"
+    if args.path == "auto":
+        args.path = "sliced"
     import sdt_pkg
     pkg = sdt_pkg.load()
     synth = pkg.synth
     cfg_d = dict(synth.CONFIGS[args.config])
-    if args.path == "auto":
-        # the sliced build is tuned for 1-word keys (K <= 31, the metric's config); at K = 63 / 127 super-k-mers are
-        # 2-4x longer, the slices lumpier (11 % of them overflow on C3) and the single-pass insert is faster
-        args.path = DEFAULT_PATH[1 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 2] if cfg_d["key_words"] == 1 and cfg_d["K"] <= 31 and not cfg_d["hot"] else "direct"
-    args.partitioned = args.path == "partitioned"
     sliced = args.path == "sliced"
     if args.pairs:
         cfg_d["n_pairs"] = args.pairs
@@ -156,13 +236,14 @@ def main():
     nwin = L - K + 1
     workload = (f"{args.config}: {'31mer' if kw == 1 else '127mer'} build K={K}, {2 * cfg_d['n_pairs']} synthetic "
                 f"{L}bp PE reads from {cfg_d['n_transcripts']} transcripts (seed {cfg_d['seed']})")
+    sample_pairs = min(args.cpu_sample_pairs, cfg_d["n_pairs"])
+    sample_desc = f"first {2 * sample_pairs} reads of the workload ({2 * sample_pairs * nwin} instances), FASTA f1/f2"
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
         threads = ref_threads()
-        sample_pairs = min(args.cpu_sample_pairs, cfg_d["n_pairs"])
         reads = host_sample(cfg_d, sample_pairs)
         vals = []
         for i in range(args.warmup + args.steps):
@@ -170,7 +251,7 @@ def main():
             if i >= args.warmup:
                 vals.append(info["count_sum"] / info["seconds"])
         v = float(np.mean(vals))
-        sample = f"first {2 * sample_pairs} reads of the workload ({2 * sample_pairs * nwin} instances) per step, FASTA f1/f2 via the reference's own parser, -p {threads}"
+        sample = f"{sample_desc} via the reference's own parser per step, -p {threads}"
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * 2 * sample_pairs * nwin / v, "higher_is_better": True,
@@ -211,17 +292,41 @@ def main():
     instances_rank = n_reads * nwin
     batch = args.batch_reads
 
-    # ---- pilot pass with a generous table to learn the distinct count, then size load <= 0.5
-    # distinct k-mers are dominated by error k-mers (a window is error-free with probability 0.99^K)
-    slot_b = 64 if K > 63 else 32
-    est_distinct = instances_rank * (1.0 - 0.99 ** K) * 1.03 + 6e7
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(est_distinct) + 1024, device=local_rank, partitioned=args.partitioned, sliced=sliced)
+    def push_all(gg):
+        for a in range(0, n_reads, batch):
+            b = min(a + batch, n_reads)
+            gg.push_reads(d_packed[a:b], None, None, n_reads=b - a, uniform_len=L, stride_bytes=stride,
+                          first_read_ordinal=2 * first_pair + a, device=True)
+
+    # ---- untimed: the fingerprint of the single-pass insert's table on this workload (one GPU)
+    parity = None
+    direct_fp = None
+    if sliced and world == 1 and not args.no_parity:
+        free_b, _ = torch.cuda.mem_get_info()
+        est = estimate_distinct(instances_rank, K)
+        slot_b = 64 if K > 63 else 32
+        if free_b > max(est / 0.85, min(2 * est, (60 << 30) / slot_b)) * slot_b + (4 << 30):
+            with pkg.PregraphGPU(K, kw, L, capacity_hint=est, device=local_rank) as gd:
+                push_all(gd)
+                gd.sync()
+                direct_fp = gd.table_checksum().tolist()
+        else:
+            parity = "skipped: no room for the single-pass insert's table beside the reads"
+
+    # the handle that is measured: no hint on one GPU; on several the closed-form estimate (identical on all ranks)
+    if args.hint >= 0:
+        hint = args.hint
+    elif sliced and world == 1:
+        hint = 0
+    else:
+        hint = estimate_distinct(instances_rank, K)
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=hint, device=local_rank, sliced=sliced)
     ext = torch.cuda.ExternalStream(g.stream, device=dev)
 
     exch, exch_kind = None, None
     if world > 1:
         from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads, SkmExchange
-        if sliced and args.exchange != "reads-replicated":
+        if sliced:
             exch, exch_kind = SkmExchange(pkg, g, world, rank, dev), "skm"
         elif args.exchange == "records":
             exch = Exchange(pkg, g, world, rank, dev, max_round_instances=min(batch, n_reads) * nwin)
@@ -230,31 +335,14 @@ def main():
 
     def one_step(gg):
         gg.reset()
-        for a in range(0, n_reads, batch):
-            b = min(a + batch, n_reads)
-            if exch is None:
-                gg.push_reads(d_packed[a:b], None, None, n_reads=b - a, uniform_len=L, stride_bytes=stride,
-                              first_read_ordinal=2 * first_pair + a, device=True)
-            else:
+        if exch is None:
+            push_all(gg)
+        else:
+            for a in range(0, n_reads, batch):
+                b = min(a + batch, n_reads)
                 exch.round(gg, d_packed[a:b], b - a, L, stride, 2 * first_pair + a)
-        if exch is not None:
             exch.flush(gg)
-        gg.sync()      # end of the step: everything staged has been inserted (flushes the epoch)
-
-    one_step(g)
-    st = g.stats()
-    distinct = st.n_nodes
-    assert (exch is not None) or st.n_instances == instances_rank, (st.n_instances, instances_rank)
-    if world > 1:       # one geometry on all ranks (the super-k-mer exchange cuts the minimizer space by it)
-        dmax = torch.tensor([distinct], dtype=torch.int64, device=dev)
-        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
-        distinct = int(dmax.item())
-    g.close()
-    # the library sizes the table from the hint: load 0.5 up to 60 GiB, denser beyond
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(distinct * 1.02) + 1024, device=local_rank, partitioned=args.partitioned, sliced=sliced)
-    ext = torch.cuda.ExternalStream(g.stream, device=dev)
-    if exch is not None:
-        exch.rebind(g)
+        gg.sync()      # end of the step: everything pushed is in the table
 
     def barrier():
         if world > 1:
@@ -264,8 +352,15 @@ def main():
     for _ in range(args.warmup):
         one_step(g)
     barrier()
+    if direct_fp is not None:
+        if args.warmup == 0:
+            one_step(g)
+        sliced_fp = g.table_checksum().tolist()
+        parity = sliced_fp == direct_fp
+        assert parity, ("the sliced build's table differs from the single-pass insert's", sliced_fp, direct_fp)
     g.kernel_time(reset=True)
-    pkg.pregraph.debug_prof(reset=True)
+    if exch is not None and hasattr(exch, "collective_ms"):
+        exch.collective_ms = 0.0
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -278,65 +373,75 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     ms = e0.elapsed_time(e1)
-    build_prof = pkg.pregraph.debug_prof(reset=True)
-    chk = g.stats()
-    assert exch is not None or (chk.n_instances == instances_rank and chk.n_nodes == distinct), (chk.n_instances, chk.n_nodes)
     st = g.stats()
+    distinct = int(st.n_nodes)
+    assert exch is not None or st.n_instances == instances_rank, (st.n_instances, instances_rank)
     phases = g.phase_times(reset=False)
-    cat_ms, cat_launches = g.kernel_times(reset=False)
     insert_ms, insert_launches, all_launches = g.kernel_time(reset=True)
-    t = torch.tensor([ms, float(st.n_instances), float(st.n_nodes)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(st.n_instances), float(st.n_nodes), float(getattr(exch, "collective_ms", 0.0))], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, total_instances, total_nodes = float(tmax[0]), float(tsum[1]), float(tsum[2])
+        collective_ms = float(tmax[3]) / args.steps
+        assert total_instances == instances_rank * world, (total_instances, instances_rank * world)
     else:
-        total_instances, total_nodes = float(st.n_instances), float(st.n_nodes)
+        total_instances, total_nodes, collective_ms = float(st.n_instances), float(st.n_nodes), None
     ms_per_step = ms / args.steps
     value = total_instances / (ms_per_step * 1e-3)
     bpi = BYTES_PER_INSTANCE[st.device_key_words]
+    slot_b = 64 if st.device_key_words == 4 else 32
     sliced_info = None
     if sliced:
-        # The insert is a pipeline of three streaming kernels (super-k-mer emit, scatter by slice, slice
-        # build); the SURVEY figure of 64 (96) algorithmic bytes per instance belongs to the whole insert, so
-        # `achieved` is taken over the SUM of their CUDA-event times (all on the handle's stream).  Each
-        # phase's own DRAM stream (bytes it must read + write per instance) is reported beside it.
+        # The insert is a pipeline of streaming kernels (super-k-mer emit into chains, merge, build); the SURVEY figure
+        # of 64 (96) algorithmic bytes per instance belongs to the whole insert, so `achieved` is taken over the SUM of
+        # their CUDA-event times (all on the handle's stream).  Each phase's own DRAM stream (bytes it must read + write
+        # per instance) is reported beside it.
         geo = g.slice_geometry()
         rec_b = geo["record_bytes"] * geo["n_records"] / max(st.n_instances, 1)      # record bytes per instance
+        mrg_b = geo["record_bytes"] * geo["n_records_merged"] / max(st.n_instances, 1)
         read_b = stride / nwin
         node_b = st.n_nodes * slot_b / max(st.n_instances, 1)
-        stream_b = {"emit": read_b + rec_b, "scatter": 2 * rec_b, "dedupe": 2 * rec_b, "build": rec_b + node_b, "scan": 0.0, "retry": 0.0}
+        stream_b = {"emit": read_b + rec_b, "scatter": 2 * mrg_b if world > 1 else 0.0, "dedupe": rec_b + mrg_b, "build": mrg_b + node_b, "scan": 0.0, "retry": 0.0}
         insert_ms = sum(phases[k][0] for k in stream_b)
         insert_launches = max(phases["build"][1] + phases["retry"][1], 1)
         sliced_info = {"geometry": geo, "windows_per_record": st.n_instances / max(geo["n_records"], 1), "phases": {
             k: {"ms_per_step": phases[k][0] / args.steps, "launches_per_step": phases[k][1] / args.steps,
                 "stream_bytes_per_instance": stream_b[k],
                 "stream_gbs": (st.n_instances * args.steps * stream_b[k] / max(phases[k][0], 1e-9) / 1e6) if stream_b[k] else None}
-            for k in stream_b}}
+            for k in stream_b},
+            "phase_names": {"emit": "skm_emit_kernel (reads -> records appended to their slice's chain)", "scatter": "skm_append_kernel (multi-GPU: received records -> chains)",
+                            "dedupe": "skm_merge_kernel (copies merged, chains -> work items)", "build": "skm_build_kernel",
+                            "scan": "blocks per chain scanned and listed", "retry": "pieces of items that overflowed, skm_split_kernel + sub-slices"}}
         dominant = max(stream_b, key=lambda k: phases[k][0])
-        sliced_info["build_phase_cycles"] = build_prof
-        sliced_info["dominant"] = "skm_" + dominant + "_kernel"
+        sliced_info["dominant"] = "skm_" + {"dedupe": "merge", "scatter": "append"}.get(dominant, dominant) + "_kernel"
         ker_ms = insert_ms / args.steps                      # one pipeline pass = one "launch" of the insert
         inst_per_launch = float(st.n_instances)
     else:
         ker_ms = max(insert_ms, 1e-9) / max(insert_launches, 1)
         inst_per_launch = st.n_instances * args.steps / max(insert_launches, 1)
     achieved = inst_per_launch * bpi / (ker_ms * 1e-3) / 1e9
-    traffic = None      # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
-    tp = os.path.join(ROOT, "profiles", "r1_traffic_sliced.json" if sliced else "r1_traffic.json")
-    if os.path.exists(tp) and world == 1 and args.path in ("direct", "sliced"):
+    traffic, traffic_src = None, None      # DRAM bytes per launch, from the committed ncu capture of this path on this config
+    tp = os.path.join(ROOT, "profiles", "r2_traffic_sliced.json" if sliced else "r1_traffic.json")
+    if os.path.exists(tp) and world == 1:
         with open(tp) as f:
             tj = json.load(f)
         if tj.get("key_words") == st.device_key_words:
             traffic = tj["dram_bytes_per_instance"] * inst_per_launch
+            traffic_src = tj.get("source")
 
     # ---- e2e: HOST (pinned) buffers, H2D inside the timed region, counters read back (D2H) every step.
     # N = 1: straight through the C ABI's host entry point (sdtgpu_push_reads).  N > 1: every rank
-    # copies its round's reads from pinned host memory, then bucket -> exchange -> insert as above.
+    # copies its round's reads from pinned host memory, then emit -> merge -> exchange -> build as above.
     e2e = None
     if not args.no_e2e:
+        if sliced and world == 1 and hint == 0:
+            # a caller that streams reads from the host knows how many it is going to push: with the closed-form hint for
+            # that number (no pass over the data) the records are made while the next batch is copied
+            g.close()
+            g = pkg.PregraphGPU(K, kw, L, capacity_hint=estimate_distinct(instances_rank, K), device=local_rank, sliced=True)
         h_packed = torch.empty((n_reads, stride), dtype=torch.uint8).pin_memory()
         h_packed.copy_(d_packed)
         torch.cuda.synchronize()
@@ -375,42 +480,59 @@ def main():
         else:
             e2e_inst = float(s2.n_instances)
         e2e = {"value": e2e_inst / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_reads * stride) * world,
-               "d2h_bytes_per_step": 2120 * world, "ms_per_step": dt * 1e3}
+               "d2h_bytes_per_step": 2120 * world, "ms_per_step": dt * 1e3,
+               "capacity_hint": "closed form from the number of reads to be pushed (instances x (1 - 0.99^K) x 1.05)"}
+        del h_packed
 
-    cpu = None
-    if not args.no_cpu_baseline and rank == 0 and world == 1:
+    # ---- the reference on a bounded sample, and our whole path FROM FILES on the same sample (like for like)
+    cpu, from_files = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = ref_threads()
-        sp = min(args.cpu_sample_pairs, n_pairs)
-        sample = unpack_reads(d_packed[: 2 * sp].cpu().numpy(), L)
+        sample = unpack_reads(d_packed[: 2 * sample_pairs].cpu().numpy(), L)
         info = reference_run(cfg_d, sample, threads)
         cpu = {"value": info["count_sum"] / info["seconds"], "unit": UNIT, "cores": threads, "kind": "reference",
-               "sample": f"first {2 * sp} reads ({info['count_sum']} instances, {info['nodes']} nodes) through the unmodified "
-                         f"reference prlRead2HashTable (oracle/_ref), FASTA f1/f2, -p {threads}, {info['seconds']:.2f} s"}
+               "sample": f"{sample_desc} ({info['count_sum']} instances, {info['nodes']} nodes) through the unmodified "
+                         f"reference prlRead2HashTable (oracle/_ref), its own parser included, -p {threads}, {info['seconds']:.2f} s"}
+        if sliced:
+            v, dt, ninst, nnodes = files_e2e(pkg, cfg_d, sample, local_rank, min(batch, 1 << 20))
+            assert ninst == info["count_sum"] and nnodes == info["nodes"], (ninst, nnodes, info["count_sum"], info["nodes"])
+            from_files = {"same_sample_as_cpu_baseline": {"value": v, "unit": UNIT, "seconds": dt, "instances": ninst, "nodes": nnodes,
+                                                          "vs_cpu_baseline": v / cpu["value"], "same_config": True,
+                                                          "what": "FASTA f1/f2 on disk -> sdtpack (mmap, parallel parse + 2-bit pack) -> sdtgpu_push_reads -> sdtgpu_get_stats, "
+                                                                  "no capacity hint; node and instance counts equal the reference's"}}
+        del sample
+        if sliced and args.files_full:
+            full = unpack_reads(d_packed.cpu().numpy(), L)
+            v, dt, ninst, nnodes = files_e2e(pkg, cfg_d, full, local_rank, batch, repeats=1)
+            assert ninst == instances_rank and nnodes == distinct
+            from_files["whole_workload"] = {"value": v, "unit": UNIT, "seconds": dt, "instances": ninst, "nodes": nnodes}
+            del full
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers sharded by owner ({'super-k-mer records of the sliced build exchanged over NCCL, one all-to-all per step' if exch_kind == 'skm' else ('packed reads all-gathered over NCCL, every rank inserts the k-mers it owns' if args.exchange != 'records' else 'k-mer records exchanged over NCCL')})" if world > 1 else ""),
+            "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers sharded by slice owner ({'super-k-mer records merged per sender and exchanged over NCCL, one all-to-all per step' if exch_kind == 'skm' else ('packed reads all-gathered over NCCL, every rank inserts the k-mers it owns' if args.exchange != 'records' else 'k-mer records exchanged over NCCL')})" if world > 1 else ""),
                        "instances_per_step": total_instances, "distinct_kmers": total_nodes,
-                       "table_slots_per_gpu": int(st.capacity), "slot_bytes": 64 if st.device_key_words == 4 else 32,
-                       "batch_reads": batch,
-                       "insert_path": args.path,
-                       "l2": "table (>= 1.6x distinct x slot bytes), k-mer records and reads are far larger than the 126 MB L2; the table is rebuilt from empty every step"},
+                       "capacity_hint": hint, "hint_source": ("none: sized inside the timed region from the number of windows pushed" if hint == 0 else
+                                                              ("closed form, instances x (1 - 0.99^K) x 1.05: no pass over the data" if args.hint < 0 else "--hint")),
+                       "node_store_slots_per_gpu": int(st.capacity), "slot_bytes": slot_b,
+                       "batch_reads": batch, "insert_path": args.path,
+                       "l2": "reads, records and node store are far larger than the 126 MB L2; the table is rebuilt from empty every step"},
+            "parity_checked": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": traffic, "kernel": ("skm_emit + skm_scatter + skm_dedupe + skm_build kernels (the sliced insert pipeline; times summed)" if sliced else
-                                    "insert_staged_kernel" if args.partitioned else "insert_reads_kernel") if (world == 1 or args.exchange == "reads") else "insert_records_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": ("skm_emit + skm_merge + skm_build kernels (the sliced insert pipeline; times summed)" if sliced else "insert_reads_kernel") if (world == 1 or sliced or args.exchange == "reads") else "insert_records_kernel",
                          "path": args.path, "sliced": sliced_info,
                          "bytes_per_instance": bpi, "kernel_ms_per_launch": ker_ms, "peak_source": peak_src,
                          "random_access": {"cold_line_requests_per_s_measured": RANDOM_REQUESTS_PER_S,
                                            "min_requests_per_instance": MIN_REQUESTS_PER_INSTANCE[st.device_key_words],
                                            "ceiling_instances_per_s_per_gpu": RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words],
                                            "frac_of_ceiling": (inst_per_launch / (ker_ms * 1e-3)) / (RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words]),
-                                           "source": "tools/randacc_bench.cu, profiles/r1_randacc_bench.txt"},
-                         "kernel_ms_per_step": {"insert": cat_ms[0] / args.steps, "partition_count": cat_ms[1] / args.steps,
-                                                "partition_scatter": cat_ms[2] / args.steps}},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(all_launches),
+                                           "source": "tools/randacc_bench.cu, profiles/r1_randacc_bench.txt"}},
+            "collective_ms_per_step": collective_ms,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_from_files": from_files, "gpu_launches": int(all_launches),
             "clocks": sampler.summary(),
         }
         sys.stdout.flush()

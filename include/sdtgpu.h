@@ -200,18 +200,23 @@ int sdtgpu_debug_prof (uint64_t out[8], int reset);
 /* ---- super-k-mer exchange: the sliced build on several GPUs, one process per GPU (SDTGPU_F_SLICED).
  * The reference shards k-mers over its threads by hash (prlHashReads.c:79-88); here the table slices
  * (ranges of minimizers) are dealt to the ranks in contiguous ranges, so whole super-k-mer records
- * travel — 4 bytes per k-mer instance instead of a 16-byte record each.  Per epoch, on every rank:
- *   sdtgpu_skm_set_world   once, before the first push: rank and number of ranks;
+ * travel — and only one copy of each per sending rank, with a multiplicity: ~1.5 bytes per k-mer instance
+ * instead of a 16-byte record each.  Per epoch, on every rank:
+ *   sdtgpu_skm_set_world   once, before the first push: rank and number of ranks (needs capacity_hint =
+ *                          expected distinct k-mers PER RANK, the same on all ranks);
+ *   sdtgpu_skm_set_ordinal_bound  optional: reads pushed on ALL ranks this epoch (lets the slice images
+ *                          keep 32-bit ordinals when they fit);
  *   sdtgpu_push_reads*     this rank's own reads (global first_read_ordinal);
- *   sdtgpu_skm_stage       groups the records by slice: *d_records = device address of the records,
- *                          offsets[r] .. offsets[r + 1] = the records (units: records of
- *                          sdtgpu_slice_geometry()[4] bytes) that belong to rank r, r < world;
+ *   sdtgpu_skm_stage       merges this rank's copies and packs the records by owner: rank r's records
+ *                          (of sdtgpu_slice_geometry()[4] bytes) are counts[r] records from record
+ *                          starts[r] of *d_records on;
  *   (caller)               all-to-all of counts and records (NCCL) into the buffer that
  *   sdtgpu_skm_import_buffer  returns for the total it is going to receive;
  *   sdtgpu_skm_import      builds this rank's slices from the n_records received.
  * Afterwards finalize / export / stats see this rank's share of the table. */
 int sdtgpu_skm_set_world (sdtgpu_t *h, int rank, int world);
-int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *offsets /* world + 1 */);
+int sdtgpu_skm_set_ordinal_bound (sdtgpu_t *h, uint64_t n_reads_all_ranks);
+int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *starts /* world */, uint64_t *counts /* world */);
 int sdtgpu_skm_import_buffer (sdtgpu_t *h, uint64_t n_records, void **d_buffer);
 int sdtgpu_skm_import (sdtgpu_t *h, uint64_t n_records);
 

@@ -19,7 +19,7 @@
 //     ATOMS.MIN instead of a 64-bit CAS loop, and 4 bytes less per slot;
 //   * home slot and probe step come from a 32-bit hash (two multiplies per key word instead of fmix64).
 #pragma once
-#include "sdt_skm.cuh"
+#include "sdt_merge.cuh"
 
 namespace sdt {
 
@@ -33,16 +33,17 @@ __host__ __device__ inline size_t skm_image2_bytes (int W, u32 S, bool ord32)
 	return (((size_t) S * (8 * W + (ord32 ? 4 : 8) + 4 * CELL_WORDS + 4 + (W > 1 ? 4 : 0))) + 15) & ~(size_t) 15;
 }
 __host__ __device__ inline size_t skm_stage_words (int W) { return (size_t) skm_rcap (W) * skm_recw (W); }
+static constexpr u32 BUILD_WL_BYTES = 8192;	// the compaction's lists of occupied slots: 32 warps x <= 128 slots x 2 bytes
 __host__ __device__ inline size_t skm_build2_smem (int W, u32 S, bool ord32)
-{	// image + two staging areas + window prefix
-	return skm_image2_bytes (W, S, ord32) + 4 * (2 * skm_stage_words (W) + skm_rcap (W) + 4);
+{	// image + staging area + slot lists + window prefix
+	return skm_image2_bytes (W, S, ord32) + 4 * (skm_stage_words (W) + skm_rcap (W) + 4) + BUILD_WL_BYTES;
 }
 // largest image that fits beside them (227 KB per CTA, ~1 KB static); sized for 64-bit ordinals so that
 // the slice geometry does not depend on how many reads are going to be pushed
 inline u32 skm_build2_max_slots (int W)
 {
-	const size_t avail = 227 * 1024 - 1024 - 4 * (2 * skm_stage_words (W) + skm_rcap (W) + 4) - 16;
-	return (u32) (avail / (8 * W + 8 + 4 * CELL_WORDS + 4 + (W > 1 ? 4 : 0)));
+	const size_t avail = 227 * 1024 - 1024 - 4 * (skm_stage_words (W) + skm_rcap (W) + 4) - BUILD_WL_BYTES - 16;
+	return (u32) std::min<size_t> (4096, avail / (8 * W + 8 + 4 * CELL_WORDS + 4 + (W > 1 ? 4 : 0)));
 }
 
 #ifdef SDT_BUILD_PROF
@@ -51,23 +52,6 @@ __device__ unsigned long long g_build_prof[8];	// phase clocks (thread 0): prepa
 #else
 #define PROF_MARK(q) do { } while (0)
 #endif
-
-// two cheap 32-bit hashes of a key: a -> home slot, b -> probe step, retry filter, sub-slice
-template <int W> __device__ __forceinline__ void skm_hash2 (const Key<W> &k, u32 &a, u32 &b)
-{
-	u32 x = 0;
-#pragma unroll
-	for (int q = 0; q < W; q++)
-	{
-		x = (x ^ (u32) k.w[q]) * 0x9E3779B1u;
-		x = (x ^ (u32) (k.w[q] >> 32)) * 0x85EBCA6Bu + (x >> 17);
-	}
-	x ^= x >> 15; x *= 0xC2B2AE35u;
-	x ^= x >> 13;
-	a = x;
-	b = x * 0x27D4EB2Fu;
-	b ^= b >> 15;
-}
 
 __device__ __forceinline__ void cp_async16 (void *smem_dst, const void *gsrc)
 {
@@ -199,13 +183,13 @@ __device__ __forceinline__ u32 skm_find2 (const SkmImage2<W, ORD32> &im, u32 S, 
 	return S;
 }
 
-struct SkmDesc { u64 r0, r1; u32 it, slice, r, R; };	// a work item with its run of records
+struct SkmDesc { u64 r0, r1; u32 it, wsum, r, R; };	// a work item with its run of records
 
-// One CTA per SM, work items handed out through *item_cursor.  items == nullptr: item i is (slice i, 0, 1).
+// One CTA per SM, work items handed out through *item_cursor.
 template <int W, bool ORD32>
 __global__ void __launch_bounds__ (BUILD_NT, 1)
 skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long long *node_cursor, SkmGeom g, int K,
-		   const u32 *rec2, const u64 *off, const u64 *end, const SkmWork *items, u32 n_items, unsigned long long *item_cursor,
+		   const u32 *rec2, const SkmWork *items, u32 n_items, unsigned long long *item_cursor,
 		   SkmWork *failed, u32 *n_failed, u32 max_failed, Counters *ctr)
 {
 	typedef typename SlotOf<W>::type S_t;
@@ -224,8 +208,9 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 	im.cell = reinterpret_cast<u32 *> (im.ord + S);
 	im.extra = im.cell + (size_t) S * CELL_WORDS;
 	im.state = im.extra + S;
-	u32 *stage0 = smem + skm_image2_bytes (W, S, ORD32) / 4;	// two staging areas of RCAP records
-	u32 *pre = stage0 + 2 * RCAP * RECW;	// [RCAP + 1] exclusive prefix of the windows of a chunk's records
+	u32 *stg = smem + skm_image2_bytes (W, S, ORD32) / 4;	// staging area of RCAP records
+	unsigned short *wl0 = reinterpret_cast<unsigned short *> (stg + RCAP * RECW);	// slot lists of the compaction
+	u32 *pre = stg + RCAP * RECW + BUILD_WL_BYTES / 4;	// [RCAP + 1] exclusive prefix of the windows of a chunk's records
 	Key<W> kmask;	// the low 2K bits
 #pragma unroll
 	for (int q = 0; q < W; q++)
@@ -239,26 +224,21 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 #endif
 	u64 nodes = 0, inst = 0;	// nodes: thread 0 only; inst: instances this thread applied (items that were written)
 
-	// a work item's descriptor: which slice, which piece of it, where its records are (one thread, two dependent loads)
+	// a work item's descriptor (one thread, one load)
 	auto load_desc = [&](u32 it, SkmDesc &d) {
 		d.it = it;
-		d.slice = 0; d.r = 0; d.R = 1;
+		d.wsum = 0; d.r = 0; d.R = 1;
 		d.r0 = d.r1 = 0;
 		if (it < n_items)
 		{
-			if (items)
-			{
-				const SkmWork wk = items[it];
-				d.slice = wk.slice; d.r = wk.r; d.R = wk.R;
-			}
-			else
-				d.slice = it;
-			d.r0 = off[d.slice];
-			d.r1 = end[d.slice];	// the run's surviving records (skm_dedupe_kernel)
+			const SkmWork wk = items[it];
+			d.wsum = wk.wsum; d.r = wk.r; d.R = wk.R;
+			d.r0 = wk.r0;
+			d.r1 = wk.r0 + wk.nrec;
 		}
 	};
 	// the first chunk of an item's records into a staging area (asynchronously; one 16-byte piece per thread and turn)
-	auto prefetch = [&](const SkmDesc &d, u32 *stg) {
+	auto prefetch = [&](const SkmDesc &d) {
 		const u32 nrec = (u32) min ((u64) RCAP, d.r1 - d.r0);
 		const uint4 *src = reinterpret_cast<const uint4 *> (rec2 + d.r0 * RECW);
 		uint4 *dst = reinterpret_cast<uint4 *> (stg);
@@ -291,19 +271,21 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 	for (u32 i = tid; i < S * CELL_WORDS; i += BUILD_NT)
 		im.cell[i] = 0u;
 	__syncthreads ();
-	prefetch (s_desc[0], stage0);
+	prefetch (s_desc[0]);
 	for (u32 round = 0;; round++)
 	{
 		const SkmDesc D = s_desc[round & 3];
 		if (D.it >= n_items)
 			break;
-		u32 *stg = stage0 + (round & 1) * RCAP * RECW;
-		// ---- the pipeline in front of this item: cursor three rounds ahead, descriptor two, records one
-		// (the first two are issued further down, in front of the compaction)
-		prefetch (s_desc[(round + 1) & 3], stage0 + ((round + 1) & 1) * RCAP * RECW);
-		cp_async_wait<1> ();	// this item's first chunk (issued a round ago) has landed
+		// ---- the pipeline in front of this item: cursor three rounds ahead, descriptor two (both issued in front of
+		// the compaction, further down), records one: they were copied under the previous item's compaction
+		cp_async_wait<0> ();
 		__syncthreads ();
 		u64 mine = 0;
+		if (D.R == 0 && tid == 0)
+			s_full = 1;	// a chain far beyond an image: straight to the failed list (it is cut into sub-slices)
+		if (D.R == 0)
+			__syncthreads ();
 		for (u64 c0 = D.r0; c0 < D.r1 && !*reinterpret_cast<volatile u32 *> (&s_full); c0 += RCAP)
 		{	// up to RCAP records at a time: their windows are flattened (exclusive prefix in pre[]) and
 			// cut into 1024 equal runs, one per thread
@@ -437,6 +419,8 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 			prof[5]++;
 #endif
 		}
+		// ---- the next item's records travel while this one's image is compacted
+		prefetch (s_desc[(round + 1) & 3]);
 		// ---- image -> node store
 		const bool full = s_full != 0;
 		// (the cursor and the descriptor loads are issued here, where few registers are live, and land under the compaction)
@@ -446,10 +430,10 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 			it3 = (u32) atomicAdd (item_cursor, 1ull);
 		if (tid == 32)
 			load_desc (s_it[(round + 2) & 3], d2);
-		// every warp lists the occupied slots of its range (the staging area is free now) and counts them
-		unsigned short *wl = reinterpret_cast<unsigned short *> (stg) + wid * spw;
+		// every warp lists the occupied slots of its range and counts them
+		unsigned short *wl = wl0 + wid * spw;
 		u32 cnt = 0;
-		if (D.r1 > D.r0)
+		if (D.r1 > D.r0 && D.R != 0)
 			for (u32 sw = 0; sw < spw; sw += 32)
 			{
 				const u32 i = wid * spw + sw + lane;
@@ -543,8 +527,8 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 			{	// retried later, split by k-mer hash
 				const u32 f = atomicAdd (n_failed, 1u);
 				SkmWork wk;
-				wk.slice = D.slice; wk.r = D.r; wk.R = D.R;
-				wk.nrec = (u32) min (D.r1 - D.r0, (u64) 0xFFFFFFFFu);
+				wk.r0 = D.r0; wk.wsum = D.wsum; wk.r = D.r; wk.R = D.R;
+				wk.nrec = (u32) (D.r1 - D.r0);
 				if (f < max_failed)
 					failed[f] = wk;
 				else
@@ -593,7 +577,7 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 		}
 		if (write)	// instances applied by a work item that is going to be retried are not counted
 			inst += mine;
-		__syncthreads ();	// the image is clean; the staging area (the slot list) may be refilled
+		__syncthreads ();	// the image is clean
 		PROF_MARK (3);
 #ifdef SDT_BUILD_PROF
 		prof[4]++;

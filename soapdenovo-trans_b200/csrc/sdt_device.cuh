@@ -307,12 +307,12 @@ template <> struct Table<2>
 
 template <> struct Table<4>
 {
-	// 4-word keys: no 256-bit CAS exists, so a new key is claimed by locking the slot's first half
-	// with a 128-bit CAS (EMPTY -> LOCKED) and published with ONE 256-bit store of the whole key.
-	// The key occupies exactly one 32-byte sector, probes read it with one 256-bit load, and a sector
-	// is written and read by the L2 as a unit, so a reader sees either LOCKED or the complete key:
-	// no fence, no second round trip (the first version published the halves separately behind a
-	// __threadfence() and ran config C4 at 2.0 G instances/s).
+	// 4-word keys: no 256-bit CAS exists, so a new key is claimed by locking the slot's first half with a
+	// 128-bit CAS (EMPTY -> LOCKED); the second half is written, a fence orders it, and the first half is
+	// published last.  A reader that finds the first half published therefore finds the whole key — if it loaded
+	// all four words with ONE 256-bit load it may still have an old second half (the PTX memory model treats a
+	// vector access as independent scalar accesses), so a slot whose first half matches and whose second half
+	// does not is looked at once more behind a fence before it is taken for another key.
 	static __device__ __forceinline__ int upsert (Slot4 *tab, u64 cap, const Key<4> &k, u32 left, u32 right, u64 ord)
 	{
 		u64 idx = slot_of (key_hash<4> (k), cap);
@@ -331,13 +331,22 @@ template <> struct Table<4>
 			{
 				if (!cas128 (&s->key[0], EMPTY64, EMPTY64, EMPTY64, LOCKED64, a0, a1))
 					continue;	// lost the race: re-examine the same slot
-				st256 (&s->key[0], k.w[0], k.w[1], k.w[2], k.w[3]);
+				st128 (&s->key[2], k.w[2], k.w[3]);
+				__threadfence ();
+				st128 (&s->key[0], k.w[0], k.w[1]);
 				created = 1;
 			}
 			else
 			{
-				if (a0 != k.w[0] || a1 != k.w[1] || b0 != k.w[2] || b1 != k.w[3])
+				if (a0 != k.w[0] || a1 != k.w[1])
 					goto next;
+				if (b0 != k.w[2] || b1 != k.w[3])
+				{	// published first half, other second half: another key, or a second half that had not arrived yet
+					__threadfence ();
+					ld128 (&s->key[2], b0, b1);
+					if (b0 != k.w[2] || b1 != k.w[3])
+						goto next;
+				}
 				ld128 (&s->p, s0, s1);
 			}
 			payload_update (&s->p, s0, s1, left, right, ord);

@@ -1,0 +1,643 @@
+// sdt_merge.cuh — what happens to the chains of records (sdt_chain.cuh) after the reads are through:
+// skm_merge_kernel (copies collapse, every chain becomes a contiguous run), skm_append_kernel (records
+// that arrive from other GPUs -> chains), skm_split_kernel (a slice that overflowed by far -> sub-slices).
+#pragma once
+#include "sdt_skm.cuh"
+
+namespace sdt {
+
+// ------------------------------------------------------------------------------------------------
+// Copies of the same super-k-mer collapse into one record, and chains become the work items of the build.
+// At the coverage of a transcriptome most records of a slice are byte-identical copies (every
+// error-free read that spans a super-k-mer emits the same bases, neighbours and window count; only
+// the ordinal differs), and a window costs the build ~20x what finding a copy costs here.  A
+// surviving record carries its multiplicity in word 2 and the smallest ordinal of its copies: window
+// t of every copy is the same (key, left, right) instance with ordinal ord0 + t, so count and link
+// counters take the multiplicity (update_kmer, newhash.c:71-96, is a sum) and the node's first
+// ordinal the minimum.
+//
+// A CTA takes MG_G consecutive chains at a time.  If their records fit one chunk (the rule) they are
+// staged together, a table of record indices keyed by the record's content finds the copies, and
+// the survivors are written out IN ORDER (block scan), so that consecutive chains are adjacent.
+// Then the CTA cuts the group into WORK ITEMS for skm_build_kernel at chain boundaries: as many
+// consecutive chains as have at most `budget` windows left between them.  Every instance of a k-mer
+// is in one chain, so an item holds all instances of its k-mers; an item has at most as many distinct
+// k-mers as windows, so with budget < image slots it CANNOT overflow an image, whatever the number of
+// slices was guessed to be (too many slices only make the chains short).  Only a single chain with
+// more windows than that — a highly expressed locus — becomes an item that the build may have to
+// split (R = 0 tells it not even to try when the chain is far beyond an image).
+// The space in out[] is reserved by the group's record count (an upper bound) before the records are
+// read, so the round trip of that reservation costs nothing.
+static constexpr int MG_NT = 512;	// 2 CTAs of 80-96 KB per SM
+static constexpr u32 MG_GMAX = 32;	// chains per group at most
+template <int W> struct MergeCfg { static constexpr u32 CHUNK = W == 1 ? 2048u : 1024u, TABLE = 2 * CHUNK; };
+template <int W> __host__ __device__ inline size_t skm_merge_smem () { return (size_t) MergeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) MergeCfg<W>::TABLE * 4 + (MergeCfg<W>::CHUNK / CH_BLK + MG_GMAX + 4) * 4; }
+
+struct MergeOut
+{
+	u32 *out;			// merged records
+	unsigned long long *out_cursor;	// next free record of out[]
+	u64 out_cap;
+	SkmWork *items;			// work items of the build
+	unsigned long long *n_items;
+	u64 max_items;
+	unsigned long long *n_kept;	// [0] records left, [1] their windows
+	u32 budget, oversize;		// windows per item at most; a single chain with more windows than `oversize` is marked R = 0
+	// multi-GPU send side: chains are global slices, `per_owner` of them per rank; the survivors of owner r are
+	// packed without gaps from region[r] on (cursor rcur[r]) and carry their slice in the last word; no items
+	u32 per_owner;
+	const u64 *region;
+	unsigned long long *rcur;
+};
+
+// HAS_MULT: word 2 of the incoming records already is a multiplicity (sub-records, records merged before an exchange)
+template <int W, bool HAS_MULT>
+__global__ void __launch_bounds__ (MG_NT)
+skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, u32 G, unsigned long long *group_cursor)
+{
+	constexpr u32 RECW = SkmRec<W>::WORDS, CH = MergeCfg<W>::CHUNK, TS = MergeCfg<W>::TABLE, VEC = RECW / 4, RPT = CH / MG_NT;
+	extern __shared__ __align__(16) u32 smem[];
+	__shared__ u32 s_scan[MG_NT / 32], s_group, s_tot, s_wtot;
+	__shared__ u32 s_nraw[MG_GMAX], s_rs[MG_GMAX + 1], s_pos[MG_GMAX + 1], s_wpre[MG_GMAX + 1];	// per chain of the group: records, first record in the chunk, first survivor, windows before it
+	__shared__ u64 s_b0[MG_GMAX];
+	__shared__ unsigned long long s_start, s_ibase;
+	u32 *st = smem;			// [CH * RECW]: the chunk's records
+	u32 *tab = smem + CH * RECW;	// [TS]: record index + 1, 0 = free
+	u32 *sbl = tab + TS;		// [CH / CH_BLK + G]: the chunk's blocks
+	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const u32 owners = mo.per_owner ? (ch.n_chains + mo.per_owner - 1) / mo.per_owner : 1;
+	const u32 span = mo.per_owner ? mo.per_owner : ch.n_chains;	// groups do not straddle owners
+	const u32 gpo = (span + G - 1) / G;
+	const u64 n_groups = (u64) gpo * owners;
+	u64 kept_total = 0, win_total = 0;	// thread 0
+
+	// dedupe of the nrec records staged in st[]
+	auto dedupe = [&](u32 nrec) {
+		for (u32 i = tid; i < nrec; i += MG_NT)
+		{
+			u32 *me = st + i * RECW;
+			const u32 h1 = me[1];
+			if ((h1 >> 15) & 1u)
+				continue;	// an N-run stays as it is
+			u32 hsh = h1 & ~0xFFu;
+#pragma unroll
+			for (u32 q = SKM_HDR; q < RECW; q++)
+				hsh = (hsh ^ me[q]) * 0x9E3779B1u + (hsh >> 15);
+			u32 slot = fmix32 (hsh) & (TS - 1);
+			for (;;)
+			{
+				u32 e = tab[slot];
+				if (e == 0u)
+					e = atomicCAS (tab + slot, 0u, i + 1);
+				if (e == 0u)
+					break;	// first of its kind
+				u32 *rep = st + (e - 1) * RECW;
+				bool same = ((*reinterpret_cast<volatile u32 *> (rep + 1) ^ h1) & ~0xFFu) == 0u;	// the low 8 bits are ordinal bits and change
+#pragma unroll
+				for (u32 q = SKM_HDR; q < RECW; q++)
+					same &= rep[q] == me[q];
+				if (same)
+				{	// words 0-1 as one 64-bit number: the header bits above the ordinal are equal, so the minimum is the ordinal's
+					atomicAdd (rep + 2, HAS_MULT ? me[2] : 1u);
+					const u64 mine = *reinterpret_cast<const u64 *> (me);
+					if (mine < *reinterpret_cast<volatile u64 *> (rep))
+						atomicMin (reinterpret_cast<unsigned long long *> (rep), mine);
+					me[2] = 0u;	// dropped
+					break;
+				}
+				slot = (slot + 1) & (TS - 1);
+			}
+		}
+	};
+	// survivors of st[0 .. nrec) to out[base ..] in order; returns their number, s_wtot their windows;
+	// the survivors / windows in front of the records listed in s_rs[0 .. nb] go to s_pos / s_wpre
+	auto write_out = [&](u32 nrec, u64 base, u32 nb, u32 slice0) -> u32 {
+		u32 keep[RPT], nw[RPT], packed = 0;	// thread t: records RPT * t .. RPT * t + RPT - 1; windows << 12 | records
+#pragma unroll
+		for (u32 k = 0; k < RPT; k++)
+		{
+			const u32 i = RPT * tid + k;
+			keep[k] = i < nrec && st[i * RECW + 2] != 0u;
+			const u32 h1 = i < nrec ? st[i * RECW + 1] : 0u;
+			nw[k] = keep[k] ? (((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1) : 0u;
+			packed += (nw[k] << 12) | keep[k];
+		}
+		u32 incl = packed;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const u32 y = __shfl_up_sync (0xFFFFFFFFu, incl, d);
+			if (lane >= (u32) d)
+				incl += y;
+		}
+		if (lane == 31)
+			s_scan[wid] = incl;
+		__syncthreads ();
+		u32 lower = 0;
+		{
+			const u32 c = lane < MG_NT / 32 ? s_scan[lane] : 0u;
+			u32 in2 = c;
+#pragma unroll
+			for (int d = 1; d < MG_NT / 32; d <<= 1)
+			{
+				const u32 y = __shfl_up_sync (0xFFFFFFFFu, in2, d);
+				if (lane >= (u32) d)
+					in2 += y;
+			}
+			lower = __shfl_sync (0xFFFFFFFFu, in2 - c, wid);
+			const u32 total = __shfl_sync (0xFFFFFFFFu, in2, MG_NT / 32 - 1);
+			if (tid == 0)
+			{
+				s_tot = total & 0xFFFu;
+				s_wtot = total >> 12;
+			}
+		}
+		u32 run = lower + incl - packed;	// survivors / windows in front of this thread's first record
+		tab[tid] = run;	// (the table is free after the dedupe)
+#pragma unroll
+		for (u32 k = 0; k < RPT; k++)
+		{
+			const u32 i = RPT * tid + k;
+			if (keep[k])
+			{
+				const u64 pos = base + (run & 0xFFFu);
+				if (pos < mo.out_cap)
+				{
+					const uint4 *src = reinterpret_cast<const uint4 *> (st + i * RECW);
+					uint4 *dst = reinterpret_cast<uint4 *> (mo.out + pos * RECW);
+#pragma unroll
+					for (u32 q = 0; q < VEC; q++)
+					{
+						uint4 x = src[q];
+						if (mo.per_owner && q == VEC - 1)
+						{	// the last base word is never used (80 / 144 / 208 bases of room for 64 / 128 / 192): the slice travels there
+							u32 g = 0;
+							while (g + 1 < nb && s_rs[g + 1] <= i)
+								g++;
+							x.w = slice0 + g;
+						}
+						dst[q] = x;
+					}
+				}
+			}
+			run += (nw[k] << 12) | keep[k];
+		}
+		__syncthreads ();
+		if (tid <= nb)
+		{	// survivors / windows in front of the first record of chain `tid` (tid == nb: all)
+			const u32 i = min (s_rs[tid], nrec);
+			u32 v;
+			if (i >= nrec)
+				v = (s_wtot << 12) | s_tot;
+			else
+			{
+				const u32 t = i / RPT;
+				v = tab[t];
+				for (u32 k = RPT * t; k < i; k++)
+					if (st[k * RECW + 2] != 0u)
+					{
+						const u32 h1 = st[k * RECW + 1];
+						v += ((((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1) << 12) | 1u;
+					}
+			}
+			s_pos[tid] = v & 0xFFFu;
+			s_wpre[tid] = v >> 12;
+		}
+		__syncthreads ();
+		return s_tot;
+	};
+
+	// the same for one chain, in any order (a warp reserves its share with one atomic): cheaper, and all a single
+	// chain needs.  s_tot / s_wtot must be zero on entry
+	auto write_any = [&](u32 nrec, u64 base, u32 slice) -> u32 {
+		u32 wsum = 0;
+		for (u32 b = 0; b < nrec; b += MG_NT)
+		{
+			const u32 i = b + tid;
+			const bool keep = i < nrec && st[i * RECW + 2] != 0u;
+			const u32 bal = __ballot_sync (0xFFFFFFFFu, keep);
+			u32 wb = 0;
+			if (lane == 0 && bal)
+				wb = atomicAdd (&s_tot, (u32) __popc (bal));
+			wb = __shfl_sync (0xFFFFFFFFu, wb, 0);
+			if (keep)
+			{
+				const u64 pos = base + wb + __popc (bal & ((1u << lane) - 1u));
+				if (pos < mo.out_cap)
+				{
+					const uint4 *src = reinterpret_cast<const uint4 *> (st + i * RECW);
+					uint4 *dst = reinterpret_cast<uint4 *> (mo.out + pos * RECW);
+#pragma unroll
+					for (u32 q = 0; q < VEC; q++)
+					{
+						uint4 x = src[q];
+						if (mo.per_owner && q == VEC - 1)
+							x.w = slice;
+						dst[q] = x;
+					}
+				}
+				const u32 h1 = st[i * RECW + 1];
+				wsum += ((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1;
+			}
+		}
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1)
+			wsum += __shfl_down_sync (0xFFFFFFFFu, wsum, d);
+		if (lane == 0 && wsum)
+			atomicAdd (&s_wtot, wsum);
+		__syncthreads ();
+		return s_tot;
+	};
+
+	for (;;)
+	{
+		if (tid == 0)
+			s_group = (u32) atomicAdd (group_cursor, 1ull);
+		__syncthreads ();
+		const u64 grp = s_group;
+		if (grp >= n_groups)
+			break;
+		const u32 owner = (u32) (grp / gpo), c0 = owner * span + (u32) (grp % gpo) * G;
+		const u32 nch = min (G, owner * span + span - c0) < ch.n_chains - c0 ? min (G, owner * span + span - c0) : ch.n_chains - c0;
+		if (tid < nch)
+		{
+			const u32 c = c0 + tid;
+			s_nraw[tid] = ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);	// (a chain of 2^32 records or more is not supported)
+			s_b0[tid] = boff[c];
+		}
+		__syncthreads ();
+		u32 total_raw = 0;
+		for (u32 g = 0; g < nch; g++)
+			total_raw += s_nraw[g];
+		if (total_raw == 0)
+		{
+			__syncthreads ();
+			continue;
+		}
+		unsigned long long resv = 0;
+		if (tid == 0 && !mo.per_owner)
+			resv = atomicAdd (mo.out_cursor, (unsigned long long) total_raw);	// (looked at after the first chunk is merged)
+		if (total_raw <= CH && nch <= MG_GMAX)
+		{	// ---- the rule: the whole group in one chunk
+			{	// first record of every chain in the chunk; its blocks; the records (coalesced 16-byte loads)
+				if (tid == 0)
+				{
+					u32 r = 0;
+					for (u32 g = 0; g < nch; g++)
+					{
+						s_rs[g] = r;
+						r += s_nraw[g];
+					}
+					s_rs[nch] = r;
+				}
+				for (u32 v = tid; v < TS; v += MG_NT)
+					tab[v] = 0u;
+				__syncthreads ();
+				for (u32 g = 0; g < nch; g++)
+				{
+					const u32 n = s_nraw[g], r0 = s_rs[g];
+					uint4 *dst = reinterpret_cast<uint4 *> (st + (size_t) r0 * RECW);
+					for (u32 v = tid; v < n * VEC; v += MG_NT)
+					{
+						const u32 i = v / VEC, part = v - i * VEC, j = i / CH_BLK;
+						const u32 blk = j == 0 ? c0 + g : __ldg (blist + s_b0[g] + j - 1);
+						uint4 x = ldg_stream (reinterpret_cast<const uint4 *> (ch.recs + ((u64) blk * CH_BLK + (i & (CH_BLK - 1))) * RECW) + part);
+						if (!HAS_MULT && part == 0)
+							x.z = 1u;
+						dst[v] = x;
+					}
+				}
+			}
+			__syncthreads ();
+			dedupe (total_raw);
+			if (tid == 0)
+				s_start = resv;
+			__syncthreads ();
+			u64 base = s_start;
+			if (mo.per_owner)
+			{	// exact space in the owner's region: count the survivors first
+				u32 k = 0;
+				for (u32 i = tid; i < total_raw; i += MG_NT)
+					k += st[i * RECW + 2] != 0u;
+#pragma unroll
+				for (int d = 16; d > 0; d >>= 1)
+					k += __shfl_down_sync (0xFFFFFFFFu, k, d);
+				if (tid == 0)
+					s_tot = 0;
+				__syncthreads ();
+				if (lane == 0 && k)
+					atomicAdd (&s_tot, k);
+				__syncthreads ();
+				if (tid == 0)
+					s_start = mo.region[owner] + atomicAdd (mo.rcur + owner, (unsigned long long) s_tot);
+				__syncthreads ();
+				base = s_start;
+			}
+			u32 kept;
+			if (nch == 1)
+			{
+				if (tid == 0)
+					s_tot = s_wtot = 0;
+				__syncthreads ();
+				kept = write_any (total_raw, base, c0);
+				if (tid == 0)
+				{
+					s_pos[0] = s_wpre[0] = 0;
+					s_pos[1] = kept;
+					s_wpre[1] = s_wtot;
+				}
+			}
+			else
+				kept = write_out (total_raw, base, nch, c0);
+			if (tid == 0)
+			{
+				kept_total += kept;
+				win_total += s_wtot;
+				if (!mo.per_owner && kept)
+				{	// work items: consecutive chains with at most `budget` windows between them
+					SkmWork it[MG_GMAX];
+					u32 n_it = 0, g0 = 0;
+					for (u32 g = 1; g <= nch; g++)
+						if (g == nch || s_wpre[g + 1] - s_wpre[g0] > mo.budget)
+						{	// chains g0 .. g - 1 are an item (one chain at least)
+							const u32 nrec = s_pos[g] - s_pos[g0], wsum = s_wpre[g] - s_wpre[g0];
+							if (nrec)
+							{
+								it[n_it].r0 = base + s_pos[g0];
+								it[n_it].nrec = nrec;
+								it[n_it].wsum = wsum;
+								it[n_it].r = 0;
+								it[n_it].R = wsum > mo.oversize ? 0u : 1u;
+								n_it++;
+							}
+							g0 = g;
+						}
+					const u64 ib = atomicAdd (mo.n_items, (unsigned long long) n_it);
+					for (u32 k = 0; k < n_it; k++)
+						if (ib + k < mo.max_items)
+							mo.items[ib + k] = it[k];
+				}
+			}
+			__syncthreads ();
+			continue;
+		}
+		// ---- a group with more records than a chunk holds: chain by chain, a chain in as many chunks as it takes.
+		// Every chain is an item of its own (copies that sit in different chunks of a chain are not merged).
+		u64 outp = 0;	// survivors of the group so far
+		if (tid == 0 && !mo.per_owner)
+			s_start = resv;
+		__syncthreads ();
+		for (u32 g = 0; g < nch; g++)
+		{
+			const u32 n_raw = s_nraw[g];
+			const u64 b0 = s_b0[g];
+			u64 first = outp, item_base = 0;
+			u32 wsum = 0;
+			for (u32 q0 = 0; q0 < n_raw; q0 += CH)
+			{
+				const u32 nrec = min (CH, n_raw - q0);
+				const u32 nbk = (nrec + CH_BLK - 1) / CH_BLK, lb0 = q0 / CH_BLK;
+				for (u32 j = tid; j < nbk; j += MG_NT)
+					sbl[j] = lb0 + j == 0 ? c0 + g : blist[b0 + lb0 + j - 1];
+				for (u32 v = tid; v < TS; v += MG_NT)
+					tab[v] = 0u;
+				if (tid == 0)
+				{
+					s_rs[0] = 0;
+					s_rs[1] = nrec;
+				}
+				__syncthreads ();
+				uint4 *dst = reinterpret_cast<uint4 *> (st);
+				for (u32 v = tid; v < nrec * VEC; v += MG_NT)
+				{
+					const u32 i = v / VEC, part = v - i * VEC;
+					uint4 x = ldg_stream (reinterpret_cast<const uint4 *> (ch.recs + ((u64) sbl[i / CH_BLK] * CH_BLK + (i & (CH_BLK - 1))) * RECW) + part);
+					if (!HAS_MULT && part == 0)
+						x.z = 1u;
+					dst[v] = x;
+				}
+				__syncthreads ();
+				dedupe (nrec);
+				__syncthreads ();
+				u64 base;
+				if (mo.per_owner)
+				{
+					u32 k = 0;
+					for (u32 i = tid; i < nrec; i += MG_NT)
+						k += st[i * RECW + 2] != 0u;
+#pragma unroll
+					for (int d = 16; d > 0; d >>= 1)
+						k += __shfl_down_sync (0xFFFFFFFFu, k, d);
+					if (tid == 0)
+						s_tot = 0;
+					__syncthreads ();
+					if (lane == 0 && k)
+						atomicAdd (&s_tot, k);
+					__syncthreads ();
+					if (tid == 0)
+						s_start = mo.region[owner] + atomicAdd (mo.rcur + owner, (unsigned long long) s_tot);
+					__syncthreads ();
+					base = s_start;
+				}
+				else
+					base = s_start + outp;
+				if (q0 == 0)
+					item_base = base;
+				if (tid == 0)
+					s_tot = s_wtot = 0;
+				__syncthreads ();
+				const u32 kept = write_any (nrec, base, c0 + g);
+				outp += kept;
+				wsum += s_wtot;
+				__syncthreads ();
+			}
+			if (tid == 0)
+			{
+				const u64 nrec = outp - first;
+				kept_total += nrec;
+				win_total += wsum;
+				if (!mo.per_owner && nrec)
+				{
+					SkmWork it;
+					it.r0 = item_base;
+					it.nrec = (u32) min (nrec, (u64) 0xFFFFFFFFu);
+					it.wsum = wsum;
+					it.r = 0;
+					it.R = wsum > mo.oversize ? 0u : 1u;
+					const u64 ib = atomicAdd (mo.n_items, 1ull);
+					if (ib < mo.max_items)
+						mo.items[ib] = it;
+				}
+			}
+		}
+		__syncthreads ();
+	}
+	if (tid == 0 && kept_total)
+	{
+		atomicAdd (mo.n_kept, kept_total);
+		atomicAdd (mo.n_kept + 1, win_total);
+	}
+}
+
+// records per owner rank (multi-GPU send side): sum of the chains' record counts over each rank's range of slices
+__global__ void chain_owner_count_kernel (SkmChains ch, u32 per_owner, unsigned long long *counts)
+{
+	__shared__ unsigned long long s_sum;
+	for (u32 owner = blockIdx.x; owner * (u64) per_owner < ch.n_chains; owner += gridDim.x)
+	{
+		if (threadIdx.x == 0)
+			s_sum = 0;
+		__syncthreads ();
+		unsigned long long s = 0;
+		const u32 lo = owner * per_owner, hi = min (ch.n_chains, lo + per_owner);
+		for (u32 c = lo + threadIdx.x; c < hi; c += blockDim.x)
+			s += (u64) ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1)
+			s += __shfl_down_sync (0xFFFFFFFFu, s, d);
+		if ((threadIdx.x & 31) == 0 && s)
+			atomicAdd (&s_sum, s);
+		__syncthreads ();
+		if (threadIdx.x == 0)
+			counts[owner] = s_sum;
+		__syncthreads ();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Records that are already made -> chains.  The receiving side of the multi-GPU exchange: the slice
+// travels in the record's last word; this rank owns slices [lo, lo + n_local).
+static constexpr int AP_NT = 256, AP_TILE = 2048;	// records a CTA appends between two looks at its block range
+
+template <int RECW>
+__global__ void __launch_bounds__ (AP_NT)
+skm_append_kernel (SkmChains ch, const u32 *rec, u64 n, u32 lo)
+{
+	__shared__ u32 s_pool[2];
+	pool_begin (ch, s_pool);
+	__syncthreads ();
+	const u64 n_tiles = (n + AP_TILE - 1) / AP_TILE;
+	for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		if (threadIdx.x == 0)
+			pool_refill (ch, s_pool, 128);
+		__syncthreads ();
+		if (s_pool[1] != 0)
+			for (u64 i = t * AP_TILE + threadIdx.x; i < min (n, (t + 1) * AP_TILE); i += AP_NT)
+			{
+				const uint4 *src = reinterpret_cast<const uint4 *> (rec + i * RECW);
+				uint4 v[RECW / 4];
+#pragma unroll
+				for (int q = 0; q < RECW / 4; q++)
+					v[q] = ldg_stream (src + q);
+				const u32 s = v[RECW / 4 - 1].w - lo;
+				if (s >= ch.n_chains)
+				{	// not this rank's: the exchange went wrong
+					atomicOr (reinterpret_cast<unsigned long long *> (&ch.ctr->overflow), (unsigned long long) OVF_FOREIGN);
+					continue;
+				}
+				v[RECW / 4 - 1].w = 0;
+				u32 *dst = chain_append (ch, s, s_pool);
+				if (dst)
+				{
+#pragma unroll
+					for (int q = 0; q < RECW / 4; q++)
+						reinterpret_cast<uint4 *> (dst)[q] = v[q];
+				}
+			}
+		__syncthreads ();
+	}
+	pool_end (ch, s_pool);
+}
+
+// ------------------------------------------------------------------------------------------------
+// A slice that overflowed its image by far is cut into q sub-slices by k-mer hash in ONE pass over
+// its records: every window becomes a one-window sub-record (the window's K bases and its
+// neighbours, the record's multiplicity, the window's ordinal) in the chain of sub-slice qbase +
+// bucket.  The sub-slices then go through skm_merge_kernel and skm_build_kernel like any slice.
+// (Retrying a slice as q work items that each filter the windows by hash scans its records q times;
+// the slices that overflow by far are the highly expressed loci — most of the reads of a skewed data set.)
+struct SkmSplit { u64 r0; u32 n, q, qbase, pad; };	// records r0 .. r0 + n of the merged runs -> sub-slices qbase .. qbase + q
+static constexpr int SP_NT = 256, SP_RECS = 256;	// records per piece of a split (one look at the CTA's block range per piece)
+
+template <int W>
+__global__ void __launch_bounds__ (SP_NT)
+skm_split_kernel (SkmChains sub, const u32 *rec2, const SkmSplit *splits, u32 n_splits, int K)
+{
+	constexpr u32 RECW = SkmRec<W>::WORDS, LAST = RECW - SKM_HDR - 1;
+	__shared__ u32 s_pool[2];
+	pool_begin (sub, s_pool);
+	__syncthreads ();
+	Key<W> kmask;
+#pragma unroll
+	for (int q = 0; q < W; q++)
+	{
+		const int bits = 2 * K - 64 * (W - 1 - q);
+		kmask.w[q] = bits >= 64 ? ~0ull : (bits > 0 ? (1ull << bits) - 1 : 0ull);
+	}
+	const int top = 2 * (K - 1);
+	for (u32 sp = blockIdx.x; sp < n_splits; sp += gridDim.x)
+	{
+		const SkmSplit S = splits[sp];
+		const u64 r1 = S.r0 + S.n;
+		// one record per thread and step; the CTA's block range is looked at once per step
+		for (u64 base = S.r0; base < r1; base += SP_NT)
+		{
+			if (threadIdx.x == 0)	// SP_NT records x ~8 windows each: ~64 blocks fill up per step, 16x that when every record is full
+				pool_refill (sub, s_pool, 256);
+			__syncthreads ();
+			const u64 i = base + threadIdx.x;
+			if (i < r1 && s_pool[1] != 0)
+			{
+				const u32 *rec = rec2 + i * RECW;
+				SkmRoll<W> st;
+				skm_roll_init<W, false> (st, rec, K, 0);
+				const u32 h1 = __ldg (rec + 1);
+				const u32 phl = (h1 >> 14) & 1u, nrun = (h1 >> 15) & 1u, pnb = h1 >> 16;
+				const u32 phr = nrun ? 0u : pnb - phl - (u32) K - (st.n - 1);
+#pragma unroll 1
+				for (u32 t = 0; t < st.n; t++)
+				{
+					Key<W> key;
+					u32 left, right, ha, hb;
+					skm_roll_window<W> (st, key, left, right);
+					skm_hash2<W> (key, ha, hb);
+					const u32 g = S.qbase + __umulhi (hb * 0x9E3779B1u, S.q);
+					u32 *dst = chain_append (sub, g, s_pool);
+					if (dst)
+					{
+						const u32 hl = nrun ? 0u : (t > 0 || phl), hr = nrun ? 0u : (t + 1 < st.n || phr);
+						const u32 nb = nrun ? 0u : hl + (u32) K + hr, first = nrun ? 0u : phl + t - hl;
+						u32 wd[4];
+						wd[0] = (u32) st.ord;
+						wd[1] = (u32) (st.ord >> 32) | (hl << 14) | (nrun << 15) | (nb << 16);	// one window: n - 1 = 0
+						wd[2] = st.add;	// multiplicity (an N-run: all of its windows)
+						const u32 nbw = (nb + 15) >> 4;
+						const u32 *rd = rec + SKM_HDR;
+#pragma unroll
+						for (u32 q = 0; q < RECW - SKM_HDR; q++)
+						{
+							u32 v = 0;
+							if (q < nbw)
+							{
+								const u32 b = first + 16 * q, wq = b >> 4, sh = 2 * (b & 15);
+								v = __funnelshift_l (__ldg (rd + min (wq + 1, LAST)), __ldg (rd + min (wq, LAST)), sh);
+								if (q == nbw - 1 && (nb & 15))
+									v &= 0xFFFFFFFFu << (32 - 2 * (nb & 15));
+							}
+							const u32 o = SKM_HDR + q;
+							wd[o & 3] = v;
+							if ((o & 3) == 3)
+								*reinterpret_cast<uint4 *> (dst + (o & ~3u)) = make_uint4 (wd[0], wd[1], wd[2], wd[3]);
+						}
+					}
+					skm_roll_step<W> (st, kmask, top);
+				}
+			}
+			__syncthreads ();
+		}
+	}
+	pool_end (sub, s_pool);
+}
+
+}	// namespace sdt

@@ -26,6 +26,7 @@
 // All updates commute: the result is bit-identical to the reference's sequential put_kmerset.
 #pragma once
 #include "sdt_sliced.cuh"
+#include "sdt_chain.cuh"
 
 namespace sdt {
 
@@ -33,7 +34,8 @@ struct SkmGeom
 {
 	u32 n_slices;		// slices of the key space (by minimizer)
 	u32 slice_slots;	// S: slots of a slice's shared-memory image
-	u32 m, w;		// minimizer length, m-mers per window (K - m + 1)
+	u32 m, w;		// minimizer length; m-mers of a window that are looked at: the central w of its K - m + 1
+	u32 lo, wfull;		// first of them, K - m + 1
 	u32 nmax;		// windows per record at most (32 for 1-word keys, else 64)
 	u32 recw;		// u32 words per record (8, 12, 16)
 	u32 slice_a;		// slice of the all-A k-mer (key 0): where the -n N-windows go
@@ -126,7 +128,7 @@ __device__ __forceinline__ bool mask_at (const u32 *mk, u32 b) { return (mk[b >>
 // reads -> super-k-mer records.  Record (recw u32 words, 16-byte aligned):
 //   word 0  instance ordinal of the first window, low 32 bits
 //   word 1  ordinal bits 32..39 | (n - 1) << 8 | has_left << 14 | n_run << 15 | n_bases << 16
-//   word 2  slice
+//   word 2  0 (the multiplicity, once copies have been merged: skm_merge_kernel)
 //   word 3.. bases, 16 per word, first base in the top bits (the layout of the read tile), starting
 //           with the base before the first window if there is one (has_left): a miniature read on
 //           which chop_window yields exactly the windows, keys and link bases of the original read.
@@ -135,20 +137,20 @@ template <int W> struct SkmRec { static constexpr u32 WORDS = W == 1 ? 8u : (W =
 
 template <int W, bool NMODE>
 __global__ void __launch_bounds__ (EMIT_NT)
-skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, unsigned long long *rec_cursor, Counters *ctr)
+skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_cursor)
 {
 	constexpr u32 RECW = SkmRec<W>::WORDS, NMAX = SkmRec<W>::NMAX;
 	extern __shared__ __align__(16) u32 smem[];
 	__shared__ u32 warp_sums[EMIT_NT / 32];
-	__shared__ u32 s_count;
-	__shared__ unsigned long long s_base;
+	__shared__ u32 s_count, s_pool[2];
+	pool_begin (ch, s_pool);
 	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int K = rb.K;
 	ReadTile<NMODE> rt;
 	tile_setup<NMODE> (rt, smem, rb);
 	u32 *mhs = smem + tile_words (rb, NMODE);	// [tile_reads * npad + 16]: m-mer hashes, later descriptors (read | first window << 8 | (n - 1) << 24) of the records
 	u32 *sls = mhs + (size_t) rb.tile_reads * g.npad + 16;	// [tile_reads * npad]: slice of every window (| SKM_NFLAG)
-	const u32 maxwin = g.npos - g.w + 1;	// windows of the longest read
+	const u32 maxwin = g.npos - g.wfull + 1;	// windows of the longest read
 	const u32 gpr = (maxwin + 3) >> 2, spr = (maxwin + EMIT_SEG - 1) / EMIT_SEG;	// groups of 4 windows, segments of EMIT_SEG windows per read
 	const u32 m_npos = 0xFFFFFFFFu / g.npos + 1, m_gpr = 0xFFFFFFFFu / gpr + 1, m_spr = 0xFFFFFFFFu / spr + 1;	// x / d = (x * m) >> 32 for x < 65536
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
@@ -171,7 +173,10 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 			}
 		}
 		__syncthreads ();
-		// ---- 2. slice of every window = slice of its minimizer value (the smallest of its w m-mer hashes).
+		// ---- 2. slice of every window = slice of its minimizer value: the smallest hash among the CENTRAL w of the
+		// window's m-mers, positions lo .. lo + w - 1 (a set that is the same for a k-mer and its reverse
+		// complement).  For K <= 31 that is every m-mer of the window; for long k-mers it keeps a minimizer from
+		// gathering the windows of 50 or 110 consecutive positions in one slice (K = 63: 11 % of the slices overflowed).
 		// One thread per four consecutive windows j0 .. j0+3: they share the hashes j0+3 .. j0+w-1, so the
 		// sliding minimum costs ~(w + 9) / 4 comparisons per window instead of w; 16-byte loads keep the
 		// stride-4 access free of bank conflicts.
@@ -181,7 +186,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 			const u32 nwin = rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r];
 			if (j0 >= nwin)
 				continue;
-			const uint4 *mh = reinterpret_cast<const uint4 *> (mhs + r * g.npad + j0);
+			const uint4 *mh = reinterpret_cast<const uint4 *> (mhs + r * g.npad + j0 + g.lo);	// (lo is a multiple of 4)
 			const uint4 c0 = mh[0];
 			const u32 a2 = c0.z, a1 = min (c0.y, a2), a0 = min (c0.x, a1);	// hashes 0..2 belong to the first windows only
 			u32 common = g.w > 3 ? c0.w : 0xFFFFFFFFu;	// hashes 3 .. w-1: in all four windows
@@ -274,26 +279,46 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 		}
 		__syncthreads ();
 		if (tid == 0)
-			s_base = s_count ? atomicAdd (rec_cursor, (unsigned long long) s_count) : 0ull;
+		{
+			if (s_count)
+				atomicAdd (rec_cursor, (unsigned long long) s_count);	// records made (also by tiles that find the pool exhausted)
+			pool_refill (ch, s_pool);
+		}
 		__syncthreads ();
-		const u64 base = s_base;
 		const u32 n_out = s_count;
-		if (base + n_out > rec_cap)
-		{	// the host re-emits the whole read log into a larger area (sdtgpu.cu)
-			if (tid == 0)
-				atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 2ull);
+		if (s_pool[1] == 0)
+		{	// the block pool is exhausted: the host enlarges it and emits the whole read log again (sdtgpu.cu)
 			__syncthreads ();
 			continue;
 		}
-		// ---- 4. one thread per record: consecutive threads write consecutive records
+		// ---- 4. one thread per record: the record goes to the end of its slice's chain
+		// (the position of a thread's NEXT record is drawn before this one is assembled: the atomic's round trip
+		// to the L2 is covered by the assembly and the stores)
+		u32 d_nx = 0, s_nx = 0;
+		u64 tk_nx = 0;
+		if (tid < n_out)
+		{
+			d_nx = mhs[tid];
+			s_nx = sls[(d_nx & 0xFFu) * g.npad + ((d_nx >> 8) & 0xFFFFu)];
+			tk_nx = chain_ticket (ch, s_nx & ~SKM_NFLAG);
+		}
 		for (u32 rid = tid; rid < n_out; rid += EMIT_NT)
 		{
-			const u32 d = mhs[rid];
+			const u32 d = d_nx, s = s_nx;
+			const u64 tk = tk_nx;
+			const bool more = rid + EMIT_NT < n_out;
+			if (more)
+			{
+				d_nx = mhs[rid + EMIT_NT];
+				s_nx = sls[(d_nx & 0xFFu) * g.npad + ((d_nx >> 8) & 0xFFFFu)];
+				tk_nx = chain_ticket (ch, s_nx & ~SKM_NFLAG);
+			}
 			const u32 r = d & 0xFFu, j0 = (d >> 8) & 0xFFFFu, n = (d >> 24) + 1;
 			const u32 len = (rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r]) + K - 1;
-			const u32 s = sls[r * g.npad + j0];
 			const u32 *rd = rt.tile + r * rt.sw;
-			u32 *rec = rec0 + (base + rid) * RECW;
+			u32 *rec = chain_place (ch, s & ~SKM_NFLAG, tk, s_pool, more ? &tk_nx : nullptr, s_nx & ~SKM_NFLAG);
+			if (!rec)
+				continue;
 			const u64 ord = (rb.first_read_ordinal + rt.r0 + r) * rb.maxwin + j0;
 			const bool nrun = NMODE && (s & SKM_NFLAG);
 			u32 has_left = j0 > 0, has_right = j0 + n - 1 + K < len;
@@ -310,7 +335,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 			u32 wd[4];
 			wd[0] = (u32) ord;
 			wd[1] = (u32) (ord >> 32) | ((n - 1) << 8) | (has_left << 14) | ((nrun ? 1u : 0u) << 15) | (nb << 16);
-			wd[2] = s & ~SKM_NFLAG;
+			wd[2] = 0;
 			const u32 nbw = (nb + 15) >> 4;
 #pragma unroll
 			for (u32 q = 0; q < RECW - SKM_HDR; q++)
@@ -328,194 +353,10 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, u32 *hist, u32 *rec0, u64 rec_cap, uns
 				if ((o & 3) == 3)
 					*reinterpret_cast<uint4 *> (rec + (o & ~3u)) = make_uint4 (wd[0], wd[1], wd[2], wd[3]);
 			}
-			atomicAdd (hist + (s & ~SKM_NFLAG), 1u);	// RED
 		}
 		__syncthreads ();	// tile, descriptors and slices are overwritten by the next iteration
 	}
-}
-
-// every record to its slice's run: cur[p] starts at off[p].  The kernel is bound by the rate at which
-// the memory system takes requests to cold lines (profiles/r1_random_access_findings.md), so a record
-// goes out in as few stores as its size allows: one 32-byte store for 1-word keys, two for 4-word keys.
-__device__ __forceinline__ void ld256_stream (const void *p, u64 &a, u64 &b, u64 &c, u64 &d)
-{
-	asm volatile ("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-}
-
-template <int RECW>
-__global__ void __launch_bounds__ (SCAT_NT)
-skm_scatter_kernel (const u32 *rec0, const unsigned long long *rec_count, unsigned long long *cur, u32 *rec2)
-{
-	const u64 n = *rec_count;
-	for (u64 i = blockIdx.x * (u64) SCAT_NT + threadIdx.x; i < n; i += (u64) gridDim.x * SCAT_NT)
-	{
-		const u32 *src = rec0 + i * RECW;
-		if constexpr (RECW % 8 == 0)
-		{
-			u64 a, b, c, d;
-			ld256_stream (src, a, b, c, d);
-			const u64 pos = atomicAdd (cur + (u32) b, 1ull);	// word 2: the slice
-			u32 *dst = rec2 + pos * RECW;
-			st256 (dst, a, b, c, d);
-#pragma unroll
-			for (int q = 1; q < RECW / 8; q++)
-			{
-				ld256_stream (src + 8 * q, a, b, c, d);
-				st256 (dst + 8 * q, a, b, c, d);
-			}
-		}
-		else
-		{
-			const uint4 *s4 = reinterpret_cast<const uint4 *> (src);
-			const uint4 h = ldg_stream (s4);
-			const u64 pos = atomicAdd (cur + h.z, 1ull);
-			uint4 *dst = reinterpret_cast<uint4 *> (rec2 + pos * RECW);
-			dst[0] = h;
-#pragma unroll
-			for (int q = 1; q < RECW / 4; q++)
-				dst[q] = ldg_stream (s4 + q);
-		}
-	}
-}
-
-// super-k-mer exchange, receiving side: records that arrived from all ranks carry global slice
-// numbers; this rank owns slices [lo, lo + n_local).  Re-base them and count records per slice.
-__global__ void __launch_bounds__ (SCAT_NT)
-skm_recount_kernel (u32 *rec, u64 n, u32 recw, u32 lo, u32 n_local, u32 *hist, Counters *ctr)
-{
-	for (u64 i = blockIdx.x * (u64) SCAT_NT + threadIdx.x; i < n; i += (u64) gridDim.x * SCAT_NT)
-	{
-		u32 *w2 = rec + i * recw + 2;
-		const u32 s = *w2 - lo;
-		if (s >= n_local)
-		{	// not this rank's: the exchange went wrong
-			atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 16ull);
-			continue;
-		}
-		*w2 = s;
-		atomicAdd (hist + s, 1u);	// RED
-	}
-}
-
-// ------------------------------------------------------------------------------------------------
-// Copies of the same super-k-mer collapse into one record before the build.  At the coverage of a
-// transcriptome most records of a slice are byte-identical copies (every error-free read that spans
-// a super-k-mer emits the same bases, neighbours and window count; only the ordinal differs), and a
-// window costs the build ~400 instructions while finding a copy costs ~100 per record.  A surviving
-// record carries its multiplicity in word 2 (the slice number is no longer needed once the record
-// sits in its slice's run) and the smallest ordinal of its copies: window t of every copy is the
-// same (key, left, right) instance with ordinal ord0 + t, so count and link counters take the
-// multiplicity (update_kmer, newhash.c:71-96, is a sum) and the node's first ordinal the minimum.
-//
-// One CTA per slice, DD_CHUNK records at a time staged in shared memory; a table of record indices
-// keyed by the record's content finds the copies; survivors go back to the front of the run.
-// end[slice] = one past the last surviving record.
-static constexpr int DD_NT = 512;	// 2 CTAs of 80-96 KB per SM: 32 warps to hide the staging loads (256 threads: 11.2 ms on C2)
-template <int W> struct DedupeCfg { static constexpr u32 CHUNK = W == 1 ? 2048u : 1024u, TABLE = 2 * CHUNK; };
-template <int W> __host__ __device__ inline size_t skm_dedupe_smem () { return (size_t) DedupeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) DedupeCfg<W>::TABLE * 4; }
-
-// HAS_MULT: word 2 of the incoming records already is a multiplicity (the sub-records of skm_resplit_kernel)
-template <int W, bool HAS_MULT>
-__global__ void __launch_bounds__ (DD_NT)
-skm_dedupe_kernel (u32 *rec2, const u64 *off, u32 n_slices, unsigned long long *end, unsigned long long *n_kept)
-{
-	constexpr u32 RECW = SkmRec<W>::WORDS, CH = DedupeCfg<W>::CHUNK, TS = DedupeCfg<W>::TABLE, VEC = RECW / 4;
-	extern __shared__ __align__(16) u32 smem[];
-	__shared__ u32 s_out;
-	u32 *st = smem;			// [CH * RECW]: the chunk's records
-	u32 *tab = smem + CH * RECW;	// [TS]: record index + 1, 0 = free
-	const u32 tid = threadIdx.x, lane = tid & 31;
-	u64 kept_total = 0;	// thread 0
-	for (u32 sl = blockIdx.x; sl < n_slices; sl += gridDim.x)
-	{
-		const u64 r0 = off[sl], r1 = off[sl + 1];
-		u64 out = r0;	// next free position of the run
-		for (u64 c0 = r0; c0 < r1; c0 += CH)
-		{
-			const u32 nrec = (u32) min ((u64) CH, r1 - c0);
-			{	// stage (coalesced 16-byte loads); word 2 becomes the multiplicity
-				const uint4 *src = reinterpret_cast<const uint4 *> (rec2 + c0 * RECW);
-				uint4 *dst = reinterpret_cast<uint4 *> (st);
-				for (u32 v = tid; v < nrec * VEC; v += DD_NT)
-				{
-					uint4 x = ldg_stream (src + v);
-					if (!HAS_MULT && v % VEC == 0)
-						x.z = 1u;
-					dst[v] = x;
-				}
-				for (u32 v = tid; v < TS; v += DD_NT)
-					tab[v] = 0u;
-				if (tid == 0)
-					s_out = 0;
-			}
-			__syncthreads ();
-			for (u32 i = tid; i < nrec; i += DD_NT)
-			{
-				u32 *me = st + i * RECW;
-				const u32 h1 = me[1];
-				if ((h1 >> 15) & 1u)
-					continue;	// an N-run stays as it is
-				u32 hsh = h1 & ~0xFFu;
-#pragma unroll
-				for (u32 q = SKM_HDR; q < RECW; q++)
-					hsh = (hsh ^ me[q]) * 0x9E3779B1u + (hsh >> 15);
-				u32 slot = fmix32 (hsh) & (TS - 1);
-				for (;;)
-				{
-					u32 e = tab[slot];
-					if (e == 0u)
-						e = atomicCAS (tab + slot, 0u, i + 1);
-					if (e == 0u)
-						break;	// first of its kind
-					u32 *rep = st + (e - 1) * RECW;
-					bool same = ((*reinterpret_cast<volatile u32 *> (rep + 1) ^ h1) & ~0xFFu) == 0u;	// the low 8 bits are ordinal bits and change
-#pragma unroll
-					for (u32 q = SKM_HDR; q < RECW; q++)
-						same &= rep[q] == me[q];
-					if (same)
-					{	// words 0-1 as one 64-bit number: the header bits above the ordinal are equal, so the minimum is the ordinal's
-						atomicAdd (rep + 2, HAS_MULT ? me[2] : 1u);
-						const u64 mine = *reinterpret_cast<const u64 *> (me);
-						if (mine < *reinterpret_cast<volatile u64 *> (rep))
-							atomicMin (reinterpret_cast<unsigned long long *> (rep), mine);
-						me[2] = 0u;	// dropped
-						break;
-					}
-					slot = (slot + 1) & (TS - 1);
-				}
-			}
-			__syncthreads ();
-			// survivors back to the run, in any order: a warp reserves its share with one atomic
-			for (u32 b = 0; b < nrec; b += DD_NT)
-			{
-				const u32 i = b + tid;
-				const bool keep = i < nrec && st[i * RECW + 2] != 0u;
-				const u32 bal = __ballot_sync (0xFFFFFFFFu, keep);
-				u32 base = 0;
-				if (lane == 0 && bal)
-					base = atomicAdd (&s_out, (u32) __popc (bal));
-				base = __shfl_sync (0xFFFFFFFFu, base, 0);
-				if (keep)
-				{
-					const uint4 *src = reinterpret_cast<const uint4 *> (st + i * RECW);
-					uint4 *dst = reinterpret_cast<uint4 *> (rec2 + (out + base + __popc (bal & ((1u << lane) - 1u))) * RECW);
-#pragma unroll
-					for (u32 q = 0; q < VEC; q++)
-						dst[q] = src[q];
-				}
-			}
-			__syncthreads ();
-			out += s_out;
-			__syncthreads ();	// s_out, the chunk and the table are rewritten by the next pass
-		}
-		if (tid == 0)
-		{
-			end[sl] = out;
-			kept_total += out - r0;
-		}
-	}
-	if (tid == 0 && kept_total)
-		atomicAdd (n_kept, kept_total);
+	pool_end (ch, s_pool);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -530,84 +371,26 @@ static constexpr int CELL_WORDS = 13;	// 25 16-bit cells, two per word
 static constexpr u32 SKM_MAX_TRIES = 128;
 static constexpr u32 CELL_STOP = 0xF000u;	// + one in-flight increment per thread of the CTA stays below 2^16
 
-template <int W> struct SkmImage
+// two cheap 32-bit hashes of a key: a -> home slot, b -> probe step, retry filter, sub-slice
+template <int W> __device__ __forceinline__ void skm_hash2 (const Key<W> &k, u32 &a, u32 &b)
 {
-	u64 *key;	// [S * W]
-	u64 *ord;	// [S]
-	u32 *cell;	// [CELL_WORDS * S]: word q of slot i at q * S + i
-	u32 *extra;	// [S]
-	u32 *state;	// [S] (W > 1): 0 empty, 1 key being written, 2 occupied
-};
-
-__host__ __device__ inline size_t skm_image_bytes (int W, u32 S)
-{
-	return (size_t) S * (8 * W + 8 + 4 * CELL_WORDS + 4 + (W > 1 ? 4 : 0));
-}
-__host__ __device__ inline size_t skm_build_smem (int W, const SkmGeom &g)
-{	// image + window prefix of a chunk of records
-	return skm_image_bytes (W, g.slice_slots) + 4 * (2 * (size_t) g.build_nt + 4);
-}
-
-// Double hashing (S is prime, 1 <= step < S): in shared memory a probe costs the same wherever it
-// lands, and a warp step lasts as long as its longest probe sequence — at half load the longest of a
-// few unsuccessful searches is ~4 probes here against ~13 with linear probing.
-template <int W>
-__device__ __forceinline__ u32 skm_find (const SkmImage<W> &im, u32 S, const Key<W> &key, u32 idx, u32 step)
-{
-	// a probe sequence that finds SKM_MAX_TRIES slots taken gives up: the image is as good as full
-	// (0.9^128 = 1e-6), and the caller has the work item retried split by k-mer hash
-	for (u32 tries = 0; tries < min (S, SKM_MAX_TRIES);)
+	u32 x = 0;
+#pragma unroll
+	for (int q = 0; q < W; q++)
 	{
-		if constexpr (W == 1)
-		{
-			u64 k = *reinterpret_cast<volatile u64 *> (im.key + idx);
-			if (k == key.w[0])
-				return idx;
-			if (k == EMPTY64)
-			{
-				k = atomicCAS (im.key + idx, EMPTY64, key.w[0]);
-				if (k == EMPTY64)
-					return idx;
-				if (k == key.w[0])
-					return idx;
-			}
-		}
-		else
-		{
-			const u32 st = *reinterpret_cast<volatile u32 *> (im.state + idx);
-			if (st == 0u)
-			{
-				if (atomicCAS (im.state + idx, 0u, 1u) == 0u)
-				{	// claimed: publish the key, then open the slot (no waiting inside this branch)
-#pragma unroll
-					for (int q = 0; q < W; q++)
-						*reinterpret_cast<volatile u64 *> (im.key + (size_t) idx * W + q) = key.w[q];
-					__threadfence_block ();
-					*reinterpret_cast<volatile u32 *> (im.state + idx) = 2u;
-					return idx;
-				}
-				continue;	// lost the race: look at the same slot again
-			}
-			if (st == 1u)
-				continue;	// its key is being written
-			bool eq = true;
-#pragma unroll
-			for (int q = 0; q < W; q++)
-				eq &= (*reinterpret_cast<volatile u64 *> (im.key + (size_t) idx * W + q) == key.w[q]);
-			if (eq)
-				return idx;
-		}
-		idx += step;
-		if (idx >= S)
-			idx -= S;
-		tries++;
+		x = (x ^ (u32) k.w[q]) * 0x9E3779B1u;
+		x = (x ^ (u32) (k.w[q] >> 32)) * 0x85EBCA6Bu + (x >> 17);
 	}
-	return S;
+	x ^= x >> 15; x *= 0xC2B2AE35u;
+	x ^= x >> 13;
+	a = x;
+	b = x * 0x27D4EB2Fu;
+	b ^= b >> 15;
 }
 
-struct SkmWork { u32 slice, r, R, nrec; };	// keys of `slice` with sub-hash % R == r; nrec: records of the slice (set when an item fails)
-
-static constexpr u32 MAX_SWEEPS = 4;	// slice_slots <= MAX_SWEEPS * threads per CTA
+// a work item of the build: records r0 .. r0 + nrec of the merged runs (all instances of their k-mers), wsum windows;
+// of these the keys with sub-hash % R == r (a piece of an item that overflowed an image); R == 0: do not even try
+struct SkmWork { u64 r0; u32 nrec, wsum, r, R; };
 
 // Rolling state of one record: what nextKmer / reverseComplement (kmer.c:209, 653) compute per base,
 // kept incrementally — the forward k-mer takes the next base at the bottom, its reverse complement
@@ -746,436 +529,6 @@ __device__ __forceinline__ void skm_roll_step (SkmRoll<W> &s, const Key<W> &mask
 	}
 	s.t++;
 	s.ord++;
-}
-
-// A slice that overflowed its image is cut into q sub-slices by k-mer hash in ONE pass over its
-// records: every window becomes a one-window sub-record (the window's K bases and its neighbours,
-// the record's multiplicity, the window's ordinal) in the run of sub-slice qbase + bucket.  The
-// sub-slices then go through skm_dedupe_kernel and skm_build_kernel like any slice.  (Retrying a
-// slice as q work items that each filter the windows by hash scans its records q times; the slices
-// that overflow are the highly expressed loci — most of the reads of a skewed data set.)
-// PASS 0 counts sub-records per sub-slice (hist2), PASS 1 writes them (cur2 starts at the scanned offsets).
-struct SkmSplit { u32 slice, q, qbase, rlo, rhi, pad[3]; };	// records [rlo, rhi) of the slice's run -> sub-slices qbase .. qbase + q
-static constexpr int RS_NT = 256;
-
-__device__ __forceinline__ u32 skm_bucket (u64 h, u32 q) { return __umulhi ((u32) (h >> 32) * 0x9E3779B1u, q); }
-
-template <int W, int PASS>
-__global__ void __launch_bounds__ (RS_NT)
-skm_resplit_kernel (const u32 *rec2, const u64 *off, const u64 *end, const SkmSplit *splits, u32 n_splits, int K,
-		    u32 *hist2, unsigned long long *cur2, u32 *rec3)
-{
-	constexpr u32 RECW = SkmRec<W>::WORDS, LAST = RECW - SKM_HDR - 1;
-	Key<W> kmask;
-#pragma unroll
-	for (int q = 0; q < W; q++)
-	{
-		const int bits = 2 * K - 64 * (W - 1 - q);
-		kmask.w[q] = bits >= 64 ? ~0ull : (bits > 0 ? (1ull << bits) - 1 : 0ull);
-	}
-	const int top = 2 * (K - 1);
-	// one CTA per chunk of a failed slice's records (the host cuts big slices into chunks so that a
-	// huge slice does not sit on one CTA)
-	for (u32 sp = blockIdx.x; sp < n_splits; sp += gridDim.x)
-	{
-		const SkmSplit S = splits[sp];
-		const u64 r0 = off[S.slice], r1 = min (end[S.slice], r0 + S.rhi);
-		for (u64 i = r0 + S.rlo + threadIdx.x; i < r1; i += RS_NT)
-		{
-			const u32 *rec = rec2 + i * RECW;
-			SkmRoll<W> st;
-			skm_roll_init<W, false> (st, rec, K, 0);
-			const u32 h1 = __ldg (rec + 1);
-			const u32 phl = (h1 >> 14) & 1u, nrun = (h1 >> 15) & 1u, pnb = h1 >> 16;
-			const u32 phr = nrun ? 0u : pnb - phl - (u32) K - (st.n - 1);
-#pragma unroll 1
-			for (u32 t = 0; t < st.n; t++)
-			{
-				Key<W> key;
-				u32 left, right;
-				skm_roll_window<W> (st, key, left, right);
-				const u32 g = S.qbase + skm_bucket (key_hash<W> (key), S.q);
-				if (PASS == 0)
-					atomicAdd (hist2 + g, 1u);
-				else
-				{
-					const u64 pos = atomicAdd (cur2 + g, 1ull);
-					u32 *dst = rec3 + pos * RECW;
-					const u32 hl = nrun ? 0u : (t > 0 || phl), hr = nrun ? 0u : (t + 1 < st.n || phr);
-					const u32 nb = nrun ? 0u : hl + (u32) K + hr, first = nrun ? 0u : phl + t - hl;
-					u32 wd[4];
-					wd[0] = (u32) st.ord;
-					wd[1] = (u32) (st.ord >> 32) | (hl << 14) | (nrun << 15) | (nb << 16);	// one window: n - 1 = 0
-					wd[2] = st.add;	// multiplicity (an N-run: all of its windows)
-					const u32 nbw = (nb + 15) >> 4;
-					const u32 *rd = rec + SKM_HDR;
-#pragma unroll
-					for (u32 q = 0; q < RECW - SKM_HDR; q++)
-					{
-						u32 v = 0;
-						if (q < nbw)
-						{
-							const u32 b = first + 16 * q, wq = b >> 4, sh = 2 * (b & 15);
-							v = __funnelshift_l (__ldg (rd + min (wq + 1, LAST)), __ldg (rd + min (wq, LAST)), sh);
-							if (q == nbw - 1 && (nb & 15))
-								v &= 0xFFFFFFFFu << (32 - 2 * (nb & 15));
-						}
-						const u32 o = SKM_HDR + q;
-						wd[o & 3] = v;
-						if ((o & 3) == 3)
-							*reinterpret_cast<uint4 *> (dst + (o & ~3u)) = make_uint4 (wd[0], wd[1], wd[2], wd[3]);
-					}
-				}
-				skm_roll_step<W> (st, kmask, top);
-			}
-		}
-	}
-}
-
-// One CTA per work item, items handed out through *item_cursor.  items == nullptr: item i is (slice i, 0, 1).
-//
-// Records -> image: the windows of up to 2 NT records are flattened and cut into NT equal runs,
-// one per thread (a slice holds about one record per thread, of 1 to 32 windows: whole records per
-// lane leave most lanes waiting for the longest).  A thread finds the record of its first window
-// (binary search in the window prefix), sets up the rolling state there (one 16-byte header load +
-// one extraction) and rolls on, re-seating itself when it crosses into the next record.  Instances
-// that meet in the same (slot, cell) within a warp step are added by one lane for all.
-// Image -> node store: every warp owns a contiguous range of slots; occupied slots are ranked by
-// ballot + a scan of the 32 warp totals, thread 0 reserves the item's space in the store, and the
-// nodes go out in slot order, 32 bytes per lane, consecutive lanes to consecutive nodes.
-template <int W, int NT>
-__global__ void __launch_bounds__ (NT, 1024 / NT)
-skm_build_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long long *node_cursor, SkmGeom g, int K,
-		  const u32 *rec2, const u64 *off, const u64 *end, const SkmWork *items, u32 n_items, unsigned long long *item_cursor,
-		  SkmWork *failed, u32 *n_failed, u32 max_failed, Counters *ctr)
-{
-	typedef typename SlotOf<W>::type S_t;
-	extern __shared__ __align__(16) u32 smem[];
-	__shared__ u32 s_full, s_item[2], s_warp[NT / 32];
-	__shared__ unsigned long long s_base;
-	const u32 S = g.slice_slots, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const u32 spw = ((S + NT - 1) / NT) * 32;	// slots per warp in the compaction (a multiple of 32)
-	SkmImage<W> im;
-	im.key = reinterpret_cast<u64 *> (smem);
-	im.ord = im.key + (size_t) S * W;
-	im.cell = reinterpret_cast<u32 *> (im.ord + S);
-	im.extra = im.cell + (size_t) S * CELL_WORDS;
-	im.state = im.extra + S;
-	u32 *pre = im.extra + S + (W > 1 ? S : 0);	// [2 NT + 1]: exclusive prefix of the windows of a chunk's records
-	Key<W> kmask;	// the low 2K bits
-#pragma unroll
-	for (int q = 0; q < W; q++)
-	{
-		const int bits = 2 * K - 64 * (W - 1 - q);
-		kmask.w[q] = bits >= 64 ? ~0ull : (bits > 0 ? (1ull << bits) - 1 : 0ull);
-	}
-	const int top = 2 * (K - 1);
-	u64 nodes = 0, inst = 0;	// nodes: thread 0 only; inst: instances this thread applied (items that were written)
-	if (tid == 0)
-	{
-		s_full = 0;
-		s_item[0] = (u32) atomicAdd (item_cursor, 1ull);
-	}
-	for (u32 i = tid; i < S; i += NT)
-	{
-#pragma unroll
-		for (int q = 0; q < W; q++)
-			im.key[(size_t) i * W + q] = EMPTY64;
-		im.ord[i] = ORD40_NONE;
-		im.extra[i] = 0u;
-		if constexpr (W > 1)
-			im.state[i] = 0u;
-	}
-	for (u32 i = tid; i < S * CELL_WORDS; i += NT)
-		im.cell[i] = 0u;
-	__syncthreads ();
-	for (u32 round = 0;; round++)
-	{
-		const u32 it = s_item[round & 1];
-		if (it >= n_items)
-			break;
-		u32 next_item = 0;
-		if (tid == 0)	// the next item is asked for now and looked at after this one: the round trip is hidden
-			next_item = (u32) atomicAdd (item_cursor, 1ull);
-		SkmWork wk;
-		if (items)
-			wk = items[it];
-		else
-		{
-			wk.slice = it;
-			wk.r = 0;
-			wk.R = 1;
-			wk.nrec = 0;
-		}
-		const u64 r0 = off[wk.slice], r1 = end[wk.slice];	// the run's surviving records (skm_dedupe_kernel)
-		u64 mine = 0;
-		for (u64 c0 = r0; c0 < r1 && !*reinterpret_cast<volatile u32 *> (&s_full); c0 += 2 * NT)
-		{	// up to 2 NT records at a time: their windows are flattened (exclusive prefix in pre[]) and
-			// cut into NT equal runs, one per thread
-			const u32 nrec = (u32) min ((u64) (2 * NT), r1 - c0);
-			const u32 *recs = rec2 + c0 * g.recw;
-			u32 nw[2] = { 0, 0 };
-#pragma unroll
-			for (int q = 0; q < 2; q++)
-				if (2 * tid + q < nrec)
-				{
-					const u32 h1 = __ldg (recs + (size_t) (2 * tid + q) * g.recw + 1);
-					nw[q] = ((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1;	// an N-run is applied in one go
-				}
-			u32 incl = nw[0] + nw[1];
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1)
-			{
-				const u32 y = __shfl_up_sync (0xFFFFFFFFu, incl, d);
-				if (lane >= (u32) d)
-					incl += y;
-			}
-			if (lane == 31)
-				s_warp[wid] = incl;
-			__syncthreads ();
-			u32 total;
-			{
-				const u32 c = lane < NT / 32 ? s_warp[lane] : 0u;
-				u32 in2 = c;
-#pragma unroll
-				for (int d = 1; d < 32; d <<= 1)
-				{
-					const u32 y = __shfl_up_sync (0xFFFFFFFFu, in2, d);
-					if (lane >= (u32) d)
-						in2 += y;
-				}
-				const u32 lower = __shfl_sync (0xFFFFFFFFu, in2 - c, wid);
-				total = __shfl_sync (0xFFFFFFFFu, in2, 31);
-				const u32 excl = lower + incl - nw[0] - nw[1];
-				if (2 * tid < nrec)
-					pre[2 * tid] = excl;
-				if (2 * tid + 1 < nrec)
-					pre[2 * tid + 1] = excl + nw[0];
-				if (tid == 0)
-					pre[nrec] = total;
-			}
-			__syncthreads ();
-			const u32 per = (total + NT - 1) / NT;	// windows per thread
-			const u32 w0 = tid * per, w1 = min (total, w0 + per);
-			SkmRoll<W> st;
-			st.n = st.t = 0;
-			u32 x = 0;
-			if (w0 < w1)
-			{
-				u32 lo = 0, hi = nrec - 1;	// record of window w0: largest x with pre[x] <= w0
-				while (lo < hi)
-				{
-					const u32 mid = (lo + hi + 1) >> 1;
-					if (pre[mid] <= w0)
-						lo = mid;
-					else
-						hi = mid - 1;
-				}
-				x = lo;
-				skm_roll_init<W> (st, recs + (size_t) x * g.recw, K, w0 - pre[x]);
-			}
-			for (u32 t = 0; t < per && !*reinterpret_cast<volatile u32 *> (&s_full); t++)
-			{
-				const bool act = w0 + t < w1;
-				if (act && st.t == st.n)	// on to the next record
-					skm_roll_init<W> (st, recs + (size_t) ++x * g.recw, K, 0);
-				u32 idx = S, cellid = 0;
-				bool wanted = false;
-				if (act)
-				{
-					Key<W> key;
-					u32 left, right;
-					skm_roll_window<W> (st, key, left, right);
-					const u64 h = key_hash<W> (key);
-					wanted = wk.R == 1 || (u32) (h >> 32) % wk.R == wk.r;
-					if (wanted)
-						idx = skm_find<W> (im, S, key, home_of (h, S), 1u + __umulhi ((u32) (h >> 32), S - 1));
-					cellid = left * 5 + right;
-				}
-				__syncwarp ();	// probe sequences differ in length: meet again before the update
-				const bool hit = idx < S;
-				// lanes of this step that meet in the same (slot, cell) with one instance each: the lowest one adds for all
-				const bool one = hit && st.add == 1;
-				const u32 peers = __match_any_sync (0xFFFFFFFFu, one ? idx * 32 + cellid : 0xFFFFFFFFu - lane);
-				if (hit)
-				{
-					u32 *cw = im.cell + (cellid >> 1) * S + idx;
-					const u32 sh = 16 * (cellid & 1);
-					if (one)
-					{
-						if ((u32) (__ffs (peers) - 1) == lane)
-						{
-							const u32 cnt = __popc (peers);
-							if (((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
-								atomicAdd (im.extra + idx, cnt);
-							else
-								atomicAdd (cw, cnt << sh);
-						}
-					}
-					else
-					{	// a multiplicity: the cell takes what can still matter to a 6-bit link counter, `extra` the rest
-						// (in flight at most 63 per thread of the CTA on top of 62: below 2^16)
-						const u32 inc = ((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= LINK_SAT ? 0u : min (st.add, LINK_SAT);
-						if (inc)
-							atomicAdd (cw, inc << sh);
-						if (st.add > inc)
-							atomicAdd (im.extra + idx, st.add - inc);
-					}
-					if (st.ord < *reinterpret_cast<volatile u64 *> (im.ord + idx))
-						atomicMin (im.ord + idx, st.ord);
-					mine += st.add;
-				}
-				else if (wanted)
-					s_full = 1;
-				if (act)
-					skm_roll_step<W> (st, kmask, top);
-			}
-			__syncthreads ();	// pre[] and s_warp[] are rewritten by the next chunk
-		}
-		// ---- image -> node store
-		const bool full = s_full != 0;
-		// every warp lists the occupied slots of its range (pre[] is free now) and counts them
-		unsigned short *wl = reinterpret_cast<unsigned short *> (pre) + wid * spw;
-		u32 cnt = 0;
-#pragma unroll
-		for (u32 sw = 0; sw < MAX_SWEEPS; sw++)
-			if (sw * 32 < spw)
-			{
-				const u32 i = wid * spw + sw * 32 + lane;
-				bool occ = false;
-				if (i < S)
-				{
-					if constexpr (W == 1)
-						occ = im.key[i] != EMPTY64;
-					else
-						occ = im.state[i] == 2u;
-				}
-				const u32 bal = __ballot_sync (0xFFFFFFFFu, occ);
-				if (occ)
-					wl[cnt + __popc (bal & ((1u << lane) - 1u))] = (unsigned short) i;
-				cnt += __popc (bal);
-			}
-		if (lane == 0)
-			s_warp[wid] = cnt;
-		__syncthreads ();
-		u32 run, tot;
-		{	// every warp scans the 32 warp totals
-			const u32 c = lane < NT / 32 ? s_warp[lane] : 0u;
-			u32 incl = c;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1)
-			{
-				const u32 y = __shfl_up_sync (0xFFFFFFFFu, incl, d);
-				if (lane >= (u32) d)
-					incl += y;
-			}
-			run = __shfl_sync (0xFFFFFFFFu, incl - c, wid);
-			tot = __shfl_sync (0xFFFFFFFFu, incl, 31);
-		}
-		if (tid == 0)
-		{
-			unsigned long long b = 0;
-			bool fail = full;
-			if (!fail && tot)
-			{
-				b = atomicAdd (node_cursor, (unsigned long long) tot);
-				if (b + tot > store_cap)
-				{
-					fail = true;
-					atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 4ull);	// node store exhausted
-				}
-			}
-			if (full)
-			{	// retried later, split by k-mer hash
-				const u32 f = atomicAdd (n_failed, 1u);
-				wk.nrec = (u32) min (r1 - r0, (u64) 0xFFFFFFFFu);
-				if (f < max_failed)
-					failed[f] = wk;
-				else
-					atomicOr (reinterpret_cast<unsigned long long *> (&ctr->overflow), 8ull);
-			}
-			s_base = fail ? ~0ull : b;
-			if (!fail)
-				nodes += tot;
-		}
-		__syncthreads ();
-		const u64 nbase = s_base;
-		const bool write = nbase != ~0ull;
-		for (u32 k = lane; k < cnt; k += 32)
-		{	// one lane per node: consecutive lanes write consecutive slots of the store
-			const u32 i = wl[k];
-			u32 row[4] = { 0, 0, 0, 0 }, col[4] = { 0, 0, 0, 0 }, count = im.extra[i];
-#pragma unroll
-			for (int q = 0; q < CELL_WORDS; q++)
-			{
-				const u32 v = im.cell[q * S + i];
-				im.cell[q * S + i] = 0u;
-#pragma unroll
-				for (int hlf = 0; hlf < 2; hlf++)
-				{
-					const int c = 2 * q + hlf;
-					if (c < 25)
-					{
-						const u32 x = hlf ? v >> 16 : v & 0xFFFFu;
-						count += x;
-						if (c / 5 < 4)
-							row[c / 5] += x;	// five 16-bit terms: no overflow
-						if (c % 5 < 4)
-							col[c % 5] += x;
-					}
-				}
-			}
-			u32 L = 0, R = 0;
-#pragma unroll
-			for (int b = 0; b < 4; b++)
-			{
-				L |= min (row[b], LINK_SAT) << (6 * b);
-				R |= min (col[b], LINK_SAT) << (6 * b);
-			}
-			const u64 w0 = (im.ord[i] << 24) | L, w1 = ((u64) count << 32) | R;
-			Key<W> k2;
-#pragma unroll
-			for (int q = 0; q < W; q++)
-			{
-				k2.w[q] = im.key[(size_t) i * W + q];
-				im.key[(size_t) i * W + q] = EMPTY64;
-			}
-			im.ord[i] = ORD40_NONE;
-			im.extra[i] = 0u;
-			if constexpr (W > 1)
-				im.state[i] = 0u;
-			if (write)
-			{
-				S_t *dst = store + nbase + run + k;
-				if constexpr (W == 1)
-					st256 (dst, k2.w[0], 0ull, w0, w1);
-				else if constexpr (W == 2)
-					st256 (dst, k2.w[0], k2.w[1], w0, w1);
-				else
-				{
-					st256 (dst, k2.w[0], k2.w[1], k2.w[2], k2.w[3]);
-					st256 (reinterpret_cast<u64 *> (dst) + 4, w0, w1, 0ull, 0ull);
-				}
-			}
-		}
-		if (write)	// instances applied by a work item that is going to be retried are not counted
-			inst += mine;
-		if (tid == 0)
-		{
-			s_full = 0;
-			s_item[(round + 1) & 1] = next_item;
-		}
-		__syncthreads ();	// the image is clean; s_item[] of the next round is in place
-	}
-	{
-#pragma unroll
-		for (int d = 16; d > 0; d >>= 1)
-			inst += __shfl_down_sync (0xFFFFFFFFu, inst, d);
-		if (lane == 0 && inst)
-			atomicAdd (&ctr->n_instances, inst);
-	}
-	if (tid == 0 && nodes)
-		atomicAdd (&ctr->n_nodes, nodes);
 }
 
 }	// namespace sdt

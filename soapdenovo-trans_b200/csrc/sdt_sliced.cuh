@@ -258,7 +258,8 @@ slice_scan_kernel (const u32 *hist, u32 n, const u64 *seg_sum, u64 *off, u64 *cu
 		if (base + i < n)
 		{
 			off[base + i] = run;
-			cur2[base + i] = run;
+			if (cur2)
+				cur2[base + i] = run;
 		}
 		run += c[i];
 	}

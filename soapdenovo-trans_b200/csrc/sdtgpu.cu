@@ -4,12 +4,15 @@
 #include "../../include/sdtgpu.h"
 #include "sdt_kernels.cuh"
 #include "sdt_skm.cuh"
+#include "sdt_merge.cuh"
 #include "sdt_build.cuh"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -33,11 +36,25 @@ struct LogSeg
 {
 	size_t off[3];	// packed, lens, mask
 	ReadBatch rb;	// pointers are resolved when the segment is used (the arenas may move)
+	u64 upper;	// windows of the batch at most
 };
 
 static constexpr int N_CAT = 8;	// timing classes: 0 insert, 1 count / emit, 2 scatter, 3 dedupe, 4 build, 5 scan, 6 build retries
 
 }	// namespace
+
+// a set of chains of record blocks (sdt_chain.cuh) with what is derived from it
+struct ChainLevel
+{
+	u32 n_chains = 0, cap_chains = 0;
+	u64 *head = nullptr, *boff = nullptr, *seg_sum = nullptr, *d_cursor = nullptr;	// d_cursor: [0] pool cursor, [1] output cursor of the merge, [2] work items, [3] group cursor (inside cta_pool's allocation)
+	u32 *bcount = nullptr, *bchain = nullptr, *bseq = nullptr, *blist = nullptr, *recs = nullptr;
+	uint2 *cta_pool = nullptr;
+	u64 pool_blocks = 0, blocks_upper = 0, blist_cap = 0, pool_high = 0;	// pool_high: the largest pool an epoch has needed
+	u32 *out = nullptr;	// the merged records, and the work items of the build that skm_merge_kernel cuts them into
+	u64 out_cap = 0;
+	SkmWork *items = nullptr;
+};
 
 struct sdtgpu
 {
@@ -82,25 +99,21 @@ struct sdtgpu
 	const u64 *seg_records[MAX_SEGMENTS];
 	u32 n_segments = 0;
 	double region_bytes = 16.0 * 1024 * 1024;
-	// sliced build (SDTGPU_F_SLICED): reads of the open epoch are kept in a log, counted per slice as
-	// they arrive, and turned into the table by sliced_flush (sdt_sliced.cuh)
-	bool sliced = false, table_built = false;
+	// sliced build (SDTGPU_F_SLICED): reads of the open epoch are kept in a log and turned into super-k-mer
+	// records in the chains of their slices as they arrive; sliced_flush merges copies and builds the slices
+	bool sliced = false, table_built = false, epoch_open = false, emitted = false, ord_bound_set = false, chains_dropped = false;
+	u64 hint = 0, store_want = 0;
 	SkmGeom geom = {};
 	void *log_mem[3] = { nullptr, nullptr, nullptr };	// packed, lens, mask arenas
 	size_t log_cap[3] = { 0, 0, 0 }, log_used[3] = { 0, 0, 0 };
 	std::vector<LogSeg> log;
-	u32 *d_hist = nullptr;
-	u64 *d_off = nullptr, *d_cur2 = nullptr, *d_seg_sum = nullptr;
-	u64 *d_small = nullptr, *h_small = nullptr;	// [0] record cursor, [1] node cursor, [2] failed work items, [3] work-item cursor, [4] records after dedupe; pinned mirror
+	ChainLevel lv[3];	// [0] the slices (several GPUs: ALL ranks' slices, the sending side), [1] sub-slices of slices that overflowed, [2] this rank's slices, receiving side
+	u64 *d_small = nullptr, *h_small = nullptr;	// [0] records made, [1] node cursor, [2] failed work items, [3] work-item cursor, [4] records after the merge, [5] their windows, [8..] owner regions; pinned mirror
 	void *d_failed = nullptr, *d_items = nullptr;	// SkmWork lists
-	u32 *rec0 = nullptr, *rec2 = nullptr;	// super-k-mer records: as emitted, grouped by slice
-	u32 *rec3 = nullptr;			// sub-records of the slices that overflowed (skm_resplit_kernel), grouped by sub-slice
-	size_t rec3_cap_b = 0, sub_cap = 0;
-	void *sub_mem = nullptr;		// run offsets, cursors, scan sums and counts of the sub-slices
-	u64 rec0_cap = 0, rec2_cap = 0, rec_upper = 0;	// records
-	u32 n_local_or_all () const { return n_local ? n_local : geom.n_slices; }
+	u32 *rx = nullptr;	// records received from other ranks
+	u64 rx_cap = 0;
 	u32 skm_world = 1, skm_rank = 0, n_local = 0;	// super-k-mer exchange (sdtgpu_skm_set_world): slices per rank; geom.n_slices = n_local * skm_world
-	u64 n_store = 0, n_records = 0, n_retried = 0, n_merged = 0;	// nodes in the store after the last build
+	u64 n_store = 0, n_records = 0, n_retried = 0, n_merged = 0, n_items = 0;	// nodes in the store after the last build
 	bool dirty = false;	// records were emitted since the last build
 	u32 n_epochs = 0;
 	struct Timed { cudaEvent_t e0, e1; int cat; };
@@ -465,7 +478,9 @@ int retain_last_batch (sdtgpu *h, const ReadBatch &rb)
 	return SDTGPU_OK;
 }
 
-// per reference set: (largest instance ordinal + 1) within the retained batch, 0 if none
+ReadBatch log_batch (const sdtgpu *h, const LogSeg &s);
+
+// per reference set: (largest instance ordinal + 1) within the retained batch (sliced build: the whole epoch), 0 if none
 int set_last_ordinals (sdtgpu *h, int thrd_num, std::vector<u64> &last)
 {
 	last.assign (thrd_num, 0);
@@ -479,7 +494,15 @@ int set_last_ordinals (sdtgpu *h, int thrd_num, std::vector<u64> &last)
 	b.counts = d_last;
 	b.capacity = (u64) h->key_words;
 	b.n_ranks = (u32) thrd_num;
-	int rc = launch_insert<4> (h, h->last_rb, b);
+	int rc = SDTGPU_OK;
+	if (h->sliced && !h->log.empty ())
+	{	// the sliced build keeps every batch of the epoch: the last instance of a set is looked for in all of
+		// them (a final batch of a few reads need not touch every set)
+		for (size_t i = 0; i < h->log.size () && !rc; i++)
+			rc = launch_insert<4> (h, log_batch (h, h->log[i]), b);
+	}
+	else
+		rc = launch_insert<4> (h, h->last_rb, b);
 	cudaError_t e = cudaSuccess;
 	if (!rc)
 	{
@@ -661,7 +684,7 @@ int stage_batch (sdtgpu *h, const ReadBatch &rb, u64 upper)
 }
 
 
-// ---- sliced build over super-k-mers (sdt_skm.cuh) ------------------------------------------------
+// ---- sliced build over super-k-mers (sdt_skm.cuh, sdt_chain.cuh, sdt_merge.cuh, sdt_build.cuh) ------------
 struct TimedLaunch
 {	// CUDA events around one launch on the handle's stream, filed under a timing class
 	sdtgpu *h;
@@ -676,74 +699,223 @@ struct TimedLaunch
 	}
 };
 
+// SDTGPU_TRACE=1: wall clock of the host-side steps of a flush (drains the stream at every mark)
+struct Trace
+{
+	sdtgpu *h;
+	bool on;
+	std::chrono::steady_clock::time_point t0;
+	Trace (sdtgpu *h_) : h (h_), on (getenv ("SDTGPU_TRACE") != nullptr), t0 (std::chrono::steady_clock::now ()) { }
+	void mark (const char *what)
+	{
+		if (!on)
+			return;
+		cudaStreamSynchronize (h->stream);
+		const auto t1 = std::chrono::steady_clock::now ();
+		size_t fr = 0, tot = 0;
+		cudaMemGetInfo (&fr, &tot);
+		fprintf (stderr, "[sdtgpu] %-28s %8.3f ms   (%.1f GB free)\n", what, std::chrono::duration<double, std::milli> (t1 - t0).count (), fr / 1e9);
+		t0 = t1;
+	}
+};
+
 u32 env_u32 (const char *name, u32 dflt)
 {
 	const char *e = getenv (name);
 	return e && atoll (e) > 0 ? (u32) atoll (e) : dflt;
 }
 
+// distinct k-mers to expect from `instances` windows when the caller gave no hint: at sequencing depth the
+// distinct k-mers are dominated by error k-mers (a window is error-free with probability 0.99^K at the 1 %
+// substitution rate of short reads), never more than the windows themselves.  Only the slice count and the first
+// size of the node store come from this; slices that overflow are split and the store grows (sliced_flush).
+u64 estimate_distinct (u64 instances, int K)
+{
+	const double e = (double) instances * (1.0 - pow (0.99, (double) K)) * 1.05 + 65536.0;
+	return (u64) std::min ((double) instances + 1024.0, e);
+}
+
 // Geometry from the expected distinct count: slices whose images run at ~half load on average
 // (minimizer slices are lumpier than hashed k-mers: sd ~14 % of the mean at 1150 keys per slice)
 int skm_setup (sdtgpu *h, u64 hint)
 {
-	if (hint == 0)
-		return fail (h, SDTGPU_EINVAL, "the sliced build needs capacity_hint (expected distinct k-mers)");
 	SkmGeom g;
-	g.build_nt = env_u32 ("SDTGPU_BUILD_OLD", 0) ? (env_u32 ("SDTGPU_BUILD_NT", 1024) == 512 ? 512 : 1024) : 0;	// 0: the two-group kernel (sdt_build.cuh)
+	g.build_nt = 0;
 	// default: what fits one CTA per SM (227 KB) beside the staging areas: 72 / 84 / 100 bytes per slot for 1- / 2- / 4-word keys
-	const u32 dflt = g.build_nt == 0 ? skm_build2_max_slots (h->W) : g.build_nt == 1024 ? (h->W == 1 ? 3104u : (h->W == 2 ? 2656u : 2240u)) : (h->W == 1 ? 1552u : (h->W == 2 ? 1330u : 1118u));
+	const u32 dflt = skm_build2_max_slots (h->W);
 	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", dflt);
-	if (g.slice_slots < 32 || g.slice_slots > (g.build_nt ? MAX_SWEEPS * g.build_nt : dflt))
+	if (g.slice_slots < 32 || g.slice_slots > dflt)
 		return fail (h, SDTGPU_EINVAL, "SDTGPU_SLICE_SLOTS out of range");
 	for (;; g.slice_slots--)
-	{	// the largest prime below: the image is probed by double hashing (skm_find)
+	{	// the largest prime below: the image is probed by double hashing (skm_find2)
 		bool prime = true;
 		for (u32 d = 2; d * d <= g.slice_slots && prime; d++)
 			prime = g.slice_slots % d != 0;
 		if (prime)
 			break;
 	}
-	double load = 0.45;
+	// a chain (the k-mers of one range of minimizers) is sized to a fraction of an image: skm_merge_kernel packs
+	// consecutive chains into work items up to an image's worth of windows, which evens out how lumpy chains are
+	// (K <= 31 with a hint: a chain is about an image's worth — 2 % faster on C2 than packing small chains;
+	// without a hint the chains are made small, so that a guess that is too low by 4x still gives items that fit)
+	double load = h->W == 1 ? (h->hint ? 0.45 : 0.12) : (h->W == 2 ? 0.12 : 0.2);	// (long k-mers: nearly every window is a k-mer of its own and chains are lumpy)
 	if (const char *e = getenv ("SDTGPU_SLICE_LOAD"))
-		if (atof (e) > 0.05 && atof (e) < 0.95)
+		if (atof (e) > 0.01 && atof (e) < 0.95)
 			load = atof (e);
-	const u64 n = std::max<u64> (1, (u64) std::ceil ((double) hint / ((double) g.slice_slots * load)));
-	if (n > (1ull << 30))
+	const u64 n = std::max<u64> (1, (u64) std::ceil ((double) std::max<u64> (hint, 1) / ((double) g.slice_slots * load)));
+	if (n > (1ull << 28))
 		return fail (h, SDTGPU_ERANGE, "capacity_hint too large for the sliced build");
 	g.n_slices = (u32) n;
 	g.m = env_u32 ("SDTGPU_MINIMIZER", h->K >= 21 ? 15u : (u32) std::max (7, h->K - 6));
 	if (g.m > 15 || (int) g.m > h->K - 2 || g.m < 5)
 		return fail (h, SDTGPU_EINVAL, "SDTGPU_MINIMIZER out of range");
-	g.w = (u32) h->K - g.m + 1;
+	g.wfull = (u32) h->K - g.m + 1;
+	g.lo = g.wfull > 24 && !getenv ("SDTGPU_FULL_WINDOW") ? 4 * ((g.wfull - 17) / 8) : 0;	// the central 17 .. 24 m-mers of a long window
+	g.w = g.wfull - 2 * g.lo;
 	g.nmax = h->W == 1 ? 32 : 64;
 	g.recw = h->W == 1 ? 8 : (h->W == 2 ? 12 : 16);
 	g.npos = (u32) h->max_read_len - g.m + 1;
-	g.npad = (std::max (g.npos, g.npos - g.w + 1 + 6) + 3) & ~3u;
+	g.npad = (std::max (g.npos, g.npos - g.wfull + 1 + 6) + 3) & ~3u;
 	g.tile_reads = std::max (4u, std::min (64u, (8192u / g.npad) & ~3u));
 	g.slice_a = slice_of_min_host (mmer_hash (0), g.n_slices);
 	if (g.npad * g.tile_reads > 60000 || h->max_read_len > 60000)
 		return fail (h, SDTGPU_ERANGE, "max_read_len too large for the sliced build");
 	h->geom = g;
-	h->cap = hint + hint / 8 + 65536;	// node store: compact, one slot per distinct k-mer
+	h->store_want = hint + hint / 8 + 65536;	// node store: compact, one slot per distinct k-mer
 	return SDTGPU_OK;
 }
 
 static constexpr u32 MAX_FAILED = 1u << 21;
+static constexpr u32 MAX_CTAS = 148 * 16 + 64;	// CTAs that keep a block range between launches (SkmChains::cta_pool)
 
-int skm_alloc (sdtgpu *h)
+int grow_device (sdtgpu *h, void **mem, size_t *cap, size_t keep, size_t need, const char *what = "buffer")
+{	// *mem holds `keep` live bytes; make room for `need`
+	if (need <= *cap)
+		return SDTGPU_OK;
+	size_t ncap = std::max (*cap + *cap / 2, need + (4u << 20));
+	void *neu = nullptr;
+	if (!keep && *mem)
+	{	// nothing to keep: the old buffer goes first
+		CK (h, cudaStreamSynchronize (h->stream));
+		CK (h, cudaFree (*mem));
+		*mem = nullptr;
+		*cap = 0;
+	}
+	if (cudaMalloc (&neu, ncap) != cudaSuccess)
+	{	// no room for the head room: exactly what is needed
+		cudaGetLastError ();
+		ncap = need;
+		if (cudaMalloc (&neu, ncap) != cudaSuccess)
+		{
+			size_t fr = 0, tot = 0;
+			cudaGetLastError ();
+			cudaMemGetInfo (&fr, &tot);
+			char b[256];
+			snprintf (b, sizeof b, "device allocation of %.2f GB for the %s failed (it holds %.2f GB now; %.2f of %.2f GB free)", need / 1e9, what, *cap / 1e9, fr / 1e9, tot / 1e9);
+			h->err = b;
+			return SDTGPU_ENOMEM;
+		}
+	}
+	if (keep)
+		CK (h, cudaMemcpyAsync (neu, *mem, keep, cudaMemcpyDeviceToDevice, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	if (*mem)
+		CK (h, cudaFree (*mem));
+	*mem = neu;
+	*cap = ncap;
+	return SDTGPU_OK;
+}
+
+// ---- a set of chains (the slices, or the sub-slices of slices that overflowed) with its block pool
+void level_free (ChainLevel &L)
 {
-	const SkmGeom &g = h->geom;
-	const u32 nseg = (g.n_slices + SCAN_SEG - 1) / SCAN_SEG;
-	CK (h, cudaMalloc (&h->d_hist, (size_t) g.n_slices * sizeof (u32)));
-	CK (h, cudaMalloc (&h->d_off, ((size_t) g.n_slices + 1) * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_cur2, (size_t) g.n_slices * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_seg_sum, (size_t) nseg * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_small, 8 * sizeof (u64)));	// [0] record cursor, [1] node cursor, [2] failed items
-	CK (h, cudaMalloc (&h->d_failed, (size_t) MAX_FAILED * sizeof (SkmWork)));
-	CK (h, cudaMalloc (&h->d_items, (size_t) MAX_FAILED * sizeof (SkmWork)));
-	CK (h, cudaMallocHost (&h->h_small, 8 * sizeof (u64)));
-	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) g.n_slices * sizeof (u32), h->stream));
-	CK (h, cudaMemsetAsync (h->d_small, 0, 8 * sizeof (u64), h->stream));
+	cudaFree (L.head); cudaFree (L.bcount); cudaFree (L.boff); cudaFree (L.seg_sum); cudaFree (L.cta_pool);
+	cudaFree (L.bchain); cudaFree (L.bseq); cudaFree (L.blist); cudaFree (L.recs);
+	cudaFree (L.items); cudaFree (L.out);
+	L = ChainLevel ();
+}
+
+SkmChains level_chains (const sdtgpu *h, const ChainLevel &L)
+{
+	SkmChains c;
+	c.head = reinterpret_cast<unsigned long long *> (L.head);
+	c.bcount = L.bcount;
+	c.bchain = L.bchain;
+	c.bseq = L.bseq;
+	c.recs = L.recs;
+	c.pool_cursor = reinterpret_cast<unsigned long long *> (L.d_cursor);
+	c.cta_pool = L.cta_pool;
+	c.ctr = h->d_ctr;
+	c.pool_blocks = L.pool_blocks;
+	c.n_chains = L.n_chains;
+	c.recw = h->geom.recw;
+	return c;
+}
+
+// chains: heads point at their first blocks, nothing linked, the pool cursor behind the first blocks
+int level_reset (sdtgpu *h, ChainLevel &L)
+{
+	if (!L.n_chains)
+		return SDTGPU_OK;
+	chain_init_kernel<<<std::min<u32> ((L.n_chains + 255) / 256, (u32) h->sm_count * 8), 256, 0, h->stream>>> (reinterpret_cast<unsigned long long *> (L.head), L.bcount, L.n_chains);
+	CK (h, cudaGetLastError ());
+	h->all_launches++;
+	if (L.pool_blocks)
+		CK (h, cudaMemsetAsync (L.bchain, 0xFF, L.pool_blocks * sizeof (u32), h->stream));
+	CK (h, cudaMemsetAsync (L.cta_pool, 0, MAX_CTAS * sizeof (uint2), h->stream));
+	h->h_small[6] = L.n_chains;
+	CK (h, cudaMemcpyAsync (L.d_cursor, h->h_small + 6, sizeof (u64), cudaMemcpyHostToDevice, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));	// (h_small[6] is reused)
+	L.blocks_upper = L.n_chains;
+	return SDTGPU_OK;
+}
+
+int level_create (sdtgpu *h, ChainLevel &L, u32 n_chains)
+{
+	if (n_chains > L.cap_chains)
+	{	// (the pool, the block list and the merged runs are kept: they do not depend on the number of chains)
+		cudaFree (L.head); cudaFree (L.bcount); cudaFree (L.boff); cudaFree (L.seg_sum); cudaFree (L.cta_pool); cudaFree (L.items);
+		L.head = L.boff = L.seg_sum = nullptr;
+		L.bcount = nullptr;
+		L.cta_pool = nullptr;
+		L.items = nullptr;
+		L.cap_chains = 0;
+		const u32 cap = n_chains + n_chains / 4 + 64;
+		const u32 nseg = (cap + SCAN_SEG - 1) / SCAN_SEG;
+		CK (h, cudaMalloc (&L.head, (size_t) cap * sizeof (u64)));
+		CK (h, cudaMalloc (&L.bcount, (size_t) cap * sizeof (u32)));
+		CK (h, cudaMalloc (&L.boff, ((size_t) cap + 1) * sizeof (u64)));
+		CK (h, cudaMalloc (&L.seg_sum, (size_t) nseg * sizeof (u64)));
+		CK (h, cudaMalloc (&L.items, (size_t) cap * sizeof (SkmWork)));
+		CK (h, cudaMalloc (&L.cta_pool, MAX_CTAS * sizeof (uint2) + 4 * sizeof (u64)));
+		L.d_cursor = reinterpret_cast<u64 *> (L.cta_pool + MAX_CTAS);
+		L.cap_chains = cap;
+	}
+	L.n_chains = n_chains;
+	return level_reset (h, L);
+}
+
+// room for `blocks` blocks in the pool (what is there is kept)
+int level_reserve (sdtgpu *h, ChainLevel &L, u64 blocks)
+{
+	L.pool_high = std::max (L.pool_high, blocks);
+	if (blocks <= L.pool_blocks)
+		return SDTGPU_OK;
+	if (L.pool_blocks == 0)
+		blocks = L.pool_high;	// (a pool that was given up for the node store comes back at its full size, in one piece)
+	if (blocks >= 0xFFFFFFF0ull)
+		return fail (h, SDTGPU_ERANGE, "too many record blocks");
+	int rc;
+	const size_t bb = (size_t) CH_BLK * h->geom.recw * 4;
+	const u64 old = L.pool_blocks;
+	size_t cap_r = old * bb, cap_c = old * 4, cap_s = old * 4;
+	if ((rc = grow_device (h, (void **) &L.recs, &cap_r, old * bb, blocks * bb, "record pool")))
+		return rc;
+	const u64 neu = cap_r / bb;
+	if ((rc = grow_device (h, (void **) &L.bchain, &cap_c, old * 4, neu * 4)) || (rc = grow_device (h, (void **) &L.bseq, &cap_s, old * 4, neu * 4)))
+		return rc;
+	CK (h, cudaMemsetAsync (L.bchain + old, 0xFF, (neu - old) * sizeof (u32), h->stream));
+	L.pool_blocks = neu;
 	return SDTGPU_OK;
 }
 
@@ -754,23 +926,6 @@ ReadBatch log_batch (const sdtgpu *h, const LogSeg &s)
 	rb.lens = s.rb.lens ? reinterpret_cast<const u32 *> (static_cast<const uint8_t *> (h->log_mem[1]) + s.off[1]) : nullptr;
 	rb.nmask = s.rb.nmask ? static_cast<const uint8_t *> (h->log_mem[2]) + s.off[2] : nullptr;
 	return rb;
-}
-
-int grow_device (sdtgpu *h, void **mem, size_t *cap, size_t keep, size_t need)
-{	// *mem holds `keep` live bytes; make room for `need`
-	if (need <= *cap)
-		return SDTGPU_OK;
-	const size_t ncap = std::max (*cap + *cap / 2, need + (4u << 20));
-	void *neu = nullptr;
-	CK (h, cudaMalloc (&neu, ncap));
-	if (keep)
-		CK (h, cudaMemcpyAsync (neu, *mem, keep, cudaMemcpyDeviceToDevice, h->stream));
-	CK (h, cudaStreamSynchronize (h->stream));
-	if (*mem)
-		CK (h, cudaFree (*mem));
-	*mem = neu;
-	*cap = ncap;
-	return SDTGPU_OK;
 }
 
 template <int W, bool NMODE> int launch_emit_t (sdtgpu *h, ReadBatch rb)
@@ -786,10 +941,10 @@ template <int W, bool NMODE> int launch_emit_t (sdtgpu *h, ReadBatch rb)
 	if (occ < 1)
 		return fail (h, SDTGPU_EINVAL, "read stride too large for one shared-memory tile");
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
-	const unsigned grid = (unsigned) std::min<u64> (n_tiles, (u64) h->sm_count * occ);
+	const unsigned grid = (unsigned) std::min<u64> (n_tiles, std::min<u64> ((u64) h->sm_count * occ, MAX_CTAS));
 	{
 		TimedLaunch tl (h, 1);
-		kern<<<grid, EMIT_NT, smem, h->stream>>> (rb, g, h->d_hist, h->rec0, h->rec0_cap, reinterpret_cast<unsigned long long *> (h->d_small), h->d_ctr);
+		kern<<<grid, EMIT_NT, smem, h->stream>>> (rb, g, level_chains (h, h->lv[0]), reinterpret_cast<unsigned long long *> (h->d_small));
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
@@ -806,88 +961,60 @@ int launch_emit (sdtgpu *h, const ReadBatch &rb)
 	}
 }
 
-struct SkmArrays { u32 *rec; u64 *off; u64 *end; };	// records grouped by slice, run starts, ends of what dedupe left
-
-template <int W, int NT> int launch_build_t (sdtgpu *h, const SkmArrays &ar, const SkmWork *items, u32 n_items, int cat)
+// blocks a batch of `upper` windows from `n_reads` reads may fill: random minimizers start a new run every
+// (w + 1) / 2 windows and every read ends one (C2: 0.124 records per window measured; K = 63: 0.076; K = 127 on
+// 150 bp: 0.069), plus what the CTAs hold back; if a batch needs more the kernels say so and the epoch is emitted again
+u64 batch_blocks (const sdtgpu *h, u64 upper, u64 n_reads)
 {
-	typedef typename SlotOf<W>::type S;
-	const SkmGeom &g = h->geom;
-	auto kern = skm_build_kernel<W, NT>;
-	const size_t smem = skm_build_smem (W, g);
-	if (smem > 48 * 1024)
-		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	int occ = 0;
-	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, NT, smem));
-	if (occ < 1)
-		return fail (h, SDTGPU_EINVAL, "slice image does not fit in shared memory (SDTGPU_SLICE_SLOTS too large)");
-	const unsigned grid = (unsigned) std::min<u64> (n_items, (u64) h->sm_count * occ);
-	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
-	CK (h, cudaMemsetAsync (small + 3, 0, sizeof (u64), h->stream));	// work-item cursor
-	{
-		TimedLaunch tl (h, cat);
-		kern<<<grid, NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, ar.rec, ar.off, ar.end, items, n_items, small + 3,
-							 static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
-	}
-	CK (h, cudaGetLastError ());
-	return SDTGPU_OK;
+	u64 rec = (u64) ((double) upper * 2.2 / (h->geom.w + 1.0)) + n_reads + n_reads / 5 + 4096;
+	if (getenv ("SDTGPU_REC_DIV"))	// tests: a pool that is too small
+		rec = upper / env_u32 ("SDTGPU_REC_DIV", 3) + n_reads / 8 + 4096;
+	return rec / CH_BLK + rec / (16 * CH_BLK) + 64;
 }
 
-template <int W, bool HAS_MULT> int launch_dedupe_t (sdtgpu *h, const SkmArrays &ar, u32 n_slices)
-{
-	auto kern = skm_dedupe_kernel<W, HAS_MULT>;
-	const size_t smem = skm_dedupe_smem<W> ();
-	CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	int occ = 0;
-	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, DD_NT, smem));
-	if (occ < 1)
-		return fail (h, SDTGPU_ECUDA, "skm_dedupe_kernel does not fit");
-	const unsigned grid = (unsigned) std::min<u64> (n_slices, (u64) h->sm_count * occ);
-	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
-	if (!HAS_MULT)
-		CK (h, cudaMemsetAsync (small + 4, 0, sizeof (u64), h->stream));	// surviving records
-	{
-		TimedLaunch tl (h, 3);
-		kern<<<grid, DD_NT, smem, h->stream>>> (ar.rec, ar.off, n_slices, reinterpret_cast<unsigned long long *> (ar.end), HAS_MULT ? small + 5 : small + 4);
-	}
-	CK (h, cudaGetLastError ());
-	return SDTGPU_OK;
-}
-
-int launch_dedupe (sdtgpu *h, const SkmArrays &ar, u32 n_slices, bool has_mult)
-{
-	switch (h->W)
-	{
-	case 1: return has_mult ? launch_dedupe_t<1, true> (h, ar, n_slices) : launch_dedupe_t<1, false> (h, ar, n_slices);
-	case 2: return has_mult ? launch_dedupe_t<2, true> (h, ar, n_slices) : launch_dedupe_t<2, false> (h, ar, n_slices);
-	default: return has_mult ? launch_dedupe_t<4, true> (h, ar, n_slices) : launch_dedupe_t<4, false> (h, ar, n_slices);
-	}
-}
-
-template <int W> int launch_resplit_t (sdtgpu *h, const SkmArrays &ar, const SkmSplit *chunks, u32 n_chunks, int pass, u32 *hist2, u64 *cur2, u32 *rec3)
-{
-	const unsigned grid = (unsigned) std::min<u64> (n_chunks, (u64) h->sm_count * 8);
-	TimedLaunch tl (h, 6);
-	if (pass == 0)
-		skm_resplit_kernel<W, 0><<<grid, RS_NT, 0, h->stream>>> (ar.rec, ar.off, ar.end, chunks, n_chunks, h->K, hist2, reinterpret_cast<unsigned long long *> (cur2), nullptr);
-	else
-		skm_resplit_kernel<W, 1><<<grid, RS_NT, 0, h->stream>>> (ar.rec, ar.off, ar.end, chunks, n_chunks, h->K, hist2, reinterpret_cast<unsigned long long *> (cur2), rec3);
-	return SDTGPU_OK;
-}
-
-int launch_resplit (sdtgpu *h, const SkmArrays &ar, const SkmSplit *chunks, u32 n_chunks, int pass, u32 *hist2, u64 *cur2, u32 *rec3)
+int emit_segment (sdtgpu *h, const LogSeg &s)
 {
 	int rc;
-	switch (h->W)
-	{
-	case 1: rc = launch_resplit_t<1> (h, ar, chunks, n_chunks, pass, hist2, cur2, rec3); break;
-	case 2: rc = launch_resplit_t<2> (h, ar, chunks, n_chunks, pass, hist2, cur2, rec3); break;
-	default: rc = launch_resplit_t<4> (h, ar, chunks, n_chunks, pass, hist2, cur2, rec3); break;
-	}
-	CK (h, cudaGetLastError ());
-	return rc;
+	ChainLevel &L = h->lv[0];
+	const u64 hold = (u64) std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS) * CH_SB;	// what the CTAs may sit on
+	L.blocks_upper += batch_blocks (h, s.upper, s.rb.n_reads);
+	if ((rc = level_reserve (h, L, L.blocks_upper + hold)))
+		return rc;
+	return launch_emit (h, log_batch (h, s));
 }
 
-template <int W, bool ORD32> int launch_build2_t (sdtgpu *h, const SkmArrays &ar, const SkmWork *items, u32 n_items, int cat)
+// the geometry is fixed when the first records are made: from the hint, or (no hint) from what has been pushed
+int skm_open_epoch (sdtgpu *h)
+{
+	int rc;
+	if (h->epoch_open)
+		return SDTGPU_OK;
+	u64 hint = h->hint;
+	if (!hint)
+		hint = estimate_distinct (h->pushed_upper, h->K);
+	if ((rc = skm_setup (h, hint)))
+		return rc;
+	if (h->skm_world > 1)
+	{
+		h->n_local = h->geom.n_slices;
+		if ((u64) h->n_local * h->skm_world > (1ull << 28))
+			return fail (h, SDTGPU_ERANGE, "too many slices");
+		h->geom.n_slices = h->n_local * h->skm_world;
+		h->geom.slice_a = slice_of_min_host (mmer_hash (0), h->geom.n_slices);
+	}
+	if (h->lv[0].n_chains != h->geom.n_slices)	// (else: same geometry as the last epoch, whose chains sdtgpu_reset has emptied)
+	{
+		if ((rc = level_create (h, h->lv[0], h->geom.n_slices)))
+			return rc;
+	}
+	else if ((rc = level_reset (h, h->lv[0])))
+		return rc;
+	h->epoch_open = true;
+	return SDTGPU_OK;
+}
+
+
+template <int W, bool ORD32> int launch_build2_t (sdtgpu *h, const u32 *rec, const SkmWork *items, u32 n_items, int cat)
 {
 	typedef typename SlotOf<W>::type S;
 	const SkmGeom &g = h->geom;
@@ -899,115 +1026,199 @@ template <int W, bool ORD32> int launch_build2_t (sdtgpu *h, const SkmArrays &ar
 	CK (h, cudaMemsetAsync (small + 3, 0, sizeof (u64), h->stream));	// work-item cursor
 	{
 		TimedLaunch tl (h, cat);
-		kern<<<grid, BUILD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, ar.rec, ar.off, ar.end, items, n_items, small + 3,
+		kern<<<grid, BUILD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, rec, items, n_items, small + 3,
 							   static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
 }
 
-int launch_build (sdtgpu *h, const SkmArrays &ar, const SkmWork *items, u32 n_items, int cat)
-{
-	if (h->geom.build_nt == 0)
-	{	// 32-bit ordinals in the slice images when every instance ordinal pushed so far fits (one GPU: the records are this handle's own)
-		const bool ord32 = h->skm_world <= 1 && h->ord_end < 0xFFFFFFFFull && !getenv ("SDTGPU_ORD64");
-		switch (h->W)
-		{
-		case 1: return ord32 ? launch_build2_t<1, true> (h, ar, items, n_items, cat) : launch_build2_t<1, false> (h, ar, items, n_items, cat);
-		case 2: return ord32 ? launch_build2_t<2, true> (h, ar, items, n_items, cat) : launch_build2_t<2, false> (h, ar, items, n_items, cat);
-		default: return ord32 ? launch_build2_t<4, true> (h, ar, items, n_items, cat) : launch_build2_t<4, false> (h, ar, items, n_items, cat);
-		}
-	}
+int launch_build (sdtgpu *h, const u32 *rec, const SkmWork *items, u32 n_items, int cat)
+{	// 32-bit ordinals in the slice images when every instance ordinal pushed so far fits (several GPUs: the caller says so)
+	const bool ord32 = h->ord_end < 0xFFFFFFFFull && !getenv ("SDTGPU_ORD64");
 	switch (h->W)
 	{
-	case 1: return h->geom.build_nt == 512 ? launch_build_t<1, 512> (h, ar, items, n_items, cat) : launch_build_t<1, 1024> (h, ar, items, n_items, cat);
-	case 2: return h->geom.build_nt == 512 ? launch_build_t<2, 512> (h, ar, items, n_items, cat) : launch_build_t<2, 1024> (h, ar, items, n_items, cat);
-	default: return h->geom.build_nt == 512 ? launch_build_t<4, 512> (h, ar, items, n_items, cat) : launch_build_t<4, 1024> (h, ar, items, n_items, cat);
+	case 1: return ord32 ? launch_build2_t<1, true> (h, rec, items, n_items, cat) : launch_build2_t<1, false> (h, rec, items, n_items, cat);
+	case 2: return ord32 ? launch_build2_t<2, true> (h, rec, items, n_items, cat) : launch_build2_t<2, false> (h, rec, items, n_items, cat);
+	default: return ord32 ? launch_build2_t<4, true> (h, rec, items, n_items, cat) : launch_build2_t<4, false> (h, rec, items, n_items, cat);
 	}
 }
 
-int skm_emit_all (sdtgpu *h)
-{	// slow path: the record area was too small for what the reads produced; the cursor has counted
-	// every record, so the area is resized to fit and the whole read log is emitted again
+// the blocks of every chain in order (scan of the blocks per chain, one pass over the linked blocks)
+int level_list (sdtgpu *h, ChainLevel &L, u64 *n_blocks)
+{
 	int rc;
-	const u64 need = h->h_small[0] + h->h_small[0] / 16 + 4096;
-	const size_t rec = 4 * (size_t) h->geom.recw;
-	size_t cap_b = h->rec0_cap * rec;
-	if ((rc = grow_device (h, (void **) &h->rec0, &cap_b, 0, need * rec)))
+	const u32 nseg = (L.n_chains + SCAN_SEG - 1) / SCAN_SEG;
+	{
+		TimedLaunch tl (h, 5);
+		slice_scan_sums_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (L.bcount, L.n_chains, L.seg_sum);
+		slice_scan_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (L.bcount, L.n_chains, L.seg_sum, L.boff, nullptr);
+		h->all_launches++;
+	}
+	CK (h, cudaGetLastError ());
+	CK (h, cudaMemcpyAsync (h->h_small + 6, L.boff + L.n_chains, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaMemcpyAsync (h->h_small + 7, L.d_cursor, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	const u64 linked = h->h_small[6], cursor = std::min<u64> (h->h_small[7], L.pool_blocks);
+	size_t cap_b = L.blist_cap * 4;
+	if ((rc = grow_device (h, (void **) &L.blist, &cap_b, 0, std::max<u64> (linked, 1) * 4)))
 		return rc;
-	h->rec0_cap = cap_b / rec;
-	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) h->geom.n_slices * sizeof (u32), h->stream));
+	L.blist_cap = cap_b / 4;
+	if (cursor > L.n_chains)
+	{
+		TimedLaunch tl (h, 5);
+		chain_list_kernel<<<(unsigned) std::min<u64> ((cursor - L.n_chains + 255) / 256, (u64) h->sm_count * 16), 256, 0, h->stream>>> (
+			L.bchain, L.bseq, L.boff, L.n_chains, reinterpret_cast<unsigned long long *> (L.d_cursor), L.pool_blocks, L.blist);
+	}
+	CK (h, cudaGetLastError ());
+	*n_blocks = L.n_chains + linked;
+	return SDTGPU_OK;
+}
+
+template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u64 n_rec, u32 per_owner, const u64 *region, u64 *rcur)
+{
+	auto kern = skm_merge_kernel<W, HAS_MULT>;
+	const size_t smem = skm_merge_smem<W> ();
+	CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	int occ = 0;
+	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, MG_NT, smem));
+	if (occ < 1)
+		return fail (h, SDTGPU_ECUDA, "skm_merge_kernel does not fit");
+	// chains per group: half a chunk's worth of records on average, so that most groups fit one chunk
+	const double avg = std::max (1.0, (double) n_rec / (double) std::max<u32> (L.n_chains, 1));
+	const u32 G = env_u32 ("SDTGPU_MERGE_GROUP", (u32) std::min<double> (MG_GMAX, std::max (1.0, std::floor (0.5 * MergeCfg<W>::CHUNK / avg))));
+	const u32 span = per_owner ? per_owner : L.n_chains;
+	const u64 n_groups = (u64) ((span + G - 1) / G) * (per_owner ? (L.n_chains + per_owner - 1) / per_owner : 1);
+	const unsigned grid = (unsigned) std::min<u64> (std::max<u64> (n_groups, 1), (u64) h->sm_count * occ);
+	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
+	CK (h, cudaMemsetAsync (small + 4, 0, 2 * sizeof (u64), h->stream));	// surviving records, their windows
+	CK (h, cudaMemsetAsync (L.d_cursor + 1, 0, 3 * sizeof (u64), h->stream));	// output cursor, work items, group cursor
+	double load = 0.9;	// windows per work item / slots of an image: an item has at most as many distinct k-mers as windows
+	if (const char *e = getenv ("SDTGPU_ITEM_LOAD"))
+		if (atof (e) > 0.05 && atof (e) < 4.0)
+			load = atof (e);
+	MergeOut mo;
+	mo.out = L.out;
+	mo.out_cursor = reinterpret_cast<unsigned long long *> (L.d_cursor + 1);
+	mo.out_cap = L.out_cap;
+	mo.items = L.items;
+	mo.n_items = reinterpret_cast<unsigned long long *> (L.d_cursor + 2);
+	mo.max_items = L.cap_chains;
+	mo.n_kept = small + 4;
+	mo.budget = std::max (1u, (u32) (load * h->geom.slice_slots));
+	mo.oversize = std::max (mo.budget, 8 * h->geom.slice_slots);	// (a hot locus has many windows but few distinct k-mers: the build finds out)
+	mo.per_owner = per_owner;
+	mo.region = region;
+	mo.rcur = reinterpret_cast<unsigned long long *> (rcur);
+	{
+		TimedLaunch tl (h, 3);
+		kern<<<grid, MG_NT, smem, h->stream>>> (level_chains (h, L), L.boff, L.blist, mo, std::min (G, MG_GMAX), reinterpret_cast<unsigned long long *> (L.d_cursor + 3));
+	}
+	CK (h, cudaGetLastError ());
+	return SDTGPU_OK;
+}
+
+int launch_merge (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, u32 per_owner = 0, const u64 *region = nullptr, u64 *rcur = nullptr)
+{
+	switch (h->W)
+	{
+	case 1: return has_mult ? launch_merge_t<1, true> (h, L, n_rec, per_owner, region, rcur) : launch_merge_t<1, false> (h, L, n_rec, per_owner, region, rcur);
+	case 2: return has_mult ? launch_merge_t<2, true> (h, L, n_rec, per_owner, region, rcur) : launch_merge_t<2, false> (h, L, n_rec, per_owner, region, rcur);
+	default: return has_mult ? launch_merge_t<4, true> (h, L, n_rec, per_owner, region, rcur) : launch_merge_t<4, false> (h, L, n_rec, per_owner, region, rcur);
+	}
+}
+
+int launch_split (sdtgpu *h, ChainLevel &sub, const u32 *rec, const SkmSplit *chunks, u32 n_chunks)
+{
+	const unsigned grid = (unsigned) std::min<u64> (n_chunks, std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS));
+	TimedLaunch tl (h, 6);
+	const SkmChains c = level_chains (h, sub);
+	switch (h->W)
+	{
+	case 1: skm_split_kernel<1><<<grid, SP_NT, 0, h->stream>>> (c, rec, chunks, n_chunks, h->K); break;
+	case 2: skm_split_kernel<2><<<grid, SP_NT, 0, h->stream>>> (c, rec, chunks, n_chunks, h->K); break;
+	default: skm_split_kernel<4><<<grid, SP_NT, 0, h->stream>>> (c, rec, chunks, n_chunks, h->K); break;
+	}
+	CK (h, cudaGetLastError ());
+	return SDTGPU_OK;
+}
+
+// every segment of the read log through skm_emit_kernel again, into a pool that holds `records` records
+int skm_emit_all (sdtgpu *h, u64 records)
+{
+	int rc;
+	ChainLevel &L = h->lv[0];
+	const u64 hold = (u64) std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS) * CH_SB;
+	if ((rc = level_reset (h, L)))
+		return rc;
+	if ((rc = level_reserve (h, L, L.n_chains + records / CH_BLK + records / (8 * CH_BLK) + hold + 4096)))
+		return rc;
 	CK (h, cudaMemsetAsync (h->d_small, 0, sizeof (u64), h->stream));
 	CK (h, cudaMemsetAsync (&h->d_ctr->overflow, 0, sizeof (u64), h->stream));
 	for (const LogSeg &s : h->log)
 		if ((rc = launch_emit (h, log_batch (h, s))))
 			return rc;
-	h->rec_upper = std::max (h->rec_upper, need);
+	L.blocks_upper = L.pool_blocks - hold;
 	return SDTGPU_OK;
 }
 
-// part 1 of a flush: how many records the pushes produced (re-emitting the read log if the record area ran out)
+// part 1 of a flush: all records are in their chains (emitting the read log again if the block pool ran out)
 int skm_collect (sdtgpu *h, u64 *n_rec)
 {
 	int rc;
+	if (!h->emitted)
+	{	// no hint: the reads were only logged so far; now their number is known and fixes the geometry
+		if ((rc = skm_open_epoch (h)))
+			return rc;
+		for (const LogSeg &s : h->log)
+			if ((rc = emit_segment (h, s)))
+				return rc;
+		h->emitted = true;
+	}
 	for (int attempt = 0;; attempt++)
 	{
 		CK (h, cudaMemcpyAsync (h->h_small, h->d_small, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaStreamSynchronize (h->stream));
-		if (!(h->h_small[3] & 2))
+		if (h->chains_dropped)
+		{	// the last flush gave the chains' memory to the node store: everything is emitted again
+			h->chains_dropped = false;
+			if (h->table)
+				CK (h, cudaFree (h->table));
+			h->table = nullptr;
+			h->cap = 0;
+			if ((rc = skm_emit_all (h, h->h_small[0])))
+				return rc;
+			continue;
+		}
+		if (!(h->h_small[3] & OVF_RECORDS))
 			break;
 		if (attempt == 2)
-			return fail (h, SDTGPU_ERANGE, "record area overflow persists");
-		if ((rc = skm_emit_all (h)))
+			return fail (h, SDTGPU_ERANGE, "record pool overflow persists");
+		if ((rc = skm_emit_all (h, h->h_small[0])))
 			return rc;
 	}
 	*n_rec = h->h_small[0];
 	return SDTGPU_OK;
 }
 
-// part 2: the n_rec records of rec0 (their count is also in d_small[0]) go to rec2, grouped by slice:
-// scan of d_hist[0 .. n_slices) -> d_off, d_cur2; scatter
-int skm_group (sdtgpu *h, u64 n_rec, u32 n_slices)
+int ensure_store (sdtgpu *h, u64 slots)
 {
-	int rc;
-	const SkmGeom &g = h->geom;
-	const size_t rec = 4 * (size_t) g.recw;
-	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
-	{
-		size_t cap_b = h->rec2_cap * rec;
-		if ((rc = grow_device (h, (void **) &h->rec2, &cap_b, 0, std::max<u64> (n_rec, 1) * rec)))
-			return rc;
-		h->rec2_cap = cap_b / rec;
-	}
-	const u32 nseg = (n_slices + SCAN_SEG - 1) / SCAN_SEG;
-	{
-		TimedLaunch tl (h, 5);
-		slice_scan_sums_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, n_slices, h->d_seg_sum);
-		slice_scan_kernel<<<nseg, SCAN_NT, 0, h->stream>>> (h->d_hist, n_slices, h->d_seg_sum, h->d_off, h->d_cur2);
-		h->all_launches++;
-	}
-	CK (h, cudaGetLastError ());
-	if (n_rec)
-	{
-		const unsigned grid = (unsigned) std::min<u64> ((n_rec + SCAT_NT - 1) / SCAT_NT, (u64) h->sm_count * 8);
-		TimedLaunch tl (h, 2);
-		unsigned long long *cur = reinterpret_cast<unsigned long long *> (h->d_cur2);
-		if (g.recw == 8)
-			skm_scatter_kernel<8><<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, cur, h->rec2);
-		else if (g.recw == 12)
-			skm_scatter_kernel<12><<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, cur, h->rec2);
-		else
-			skm_scatter_kernel<16><<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, small, cur, h->rec2);
-	}
-	CK (h, cudaGetLastError ());
+	if (slots <= h->cap && h->table)
+		return SDTGPU_OK;
+	if (h->table)
+		CK (h, cudaFree (h->table));
+	h->table = nullptr;
+	h->cap = 0;
+	CK (h, cudaMalloc (&h->table, slots * slot_bytes (h->W)));
+	h->cap = slots;
 	return SDTGPU_OK;
 }
 
-int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices);
+// part 2: the chains of level L -> contiguous runs (copies merged) -> node store
+int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, bool top);
 
-// Everything pushed since the last reset becomes the node store: scan the per-slice record counts,
-// move every record to its slice's run, build the slices.  Records persist until sdtgpu_reset, so a
+// Everything pushed since the last reset becomes the node store.  Records persist until sdtgpu_reset, so a
 // later push followed by another flush rebuilds the store from all of them.
 int sliced_flush (sdtgpu *h)
 {
@@ -1024,128 +1235,196 @@ int sliced_flush (sdtgpu *h)
 	if (h->skm_world > 1)
 		return fail (h, SDTGPU_ESTATE, "super-k-mer exchange: reads were pushed but sdtgpu_skm_stage / sdtgpu_skm_import have not run");
 	u64 n_rec = 0;
+	Trace tr (h);
 	if ((rc = skm_collect (h, &n_rec)))
 		return rc;
+	tr.mark ("collect (emit done)");
 	h->n_records = n_rec;
-	if ((rc = skm_group (h, n_rec, h->geom.n_slices)))
-		return rc;
-	return skm_build_all (h, n_rec, h->geom.n_slices);
+	rc = skm_build_level (h, h->lv[0], false, n_rec, true);
+	tr.mark ("build level 0 (total)");
+	return rc;
 }
 
-// part 3: rec2 (grouped by slice, n_slices slices) -> node store
-int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
+static constexpr int STORE_FULL = -100;	// internal: the node store ran out; the top level enlarges it and builds again
+
+// the work items of level L -> node store; items that overflow an image are retried in pieces or, far
+// beyond an image, cut into sub-slices
+int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top)
 {
 	int rc;
 	const SkmGeom g = h->geom;
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
-	SkmArrays ar = { h->rec2, h->d_off, h->d_cur2 };
-	if (n_rec)
-	{	// copies of a super-k-mer collapse into one record with a multiplicity; d_cur2[slice] becomes the end of what is left
-		if ((rc = launch_dedupe (h, ar, n_slices, false)))
-			return rc;
-	}
-	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over
-	CK (h, cudaMemsetAsync (small + 1, 0, 2 * sizeof (u64), h->stream));
-	CK (h, cudaMemsetAsync (&h->d_ctr->n_nodes, 0, 2 * sizeof (u64), h->stream));	// n_nodes, n_instances
-	if ((rc = launch_build (h, ar, nullptr, n_slices, 4)))
+	Trace tr (h);
+	if (n_items && (rc = launch_build (h, L.out, L.items, n_items, top ? 4 : 6)))
 		return rc;
-	h->n_retried = 0;
+	tr.mark ("  build all items");
 	std::vector<SkmWork> items, failed;
-	const double wpr = 0.5 * g.w + 1.0;	// windows per record, about
+	std::vector<SkmSplit> splits;
+	u64 Q = 0, sub_windows = 0;
 	for (u32 depth = 0;; depth++)
 	{
 		CK (h, cudaMemcpyAsync (h->h_small + 1, small + 1, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-		CK (h, cudaMemcpyAsync (h->h_small + 4, small + 4, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaStreamSynchronize (h->stream));
-		if (depth == 0)
-			h->n_merged = n_rec ? h->h_small[4] : 0;
-		if (h->h_small[3] & 4)
-			return fail (h, SDTGPU_ERANGE, "node store exhausted: capacity_hint was too small for the sliced build");
-		if (h->h_small[3] & 16)
-			return fail (h, SDTGPU_EINVAL, "super-k-mer exchange: a received record belongs to another rank's slices");
+		if (h->h_small[3] & OVF_STORE)
+			return STORE_FULL;
 		const u32 n_failed = (u32) h->h_small[2];
 		if (n_failed == 0)
 			break;
-		if ((h->h_small[3] & 8) || n_failed > MAX_FAILED || depth == 8)
-			return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
+		if ((h->h_small[3] & OVF_FAILED) || n_failed > MAX_FAILED || depth == 10)
+			return fail (h, SDTGPU_ERANGE, "too many work items overflowed their images");
 		failed.resize (n_failed);
 		CK (h, cudaMemcpy (failed.data (), h->d_failed, n_failed * sizeof (SkmWork), cudaMemcpyDeviceToHost));
 		h->n_retried += n_failed;
 		CK (h, cudaMemsetAsync (small + 2, 0, sizeof (u64), h->stream));
-		if (depth == 0 && env_u32 ("SDTGPU_RESPLIT", 0))
-		{	// EXPERIMENTAL, off by default.  Slices that overflowed their image are cut into sub-slices by
-			// k-mer hash in one pass over their records (skm_resplit_kernel): sub-records are counted,
-			// scanned, written, merged and built like slices.  It removes the quadratic cost of retrying a
-			// hot slice as q filtered scans (C5: retries 51 -> ~5 ms), but the per-sub-slice counts of its
-			// two passes disagree in some runs (1-word keys, K = 31: cursors do not end at the next run's
-			// offset, sub-records overwrite each other, instances are lost) although each pass alone is
-			// reproducible.  Until that is understood the hash-split retry below is the default.
-			std::vector<SkmSplit> chunks;
-			u64 Q = 0;
-			for (const SkmWork &f : failed)
-			{
-				const double est = 0.5 * g.slice_slots + 0.5 * (double) f.nrec * wpr;
-				const u32 q = (u32) std::min (65536.0, std::max (2.0, std::ceil (est / (0.6 * g.slice_slots))));
-				for (u64 lo = 0; lo < std::max<u64> (f.nrec, 1); lo += 32768)
-					chunks.push_back ({ f.slice, q, (u32) Q, (u32) lo, (u32) std::min<u64> (f.nrec, lo + 32768), { 0, 0, 0 } });
-				Q += q;
-			}
-			if (Q > (1ull << 28) || chunks.size () * sizeof (SkmSplit) > (size_t) MAX_FAILED * sizeof (SkmWork))
-				return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
-			const u32 nq = (u32) Q, nseg2 = (nq + SCAN_SEG - 1) / SCAN_SEG;
-			size_t need = (size_t) nq * 4 + ((size_t) nq + 1) * 8 + (size_t) nq * 8 + (size_t) nseg2 * 8 + 64;
-			if ((rc = grow_device (h, &h->sub_mem, &h->sub_cap, 0, need)))
-				return rc;
-			u64 *off2 = static_cast<u64 *> (h->sub_mem), *cur2 = off2 + nq + 1, *seg2 = cur2 + nq;
-			u32 *hist2 = reinterpret_cast<u32 *> (seg2 + nseg2);
-			CK (h, cudaMemsetAsync (hist2, 0, (size_t) nq * 4, h->stream));
-			CK (h, cudaStreamSynchronize (h->stream));
-			CK (h, cudaMemcpy (h->d_items, chunks.data (), chunks.size () * sizeof (SkmSplit), cudaMemcpyHostToDevice));	// blocking: pageable source
-			const SkmSplit *d_chunks = static_cast<const SkmSplit *> (h->d_items);
-			if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 0, hist2, nullptr, nullptr)))
-				return rc;
-			{
-				TimedLaunch tl (h, 5);
-				slice_scan_sums_kernel<<<nseg2, SCAN_NT, 0, h->stream>>> (hist2, nq, seg2);
-				slice_scan_kernel<<<nseg2, SCAN_NT, 0, h->stream>>> (hist2, nq, seg2, off2, cur2);
-			}
-			CK (h, cudaGetLastError ());
-			u64 n_sub = 0;
-			CK (h, cudaMemcpyAsync (&n_sub, off2 + nq, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-			CK (h, cudaStreamSynchronize (h->stream));
-			const size_t rec = 4 * (size_t) g.recw;
-			if ((rc = grow_device (h, (void **) &h->rec3, &h->rec3_cap_b, 0, std::max<u64> (n_sub, 1) * rec)))
-				return rc;
-			if ((rc = launch_resplit (h, ar, d_chunks, (u32) chunks.size (), 1, nullptr, cur2, h->rec3)))
-				return rc;
-			ar = SkmArrays { h->rec3, off2, cur2 };	// from here on the work items are sub-slices
-			CK (h, cudaMemsetAsync (small + 5, 0, sizeof (u64), h->stream));
-			if (n_sub && (rc = launch_dedupe (h, ar, nq, true)))
-				return rc;
-			CK (h, cudaStreamSynchronize (h->stream));	// d_items is about to be reused
-			if ((rc = launch_build (h, ar, nullptr, nq, 6)))
-				return rc;
-			continue;
-		}
-		// A failed item is split by k-mer hash into pieces (keys with hash % R == r).  Every piece scans
-		// all records of the (sub-)slice again — a window that is not the piece's costs a roll and a hash,
-		// about a third of an insert — so the factor is sized to what the slice holds.
+		// A failed item holds more distinct k-mers than an image takes (it is a single chain with more windows than
+		// the budget of an item, or a piece of one).  Few pieces (<= 4) are retried in place, each piece scanning
+		// the item's records for its keys (hash % R == r: a window that is not the piece's costs a roll and a hash,
+		// about a third of an insert); an item that needs more — a highly expressed locus — is cut into
+		// sub-slices in one pass (skm_split_kernel), top level only.  Distinct k-mers of an item: more than an image
+		// took if it was tried, about 0.55 of its windows (C2: 0.48); pieces that still overflow are split again.
 		items.clear ();
 		for (const SkmWork &f : failed)
 		{
-			const double est = (0.5 * g.slice_slots + 0.2 * (double) f.nrec * wpr) / f.R;
-			const u32 q = (u32) std::min (4096.0, std::max (2.0, std::ceil (est / (0.7 * g.slice_slots))));
-			for (u32 i = 0; i < q; i++)
-				items.push_back ({ f.slice, f.r + f.R * i, f.R * q, f.nrec });
+			const u32 R0 = std::max (f.R, 1u);
+			const double est = std::max (f.R ? (double) g.slice_slots : 0.0, 0.6 * (double) f.wsum) / R0;
+			const u32 q = (u32) std::min (1048576.0, std::max (2.0, std::ceil (est / (0.7 * g.slice_slots))));
+			if (top && f.R <= 1 && q > 4 && !getenv ("SDTGPU_NO_SPLIT"))
+			{
+				for (u64 lo = 0; lo < std::max<u64> (f.nrec, 1); lo += 8192)
+					splits.push_back ({ f.r0 + lo, (u32) std::min<u64> (f.nrec - lo, 8192), q, (u32) Q, lo ? 0u : f.wsum });
+				Q += q;
+				sub_windows += f.wsum;
+				continue;
+			}
+			const u32 qq = std::min (q, 4096u);
+			for (u32 i = 0; i < qq; i++)
+				items.push_back ({ f.r0, f.nrec, f.wsum, f.r + R0 * i, R0 * qq });
 		}
-		if (items.size () > MAX_FAILED)
-			return fail (h, SDTGPU_ERANGE, "too many table slices overflowed: capacity_hint was too small for the sliced build");
+		if (items.size () > MAX_FAILED || Q > (1ull << 27) || splits.size () * sizeof (SkmSplit) > (size_t) MAX_FAILED * sizeof (SkmWork))
+			return fail (h, SDTGPU_ERANGE, "too many work items overflowed their images");
+		if (items.empty ())
+			break;
 		CK (h, cudaMemcpyAsync (h->d_items, items.data (), items.size () * sizeof (SkmWork), cudaMemcpyHostToDevice, h->stream));
-		if ((rc = launch_build (h, ar, static_cast<const SkmWork *> (h->d_items), (u32) items.size (), 6)))
+		if ((rc = launch_build (h, L.out, static_cast<const SkmWork *> (h->d_items), (u32) items.size (), 6)))
 			return rc;
 		CK (h, cudaStreamSynchronize (h->stream));	// `items` is pageable host memory
+		tr.mark ("  retry pieces");
 	}
+	if (!splits.empty ())
+	{	// the highly expressed loci: sub-slices by k-mer hash, then merged and built like slices — as many of them
+		// at a time as the memory that is left takes (a sub-record per window, twice: chains and merged runs)
+		ChainLevel &S = h->lv[1];
+		const size_t recb = 4 * (size_t) g.recw;
+		const u64 hold = (u64) std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS) * 8 * 256;
+		size_t a = 0;
+		while (a < splits.size ())
+		{
+			size_t fr = 0, tot = 0;
+			cudaMemGetInfo (&fr, &tot);
+			const double room = (double) fr + (double) S.pool_blocks * CH_BLK * recb + (double) S.out_cap * recb - (2.0 * hold * CH_BLK * recb + (2u << 30));
+			const u64 max_win = (u64) std::max (1e6, room / (2.6 * recb));
+			size_t b = a;
+			u64 win = 0, q0 = splits[a].qbase, q1 = q0;
+			while (b < splits.size () && (b == a || win + splits[b].pad <= max_win || splits[b].qbase == splits[b - 1].qbase))
+			{	// (pad: windows of the item, on its first piece; the pieces of an item stay together)
+				win += splits[b].pad;
+				q1 = splits[b].qbase + splits[b].q;
+				b++;
+			}
+			for (size_t k = a; k < b; k++)
+				splits[k].qbase -= (u32) q0;
+			if ((rc = level_create (h, S, (u32) (q1 - q0))))
+				return rc;
+			if ((rc = level_reserve (h, S, (q1 - q0) + win / CH_BLK + win / (4 * CH_BLK) + hold + 4096)))
+				return rc;
+			CK (h, cudaMemcpyAsync (h->d_items, splits.data () + a, (b - a) * sizeof (SkmSplit), cudaMemcpyHostToDevice, h->stream));
+			if ((rc = launch_split (h, S, L.out, static_cast<const SkmSplit *> (h->d_items), (u32) (b - a))))
+				return rc;
+			CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+			CK (h, cudaStreamSynchronize (h->stream));	// `splits` is pageable host memory; d_items is reused below
+			if (h->h_small[3] & OVF_RECORDS)
+				return fail (h, SDTGPU_ERANGE, "sub-slice pool overflow");
+			tr.mark ("  split");
+			if ((rc = skm_build_level (h, S, true, win, false)))
+				return rc;
+			tr.mark ("  sub-slices");
+			a = b;
+		}
+	}
+	return SDTGPU_OK;
+}
+
+int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, bool top)
+{
+	int rc;
+	const SkmGeom g = h->geom;
+	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
+	u64 n_blocks = 0;
+	Trace tr (h);
+	if ((rc = level_list (h, L, &n_blocks)))
+		return rc;
+	tr.mark (" list");
+	{	// the merged runs: at most as many records as went in
+		const size_t rec = 4 * (size_t) g.recw;
+		size_t cap_b = L.out_cap * rec;
+		if ((rc = grow_device (h, (void **) &L.out, &cap_b, 0, std::max<u64> (n_rec, 1) * rec, "merged records")))
+			return rc;
+		L.out_cap = cap_b / rec;
+	}
+	if ((rc = launch_merge (h, L, has_mult, n_rec)))
+		return rc;
+	CK (h, cudaMemcpyAsync (h->h_small + 4, small + 4, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaMemcpyAsync (h->h_small + 6, L.d_cursor + 2, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	tr.mark (" merge");
+	const u32 n_items = (u32) std::min<u64> (h->h_small[6], L.cap_chains);
+	if (h->h_small[6] > L.cap_chains)
+		return fail (h, SDTGPU_ERANGE, "work item list overflow");
+	if (!top)
+		return skm_build_runs (h, L, n_items, false);
+	h->n_items = n_items;
+	h->n_merged = n_rec ? h->h_small[4] : 0;
+	const u64 win_upper = h->h_small[5] + 1024;	// every node needs a window of its own
+	for (int attempt = 0;; attempt++)
+	{	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over.
+		// Its size: the hint's (or the estimate's) worth, never more than the windows the merge left
+		u64 want = std::min<u64> (h->store_want, win_upper);
+		{	// no room for the node store beside the chains?  The chains are not needed any more (their records are
+			// merged): they go, and a later flush of this epoch emits the read log again
+			size_t fr = 0, tot = 0;
+			cudaMemGetInfo (&fr, &tot);
+			const double need_store = want > h->cap || !h->table ? (double) want * slot_bytes (h->W) - (double) h->cap * slot_bytes (h->W) : 0.0;
+			if ((double) fr < need_store + 0.15 * (double) tot && L.recs)	// (15 % of the memory stays free for sub-slices)
+			{
+				cudaFree (L.recs); cudaFree (L.bchain); cudaFree (L.bseq); cudaFree (L.blist);
+				L.recs = L.bchain = L.bseq = L.blist = nullptr;
+				L.pool_blocks = L.blist_cap = 0;
+				h->chains_dropped = true;
+				cudaMemGetInfo (&fr, &tot);
+			}
+			// never more than the memory takes (15 % of it stays free for sub-slices): if that store runs out, so be it
+			const double room = (double) fr + (double) h->cap * slot_bytes (h->W) - 0.15 * (double) tot;
+			if (room > 0 && (double) want * slot_bytes (h->W) > room)
+				want = std::max<u64> ((u64) (room / slot_bytes (h->W)), std::min<u64> (h->cap, want));
+		}
+		if ((rc = ensure_store (h, want)))
+			return rc;
+		CK (h, cudaMemsetAsync (small + 1, 0, 2 * sizeof (u64), h->stream));
+		CK (h, cudaMemsetAsync (&h->d_ctr->n_nodes, 0, 2 * sizeof (u64), h->stream));	// n_nodes, n_instances
+		h->n_retried = 0;
+		rc = skm_build_runs (h, L, n_items, true);
+		if (rc != STORE_FULL)
+			break;
+		if (attempt == 1 || h->cap >= win_upper)
+			return fail (h, SDTGPU_ERANGE, "node store exhausted");
+		h->store_want = win_upper;	// the estimate was too low: a store that cannot run out, and once more
+		CK (h, cudaMemsetAsync (&h->d_ctr->overflow, 0, sizeof (u64), h->stream));
+	}
+	if (rc)
+		return rc;
+	CK (h, cudaMemcpyAsync (h->h_small + 1, small + 1, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
 	h->n_store = h->h_small[1];
 	h->table_built = true;
 	h->dirty = false;
@@ -1153,7 +1432,7 @@ int skm_build_all (sdtgpu *h, u64 n_rec, u32 n_slices)
 	return SDTGPU_OK;
 }
 
-// one batch: into the read log (kept for the slow path above) and through skm_emit_kernel
+// one batch: into the read log (kept for re-emission and the hand-back) and through skm_emit_kernel
 int sliced_push (sdtgpu *h, const ReadBatch &rb, u64 upper)
 {
 	int rc;
@@ -1164,32 +1443,28 @@ int sliced_push (sdtgpu *h, const ReadBatch &rb, u64 upper)
 	const size_t exact[3] = { (size_t) rb.n_reads * rb.stride_bytes, (size_t) rb.n_reads * 4, (size_t) rb.n_reads * rb.mask_stride };
 	LogSeg s;
 	s.rb = rb;
+	s.upper = upper;
 	for (int i = 0; i < 3; i++)
 	{
 		s.off[i] = h->log_used[i];
 		if (!bytes[i])
 			continue;
-		if ((rc = grow_device (h, &h->log_mem[i], &h->log_cap[i], h->log_used[i], h->log_used[i] + bytes[i])))
+		if ((rc = grow_device (h, &h->log_mem[i], &h->log_cap[i], h->log_used[i], h->log_used[i] + bytes[i], "read log")))
 			return rc;
 		CK (h, cudaMemcpyAsync (static_cast<uint8_t *> (h->log_mem[i]) + s.off[i], src[i], exact[i], cudaMemcpyDeviceToDevice, h->stream));
 		h->log_used[i] += bytes[i];
 	}
 	h->log.push_back (s);
 	h->pushed_upper += upper;
-	// record area: random minimizers start a new run every (w + 1) / 2 windows and every read ends one
-	// (C2: 0.124 records per window measured, 0.139 reserved; K = 63: 0.076; K = 127 on 150 bp: 0.069);
-	// if a batch needs more the emit kernel says so and sliced_flush re-emits into a larger area
-	const size_t rec = 4 * (size_t) h->geom.recw;
-	u64 want = h->rec_upper + (u64) ((double) upper * 2.2 / (h->geom.w + 1.0)) + rb.n_reads + rb.n_reads / 5 + 4096;
-	if (getenv ("SDTGPU_REC_DIV"))	// tests: an area that is too small
-		want = h->rec_upper + upper / env_u32 ("SDTGPU_REC_DIV", 3) + rb.n_reads / 8 + 4096;
-	size_t cap_b = h->rec0_cap * rec;
-	if ((rc = grow_device (h, (void **) &h->rec0, &cap_b, cap_b, want * rec)))
-		return rc;
-	h->rec0_cap = cap_b / rec;
-	h->rec_upper = want;
 	h->dirty = true;
-	return launch_emit (h, log_batch (h, h->log.back ()));
+	if (!h->hint && !h->epoch_open)
+		return SDTGPU_OK;	// no hint: the geometry waits for the end of the epoch (skm_collect)
+	if (h->chains_dropped)
+		return SDTGPU_OK;	// the next flush emits the whole read log again
+	if ((rc = skm_open_epoch (h)))
+		return rc;
+	h->emitted = true;
+	return emit_segment (h, h->log.back ());
 }
 
 u64 iter_slots (const sdtgpu *h) { return h->sliced ? h->n_store : h->cap; }
@@ -1262,13 +1537,17 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 		h->cap = capacity_hint ? pick_capacity (capacity_hint, slot_bytes (h->W)) : (1ull << 20);
 		int rc;
 		if (h->sliced)
-		{	// the first build writes every slot, empty ones included: no initialisation pass
-			if ((rc = skm_setup (h, capacity_hint)))
-				return rc;
-			CK (h, cudaMalloc (&h->table, h->cap * slot_bytes (h->W)));
-			if ((rc = skm_alloc (h)))
-				return rc;
+		{	// the geometry is fixed when the first records are made (skm_open_epoch), the node store is sized after the merge
+			h->hint = capacity_hint;
+			h->cap = 0;
+			CK (h, cudaMalloc (&h->d_small, 160 * sizeof (u64)));
+			CK (h, cudaMalloc (&h->d_failed, (size_t) MAX_FAILED * sizeof (SkmWork)));
+			CK (h, cudaMalloc (&h->d_items, (size_t) MAX_FAILED * sizeof (SkmWork)));
+			CK (h, cudaMallocHost (&h->h_small, 160 * sizeof (u64)));
+			CK (h, cudaMemsetAsync (h->d_small, 0, 160 * sizeof (u64), h->stream));
 			CK (h, cudaStreamSynchronize (h->stream));
+			if (capacity_hint && (rc = skm_open_epoch (h)))	// (reports a bad geometry at create time)
+				return rc;
 			return SDTGPU_OK;
 		}
 		CK (h, cudaMalloc (&h->table, h->cap * slot_bytes (h->W)));
@@ -1305,9 +1584,9 @@ void sdtgpu_destroy (sdtgpu_t *h)
 	cudaFree (h->staging); cudaFree (h->d_counts); cudaFree (h->d_cursors); cudaFree (h->d_seg_offsets); cudaFree (h->d_chunk_prefix); cudaFree (h->d_next_chunk);
 	for (auto e : h->ev_pool) cudaEventDestroy (e);
 	for (void *m : h->log_mem) cudaFree (m);
-	cudaFree (h->d_hist); cudaFree (h->d_off); cudaFree (h->d_cur2); cudaFree (h->d_seg_sum); cudaFree (h->d_small);
-	cudaFree (h->rec3); cudaFree (h->sub_mem);
-	cudaFree (h->d_failed); cudaFree (h->d_items); cudaFree (h->rec0); cudaFree (h->rec2);
+	for (auto &L : h->lv)
+		level_free (L);
+	cudaFree (h->d_small); cudaFree (h->d_failed); cudaFree (h->d_items); cudaFree (h->rx);
 	if (h->h_small) cudaFreeHost (h->h_small);
 	cudaFree (h->table);
 	cudaFree (h->d_ctr);
@@ -1327,14 +1606,20 @@ int sdtgpu_reset (sdtgpu_t *h)
 	CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
 	if (h->sliced)
 	{	// records, their per-slice counts and the read log go; the store is rewritten by the next build
-		if (!h->log.empty () || h->skm_world > 1)	// (exchange: sdtgpu_skm_import leaves its own counts in d_hist even if this rank pushed nothing)
+		CK (h, cudaMemsetAsync (h->d_small, 0, 8 * sizeof (u64), h->stream));
+		if (h->hint && h->epoch_open)
 		{
-			CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) h->geom.n_slices * sizeof (u32), h->stream));
-			CK (h, cudaMemsetAsync (h->d_small, 0, 8 * sizeof (u64), h->stream));
+			int rc = level_reset (h, h->lv[0]);
+			if (rc)
+				return rc;
 		}
+		else
+			h->epoch_open = false;	// no hint: the next epoch's geometry comes from what is pushed then (skm_open_epoch empties the chains)
+		h->emitted = false;
+		h->chains_dropped = false;
+		h->ord_bound_set = false;
 		h->log.clear ();
 		h->log_used[0] = h->log_used[1] = h->log_used[2] = 0;
-		h->rec_upper = 0;
 		h->n_store = 0;
 		h->table_built = false;
 		h->dirty = false;
@@ -1477,60 +1762,91 @@ int sdtgpu_set_owner (sdtgpu_t *h, int rank, int n_ranks)
 }
 
 // ---- super-k-mer exchange (multi-GPU sliced build): the slices are dealt to the ranks in contiguous
-// ranges; a rank turns ITS reads into records, groups them by (global) slice — which groups them by
-// owner — hands the runs to the caller's all-to-all, and builds its own slices from what it receives.
+// ranges; a rank turns ITS reads into records (chains over ALL slices), merges its own copies, hands each
+// owner's records to the caller's all-to-all, and builds its own slices from what it receives.
 int sdtgpu_skm_set_world (sdtgpu_t *h, int rank, int world)
 {
 	if (!h)
 		return SDTGPU_EINVAL;
 	if (!h->sliced)
 		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_set_world needs SDTGPU_F_SLICED");
-	if (world < 1 || rank < 0 || rank >= world)
-		return fail (h, SDTGPU_EINVAL, "sdtgpu_skm_set_world: need 0 <= rank < world");
+	if (world < 1 || world > 64 || rank < 0 || rank >= world)
+		return fail (h, SDTGPU_EINVAL, "sdtgpu_skm_set_world: need 0 <= rank < world <= 64");
 	if (!h->log.empty ())
 		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_set_world must precede the pushes of an epoch");
+	if (!h->hint)
+		return fail (h, SDTGPU_ESTATE, "the super-k-mer exchange needs capacity_hint (every rank must cut the minimizer space the same way)");
 	CK (h, cudaSetDevice (h->device));
-	if (h->n_local == 0)
-		h->n_local = h->geom.n_slices;	// from capacity_hint = the distinct k-mers expected on THIS rank
-	if ((u64) h->n_local * (u64) world > (1ull << 30))
-		return fail (h, SDTGPU_ERANGE, "too many slices");
-	CK (h, cudaStreamSynchronize (h->stream));
-	cudaFree (h->d_hist); cudaFree (h->d_off); cudaFree (h->d_cur2); cudaFree (h->d_seg_sum);
-	h->d_hist = nullptr; h->d_off = h->d_cur2 = h->d_seg_sum = nullptr;
+	if (h->epoch_open && ((u32) world != h->skm_world || (u32) rank != h->skm_rank))
+	{
+		h->epoch_open = false;
+		level_free (h->lv[0]);
+	}
 	h->skm_world = (u32) world;
 	h->skm_rank = (u32) rank;
-	SkmGeom &g = h->geom;
-	g.n_slices = h->n_local * (u32) world;
-	g.slice_a = slice_of_min_host (mmer_hash (0), g.n_slices);
-	const u32 nseg = (g.n_slices + SCAN_SEG - 1) / SCAN_SEG;
-	CK (h, cudaMalloc (&h->d_hist, (size_t) g.n_slices * sizeof (u32)));
-	CK (h, cudaMalloc (&h->d_off, ((size_t) g.n_slices + 1) * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_cur2, (size_t) g.n_slices * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_seg_sum, (size_t) nseg * sizeof (u64)));
-	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) g.n_slices * sizeof (u32), h->stream));
+	return skm_open_epoch (h);	// the geometry is known from here on (sdtgpu_slice_geometry)
+}
+
+int sdtgpu_skm_set_ordinal_bound (sdtgpu_t *h, uint64_t n_reads_all_ranks)
+{
+	if (!h)
+		return SDTGPU_EINVAL;
+	h->ord_end = std::max<u64> (h->ord_end, n_reads_all_ranks * h->maxwin);
+	h->ord_bound_set = true;
 	return SDTGPU_OK;
 }
 
-int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *offsets)
+int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *starts, uint64_t *counts)
 {
 	int rc;
-	if (!h || !d_records || !offsets)
+	if (!h || !d_records || !starts || !counts)
 		return SDTGPU_EINVAL;
 	if (!h->sliced)
 		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_stage needs SDTGPU_F_SLICED");
 	CK (h, cudaSetDevice (h->device));
+	if ((rc = skm_open_epoch (h)))
+		return rc;
+	ChainLevel &L = h->lv[0];
+	const u32 world = h->skm_world, per_owner = world > 1 ? h->n_local : L.n_chains;
 	u64 n_rec = 0;
-	if (h->log.empty ())
-		CK (h, cudaMemsetAsync (h->d_small, 0, sizeof (u64), h->stream));
+	h->emitted = true;	// (a rank without reads still takes part)
 	if ((rc = skm_collect (h, &n_rec)))
 		return rc;
 	h->n_records = n_rec;
-	if ((rc = skm_group (h, n_rec, h->geom.n_slices)))
+	u64 n_blocks = 0;
+	if ((rc = level_list (h, L, &n_blocks)))
 		return rc;
-	for (u32 r = 0; r <= h->skm_world; r++)	// first record of every rank's slice range
-		CK (h, cudaMemcpyAsync (offsets + r, h->d_off + (size_t) r * h->n_local_or_all (), sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	// records per owner (an upper bound of what survives the merge) -> where each owner's region starts
+	u64 *d_reg = h->d_small + 8;	// [world] region starts, [world] cursors
+	chain_owner_count_kernel<<<world, 256, 0, h->stream>>> (level_chains (h, L), per_owner, reinterpret_cast<unsigned long long *> (d_reg));
+	CK (h, cudaGetLastError ());
+	h->all_launches++;
+	CK (h, cudaMemcpyAsync (h->h_small + 8, d_reg, world * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 	CK (h, cudaStreamSynchronize (h->stream));
-	*d_records = h->rec2;
+	u64 run = 0;
+	for (u32 r = 0; r < world; r++)
+	{
+		const u64 c = h->h_small[8 + r];
+		starts[r] = run;
+		h->h_small[8 + r] = run;
+		h->h_small[8 + world + r] = 0;
+		run += c;
+	}
+	CK (h, cudaMemcpyAsync (d_reg, h->h_small + 8, 2 * world * sizeof (u64), cudaMemcpyHostToDevice, h->stream));
+	{
+		const size_t rec = 4 * (size_t) h->geom.recw;
+		size_t cap_b = L.out_cap * rec;
+		if ((rc = grow_device (h, (void **) &L.out, &cap_b, 0, std::max<u64> (run, 1) * rec)))
+			return rc;
+		L.out_cap = cap_b / rec;
+	}
+	if ((rc = launch_merge (h, L, false, n_rec, per_owner, d_reg, d_reg + world)))
+		return rc;
+	CK (h, cudaMemcpyAsync (h->h_small + 8 + world, d_reg + world, world * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+	CK (h, cudaStreamSynchronize (h->stream));
+	for (u32 r = 0; r < world; r++)
+		counts[r] = h->h_small[8 + world + r];
+	*d_records = L.out;
 	return SDTGPU_OK;
 }
 
@@ -1543,11 +1859,11 @@ int sdtgpu_skm_import_buffer (sdtgpu_t *h, uint64_t n_records, void **d_buffer)
 		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_import_buffer needs SDTGPU_F_SLICED");
 	CK (h, cudaSetDevice (h->device));
 	const size_t rec = 4 * (size_t) h->geom.recw;
-	size_t cap_b = h->rec0_cap * rec;
-	if ((rc = grow_device (h, (void **) &h->rec0, &cap_b, 0, std::max<u64> (n_records, 1) * rec)))
+	size_t cap_b = h->rx_cap * rec;
+	if ((rc = grow_device (h, (void **) &h->rx, &cap_b, 0, std::max<u64> (n_records, 1) * rec)))
 		return rc;
-	h->rec0_cap = cap_b / rec;
-	*d_buffer = h->rec0;
+	h->rx_cap = cap_b / rec;
+	*d_buffer = h->rx;
 	return SDTGPU_OK;
 }
 
@@ -1558,24 +1874,51 @@ int sdtgpu_skm_import (sdtgpu_t *h, uint64_t n_records)
 		return SDTGPU_EINVAL;
 	if (!h->sliced)
 		return fail (h, SDTGPU_ESTATE, "sdtgpu_skm_import needs SDTGPU_F_SLICED");
-	if (n_records > h->rec0_cap)
+	if (n_records > h->rx_cap)
 		return fail (h, SDTGPU_EINVAL, "sdtgpu_skm_import: more records than sdtgpu_skm_import_buffer made room for");
 	CK (h, cudaSetDevice (h->device));
-	const u32 n_local = h->n_local_or_all ();
-	h->h_small[5] = n_records;
-	CK (h, cudaMemcpyAsync (h->d_small, h->h_small + 5, sizeof (u64), cudaMemcpyHostToDevice, h->stream));
-	CK (h, cudaMemsetAsync (h->d_hist, 0, (size_t) n_local * sizeof (u32), h->stream));
-	if (n_records)
-	{
-		const unsigned grid = (unsigned) std::min<u64> ((n_records + SCAT_NT - 1) / SCAT_NT, (u64) h->sm_count * 8);
-		TimedLaunch tl (h, 1);
-		skm_recount_kernel<<<grid, SCAT_NT, 0, h->stream>>> (h->rec0, n_records, h->geom.recw, h->skm_rank * n_local, n_local, h->d_hist, h->d_ctr);
-	}
-	CK (h, cudaGetLastError ());
-	h->n_store = 0;
-	if ((rc = skm_group (h, n_records, n_local)))
+	if ((rc = skm_open_epoch (h)))
 		return rc;
-	return skm_build_all (h, n_records, n_local);
+	const u32 n_local = h->skm_world > 1 ? h->n_local : h->geom.n_slices;
+	ChainLevel &R = h->lv[2];
+	if ((rc = level_create (h, R, n_local)))
+		return rc;
+	const u64 hold = (u64) std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS) * CH_SB;
+	for (int attempt = 0;; attempt++)
+	{
+		const u64 slack = attempt ? n_records / CH_BLK : n_records / (8 * CH_BLK);	// (blocks the CTAs drop when they refill their ranges)
+		if ((rc = level_reserve (h, R, n_local + n_records / CH_BLK + slack + hold + 4096)))
+			return rc;
+		if (n_records)
+		{
+			const unsigned grid = (unsigned) std::min<u64> ((n_records + AP_TILE - 1) / AP_TILE, std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS));
+			TimedLaunch tl (h, 2);
+			const SkmChains c = level_chains (h, R);
+			const u32 lo = h->skm_rank * n_local;
+			if (h->geom.recw == 8)
+				skm_append_kernel<8><<<grid, AP_NT, 0, h->stream>>> (c, h->rx, n_records, lo);
+			else if (h->geom.recw == 12)
+				skm_append_kernel<12><<<grid, AP_NT, 0, h->stream>>> (c, h->rx, n_records, lo);
+			else
+				skm_append_kernel<16><<<grid, AP_NT, 0, h->stream>>> (c, h->rx, n_records, lo);
+		}
+		CK (h, cudaGetLastError ());
+		CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaStreamSynchronize (h->stream));
+		if (h->h_small[3] & OVF_FOREIGN)
+			return fail (h, SDTGPU_EINVAL, "super-k-mer exchange: a received record belongs to another rank's slices");
+		if (!(h->h_small[3] & OVF_RECORDS))
+			break;
+		if (attempt == 1)
+			return fail (h, SDTGPU_ERANGE, "record pool overflow persists (import)");
+		CK (h, cudaMemsetAsync (&h->d_ctr->overflow, 0, sizeof (u64), h->stream));
+		if ((rc = level_reset (h, R)))
+			return rc;
+	}
+	h->n_store = 0;
+	if (!h->ord_bound_set && h->skm_world > 1)
+		h->ord_end = ~0ull;	// records of other ranks' reads: their ordinals are not bounded by what this rank pushed
+	return skm_build_level (h, R, true, n_records, true);
 }
 
 size_t sdtgpu_record_bytes (const sdtgpu_t *h) { return h ? 8 * (size_t) (h->W + 1) : 0; }
@@ -1968,7 +2311,7 @@ int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[12])
 		return SDTGPU_ESTATE;
 	out[0] = h->geom.n_slices; out[1] = h->geom.slice_slots; out[2] = h->geom.m; out[3] = h->geom.w;
 	out[4] = 4 * (uint64_t) h->geom.recw; out[5] = h->n_records; out[6] = h->n_store; out[7] = h->n_retried;
-	out[8] = h->n_merged; out[9] = out[10] = out[11] = 0;
+	out[8] = h->n_merged; out[9] = h->n_items; out[10] = out[11] = 0;
 	return SDTGPU_OK;
 }
 

@@ -89,13 +89,14 @@ class Exchange:
         self.main = torch.cuda.ExternalStream(g.stream, device=self.dev)
         self.aux = torch.cuda.ExternalStream(g.aux_stream, device=self.dev)
 
-    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None):
+    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None, d_nmask=None):
+        """d_nmask: the -n N mask of the round's reads (stride / 2 bytes per read), for handles created with n_kmer."""
         b = self.r & 1
         self.r += 1
         with torch.cuda.stream(self.aux):
             self.aux.wait_event(self.inserted[b])          # buffer set b is free again
             self.counts[b].zero_()
-            g.bucket_reads_device(d_packed, d_lens, None, n_reads, uniform_len, stride, first_read_ordinal,
+            g.bucket_reads_device(d_packed, d_lens, d_nmask, n_reads, uniform_len, stride, first_read_ordinal,
                                   self.world, self.send[b], self.cap, self.counts[b])
             total, rc = exchange_records(self.send[b], self.counts[b], self.recv[b])
             self.received.record(self.aux)
@@ -119,6 +120,7 @@ class ReplicatedReads:
         g.set_owner(rank, world)
         self.buf = [torch.empty((world, max_round_reads, stride), dtype=torch.uint8, device=dev) for _ in range(2)]
         self.lens = [torch.empty((world, max_round_reads), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.mask = None        # [world, max_round_reads, stride / 2] x 2, made when a round first brings an N mask
         self.meta = [torch.empty((world, 2), dtype=torch.int64, device=dev) for _ in range(2)]
         self.inserted = [torch.cuda.Event() for _ in range(2)]
         self.received = torch.cuda.Event()
@@ -131,11 +133,13 @@ class ReplicatedReads:
         self.main = torch.cuda.ExternalStream(g.stream, device=self.dev)
         self.aux = torch.cuda.ExternalStream(g.aux_stream, device=self.dev)
 
-    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None):
+    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None, d_nmask=None):
         """d_packed: this rank's reads of the round ([n_reads, stride] uint8 on the device).  Ranks may
-        bring different numbers of reads (<= max_round_reads)."""
+        bring different numbers of reads (<= max_round_reads).  d_nmask: their -n N mask (all ranks or none)."""
         b = self.r & 1
         self.r += 1
+        if d_nmask is not None and self.mask is None:
+            self.mask = [torch.zeros((self.world, self.max_round_reads, stride // 2), dtype=torch.uint8, device=self.dev) for _ in range(2)]
         with torch.cuda.stream(self.aux):
             self.aux.wait_event(self.inserted[b])
             mine = torch.tensor([first_read_ordinal, n_reads], dtype=torch.int64, device=self.dev)
@@ -149,6 +153,10 @@ class ReplicatedReads:
                 ls = self.lens[b][self.rank]
                 ls[:n_reads].copy_(d_lens[:n_reads])
                 dist.all_gather_into_tensor(self.lens[b].view(-1), ls, group=self.group)
+            if d_nmask is not None:
+                mk = self.mask[b][self.rank]
+                mk[:n_reads].copy_(d_nmask[:n_reads].reshape(n_reads, -1))
+                dist.all_gather_into_tensor(self.mask[b].view(-1), mk.reshape(-1), group=self.group)
             meta = self.meta[b].tolist()
             self.received.record(self.aux)
         self.nvlink_bytes += sum(m[1] for i, m in enumerate(meta) if i != self.rank) * self.stride
@@ -156,8 +164,8 @@ class ReplicatedReads:
             self.main.wait_event(self.received)
             for s_rank, (first, n) in enumerate(meta):
                 if n:
-                    g.push_reads(self.buf[b][s_rank], self.lens[b][s_rank] if d_lens is not None else None, None,
-                                 n_reads=int(n), uniform_len=uniform_len, stride_bytes=stride,
+                    g.push_reads(self.buf[b][s_rank], self.lens[b][s_rank] if d_lens is not None else None,
+                                 self.mask[b][s_rank] if d_nmask is not None else None, n_reads=int(n), uniform_len=uniform_len, stride_bytes=stride,
                                  first_read_ordinal=int(first), device=True)
             self.inserted[b].record(self.main)
 
@@ -165,21 +173,38 @@ class ReplicatedReads:
         pass
 
 
-def exchange_runs(send: torch.Tensor, send_counts, words: int, make_recv, group=None):
+def exchange_runs(send_list, words: int, make_recv, group=None):
     """The super-k-mer exchange's plumbing, backend-agnostic (NCCL on the GPUs, gloo in tests/test_exchange_cpu.py).
-    send: flat int64 tensor holding, back to back, the records for rank 0, 1, ... (`send_counts[r]` records of
-    `words` int64 each — the runs sdtgpu_skm_stage hands out are already in this order, so nothing is packed).
-    make_recv(total_records) -> flat int64 tensor to receive into (sdtgpu_skm_import_buffer).
-    Two collectives: the counts, then the records.  Returns (total_records, recv_counts)."""
+    send_list[r]: flat int64 tensor with the records for rank r (`words` int64 each; views into the buffer that
+    sdtgpu_skm_stage hands out — nothing is packed).  make_recv(total_records) -> flat int64 tensor to receive into
+    (sdtgpu_skm_import_buffer); the runs arrive in source-rank order.
+    Two collectives: the counts, then the records (one grouped send/recv).  Returns (total_records, recv_counts)."""
     world = dist.get_world_size(group)
-    sc = torch.tensor([int(x) for x in send_counts], dtype=torch.int64, device=send.device)
-    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    rank = dist.get_rank(group)
+    dev = send_list[0].device
+    send_counts = [int(t.numel()) // words for t in send_list]
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    rc = torch.empty(world, dtype=torch.int64, device=dev)
     dist.all_to_all_single(rc, sc, group=group)
     recv_counts = [int(x) for x in rc.tolist()]
     total = sum(recv_counts)
     recv = make_recv(total)
-    dist.all_to_all_single(recv, send, output_split_sizes=[n * words for n in recv_counts],
-                           input_split_sizes=[int(n) * words for n in send_counts], group=group)
+    ops, off = [], 0
+    for src, n in enumerate(recv_counts):
+        seg = recv[off * words:(off + n) * words]
+        off += n
+        if n == 0:
+            continue
+        if src == rank:
+            seg.copy_(send_list[rank])      # own records: device-local copy, never touches the fabric
+        else:
+            ops.append(dist.P2POp(dist.irecv, seg, src, group=group))
+    for dst in range(world):
+        if dst != rank and send_counts[dst]:
+            ops.append(dist.P2POp(dist.isend, send_list[dst], dst, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):      # NCCL: one grouped ncclSend/ncclRecv launch
+            req.wait()
     return total, recv_counts
 
 
@@ -204,6 +229,7 @@ class SkmExchange:
     def __init__(self, pkg, g, world: int, rank: int, dev, group=None):
         self.world, self.rank, self.dev, self.group = world, rank, dev, group
         self.nvlink_bytes = 0
+        self.collective_ms = 0.0        # device time of the counts + records exchange (CUDA events on the handle's stream)
         self.rebind(g)
 
     def rebind(self, g):
@@ -214,6 +240,7 @@ class SkmExchange:
         self.aux = torch.cuda.ExternalStream(g.aux_stream, device=self.dev)     # the caller may stage a round's reads on it
         self.inserted = [torch.cuda.Event() for _ in range(2)]
         self.r = 0
+        self.reads_end = 0
         # every rank must cut the minimizer space the same way: same capacity_hint, K and minimizer length
         mine = torch.tensor([geo["n_slices"], geo["m"], geo["slice_slots"]], dtype=torch.int64, device=self.dev)
         seen = torch.empty((self.world, 3), dtype=torch.int64, device=self.dev)
@@ -221,23 +248,30 @@ class SkmExchange:
         if not bool((seen == mine).all()):
             raise ValueError(f"SkmExchange: ranks disagree on the slice geometry (pass the same capacity_hint everywhere): {seen.tolist()}")
 
-    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None):
+    def round(self, g, d_packed, n_reads, uniform_len, stride, first_read_ordinal, d_lens=None, d_nmask=None):
         b = self.r & 1
         self.r += 1
+        self.reads_end = max(self.reads_end, int(first_read_ordinal) + int(n_reads))
         staged = torch.cuda.Event()
         staged.record(self.aux)                     # whatever the caller queued on the auxiliary stream (an H2D copy of the round)
         self.main.wait_event(staged)
-        g.push_reads(d_packed, d_lens, None, n_reads=int(n_reads), uniform_len=uniform_len, stride_bytes=stride,
+        g.push_reads(d_packed, d_lens, d_nmask, n_reads=int(n_reads), uniform_len=uniform_len, stride_bytes=stride,
                      first_read_ordinal=int(first_read_ordinal), device=True)
         self.inserted[b].record(self.main)          # the round's buffer is free again (the library keeps its own copy of the reads)
 
     def flush(self, g):
-        ptr, offs = g.skm_stage()                   # synchronises the handle's stream
+        bound = torch.tensor([self.reads_end], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(bound, op=dist.ReduceOp.MAX, group=self.group)
+        g.skm_set_ordinal_bound(int(bound.item()))  # reads of all ranks this epoch: 32-bit ordinals in the slice images when they fit
+        ptr, starts, counts = g.skm_stage()         # merges this rank's copies, packs by owner; synchronises the handle's stream
         rb, w8 = self.rec_bytes, self.rec_bytes // 8
-        send_counts = [offs[r + 1] - offs[r] for r in range(self.world)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self.main):
-            send = _wrap(ptr + offs[0] * rb, (offs[-1] - offs[0]) * rb, self.dev)
-            total, _ = exchange_runs(send, send_counts, w8, lambda n: _wrap(g.skm_import_buffer(n), n * rb, self.dev), group=self.group)
-            self.nvlink_bytes += (sum(send_counts) - send_counts[self.rank]) * rb
-        g.skm_import(total)                         # on the handle's stream, after the all-to-all
+            send = [_wrap(ptr + starts[r] * rb, counts[r] * rb, self.dev) for r in range(self.world)]
+            e0.record(self.main)
+            total, _ = exchange_runs(send, w8, lambda n: _wrap(g.skm_import_buffer(n), n * rb, self.dev), group=self.group)
+            e1.record(self.main)
+            self.nvlink_bytes += (sum(counts) - counts[self.rank]) * rb
+        g.skm_import(total)                         # on the handle's stream, after the exchange (drains the stream)
+        self.collective_ms += e0.elapsed_time(e1)
         return total

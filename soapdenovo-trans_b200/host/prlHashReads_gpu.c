@@ -29,8 +29,8 @@
  * separated CUDA ordinals; with more than one, every GPU receives every batch and inserts the k-mers
  * it owns — the reference's own "each worker scans the batch and keeps hash % thrd_num == id",
  * prlHashReads.c:79-88 — and the nodes of all GPUs are merged at hand-back), SDTGPU_DEVICE (one
- * ordinal), SDTGPU_CAPACITY_HINT (expected distinct k-mers in total; 0 = grow on the device),
- * SDTGPU_BATCH_READS.
+ * ordinal), SDTGPU_CAPACITY_HINT (expected distinct k-mers in total; optional), SDTGPU_DIRECT=1 (single-pass
+ * insert into one open-addressing table instead of the sliced build), SDTGPU_BATCH_READS.
  * BAM libraries (b=) are not supported by this path.
  */
 #include "stdinc.h"
@@ -164,8 +164,9 @@ boolean prlRead2HashTable (char *libfile, char *outfile)
 			hs.n_gpus = 1;
 		}
 	}
-	/* SDTGPU_SLICED=1 (needs SDTGPU_CAPACITY_HINT): the sliced build instead of the single-pass insert */
-	if ((env = getenv ("SDTGPU_SLICED")) && atoi (env) > 0 && hint)
+	/* the sliced build is the default: it needs no estimate of the distinct k-mers (SDTGPU_CAPACITY_HINT only tunes
+	 * it); SDTGPU_DIRECT=1 selects the single-pass insert instead */
+	if (!((env = getenv ("SDTGPU_DIRECT")) && atoi (env) > 0))
 		flags |= SDTGPU_F_SLICED;
 	for (b = 0; b < hs.n_gpus; b++)
 	{

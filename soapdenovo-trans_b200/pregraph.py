@@ -80,7 +80,8 @@ def library() -> C.CDLL:
     L.sdtgpu_push_reads_device.argtypes = [vp, vp, vp, vp, u64, u32, u32, u64]
     L.sdtgpu_set_owner.argtypes = [vp, i32, i32]
     L.sdtgpu_skm_set_world.argtypes = [vp, i32, i32]
-    L.sdtgpu_skm_stage.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.sdtgpu_skm_stage.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    L.sdtgpu_skm_set_ordinal_bound.argtypes = [vp, u64]
     L.sdtgpu_skm_import_buffer.argtypes = [vp, u64, C.POINTER(vp)]
     L.sdtgpu_skm_import.argtypes = [vp, u64]
     L.sdtgpu_record_bytes.restype = C.c_size_t
@@ -247,11 +248,14 @@ class PregraphGPU:
         self._skm_world = world
 
     def skm_stage(self):
-        """-> (device address of the records grouped by slice, offsets[world + 1] in records)."""
+        """-> (device address of the records, starts[world], counts[world] in records): rank r's share."""
         world = getattr(self, "_skm_world", 1)
-        ptr, offs = C.c_void_p(), (C.c_uint64 * (world + 1))()
-        self._ck(self.L.sdtgpu_skm_stage(self.h, C.byref(ptr), offs))
-        return int(ptr.value or 0), [int(x) for x in offs]
+        ptr, starts, counts = C.c_void_p(), (C.c_uint64 * world)(), (C.c_uint64 * world)()
+        self._ck(self.L.sdtgpu_skm_stage(self.h, C.byref(ptr), starts, counts))
+        return int(ptr.value or 0), [int(x) for x in starts], [int(x) for x in counts]
+
+    def skm_set_ordinal_bound(self, n_reads_all_ranks: int):
+        self._ck(self.L.sdtgpu_skm_set_ordinal_bound(self.h, n_reads_all_ranks))
 
     def skm_import_buffer(self, n_records: int) -> int:
         ptr = C.c_void_p()
@@ -320,7 +324,7 @@ class PregraphGPU:
         out = (C.c_uint64 * 12)()
         self._ck(self.L.sdtgpu_slice_geometry(self.h, out))
         return dict(n_slices=out[0], slice_slots=out[1], m=out[2], mmers_per_window=out[3], record_bytes=out[4],
-                    n_records=out[5], n_nodes=out[6], retried_items=out[7], n_records_merged=out[8])
+                    n_records=out[5], n_nodes=out[6], retried_items=out[7], n_records_merged=out[8], work_items=out[9])
 
     def kernel_times(self, reset: bool = True):
         """(ms[3], launches[3]) for insert / partition-count / partition-scatter kernels."""

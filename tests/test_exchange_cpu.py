@@ -95,13 +95,13 @@ def _worker_runs(rank, world, port, words, q):
             # the runs for rank 0, 1, ... back to back, as sdtgpu_skm_stage hands them out; a record encodes (src, dst, index)
             recs = [torch.full((int(counts[d]), words), 0, dtype=torch.int64) + (rank * 1_000_000 + d * 10_000) +
                     torch.arange(int(counts[d]), dtype=torch.int64)[:, None] for d in range(world)]
-            send = torch.cat(recs).reshape(-1)
+            send = [r.reshape(-1) for r in recs]
             got = {}
 
             def make_recv(n):
                 got["buf"] = torch.full((n * words,), -1, dtype=torch.int64)
                 return got["buf"]
-            total, rc = exchange_runs(send, counts.tolist(), words, make_recv)
+            total, rc = exchange_runs(send, words, make_recv)
             allc = [None] * world
             dist.all_gather_object(allc, counts.tolist())
             want = [allc[src][rank] for src in range(world)]

@@ -54,15 +54,6 @@ def test_sliced_minimizer_lengths(pkg, oracle, tiny_transcriptome, monkeypatch, 
     check_against_oracle(pkg, oracle, reads, lens, K, kw, d=0, batches=2, hint=400_000, sliced=True)
 
 
-@pytest.mark.parametrize("K,kw", [(31, 1), (25, 1), (63, 2), (127, 4)])
-def test_sliced_two_ctas_per_sm(pkg, oracle, tiny_transcriptome, monkeypatch, K, kw):
-    """SDTGPU_BUILD_NT=512: half-size slice images, two build CTAs of 512 threads per SM."""
-    monkeypatch.setenv("SDTGPU_BUILD_NT", "512")
-    L = 150 if K > 63 else 100
-    reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, L, 3 + K, ragged=30)
-    check_against_oracle(pkg, oracle, reads, lens, K, kw, d=1, batches=2, hint=400_000, sliced=True)
-
-
 @pytest.mark.parametrize("K,kw", [(31, 1), (63, 2), (127, 4)])
 def test_skm_stage_import_one_rank(pkg, oracle, tiny_transcriptome, K, kw):
     """The two halves of the multi-GPU super-k-mer exchange on one GPU: stage (records grouped by slice),
@@ -79,10 +70,10 @@ def test_skm_stage_import_one_rank(pkg, oracle, tiny_transcriptome, K, kw):
     with pkg.PregraphGPU(K, kw, L, capacity_hint=400_000, sliced=True) as g:
         g.skm_set_world(0, 1)
         g.push_reads(packed, lens, None, n_reads=len(reads), stride_bytes=stride)
-        ptr, offs = g.skm_stage()
-        n = offs[1] - offs[0]
+        ptr, starts, counts = g.skm_stage()
+        n = counts[0]
         rb = g.slice_geometry()["record_bytes"]
-        assert offs[0] == 0 and n == g.slice_geometry()["n_records"] > 0
+        assert starts[0] == 0 and 0 < n <= g.slice_geometry()["n_records"]       # (this rank's copies are merged before they travel)
         src = _wrap(ptr, n * rb, dev).clone()
         torch.cuda.synchronize()
         dst = _wrap(g.skm_import_buffer(n), n * rb, dev)
@@ -177,11 +168,35 @@ def test_sliced_reset_and_reuse(pkg, oracle, tiny_transcriptome):
         assert np.array_equal(pkg.nodes_to_records(g.export_nodes(8)), oracle.sorted_multiset(ref.records))
 
 
-def test_sliced_errors(pkg, tiny_transcriptome):
-    with pytest.raises(pkg.SdtGpuError):
-        pkg.PregraphGPU(31, 1, 100, capacity_hint=0, sliced=True)      # the sliced build needs a hint
-    # a hint far too small: a slice fills up and the build reports it instead of dropping k-mers
+def test_sliced_without_hint_and_with_a_hint_far_too_small(pkg, oracle, tiny_transcriptome):
+    """capacity_hint = 0: the reads are logged, the geometry comes from their number at the end of the epoch.
+    A hint far too small: one slice for everything — it overflows, is cut into sub-slices in one pass
+    (skm_split_kernel) and the node store grows; nothing is dropped, nothing fails."""
     reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, 100, 1)
-    with pytest.raises(pkg.SdtGpuError) as e:
-        run_gpu(pkg, reads, lens, 31, 1, hint=1000, sliced=True)
-    assert e.value.code == 4
+    for hint in (0, 1000):
+        check_against_oracle(pkg, oracle, reads, lens, 31, 1, d=1, batches=3, hint=hint, sliced=True)
+    check_against_oracle(pkg, oracle, reads, lens, 63, 2, d=0, batches=2, hint=0, sliced=True)
+    reads, lens = make_dataset(pkg, tiny_transcriptome, 1500, 150, 2)
+    check_against_oracle(pkg, oracle, reads, lens, 127, 4, d=0, batches=2, hint=500, sliced=True)
+
+
+@pytest.mark.parametrize("K,kw", [(31, 1), (63, 2), (127, 4)])
+def test_sliced_split_into_sub_slices(pkg, oracle, monkeypatch, K, kw):
+    """Config-5 flavour with small images: the hot loci overflow their slices by far and go through the
+    one-pass split; with SDTGPU_NO_SPLIT the same input goes through the hash-filtered retries."""
+    monkeypatch.setenv("SDTGPU_SLICE_SLOTS", "256")
+    L = 150 if K > 63 else 100
+    tr = pkg.synth.make_transcriptome(60, 13, hot=2)
+    reads, lens = make_dataset(pkg, tr, 20000, L, 17)
+    ref = oracle.run_hashing(reads, lens, K, kw, 8, 0)
+    for no_split in (False, True):
+        if no_split:
+            monkeypatch.setenv("SDTGPU_NO_SPLIT", "1")
+        g, freq, st = run_gpu(pkg, reads, lens, K, kw, d=0, batches=3, hint=int(ref.nodes * 1.05), sliced=True)
+        try:
+            assert g.slice_geometry()["retried_items"] > 0
+            assert (st.n_instances, st.n_nodes, st.n_linear) == (ref.instances, ref.nodes, ref.linear)
+            assert np.array_equal(freq, ref.kmerfreq)
+            assert np.array_equal(pkg.nodes_to_records(g.export_nodes(8)), oracle.sorted_multiset(ref.records))
+        finally:
+            g.close()

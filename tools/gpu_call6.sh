@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_sliced.py -x -q -m gpu > $O/c6_tests.log 2>&1
+tail -15 $O/c6_tests.log
+summ() { python - "$1" <<'PY'
+import json,sys
+f=sys.argv[1]
+try:
+    j=json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, round(j['value']/1e9,2), round(j['ms_per_step'],2), 'e2e', j['e2e'] and round(j['e2e']['value']/1e9,2))
+    ph=j['roofline']['sliced']['phases']
+    print({k:round(v['ms_per_step'],2) for k,v in ph.items()}, j['roofline']['sliced']['geometry'])
+except Exception as e: print(f, 'ERR', e)
+PY
+}
+timeout 400 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > $O/c6_bench.json 2> $O/c6_bench.err; tail -c 600 $O/c6_bench.err; summ $O/c6_bench.json
