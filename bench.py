@@ -73,6 +73,8 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
 
     def run(self):
+        if self.index < 0:      # (several GPUs: rank 0 samples its GPU; every nvidia-smi call takes a driver-wide lock)
+            return
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
@@ -81,7 +83,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.5)
 
     def summary(self):
         sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
@@ -361,7 +363,7 @@ def main():
     g.kernel_time(reset=True)
     if exch is not None and hasattr(exch, "collective_ms"):
         exch.collective_ms = 0.0
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank if rank == 0 else -1)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -75,17 +75,17 @@ typedef struct sdtgpu_stats {
  * and creatThrds.  K odd, 13..127 (pregraph.c:38-59).  key_words is the reference build being
  * served (1 = MER31, 2 = MER63, 4 = MER127) and fixes hash_kmer's byte count and the exported
  * kmer_t size; the device key width is ceil(2K/64) words independently of it.
- * capacity_hint = expected distinct k-mers (0: start small and grow by device re-hash).
+ * capacity_hint = expected distinct k-mers (0: single-pass insert: start small and grow by device re-hash;
+ * sliced build: sized from the number of windows pushed).
  * device = CUDA ordinal.  flags: SDTGPU_F_* */
 #define SDTGPU_F_NKMER     1u	/* the reference's -n (N_kmer): windows containing N become key 0 without links */
-#define SDTGPU_F_PARTITIONED 2u	/* experimental: stage records, radix-partition them by table slot range and
-				 * insert bucket by bucket (L2-resident table regions) instead of the default
-				 * single-pass insert; measured slower on B200 */
-#define SDTGPU_F_SLICED    4u	/* sliced build: pushes turn reads into super-k-mer records (runs of windows that share
-				 * a minimizer, bases included) and count them per table slice; sdtgpu_sync / finalize /
-				 * export move every record to its slice and build each slice in shared memory, one
-				 * CTA per slice, into a compact node store.  No random DRAM access; needs
-				 * capacity_hint.  Same multiset, same hand-back layout as the single-pass insert. */
+#define SDTGPU_F_SLICED    4u	/* sliced build (the default of the drop-in and of bench.py): pushes turn reads into super-k-mer
+				 * records (runs of windows that share a minimizer, bases included) appended to the chain of
+				 * their table slice; sdtgpu_sync / finalize / export merge copies, cut the chains into work
+				 * items and build each item in shared memory, one CTA per item, into a compact node store.
+				 * No random DRAM access.  capacity_hint is optional (0: the reads are logged and the slice
+				 * count comes from the number of windows pushed; slices that overflow are split, the store
+				 * grows).  Same multiset, same hand-back layout as the single-pass insert. */
 int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_read_len,
 		   uint64_t capacity_hint, unsigned flags);
 void sdtgpu_destroy (sdtgpu_t *h);

@@ -9,10 +9,7 @@
 //            the queue is drained with every lane issuing an upsert;
 //         0  upsert straight from the chop loop (kept for A/B, SDTGPU_NO_QUEUE=1);
 //         1  send side of the record exchange: records into per-owner bins;
-//         2, 3  count and scatter passes of the exact radix partition by table slot range
-//            (experimental partitioned path);
 //         4  per reference set, the largest instance ordinal of the batch (hand-back helper).
-//   insert_staged_kernel   upserts staged records bucket by bucket (experimental partitioned path).
 //   insert_records_kernel  receive side of the record exchange.
 //   init / rehash / finalize / export / checksum kernels: table maintenance, the post-pass
 //       (thread_delow prlHashReads.c:844-887, thread_mark :911-967) and verification.
@@ -54,10 +51,10 @@ struct Counters
 
 struct Bins
 {
-	u64 *records;		// MODE 1: n_ranks x capacity x (W + 1) u64; MODE 3: the staging area
-	u64 *counts;		// per bin: fill (MODE 1), count (MODE 2), cursor (MODE 3), last ordinal + 1 (MODE 4)
+	u64 *records;		// MODE 1: n_ranks x capacity x (W + 1) u64
+	u64 *counts;		// per bin: fill (MODE 1), last ordinal + 1 (MODE 4)
 	u64 capacity;		// MODE 1: records per bin; MODE 4: key_words of the reference build
-	u32 n_ranks;		// bins: owner ranks (MODE 1), slot-range buckets (MODE 2, 3), reference sets (MODE 4)
+	u32 n_ranks;		// bins: owner ranks (MODE 1), reference sets (MODE 4)
 };
 
 __device__ __forceinline__ u32 bswap32 (u32 x) { return __byte_perm (x, 0, 0x0123); }
@@ -187,7 +184,7 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 	u32 *tile = smem + TILE_PAD;
 	u32 *prefix = smem + TILE_PAD + rb.tile_reads * sw + TILE_PAD;	// tile_reads + 1 entries
 	u32 *mtile = prefix + rb.tile_reads + 4;
-	u32 *hist = mtile + rb.tile_reads * mw;	// MODE 2 / 3: bins.n_ranks counters (MODE 3: + u64 bases behind them)
+	u32 *hist = mtile + rb.tile_reads * mw;	// MODE 1: bins.n_ranks counters + u64 bases behind them
 	u64 *base = reinterpret_cast<u64 *> (hist + ((bins.n_ranks + 1) & ~1u));
 	__shared__ u32 warp_sums[BLOCK / 32];
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
@@ -290,13 +287,13 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		__syncthreads ();
 		instances += (tid == 0) ? total : 0;
 
-		// MODE 1 / 3 walk the tile twice: sweep 0 counts the tile's records per bin, ONE global atomic per
+		// MODE 1 walks the tile twice: sweep 0 counts the tile's records per bin, ONE global atomic per
 		// non-empty bin then reserves their space, sweep 1 writes the records (chopping twice is cheap;
 		// a contended global cursor atomic per warp was 3x slower, profiles/r1_multi_gpu.md)
 		for (u32 chunk0 = 0; chunk0 < total; chunk0 += (MODE == 5 ? rb.queue_windows : total))
 		{
 		const u32 chunk1 = MODE == 5 ? min (total, chunk0 + rb.queue_windows) : total;
-		for (int sweep = ((MODE == 3 || MODE == 1) ? 0 : 1); sweep < 2; sweep++)
+		for (int sweep = (MODE == 1 ? 0 : 1); sweep < 2; sweep++)
 		{
 		for (u32 w = chunk0 + tid; w < chunk1; w += BLOCK)
 		{
@@ -365,21 +362,8 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 				if (ord + 1 > smax[set])
 					atomicMax (&smax[set], ord + 1);	// stored +1 so that 0 means "no instance"
 			}
-			else if (MODE == 2)	// partition pass 1: how many records per slot-range bucket
-				atomicAdd (&hist[(u32) __umul64hi (key_hash<W> (key), (u64) bins.n_ranks)], 1u);
-			else
-			{	// partition pass 2: exact scatter, cursors were initialised to the bucket offsets
-				const u32 b = (u32) __umul64hi (key_hash<W> (key), (u64) bins.n_ranks);
-				if (sweep == 0)
-					atomicAdd (&hist[b], 1u);
-				else
-				{
-					const u64 pos = base[b] + atomicAdd (&hist[b], 1u);
-					store_record<W> (bins.records + pos * (W + 1), key, left, right, ord);
-				}
-			}
 		}
-		if (MODE == 3 || MODE == 1)
+		if (MODE == 1)
 		{
 			__syncthreads ();
 			if (sweep == 0)
@@ -422,13 +406,6 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		}
 		__syncthreads ();	// the tile is overwritten by the next iteration
 	}
-	if (MODE == 2)
-	{
-		__syncthreads ();
-		for (u32 b = tid; b < bins.n_ranks; b += BLOCK)
-			if (hist[b])
-				atomicAdd (bins.counts + b, (u64) hist[b]);
-	}
 	if (MODE == 4)
 	{
 		__syncthreads ();
@@ -448,163 +425,6 @@ insert_reads_kernel (typename SlotOf<W>::type *table, u64 cap, ReadBatch rb, Bin
 		atomicAdd (&ctr->n_instances, instances);
 	if (MODE == 5 && tid == 0 && owned)
 		atomicAdd (&ctr->n_instances, owned);
-}
-
-// ------------------------------------------------------------------------------------------------
-// staged (partitioned) insert
-static constexpr int STAGE_CHUNK = 1024;	// records per work item
-static constexpr int MAX_SEGMENTS = 64;		// batches per epoch
-
-struct Staged
-{
-	const u64 *seg_records[MAX_SEGMENTS];	// record base of each batch
-	const u64 *seg_offsets;			// [n_segments][P + 1] exclusive bucket offsets (records) of each batch
-	const u64 *chunk_prefix;		// [P * n_segments + 1] exclusive prefix of work items, bucket-major
-	u64 *next_chunk;			// work-stealing cursor (zeroed at the start of an epoch)
-	u64 node_limit;				// stop handing out chunks once the table holds this many nodes
-	u32 n_segments, P;
-};
-
-// offsets[s][b] (exclusive scan of counts[b]) for ONE batch, cursors[b] = base + offsets[b]; one CTA
-__global__ void __launch_bounds__ (1024)
-bucket_scan_kernel (const u64 *counts, u32 P, u64 base, u64 *offsets, u64 *cursors)
-{
-	__shared__ u64 part[1024];
-	__shared__ u64 carry;
-	if (threadIdx.x == 0)
-		carry = 0;
-	__syncthreads ();
-	for (u32 b0 = 0; b0 < P; b0 += 1024)
-	{
-		const u32 b = b0 + threadIdx.x;
-		const u64 c = b < P ? counts[b] : 0;
-		part[threadIdx.x] = c;
-		__syncthreads ();
-		for (int d = 1; d < 1024; d <<= 1)
-		{
-			const u64 y = threadIdx.x >= (u32) d ? part[threadIdx.x - d] : 0;
-			__syncthreads ();
-			part[threadIdx.x] += y;
-			__syncthreads ();
-		}
-		const u64 excl = carry + part[threadIdx.x] - c;
-		if (b < P)
-		{
-			offsets[b] = excl;
-			cursors[b] = base + excl;
-		}
-		__syncthreads ();
-		if (threadIdx.x == 1023)
-			carry += part[1023];
-		__syncthreads ();
-	}
-	if (threadIdx.x == 0)
-		offsets[P] = carry;
-}
-
-// chunk_prefix over (bucket-major, segment-minor) work items; one CTA
-__global__ void __launch_bounds__ (1024)
-chunk_prefix_kernel (const u64 *seg_offsets, u32 n_segments, u32 P, u64 *chunk_prefix)
-{
-	__shared__ u64 part[1024];
-	__shared__ u64 carry;
-	const u32 n = P * n_segments;
-	if (threadIdx.x == 0)
-		carry = 0;
-	__syncthreads ();
-	for (u32 i0 = 0; i0 < n; i0 += 1024)
-	{
-		const u32 i = i0 + threadIdx.x;
-		u64 c = 0;
-		if (i < n)
-		{
-			const u32 b = i / n_segments, t = i - b * n_segments;
-			const u64 *off = seg_offsets + (u64) t * (P + 1);
-			c = (off[b + 1] - off[b] + STAGE_CHUNK - 1) / STAGE_CHUNK;
-		}
-		part[threadIdx.x] = c;
-		__syncthreads ();
-		for (int d = 1; d < 1024; d <<= 1)
-		{
-			const u64 y = threadIdx.x >= (u32) d ? part[threadIdx.x - d] : 0;
-			__syncthreads ();
-			part[threadIdx.x] += y;
-			__syncthreads ();
-		}
-		if (i < n)
-			chunk_prefix[i] = carry + part[threadIdx.x] - c;
-		__syncthreads ();
-		if (threadIdx.x == 1023)
-			carry += part[1023];
-		__syncthreads ();
-	}
-	if (threadIdx.x == 0)
-		chunk_prefix[n] = carry;
-}
-
-// Chunks are handed out in bucket order, so at any moment all CTAs update the same few table
-// regions.  The number of distinct keys in an epoch is not known in advance: when the live node
-// count reaches node_limit the kernel stops taking chunks; the host grows the table and relaunches
-// (next_chunk persists), so the table can never fill up while a launch is running.
-template <int W>
-__global__ void __launch_bounds__ (BLOCK)
-insert_staged_kernel (typename SlotOf<W>::type *table, u64 cap, Staged st, Counters *ctr)
-{
-	__shared__ u64 s_chunk;
-	__shared__ u32 s_created;
-	const u32 n_items = st.P * st.n_segments;
-	const u64 total = st.chunk_prefix[n_items];
-	u64 done = 0;
-	if (threadIdx.x == 0)
-		s_created = 0;
-	for (;;)
-	{
-		if (threadIdx.x == 0)
-		{
-			const u64 live = *reinterpret_cast<volatile u64 *> (&ctr->n_nodes);
-			s_chunk = live >= st.node_limit ? ~0ull : atomicAdd (st.next_chunk, 1ull);
-		}
-		__syncthreads ();
-		const u64 c = s_chunk;
-		if (c >= total)
-			break;
-		u32 lo = 0, hi = n_items - 1;	// largest item with chunk_prefix[item] <= c
-		while (lo < hi)
-		{
-			const u32 mid = (lo + hi + 1) >> 1;
-			if (st.chunk_prefix[mid] <= c)
-				lo = mid;
-			else
-				hi = mid - 1;
-		}
-		const u32 b = lo / st.n_segments, t = lo - b * st.n_segments;
-		const u64 *off = st.seg_offsets + (u64) t * (st.P + 1);
-		const u64 first = off[b] + (c - st.chunk_prefix[lo]) * STAGE_CHUNK;
-		const u64 last = min (first + STAGE_CHUNK, off[b + 1]);
-		const u64 *recs = st.seg_records[t];
-		u32 created = 0;
-		for (u64 i = first + threadIdx.x; i < last; i += BLOCK)
-		{
-			Key<W> key;
-			u64 meta;
-			load_record<W> (recs + i * (W + 1), key, meta);
-			created += Table<W>::upsert (table, cap, key, (u32) (meta >> 4) & 15u, (u32) meta & 15u, meta >> 8);
-		}
-		if (created)
-			atomicAdd (&s_created, created);
-		__syncthreads ();
-		if (threadIdx.x == 0)
-		{
-			done += last - first;
-			if (s_created)
-			{
-				atomicAdd (&ctr->n_nodes, (u64) s_created);
-				s_created = 0;
-			}
-		}
-	}
-	if (threadIdx.x == 0 && done)
-		atomicAdd (&ctr->n_instances, done);
 }
 
 template <int W>

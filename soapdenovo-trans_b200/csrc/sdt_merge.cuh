@@ -53,13 +53,15 @@ struct MergeOut
 // HAS_MULT: word 2 of the incoming records already is a multiplicity (sub-records, records merged before an exchange)
 template <int W, bool HAS_MULT>
 __global__ void __launch_bounds__ (MG_NT)
-skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, u32 G, unsigned long long *group_cursor)
+skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, u32 G)
 {
 	constexpr u32 RECW = SkmRec<W>::WORDS, CH = MergeCfg<W>::CHUNK, TS = MergeCfg<W>::TABLE, VEC = RECW / 4, RPT = CH / MG_NT;
 	extern __shared__ __align__(16) u32 smem[];
-	__shared__ u32 s_scan[MG_NT / 32], s_group, s_tot, s_wtot;
-	__shared__ u32 s_nraw[MG_GMAX], s_rs[MG_GMAX + 1], s_pos[MG_GMAX + 1], s_wpre[MG_GMAX + 1];	// per chain of the group: records, first record in the chunk, first survivor, windows before it
-	__shared__ u64 s_b0[MG_GMAX];
+	__shared__ u32 s_scan[MG_NT / 32], s_tot, s_wtot;
+	__shared__ u32 s_nraw2[2 * MG_GMAX], s_rs[MG_GMAX + 1], s_pos[MG_GMAX + 1], s_wpre[MG_GMAX + 1];	// per chain of the group: records (this group's and the next one's), first record in the chunk, first survivor, windows before it
+	__shared__ u64 s_b02[2 * MG_GMAX];
+	u32 *s_nraw = s_nraw2;	// (the first group's)
+	u64 *s_b0 = s_b02;
 	__shared__ unsigned long long s_start, s_ibase;
 	u32 *st = smem;			// [CH * RECW]: the chunk's records
 	u32 *tab = smem + CH * RECW;	// [TS]: record index + 1, 0 = free
@@ -249,31 +251,52 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		return s_tot;
 	};
 
-	for (;;)
+	// groups are dealt to the CTAs round robin; the chains' record counts and block lists of the NEXT group are
+	// loaded while this one is merged (two dependent round trips less per group)
+	auto geom = [&](u64 grp, u32 &owner, u32 &c0, u32 &nch) {
+		owner = (u32) (grp / gpo);
+		c0 = owner * span + (u32) (grp % gpo) * G;
+		nch = min (min (G, owner * span + span - c0), ch.n_chains - c0);
+	};
+	u32 pb = 0;	// which half of s_nraw / s_b0 holds this group's
+	if (blockIdx.x < n_groups)
 	{
-		if (tid == 0)
-			s_group = (u32) atomicAdd (group_cursor, 1ull);
-		__syncthreads ();
-		const u64 grp = s_group;
-		if (grp >= n_groups)
-			break;
-		const u32 owner = (u32) (grp / gpo), c0 = owner * span + (u32) (grp % gpo) * G;
-		const u32 nch = min (G, owner * span + span - c0) < ch.n_chains - c0 ? min (G, owner * span + span - c0) : ch.n_chains - c0;
+		u32 owner, c0, nch;
+		geom (blockIdx.x, owner, c0, nch);
 		if (tid < nch)
 		{
 			const u32 c = c0 + tid;
 			s_nraw[tid] = ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);	// (a chain of 2^32 records or more is not supported)
 			s_b0[tid] = boff[c];
 		}
-		__syncthreads ();
+	}
+	__syncthreads ();
+	for (u64 grp = blockIdx.x; grp < n_groups; grp += gridDim.x, pb ^= MG_GMAX)
+	{
+		u32 owner, c0, nch;
+		geom (grp, owner, c0, nch);
+		u32 nx_raw = 0;
+		u64 nx_b0 = 0;
+		if (grp + gridDim.x < n_groups)
+		{
+			u32 o2, c2, n2;
+			geom (grp + gridDim.x, o2, c2, n2);
+			if (tid < n2)
+			{
+				const u32 c = c2 + tid;
+				nx_raw = ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);
+				nx_b0 = boff[c];
+			}
+		}
+		s_nraw = s_nraw2 + pb;
+		s_b0 = s_b02 + pb;
+		do
+		{
 		u32 total_raw = 0;
 		for (u32 g = 0; g < nch; g++)
 			total_raw += s_nraw[g];
 		if (total_raw == 0)
-		{
-			__syncthreads ();
-			continue;
-		}
+			break;
 		unsigned long long resv = 0;
 		if (tid == 0 && !mo.per_owner)
 			resv = atomicAdd (mo.out_cursor, (unsigned long long) total_raw);	// (looked at after the first chunk is merged)
@@ -379,7 +402,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 				}
 			}
 			__syncthreads ();
-			continue;
+			break;
 		}
 		// ---- a group with more records than a chunk holds: chain by chain, a chain in as many chunks as it takes.
 		// Every chain is an item of its own (copies that sit in different chunks of a chain are not merged).
@@ -469,6 +492,14 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 						mo.items[ib] = it;
 				}
 			}
+		}
+		__syncthreads ();
+		} while (0);
+		// the next group's chains
+		if (tid < MG_GMAX)
+		{
+			s_nraw2[(pb ^ MG_GMAX) + tid] = nx_raw;
+			s_b02[(pb ^ MG_GMAX) + tid] = nx_b0;
 		}
 		__syncthreads ();
 	}

@@ -1,5 +1,5 @@
 // sdt_sliced.cuh — shared pieces of the sliced build (sdt_skm.cuh): the shared-memory read tile
-// (stage, flatten, locate a window) and the exclusive scan of records per slice.
+// (stage, flatten, locate a window) and the exclusive scan of a per-chain count.
 //
 // Why a sliced build at all: on B200 a request to a cold line of a larger-than-L2 table completes at
 // 36.65 G/s whatever its width (profiles/r1_random_access_findings.md), so a single-pass insert (one
@@ -12,22 +12,6 @@
 #include "sdt_kernels.cuh"
 
 namespace sdt {
-
-struct SliceGeom
-{
-	u32 n_slices;		// table capacity = n_slices * slice_slots
-	u32 slice_slots;	// S
-	u32 P1, P2;		// level-1 partitions, slices per level-1 partition (P1 = ceil (n_slices / P2))
-};
-
-__device__ __forceinline__ u32 slice_of (u64 h, u32 n_slices) { return (u32) __umul64hi (h, (u64) n_slices); }
-__device__ __forceinline__ u32 home_of (u64 h, u32 S) { return __umulhi ((u32) h, S); }
-
-static constexpr int CNT_NT = 256;	// slice_count_kernel
-static constexpr int SC_NT = 512;	// scatter kernels
-static constexpr int BD_NT = 1024;	// slice_build_kernel
-template <int W> struct ScatterCfg { static constexpr int RPT = W == 4 ? 4 : 8; };	// records per thread and tile
-static constexpr u32 NO_BIN = 0xFFFFFFFFu;
 
 // ------------------------------------------------------------------------------------------------
 // a tile of 2-bit packed reads in shared memory (same layout as insert_reads_kernel's)

@@ -89,16 +89,7 @@ struct sdtgpu
 	u32 n_grows = 0;
 	bool finalized = false;
 	int deLowKmer = 0;
-	// partitioned (staged) insert: records of an epoch are radix-partitioned by table slot range
 	u32 owner_rank = 0, owner_ranks = 1;	// sdtgpu_set_owner
-	bool direct = true;		// default; SDTGPU_F_PARTITIONED selects the staged path
-	u64 *staging = nullptr;		// records, (W + 1) u64 each
-	u64 staging_cap = 0, staging_used = 0, staged_upper = 0;	// in records
-	u32 P = 0;			// buckets of the current epoch
-	u64 *d_counts = nullptr, *d_cursors = nullptr, *d_seg_offsets = nullptr, *d_chunk_prefix = nullptr, *d_next_chunk = nullptr;
-	const u64 *seg_records[MAX_SEGMENTS];
-	u32 n_segments = 0;
-	double region_bytes = 16.0 * 1024 * 1024;
 	// sliced build (SDTGPU_F_SLICED): reads of the open epoch are kept in a log and turned into super-k-mer
 	// records in the chains of their slices as they arrive; sliced_flush merges copies and builds the slices
 	bool sliced = false, table_built = false, epoch_open = false, emitted = false, ord_bound_set = false, chains_dropped = false;
@@ -282,7 +273,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 {
 	typedef typename SlotOf<W>::type S;
 	auto kern = insert_reads_kernel<W, NMODE, MODE>;
-	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 2 ? bins.n_ranks : ((MODE == 3 || MODE == 1) ? 3 * (size_t) bins.n_ranks + 4 : (MODE == 4 ? 2 * (size_t) bins.n_ranks + 2 : (MODE == 5 ? 2 * (size_t) rb.queue_cap * (W + 1) + 2 : 0))));
+	const size_t smem = insert_smem_bytes (rb, NMODE, MODE == 1 ? 3 * (size_t) bins.n_ranks + 4 : (MODE == 4 ? 2 * (size_t) bins.n_ranks + 2 : (MODE == 5 ? 2 * (size_t) rb.queue_cap * (W + 1) + 2 : 0)));
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
@@ -297,7 +288,7 @@ template <int W, bool NMODE, int MODE> int launch_insert_t (sdtgpu *h, const Rea
 	kern<<<grid, BLOCK, smem, ls>>> (static_cast<S *> (h->table), h->cap, rb, bins, h->d_ctr);
 	CK (h, cudaGetLastError ());
 	CK (h, cudaEventRecord (e1, ls));
-	h->timing.push_back ({ e0, e1, MODE == 2 ? 1 : ((MODE == 0 || MODE == 5) ? 0 : 2) });
+	h->timing.push_back ({ e0, e1, (MODE == 0 || MODE == 5) ? 0 : 2 });
 	h->all_launches++;
 	return SDTGPU_OK;
 }
@@ -517,172 +508,13 @@ int set_last_ordinals (sdtgpu *h, int thrd_num, std::vector<u64> &last)
 	return SDTGPU_OK;
 }
 
-// ---- partitioned insert -----------------------------------------------------------------------
-static constexpr u32 MAX_BUCKETS = 4096;
-
-int alloc_staging (sdtgpu *h, u64 want_records)
-{
-	size_t free_b = 0, total_b = 0;
-	CK (h, cudaMemGetInfo (&free_b, &total_b));
-	const size_t rec = 8 * (size_t) (h->W + 1);
-	double budget = (h->grow_mode ? 0.25 : 0.45) * (double) free_b;
-	if (const char *e = getenv ("SDTGPU_STAGING_MB"))
-		budget = atof (e) * 1024.0 * 1024.0;
-	u64 records = (u64) (budget / (double) rec);
-	records = std::max<u64> (records, 1u << 20);
-	(void) want_records;
-	CK (h, cudaMalloc (&h->staging, records * rec));
-	h->staging_cap = records;
-	CK (h, cudaMalloc (&h->d_counts, MAX_BUCKETS * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_cursors, MAX_BUCKETS * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_seg_offsets, (size_t) MAX_SEGMENTS * (MAX_BUCKETS + 1) * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_chunk_prefix, ((size_t) MAX_SEGMENTS * MAX_BUCKETS + 1) * sizeof (u64)));
-	CK (h, cudaMalloc (&h->d_next_chunk, sizeof (u64)));
-	if (const char *e = getenv ("SDTGPU_REGION_MB"))
-		if (atof (e) > 0)
-			h->region_bytes = atof (e) * 1024.0 * 1024.0;
-	return SDTGPU_OK;
-}
-
-template <int W> int launch_staged (sdtgpu *h, const Staged &st, unsigned max_grid)
-{
-	typedef typename SlotOf<W>::type S;
-	int occ = 0;
-	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, insert_staged_kernel<W>, BLOCK, 0));
-	const unsigned grid = std::max (1u, std::min ((unsigned) (h->sm_count * std::max (occ, 1)), max_grid));
-	cudaEvent_t e0 = get_event (h), e1 = get_event (h);
-	CK (h, cudaEventRecord (e0, h->stream));
-	insert_staged_kernel<W><<<grid, BLOCK, 0, h->stream>>> (static_cast<S *> (h->table), h->cap, st, h->d_ctr);
-	CK (h, cudaGetLastError ());
-	CK (h, cudaEventRecord (e1, h->stream));
-	h->timing.push_back ({ e0, e1, 0 });
-	h->all_launches++;
-	return SDTGPU_OK;
-}
-
-int grow_table (sdtgpu *h, u64 new_cap)
-{
-	void *neu = nullptr;
-	CK (h, cudaMalloc (&neu, new_cap * slot_bytes (h->W)));
-	int rc = init_table (h, neu, new_cap);
-	if (rc)
-		return rc;
-	switch (h->W)
-	{
-	case 1: launch_rehash<1> (h, h->table, h->cap, neu, new_cap); break;
-	case 2: launch_rehash<2> (h, h->table, h->cap, neu, new_cap); break;
-	default: launch_rehash<4> (h, h->table, h->cap, neu, new_cap); break;
-	}
-	CK (h, cudaGetLastError ());
-	CK (h, cudaStreamSynchronize (h->stream));
-	CK (h, cudaFree (h->table));
-	h->table = neu;
-	h->cap = new_cap;
-	h->n_grows++;
-	return SDTGPU_OK;
-}
-
-// End of an epoch: upsert everything that was staged, bucket by bucket.  The distinct count of
-// the epoch is unknown, so the kernel runs optimistically and stops itself when the table reaches
-// 85 % load; the table is then grown by device re-hash (the reference's encap_kmerset,
-// newhash.c:293-409, moved to the device) and the kernel resumes where it stopped.
 int sliced_flush (sdtgpu *h);
 
+// everything pushed is in the table (the sliced build does its work here; the single-pass insert has nothing pending)
 int flush_epoch (sdtgpu *h)
 {
-	if (h->sliced)
-		return sliced_flush (h);
-	if (h->n_segments == 0)
-		return SDTGPU_OK;
-	int rc;
-	chunk_prefix_kernel<<<1, 1024, 0, h->stream>>> (h->d_seg_offsets, h->n_segments, h->P, h->d_chunk_prefix);
-	CK (h, cudaGetLastError ());
-	CK (h, cudaMemsetAsync (h->d_next_chunk, 0, sizeof (u64), h->stream));
-	h->all_launches++;
-	Staged st;
-	memset (&st, 0, sizeof st);
-	for (u32 i = 0; i < h->n_segments; i++)
-		st.seg_records[i] = h->seg_records[i];
-	st.seg_offsets = h->d_seg_offsets;
-	st.chunk_prefix = h->d_chunk_prefix;
-	st.next_chunk = h->d_next_chunk;
-	st.n_segments = h->n_segments;
-	st.P = h->P;
-	for (;;)
-	{
-		// every CTA may finish one more chunk after the limit is seen: keep that much head room
-		const unsigned max_grid = (unsigned) std::max<u64> (1, h->cap / 8 / STAGE_CHUNK);
-		const u64 head = (u64) std::min<u64> (max_grid, (u64) h->sm_count * 8) * STAGE_CHUNK;
-		const u64 lim = (u64) (0.85 * (double) h->cap);
-		st.node_limit = lim > head ? lim - head : 1;
-		switch (h->W)
-		{
-		case 1: rc = launch_staged<1> (h, st, max_grid); break;
-		case 2: rc = launch_staged<2> (h, st, max_grid); break;
-		default: rc = launch_staged<4> (h, st, max_grid); break;
-		}
-		if (rc)
-			return rc;
-		u64 *hv = h->h_nodes_snap + 1;	// pinned scratch: next_chunk, total chunks
-		CK (h, cudaMemcpyAsync (hv, h->d_next_chunk, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-		CK (h, cudaMemcpyAsync (hv + 1, h->d_chunk_prefix + (size_t) h->P * h->n_segments, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-		CK (h, cudaMemcpyAsync (hv + 2, &h->d_ctr->n_nodes, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-		CK (h, cudaStreamSynchronize (h->stream));
-		const u64 next = hv[0], total = hv[1], nodes = hv[2];
-		if (next >= total)
-			break;
-		// stopped early: project the final node count from the fraction done and re-hash
-		const double frac = std::max (0.02, (double) next / (double) total);
-		const u64 projected = (u64) ((double) nodes / frac);
-		const u64 new_cap = std::max<u64> (h->cap + h->cap / 2, pick_capacity (projected, slot_bytes (h->W)));
-		if ((rc = grow_table (h, new_cap)))
-			return rc;
-	}
-	h->pushed_upper += h->staged_upper;
-	h->n_segments = 0;
-	h->staging_used = 0;
-	h->staged_upper = 0;
-	h->snap_pending = false;
-	h->known_nodes = h->h_nodes_snap[3];
-	h->known_at = h->pushed_upper;
-	return SDTGPU_OK;
+	return h->sliced ? sliced_flush (h) : SDTGPU_OK;
 }
-
-// one batch (or part of one) into the staging area: count -> scan -> scatter
-int stage_batch (sdtgpu *h, const ReadBatch &rb, u64 upper)
-{
-	int rc;
-	if (h->staging_used + upper > h->staging_cap || h->n_segments == MAX_SEGMENTS)
-		if ((rc = flush_epoch (h)))
-			return rc;
-	if (h->n_segments == 0)
-	{
-		const double table_bytes = (double) h->cap * (double) slot_bytes (h->W);
-		h->P = (u32) std::min<double> (MAX_BUCKETS, std::max (1.0, std::ceil (table_bytes / h->region_bytes)));
-	}
-	CK (h, cudaMemsetAsync (h->d_counts, 0, h->P * sizeof (u64), h->stream));
-	Bins b;
-	b.records = nullptr;
-	b.counts = h->d_counts;
-	b.capacity = 0;
-	b.n_ranks = h->P;
-	if ((rc = launch_insert<2> (h, rb, b)))
-		return rc;
-	u64 *offsets = h->d_seg_offsets + (size_t) h->n_segments * (h->P + 1);
-	bucket_scan_kernel<<<1, 1024, 0, h->stream>>> (h->d_counts, h->P, h->staging_used, offsets, h->d_cursors);
-	CK (h, cudaGetLastError ());
-	h->all_launches++;
-	b.records = h->staging;
-	b.counts = h->d_cursors;
-	if ((rc = launch_insert<3> (h, rb, b)))
-		return rc;
-	h->seg_records[h->n_segments] = h->staging + h->staging_used * (u64) (h->W + 1);
-	h->n_segments++;
-	h->staging_used += upper;
-	h->staged_upper += upper;
-	return SDTGPU_OK;
-}
-
 
 // ---- sliced build over super-k-mers (sdt_skm.cuh, sdt_chain.cuh, sdt_merge.cuh, sdt_build.cuh) ------------
 struct TimedLaunch
@@ -758,7 +590,7 @@ int skm_setup (sdtgpu *h, u64 hint)
 	// consecutive chains into work items up to an image's worth of windows, which evens out how lumpy chains are
 	// (K <= 31 with a hint: a chain is about an image's worth — 2 % faster on C2 than packing small chains;
 	// without a hint the chains are made small, so that a guess that is too low by 4x still gives items that fit)
-	double load = h->W == 1 ? (h->hint ? 0.45 : 0.12) : (h->W == 2 ? 0.12 : 0.2);	// (long k-mers: nearly every window is a k-mer of its own and chains are lumpy)
+	double load = h->W == 1 ? (h->hint ? 0.45 : 0.25) : (h->W == 2 ? 0.12 : 0.2);	// (long k-mers: nearly every window is a k-mer of its own and chains are lumpy)
 	if (const char *e = getenv ("SDTGPU_SLICE_LOAD"))
 		if (atof (e) > 0.01 && atof (e) < 0.95)
 			load = atof (e);
@@ -902,7 +734,21 @@ int level_reserve (sdtgpu *h, ChainLevel &L, u64 blocks)
 	if (blocks <= L.pool_blocks)
 		return SDTGPU_OK;
 	if (L.pool_blocks == 0)
-		blocks = L.pool_high;	// (a pool that was given up for the node store comes back at its full size, in one piece)
+	{	// a pool that was given up for the node store comes back at its full size, in one piece — and if the store
+		// of the last epoch is in its way, the store goes (it is rebuilt by the next flush anyway)
+		blocks = L.pool_high;
+		size_t fr = 0, tot = 0;
+		cudaMemGetInfo (&fr, &tot);
+		if (h->table && (double) fr < (double) blocks * CH_BLK * h->geom.recw * 4.4 + (1u << 30))
+		{
+			CK (h, cudaStreamSynchronize (h->stream));
+			CK (h, cudaFree (h->table));
+			h->table = nullptr;
+			h->cap = 0;
+			h->n_store = 0;
+			h->table_built = false;
+		}
+	}
 	if (blocks >= 0xFFFFFFF0ull)
 		return fail (h, SDTGPU_ERANGE, "too many record blocks");
 	int rc;
@@ -1112,7 +958,7 @@ template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u6
 	mo.rcur = reinterpret_cast<unsigned long long *> (rcur);
 	{
 		TimedLaunch tl (h, 3);
-		kern<<<grid, MG_NT, smem, h->stream>>> (level_chains (h, L), L.boff, L.blist, mo, std::min (G, MG_GMAX), reinterpret_cast<unsigned long long *> (L.d_cursor + 3));
+		kern<<<grid, MG_NT, smem, h->stream>>> (level_chains (h, L), L.boff, L.blist, mo, std::min (G, MG_GMAX));
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
@@ -1489,6 +1335,11 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 	if (!out)
 		return SDTGPU_EINVAL;
 	*out = nullptr;
+	if (flags & ~(SDTGPU_F_NKMER | SDTGPU_F_SLICED))
+	{
+		g_create_error = "unknown flag (the experimental partitioned insert of round 1, flag 2, was measured slower and removed)";
+		return SDTGPU_EINVAL;
+	}
 	if ((key_words != 1 && key_words != 2 && key_words != 4) || !(K & 1) || K < 13 || K > 32 * key_words - 1)
 	{
 		g_create_error = "K must be odd, 13 <= K <= 32*key_words-1, key_words in {1,2,4} (pregraph.c:38-59)";
@@ -1510,7 +1361,6 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 	h->device = device; h->K = K; h->key_words = key_words; h->max_read_len = max_read_len; h->flags = flags;
 	h->W = K <= 31 ? 1 : (K <= 63 ? 2 : 4);
 	h->sliced = (flags & SDTGPU_F_SLICED) != 0;
-	h->direct = (flags & (SDTGPU_F_PARTITIONED | SDTGPU_F_SLICED)) == 0;
 	h->maxwin = (u32) (max_read_len - K + 1);
 	auto bail = [&](int rc) { g_create_error = h->err; sdtgpu_destroy (h); return rc; };
 	auto body = [&]() -> int {
@@ -1581,7 +1431,6 @@ void sdtgpu_destroy (sdtgpu_t *h)
 	}
 	for (auto &p : h->timing) { cudaEventDestroy (p.e0); cudaEventDestroy (p.e1); }
 	cudaFree (h->last_packed); cudaFree (h->last_mask); cudaFree (h->last_lens);
-	cudaFree (h->staging); cudaFree (h->d_counts); cudaFree (h->d_cursors); cudaFree (h->d_seg_offsets); cudaFree (h->d_chunk_prefix); cudaFree (h->d_next_chunk);
 	for (auto e : h->ev_pool) cudaEventDestroy (e);
 	for (void *m : h->log_mem) cudaFree (m);
 	for (auto &L : h->lv)
@@ -1631,7 +1480,6 @@ int sdtgpu_reset (sdtgpu_t *h)
 			return rc;
 	}
 	h->pushed_upper = 0; h->n_reads = 0; h->ord_end = 0; h->finalized = false; h->deLowKmer = 0;
-	h->n_segments = 0; h->staging_used = 0; h->staged_upper = 0;
 	if (h->snap_pending)
 		CK (h, cudaEventSynchronize (h->snap_ev));
 	h->snap_pending = false;
@@ -1675,7 +1523,6 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 			upper = upper / h->owner_ranks + upper / (2 * h->owner_ranks) + 1024;
 		return sliced_push (h, rb, upper);	// (with owner filtering the record area is simply sized generously)
 	}
-	if (h->direct)
 	{	// single pass: every window goes straight to its (random) slot
 		u64 upper = instances_upper (h, n_reads, uniform_len, d_lens != nullptr);
 		if (h->owner_ranks > 1)	// owners are a uniform hash of the key: this rank keeps ~1/n (allow 1.5x)
@@ -1689,23 +1536,6 @@ int sdtgpu_push_reads_device (sdtgpu_t *h, const uint8_t *d_packed, const uint32
 		rc = getenv ("SDTGPU_NO_QUEUE") && h->owner_ranks <= 1 ? launch_insert<0> (h, rb, Bins ()) : launch_insert<5> (h, rb, Bins ());
 		return rc ? rc : snapshot_nodes (h);
 	}
-	// partitioned: stage the batch (in pieces if it is larger than the staging area)
-	if (!h->staging && (rc = alloc_staging (h, 0)))
-		return rc;
-	const u64 per_read = std::max<u64> (instances_upper (h, 1, uniform_len, d_lens != nullptr), 1);
-	const u64 max_reads = std::max<u64> ((h->staging_cap / per_read) & ~1023ull, 1024);
-	for (u64 a = 0; a < n_reads; a += max_reads)
-	{
-		ReadBatch part = rb;
-		part.n_reads = std::min<u64> (max_reads, n_reads - a);
-		part.packed = rb.packed + a * stride_bytes;
-		part.lens = rb.lens ? rb.lens + a : nullptr;
-		part.nmask = rb.nmask ? rb.nmask + a * rb.mask_stride : nullptr;
-		part.first_read_ordinal = first_read_ordinal + a;
-		if ((rc = stage_batch (h, part, part.n_reads * per_read)))
-			return rc;
-	}
-	return SDTGPU_OK;
 }
 
 int sdtgpu_push_reads (sdtgpu_t *h, const uint8_t *packed, const uint32_t *lens, const uint8_t *nmask,
@@ -1752,8 +1582,6 @@ int sdtgpu_set_owner (sdtgpu_t *h, int rank, int n_ranks)
 		return SDTGPU_EINVAL;
 	if (n_ranks < 1 || rank < 0 || rank >= n_ranks)
 		return fail (h, SDTGPU_EINVAL, "sdtgpu_set_owner: need 0 <= rank < n_ranks");
-	if (!h->direct && !h->sliced && n_ranks > 1)
-		return fail (h, SDTGPU_ESTATE, "owner filtering is not implemented for the staged (SDTGPU_F_PARTITIONED) path");
 	if (h->sliced && !h->log.empty ())
 		return fail (h, SDTGPU_ESTATE, "sdtgpu_set_owner must precede the pushes of an epoch");
 	h->owner_rank = (u32) rank;

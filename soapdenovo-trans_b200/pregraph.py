@@ -20,7 +20,6 @@ NODE_DTYPE = np.dtype([("key", "<u8", (4,)), ("l_links", "<u4"), ("rword", "<u4"
 assert NODE_DTYPE.itemsize == 56
 
 F_NKMER = 1
-F_PARTITIONED = 2
 F_SLICED = 4
 PHASES = ("insert", "emit", "scatter", "dedupe", "build", "scan", "retry", "-")
 _ERR = {1: "EINVAL", 2: "ECUDA", 3: "ENOMEM", 4: "ERANGE", 5: "ESTATE"}
@@ -188,13 +187,12 @@ class PregraphGPU:
     stage of `pregraph` (prlRead2HashTable, prlHashReads.c:338)."""
 
     def __init__(self, K: int, key_words: int, max_read_len: int, capacity_hint: int = 0, device: int = 0,
-                 n_kmer: bool = False, partitioned: bool = False, sliced: bool = False):
+                 n_kmer: bool = False, sliced: bool = False):
         self.L = library()
         self.h = C.c_void_p()
         self.K, self.key_words, self.max_read_len, self.device = K, key_words, max_read_len, device
         rc = self.L.sdtgpu_create(C.byref(self.h), device, K, key_words, max_read_len, capacity_hint,
-                                  (F_NKMER if n_kmer else 0) | (F_PARTITIONED if partitioned else 0)
-                                  | (F_SLICED if sliced else 0))
+                                  (F_NKMER if n_kmer else 0) | (F_SLICED if sliced else 0))
         if rc:
             raise SdtGpuError(rc, self.L.sdtgpu_last_error(None).decode())
 

@@ -1,6 +1,7 @@
 """Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot run
 3.5e9 instances in a test): conservation of instances, and an order-independent fingerprint of the
-table (sdtgpu_table_checksum) that must not depend on batching, capacity, insert path or rounds —
+table (sdtgpu_table_checksum) that must not depend on batching, capacity, insert path (single-pass insert, sliced
+build with and without a capacity hint) or rounds —
 anchored to the oracle by (a) fingerprint equality on small inputs for every key width and (b) a
 sub-sample of the full-size device-generated reads checked against the oracle bit for bit."""
 import numpy as np
@@ -70,27 +71,22 @@ def test_full_size_properties(pkg, oracle, name, n_pairs):
     g.close()
     assert st.n_instances == instances == int(fp1[1])          # conservation: "kmer in reads" == "kmer processed"
     assert st.n_nodes == int(fp1[3])
-    # a different capacity, batch size and (where memory allows) the partitioned path: same multiset
+    # a different capacity and batch size: same multiset
     g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(st.n_nodes * 1.08))
     _insert_all(pkg, g, d_packed, L, stride, (1 << 21) + 4 * 12345)
     fp2 = g.table_checksum()
     g.close()
     assert np.array_equal(fp1, fp2)
-    free_b, _ = torch.cuda.mem_get_info()
-    if free_b > 2.1 * st.n_nodes * slot + 0.4 * instances * 8 * (2 if K <= 31 else (3 if K <= 63 else 5)):
-        g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(st.n_nodes), partitioned=True)
+    # the sliced build (bench.py's path and the drop-in's default) at full size, WITHOUT a capacity hint and with one:
+    # same counters, same fingerprint as the single-pass insert
+    for hint in (0, int(st.n_nodes * 1.02) + 1024):
+        g = pkg.PregraphGPU(K, kw, L, capacity_hint=hint, sliced=True)
         _insert_all(pkg, g, d_packed, L, stride, 1 << 22)
-        fp3 = g.table_checksum()
+        st_s = g.stats()
+        fp_s = g.table_checksum()
         g.close()
-        assert np.array_equal(fp1, fp3)
-    # the sliced build (bench.py's path) at full size: same fingerprint as the single-pass insert
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=int(st.n_nodes * 1.02) + 1024, sliced=True)
-    _insert_all(pkg, g, d_packed, L, stride, 1 << 22)
-    st_s = g.stats()
-    fp_s = g.table_checksum()
-    g.close()
-    assert (st_s.n_instances, st_s.n_nodes) == (st.n_instances, st.n_nodes)
-    assert np.array_equal(fp1, fp_s)
+        assert (st_s.n_instances, st_s.n_nodes) == (st.n_instances, st.n_nodes), (name, hint)
+        assert np.array_equal(fp1, fp_s), (name, hint)
     # anchor to the oracle: the first 40 000 device-generated reads, bit for bit
     n_sub = 40_000
     sub = d_packed[:n_sub].cpu().numpy()

@@ -10,14 +10,14 @@ from conftest import make_dataset
 pytestmark = pytest.mark.gpu
 
 
-def run_gpu(pkg, reads, lens, K, kw, d=0, batches=1, thrd_num=8, hint=0, n_kmer=False, uniform=False, max_read_len=None, partitioned=False, sliced=False):
+def run_gpu(pkg, reads, lens, K, kw, d=0, batches=1, thrd_num=8, hint=0, n_kmer=False, uniform=False, max_read_len=None, sliced=False):
     synth = pkg.synth
     L = reads.shape[1]
     max_read_len = max_read_len or L
     stride = synth.stride_bytes(max_read_len)
     packed = synth.pack_reads(reads, lens, stride)
     nmask = synth.nmask_reads(reads, stride) if n_kmer else None
-    g = pkg.PregraphGPU(K, kw, max_read_len, capacity_hint=hint, n_kmer=n_kmer, partitioned=partitioned, sliced=sliced)
+    g = pkg.PregraphGPU(K, kw, max_read_len, capacity_hint=hint, n_kmer=n_kmer, sliced=sliced)
     n = len(reads)
     step = max((n + batches - 1) // batches, 1)
     for a in range(0, n, step):
@@ -53,21 +53,12 @@ def check_against_oracle(pkg, oracle, reads, lens, K, kw, d=0, thrd_num=8, layou
         g.close()
 
 
-@pytest.mark.parametrize("partitioned", [False, True], ids=["direct", "partitioned"])
 @pytest.mark.parametrize("K,kw,d", [(25, 1, 0), (25, 1, 2), (31, 1, 0), (13, 1, 1), (33, 2, 0), (63, 2, 1), (63, 4, 0),
                                     (25, 4, 2), (65, 4, 0), (95, 4, 0), (97, 4, 1), (127, 4, 0)])
-def test_table_parity_ragged(pkg, oracle, tiny_transcriptome, K, kw, d, partitioned):
+def test_table_parity_ragged(pkg, oracle, tiny_transcriptome, K, kw, d):
     L = 150 if K > 63 else 100
     reads, lens = make_dataset(pkg, tiny_transcriptome, 3000, L, 11 + K, ragged=40)
-    check_against_oracle(pkg, oracle, reads, lens, K, kw, d=d, batches=3, partitioned=partitioned)
-
-
-def test_partitioned_small_staging_many_epochs(pkg, oracle, tiny_transcriptome, monkeypatch):
-    """A staging area much smaller than the input: batches are split and flushed in many epochs."""
-    monkeypatch.setenv("SDTGPU_STAGING_MB", "2")
-    monkeypatch.setenv("SDTGPU_REGION_MB", "1")
-    reads, lens = make_dataset(pkg, tiny_transcriptome, 12000, 100, 23, ragged=20)
-    check_against_oracle(pkg, oracle, reads, lens, 31, 1, d=1, batches=2, hint=1_200_000, partitioned=True)
+    check_against_oracle(pkg, oracle, reads, lens, K, kw, d=d, batches=3)
 
 
 @pytest.mark.parametrize("K,kw", [(25, 1), (63, 2), (127, 4)])
@@ -81,8 +72,6 @@ def test_growth_by_device_rehash(pkg, oracle, tiny_transcriptome):
     """capacity_hint = 0: the table starts at 2^20 slots and must re-hash on the device."""
     reads, lens = make_dataset(pkg, pkg.synth.make_transcriptome(400, 3), 30000, 100, 9)
     st = check_against_oracle(pkg, oracle, reads, lens, 31, 1, d=0, batches=6, layout=False)
-    assert st.n_grows >= 1
-    st = check_against_oracle(pkg, oracle, reads, lens, 31, 1, d=0, batches=6, layout=False, partitioned=True)
     assert st.n_grows >= 1
 
 
@@ -143,7 +132,6 @@ def test_hot_kmer_contention(pkg, oracle, tiny_transcriptome):
     tr = pkg.synth.make_transcriptome(60, 13, hot=2)
     reads, lens = make_dataset(pkg, tr, 40000, 100, 17)
     check_against_oracle(pkg, oracle, reads, lens, 31, 1, d=2, hint=2_000_000)
-    check_against_oracle(pkg, oracle, reads, lens, 31, 1, d=2, hint=2_000_000, partitioned=True, layout=False)
     check_against_oracle(pkg, oracle, reads, lens, 63, 2, d=0, hint=2_000_000, layout=False)
     check_against_oracle(pkg, oracle, reads, lens, 127 if reads.shape[1] > 127 else 99, 4, d=0, hint=2_000_000, layout=False)
 
