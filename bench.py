@@ -63,7 +63,9 @@ def estimate_distinct(instances: int, K: int) -> int:
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks and throttle reasons during the timed region (B200_PROFILING.md's clocks line), read through NVML
+    (nvidia_ml_py) on this rank's GPU: an `nvidia-smi` process per sample takes a driver-wide lock for tens of
+    milliseconds and stalls every CUDA call of every rank meanwhile.  Falls back to nvidia-smi without NVML."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -71,19 +73,50 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.nvml, self.handle = None, None
+        if index >= 0 and not os.environ.get("BENCH_NO_SAMPLER"):
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                # CUDA_VISIBLE_DEVICES may renumber the devices: go by the PCI bus id of the CUDA device
+                import torch
+                pr = torch.cuda.get_device_properties(index)
+                try:
+                    bus_id = f"{getattr(pr, 'pci_domain_id', 0):08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0"
+                    self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+                except Exception:
+                    self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.nvml = pynvml
+            except Exception:
+                self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [("hw_slowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)), ("hw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)), ("sw_power_cap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4))]
+        self.samples.append([str(sm), str(mx)] + ["Active" if r & bit else "Not Active" for _, bit in flags])
 
     def run(self):
-        if self.index < 0:      # (several GPUs: rank 0 samples its GPU; every nvidia-smi call takes a driver-wide lock)
+        if self.index < 0 or os.environ.get("BENCH_NO_SAMPLER"):      # (several GPUs: rank 0 samples its GPU)
             return
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.5)
+            self.stop_flag.wait(0.1 if self.nvml is not None else 0.5)
 
     def summary(self):
         sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
@@ -91,7 +124,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def unpack_reads(packed: np.ndarray, read_len: int) -> np.ndarray:
@@ -233,6 +266,8 @@ def main():
         cfg_d["n_transcripts"] = args.transcripts
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("BENCH_TRACE_RANK0") and rank == 0:
+        os.environ["SDTGPU_TRACE"] = "1"
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, kw, L = cfg_d["K"], cfg_d["key_words"], cfg_d["read_len"]
     nwin = L - K + 1
@@ -335,16 +370,27 @@ def main():
         else:
             exch = ReplicatedReads(pkg, g, world, rank, dev, max_round_reads=min(batch, n_reads), stride=stride)
 
+    host_t = {"reset": 0.0, "push": 0.0, "flush": 0.0, "sync": 0.0, "n": 0}
+
     def one_step(gg):
+        t0 = time.perf_counter()
         gg.reset()
+        t1 = time.perf_counter()
         if exch is None:
             push_all(gg)
+            t2 = t3 = time.perf_counter()
         else:
             for a in range(0, n_reads, batch):
                 b = min(a + batch, n_reads)
                 exch.round(gg, d_packed[a:b], b - a, L, stride, 2 * first_pair + a)
+            t2 = time.perf_counter()
             exch.flush(gg)
+            t3 = time.perf_counter()
         gg.sync()      # end of the step: everything pushed is in the table
+        t4 = time.perf_counter()
+        for k, v in zip(("reset", "push", "flush", "sync"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            host_t[k] += 1e3 * v
+        host_t["n"] += 1
 
     def barrier():
         if world > 1:
@@ -361,8 +407,11 @@ def main():
         parity = sliced_fp == direct_fp
         assert parity, ("the sliced build's table differs from the single-pass insert's", sliced_fp, direct_fp)
     g.kernel_time(reset=True)
+    for k in host_t:
+        host_t[k] = 0
     if exch is not None and hasattr(exch, "collective_ms"):
         exch.collective_ms = 0.0
+        exch.host_ms = {}
     sampler = ClockSampler(local_rank if rank == 0 else -1)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -375,6 +424,7 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     ms = e0.elapsed_time(e1)
+    host_ms = {k: v / max(host_t["n"], 1) for k, v in host_t.items() if k != "n"}      # wall clock of the host calls of a timed step (this rank)
     st = g.stats()
     distinct = int(st.n_nodes)
     assert exch is not None or st.n_instances == instances_rank, (st.n_instances, instances_rank)
@@ -533,7 +583,9 @@ def main():
                                            "ceiling_instances_per_s_per_gpu": RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words],
                                            "frac_of_ceiling": (inst_per_launch / (ker_ms * 1e-3)) / (RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words]),
                                            "source": "tools/randacc_bench.cu, profiles/r1_randacc_bench.txt"}},
+            "host_call_ms_per_step_rank0": host_ms,
             "collective_ms_per_step": collective_ms,
+            "exchange_host_ms_per_step_rank0": ({k: v / max(exch.host_ms.get("flushes", 1), 1) for k, v in exch.host_ms.items() if k != "flushes"} if exch is not None and getattr(exch, "host_ms", None) else None),
             "cpu_baseline": cpu, "e2e": e2e, "e2e_from_files": from_files, "gpu_launches": int(all_launches),
             "clocks": sampler.summary(),
         }

@@ -189,7 +189,7 @@ struct SkmDesc { u64 r0, r1; u32 it, wsum, r, R; };	// a work item with its run 
 template <int W, bool ORD32>
 __global__ void __launch_bounds__ (BUILD_NT, 1)
 skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long long *node_cursor, SkmGeom g, int K,
-		   const u32 *rec2, const SkmWork *items, u32 n_items, unsigned long long *item_cursor,
+		   const u32 *rec2, const SkmWork *items, u32 n_items, const unsigned long long *n_items_dev, unsigned long long *item_cursor,
 		   SkmWork *failed, u32 *n_failed, u32 max_failed, Counters *ctr)
 {
 	typedef typename SlotOf<W>::type S_t;
@@ -202,6 +202,8 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 	__shared__ unsigned long long s_base;
 	const u32 S = g.slice_slots, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const u32 spw = ((S + BUILD_NT - 1) / BUILD_NT) * 32;	// slots per warp in the compaction (a multiple of 32)
+	if (n_items_dev)	// the number of work items as skm_merge_kernel left it on the device (the host has not looked)
+		n_items = (u32) min ((unsigned long long) n_items, *n_items_dev);
 	SkmImage2<W, ORD32> im;
 	im.key = reinterpret_cast<u64 *> (smem);
 	im.ord = reinterpret_cast<ord_t *> (im.key + (size_t) S * W);

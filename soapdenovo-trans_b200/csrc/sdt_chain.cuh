@@ -136,8 +136,10 @@ __device__ __forceinline__ u32 *chain_append (const SkmChains &c, u32 chain, u32
 }
 
 // ---- chain state
-__global__ void chain_init_kernel (unsigned long long *head, u32 *bcount, u32 n_chains)
+__global__ void chain_init_kernel (unsigned long long *head, u32 *bcount, u32 n_chains, unsigned long long *pool_cursor)
 {
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		*pool_cursor = n_chains;	// the pool behind the chains' first blocks
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chains; i += gridDim.x * blockDim.x)
 	{
 		head[i] = (u64) i << 32;

@@ -45,7 +45,7 @@ struct MergeOut
 	u32 budget, oversize;		// windows per item at most; a single chain with more windows than `oversize` is marked R = 0
 	// multi-GPU send side: chains are global slices, `per_owner` of them per rank; the survivors of owner r are
 	// packed without gaps from region[r] on (cursor rcur[r]) and carry their slice in the last word; no items
-	u32 per_owner;
+	u32 per_owner, tagged;	// tagged: the records carry their slice already (a chain holds several slices)
 	const u64 *region;
 	unsigned long long *rcur;
 };
@@ -171,7 +171,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 					for (u32 q = 0; q < VEC; q++)
 					{
 						uint4 x = src[q];
-						if (mo.per_owner && q == VEC - 1)
+						if (mo.per_owner && !mo.tagged && q == VEC - 1)
 						{	// the last base word is never used (80 / 144 / 208 bases of room for 64 / 128 / 192): the slice travels there
 							u32 g = 0;
 							while (g + 1 < nb && s_rs[g + 1] <= i)
@@ -233,7 +233,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 					for (u32 q = 0; q < VEC; q++)
 					{
 						uint4 x = src[q];
-						if (mo.per_owner && q == VEC - 1)
+						if (mo.per_owner && !mo.tagged && q == VEC - 1)
 							x.w = slice;
 						dst[q] = x;
 					}

@@ -39,6 +39,7 @@ struct SkmGeom
 	u32 nmax;		// windows per record at most (32 for 1-word keys, else 64)
 	u32 recw;		// u32 words per record (8, 12, 16)
 	u32 slice_a;		// slice of the all-A k-mer (key 0): where the -n N-windows go
+	u32 send_group;		// several GPUs, sending side: a chain holds this many consecutive slices and every record carries its slice in its last word (1: a chain is a slice)
 	u32 tile_reads;		// reads per shared-memory tile of skm_emit_kernel
 	u32 npos;		// m-mer positions per read at most (max_read_len - m + 1)
 	u32 npad;		// row stride of the per-read arrays of skm_emit_kernel (a multiple of 4, >= npos)
@@ -300,7 +301,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 		{
 			d_nx = mhs[tid];
 			s_nx = sls[(d_nx & 0xFFu) * g.npad + ((d_nx >> 8) & 0xFFFFu)];
-			tk_nx = chain_ticket (ch, s_nx & ~SKM_NFLAG);
+			tk_nx = chain_ticket (ch, (s_nx & ~SKM_NFLAG) / g.send_group);
 		}
 		for (u32 rid = tid; rid < n_out; rid += EMIT_NT)
 		{
@@ -311,12 +312,12 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			{
 				d_nx = mhs[rid + EMIT_NT];
 				s_nx = sls[(d_nx & 0xFFu) * g.npad + ((d_nx >> 8) & 0xFFFFu)];
-				tk_nx = chain_ticket (ch, s_nx & ~SKM_NFLAG);
+				tk_nx = chain_ticket (ch, (s_nx & ~SKM_NFLAG) / g.send_group);
 			}
 			const u32 r = d & 0xFFu, j0 = (d >> 8) & 0xFFFFu, n = (d >> 24) + 1;
 			const u32 len = (rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r]) + K - 1;
 			const u32 *rd = rt.tile + r * rt.sw;
-			u32 *rec = chain_place (ch, s & ~SKM_NFLAG, tk, s_pool, more ? &tk_nx : nullptr, s_nx & ~SKM_NFLAG);
+			u32 *rec = chain_place (ch, (s & ~SKM_NFLAG) / g.send_group, tk, s_pool, more ? &tk_nx : nullptr, (s_nx & ~SKM_NFLAG) / g.send_group);
 			if (!rec)
 				continue;
 			const u64 ord = (rb.first_read_ordinal + rt.r0 + r) * rb.maxwin + j0;
@@ -349,6 +350,8 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 						v &= 0xFFFFFFFFu << (32 - 2 * (nb & 15));	// nothing of the read beyond the record's bases
 				}
 				const u32 o = SKM_HDR + q;
+				if (q == RECW - SKM_HDR - 1 && g.send_group > 1)
+					v = s & ~SKM_NFLAG;	// (the last word is never used by bases: the slice travels there)
 				wd[o & 3] = v;
 				if ((o & 3) == 3)
 					*reinterpret_cast<uint4 *> (rec + (o & ~3u)) = make_uint4 (wd[0], wd[1], wd[2], wd[3]);

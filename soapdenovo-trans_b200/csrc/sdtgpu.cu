@@ -71,6 +71,7 @@ struct sdtgpu
 	Staging stage[2];
 	int next_stage = 0;
 	int sm_count = 0;
+	size_t mem_total = 0;	// device memory (cudaMemGetInfo is slow — milliseconds with several processes on a box — so it is only asked when an allocation is about to happen)
 	u64 pushed_upper = 0;	// upper bound of instances pushed (host-side arithmetic)
 	// the most recent batch stays on the device until the next one arrives: the hand-back needs the
 	// per-set last instance ordinal (put_kmerset runs encap_kmerset on every call, newhash.c:415)
@@ -100,7 +101,8 @@ struct sdtgpu
 	std::vector<LogSeg> log;
 	ChainLevel lv[3];	// [0] the slices (several GPUs: ALL ranks' slices, the sending side), [1] sub-slices of slices that overflowed, [2] this rank's slices, receiving side
 	u64 *d_small = nullptr, *h_small = nullptr;	// [0] records made, [1] node cursor, [2] failed work items, [3] work-item cursor, [4] records after the merge, [5] their windows, [8..] owner regions; pinned mirror
-	void *d_failed = nullptr, *d_items = nullptr;	// SkmWork lists
+	void *d_failed = nullptr, *d_items = nullptr, *h_failed = nullptr;	// SkmWork lists (h_failed: pinned, the first FAILED_PREFIX of d_failed)
+	u64 win_left = 0;	// windows the last merge left
 	u32 *rx = nullptr;	// records received from other ranks
 	u64 rx_cap = 0;
 	u32 skm_world = 1, skm_rank = 0, n_local = 0;	// super-k-mer exchange (sdtgpu_skm_set_world): slices per rank; geom.n_slices = n_local * skm_world
@@ -545,8 +547,11 @@ struct Trace
 		cudaStreamSynchronize (h->stream);
 		const auto t1 = std::chrono::steady_clock::now ();
 		size_t fr = 0, tot = 0;
-		cudaMemGetInfo (&fr, &tot);
+		if (atoi (getenv ("SDTGPU_TRACE")) > 1)
+			cudaMemGetInfo (&fr, &tot);
 		fprintf (stderr, "[sdtgpu] %-28s %8.3f ms   (%.1f GB free)\n", what, std::chrono::duration<double, std::milli> (t1 - t0).count (), fr / 1e9);
+		t0 = std::chrono::steady_clock::now ();
+		return;
 		t0 = t1;
 	}
 };
@@ -689,15 +694,13 @@ int level_reset (sdtgpu *h, ChainLevel &L)
 {
 	if (!L.n_chains)
 		return SDTGPU_OK;
-	chain_init_kernel<<<std::min<u32> ((L.n_chains + 255) / 256, (u32) h->sm_count * 8), 256, 0, h->stream>>> (reinterpret_cast<unsigned long long *> (L.head), L.bcount, L.n_chains);
+	chain_init_kernel<<<std::min<u32> ((L.n_chains + 255) / 256, (u32) h->sm_count * 8), 256, 0, h->stream>>> (reinterpret_cast<unsigned long long *> (L.head), L.bcount, L.n_chains,
+														   reinterpret_cast<unsigned long long *> (L.d_cursor));
 	CK (h, cudaGetLastError ());
 	h->all_launches++;
 	if (L.pool_blocks)
 		CK (h, cudaMemsetAsync (L.bchain, 0xFF, L.pool_blocks * sizeof (u32), h->stream));
 	CK (h, cudaMemsetAsync (L.cta_pool, 0, MAX_CTAS * sizeof (uint2), h->stream));
-	h->h_small[6] = L.n_chains;
-	CK (h, cudaMemcpyAsync (L.d_cursor, h->h_small + 6, sizeof (u64), cudaMemcpyHostToDevice, h->stream));
-	CK (h, cudaStreamSynchronize (h->stream));	// (h_small[6] is reused)
 	L.blocks_upper = L.n_chains;
 	return SDTGPU_OK;
 }
@@ -840,17 +843,22 @@ int skm_open_epoch (sdtgpu *h)
 		hint = estimate_distinct (h->pushed_upper, h->K);
 	if ((rc = skm_setup (h, hint)))
 		return rc;
+	h->geom.send_group = 1;
 	if (h->skm_world > 1)
-	{
-		h->n_local = h->geom.n_slices;
+	{	// the sending side keeps `world` consecutive slices in one chain (chains as long as on one GPU: the merge in front
+		// of the exchange costs what it costs there); the records carry their slice
+		const u32 grp = h->skm_world;
+		h->n_local = (h->geom.n_slices + grp - 1) / grp * grp;
 		if ((u64) h->n_local * h->skm_world > (1ull << 28))
 			return fail (h, SDTGPU_ERANGE, "too many slices");
 		h->geom.n_slices = h->n_local * h->skm_world;
 		h->geom.slice_a = slice_of_min_host (mmer_hash (0), h->geom.n_slices);
+		h->geom.send_group = getenv ("SDTGPU_NO_SEND_GROUP") ? 1 : grp;
 	}
-	if (h->lv[0].n_chains != h->geom.n_slices)	// (else: same geometry as the last epoch, whose chains sdtgpu_reset has emptied)
+	const u32 n_chains0 = h->geom.n_slices / h->geom.send_group;
+	if (h->lv[0].n_chains != n_chains0)	// (else: same geometry as the last epoch, whose chains sdtgpu_reset has emptied)
 	{
-		if ((rc = level_create (h, h->lv[0], h->geom.n_slices)))
+		if ((rc = level_create (h, h->lv[0], n_chains0)))
 			return rc;
 	}
 	else if ((rc = level_reset (h, h->lv[0])))
@@ -860,7 +868,7 @@ int skm_open_epoch (sdtgpu *h)
 }
 
 
-template <int W, bool ORD32> int launch_build2_t (sdtgpu *h, const u32 *rec, const SkmWork *items, u32 n_items, int cat)
+template <int W, bool ORD32> int launch_build2_t (sdtgpu *h, const u32 *rec, const SkmWork *items, u32 n_items, const u64 *n_items_dev, int cat)
 {
 	typedef typename SlotOf<W>::type S;
 	const SkmGeom &g = h->geom;
@@ -872,21 +880,21 @@ template <int W, bool ORD32> int launch_build2_t (sdtgpu *h, const u32 *rec, con
 	CK (h, cudaMemsetAsync (small + 3, 0, sizeof (u64), h->stream));	// work-item cursor
 	{
 		TimedLaunch tl (h, cat);
-		kern<<<grid, BUILD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, rec, items, n_items, small + 3,
+		kern<<<grid, BUILD_NT, smem, h->stream>>> (static_cast<S *> (h->table), h->cap, small + 1, g, h->K, rec, items, n_items, reinterpret_cast<const unsigned long long *> (n_items_dev), small + 3,
 							   static_cast<SkmWork *> (h->d_failed), reinterpret_cast<u32 *> (small + 2), MAX_FAILED, h->d_ctr);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;
 }
 
-int launch_build (sdtgpu *h, const u32 *rec, const SkmWork *items, u32 n_items, int cat)
+int launch_build (sdtgpu *h, const u32 *rec, const SkmWork *items, u32 n_items, int cat, const u64 *n_items_dev = nullptr)
 {	// 32-bit ordinals in the slice images when every instance ordinal pushed so far fits (several GPUs: the caller says so)
 	const bool ord32 = h->ord_end < 0xFFFFFFFFull && !getenv ("SDTGPU_ORD64");
 	switch (h->W)
 	{
-	case 1: return ord32 ? launch_build2_t<1, true> (h, rec, items, n_items, cat) : launch_build2_t<1, false> (h, rec, items, n_items, cat);
-	case 2: return ord32 ? launch_build2_t<2, true> (h, rec, items, n_items, cat) : launch_build2_t<2, false> (h, rec, items, n_items, cat);
-	default: return ord32 ? launch_build2_t<4, true> (h, rec, items, n_items, cat) : launch_build2_t<4, false> (h, rec, items, n_items, cat);
+	case 1: return ord32 ? launch_build2_t<1, true> (h, rec, items, n_items, n_items_dev, cat) : launch_build2_t<1, false> (h, rec, items, n_items, n_items_dev, cat);
+	case 2: return ord32 ? launch_build2_t<2, true> (h, rec, items, n_items, n_items_dev, cat) : launch_build2_t<2, false> (h, rec, items, n_items, n_items_dev, cat);
+	default: return ord32 ? launch_build2_t<4, true> (h, rec, items, n_items, n_items_dev, cat) : launch_build2_t<4, false> (h, rec, items, n_items, n_items_dev, cat);
 	}
 }
 
@@ -902,12 +910,10 @@ int level_list (sdtgpu *h, ChainLevel &L, u64 *n_blocks)
 		h->all_launches++;
 	}
 	CK (h, cudaGetLastError ());
-	CK (h, cudaMemcpyAsync (h->h_small + 6, L.boff + L.n_chains, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-	CK (h, cudaMemcpyAsync (h->h_small + 7, L.d_cursor, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-	CK (h, cudaStreamSynchronize (h->stream));
-	const u64 linked = h->h_small[6], cursor = std::min<u64> (h->h_small[7], L.pool_blocks);
+	// (no look at the counts: the list is given room for every block of the pool, the kernel reads the cursor itself)
+	const u64 linked = L.pool_blocks > L.n_chains ? L.pool_blocks - L.n_chains : 0, cursor = L.pool_blocks;
 	size_t cap_b = L.blist_cap * 4;
-	if ((rc = grow_device (h, (void **) &L.blist, &cap_b, 0, std::max<u64> (linked, 1) * 4)))
+	if ((rc = grow_device (h, (void **) &L.blist, &cap_b, 0, std::max<u64> (linked, 1) * 4, "block list")))
 		return rc;
 	L.blist_cap = cap_b / 4;
 	if (cursor > L.n_chains)
@@ -954,6 +960,7 @@ template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u6
 	mo.budget = std::max (1u, (u32) (load * h->geom.slice_slots));
 	mo.oversize = std::max (mo.budget, 8 * h->geom.slice_slots);	// (a hot locus has many windows but few distinct k-mers: the build finds out)
 	mo.per_owner = per_owner;
+	mo.tagged = h->geom.send_group > 1;
 	mo.region = region;
 	mo.rcur = reinterpret_cast<unsigned long long *> (rcur);
 	{
@@ -1009,7 +1016,7 @@ int skm_emit_all (sdtgpu *h, u64 records)
 }
 
 // part 1 of a flush: all records are in their chains (emitting the read log again if the block pool ran out)
-int skm_collect (sdtgpu *h, u64 *n_rec)
+int skm_collect (sdtgpu *h, u64 *n_rec, bool wait = true)
 {
 	int rc;
 	if (!h->emitted)
@@ -1021,6 +1028,8 @@ int skm_collect (sdtgpu *h, u64 *n_rec)
 				return rc;
 		h->emitted = true;
 	}
+	if (!wait)
+		return SDTGPU_OK;
 	for (int attempt = 0;; attempt++)
 	{
 		CK (h, cudaMemcpyAsync (h->h_small, h->d_small, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
@@ -1061,8 +1070,11 @@ int ensure_store (sdtgpu *h, u64 slots)
 	return SDTGPU_OK;
 }
 
+static constexpr int STORE_FULL = -100;	// internal: the node store ran out; the top level enlarges it and builds again
+static constexpr int RECORDS_FULL = -101;	// internal: the block pool ran out while the records were made; the flush emits them again
+
 // part 2: the chains of level L -> contiguous runs (copies merged) -> node store
-int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, bool top);
+int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, u64 n_est, bool top);
 
 // Everything pushed since the last reset becomes the node store.  Records persist until sdtgpu_reset, so a
 // later push followed by another flush rebuilds the store from all of them.
@@ -1080,28 +1092,49 @@ int sliced_flush (sdtgpu *h)
 	}
 	if (h->skm_world > 1)
 		return fail (h, SDTGPU_ESTATE, "super-k-mer exchange: reads were pushed but sdtgpu_skm_stage / sdtgpu_skm_import have not run");
-	u64 n_rec = 0;
 	Trace tr (h);
-	if ((rc = skm_collect (h, &n_rec)))
-		return rc;
-	tr.mark ("collect (emit done)");
-	h->n_records = n_rec;
-	rc = skm_build_level (h, h->lv[0], false, n_rec, true);
+	ChainLevel &L = h->lv[0];
+	for (int attempt = 0;; attempt++)
+	{
+		u64 n_rec = 0;
+		if (!h->emitted && (rc = skm_collect (h, &n_rec, false)))	// (no hint: the records are made now)
+			return rc;
+		// How many records there are is only needed as a bound (room for the merged runs): the pool's size will do,
+		// and nobody has to wait for the kernels to ask them — unless memory is short or something went wrong before
+		const bool look = attempt > 0 || h->chains_dropped || (double) L.pool_blocks * CH_BLK * h->geom.recw * 4 > 0.1 * (double) h->mem_total || getenv ("SDTGPU_SLOW_FLUSH");
+		if (look)
+		{
+			if ((rc = skm_collect (h, &n_rec, true)))
+				return rc;
+			tr.mark ("collect (emit done)");
+		}
+		else
+			n_rec = L.pool_blocks * CH_BLK;
+		const u64 n_est = look ? n_rec : (h->n_records ? h->n_records : n_rec - n_rec / 8);
+		rc = skm_build_level (h, L, false, n_rec, n_est, true);
+		if (rc != RECORDS_FULL || attempt == 2)
+			break;
+		CK (h, cudaMemsetAsync (&h->d_ctr->overflow, 0, sizeof (u64), h->stream));	// (the pool ran out: the second round looks, and emits again)
+	}
+	if (rc == RECORDS_FULL)
+		return fail (h, SDTGPU_ERANGE, "record pool overflow persists");
+	h->n_records = h->h_small[0];
 	tr.mark ("build level 0 (total)");
 	return rc;
 }
 
-static constexpr int STORE_FULL = -100;	// internal: the node store ran out; the top level enlarges it and builds again
 
 // the work items of level L -> node store; items that overflow an image are retried in pieces or, far
 // beyond an image, cut into sub-slices
-int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top)
+static constexpr u32 FAILED_PREFIX = 4096;	// failed work items that are fetched together with the counters (pinned: h_failed)
+
+int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top, const u64 *n_items_dev = nullptr)
 {
 	int rc;
 	const SkmGeom g = h->geom;
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	Trace tr (h);
-	if (n_items && (rc = launch_build (h, L.out, L.items, n_items, top ? 4 : 6)))
+	if (n_items && (rc = launch_build (h, L.out, L.items, n_items, top ? 4 : 6, n_items_dev)))
 		return rc;
 	tr.mark ("  build all items");
 	std::vector<SkmWork> items, failed;
@@ -1109,9 +1142,28 @@ int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top)
 	u64 Q = 0, sub_windows = 0;
 	for (u32 depth = 0;; depth++)
 	{
+		// one look at the device: node cursor, failed items (count and the first of them), overflow flags, and what
+		// the merge counted (records and windows left, work items) if nobody has looked yet
 		CK (h, cudaMemcpyAsync (h->h_small + 1, small + 1, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaMemcpyAsync (h->h_small + 3, &h->d_ctr->overflow, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (h->h_small + 4, small + 4, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (h->h_small + 6, L.d_cursor + 2, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (h->h_small, small, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaMemcpyAsync (h->h_failed, h->d_failed, FAILED_PREFIX * sizeof (SkmWork), cudaMemcpyDeviceToHost, h->stream));
 		CK (h, cudaStreamSynchronize (h->stream));
+		if (depth == 0)
+		{
+			if (h->h_small[6] > L.cap_chains)
+				return fail (h, SDTGPU_ERANGE, "work item list overflow");
+			if (top)
+			{
+				h->n_merged = h->h_small[4];
+				h->n_items = h->h_small[6];
+				h->win_left = h->h_small[5];
+			}
+		}
+		if (h->h_small[3] & OVF_RECORDS)
+			return RECORDS_FULL;
 		if (h->h_small[3] & OVF_STORE)
 			return STORE_FULL;
 		const u32 n_failed = (u32) h->h_small[2];
@@ -1120,7 +1172,9 @@ int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top)
 		if ((h->h_small[3] & OVF_FAILED) || n_failed > MAX_FAILED || depth == 10)
 			return fail (h, SDTGPU_ERANGE, "too many work items overflowed their images");
 		failed.resize (n_failed);
-		CK (h, cudaMemcpy (failed.data (), h->d_failed, n_failed * sizeof (SkmWork), cudaMemcpyDeviceToHost));
+		memcpy (failed.data (), h->h_failed, std::min (n_failed, FAILED_PREFIX) * sizeof (SkmWork));
+		if (n_failed > FAILED_PREFIX)
+			CK (h, cudaMemcpy (failed.data () + FAILED_PREFIX, static_cast<const SkmWork *> (h->d_failed) + FAILED_PREFIX, (n_failed - FAILED_PREFIX) * sizeof (SkmWork), cudaMemcpyDeviceToHost));
 		h->n_retried += n_failed;
 		CK (h, cudaMemsetAsync (small + 2, 0, sizeof (u64), h->stream));
 		// A failed item holds more distinct k-mers than an image takes (it is a single chain with more windows than
@@ -1164,12 +1218,17 @@ int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top)
 		const size_t recb = 4 * (size_t) g.recw;
 		const u64 hold = (u64) std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS) * 8 * 256;
 		size_t a = 0;
+		size_t fr = 0, tot = h->mem_total;
+		// (the free memory is asked for only if what the sub-slices hold from earlier epochs is not enough for everything at once)
+		const bool all_fits = S.pool_blocks >= Q + sub_windows / CH_BLK + sub_windows / (4 * CH_BLK) + hold + 4096 && S.out_cap >= sub_windows && S.cap_chains >= Q;
+		if (!all_fits)
+			cudaMemGetInfo (&fr, &tot);
 		while (a < splits.size ())
 		{
-			size_t fr = 0, tot = 0;
-			cudaMemGetInfo (&fr, &tot);
+			if (a)
+				cudaMemGetInfo (&fr, &tot);	// (a further batch: only when memory is short)
 			const double room = (double) fr + (double) S.pool_blocks * CH_BLK * recb + (double) S.out_cap * recb - (2.0 * hold * CH_BLK * recb + (2u << 30));
-			const u64 max_win = (u64) std::max (1e6, room / (2.6 * recb));
+			const u64 max_win = all_fits ? ~0ull : (u64) std::max (1e6, std::min (room, 0.08 * (double) tot) / (2.6 * recb));	// (never more than 8 % of the memory: it stays allocated)
 			size_t b = a;
 			u64 win = 0, q0 = splits[a].qbase, q1 = q0;
 			while (b < splits.size () && (b == a || win + splits[b].pad <= max_win || splits[b].qbase == splits[b - 1].qbase))
@@ -1192,7 +1251,7 @@ int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top)
 			if (h->h_small[3] & OVF_RECORDS)
 				return fail (h, SDTGPU_ERANGE, "sub-slice pool overflow");
 			tr.mark ("  split");
-			if ((rc = skm_build_level (h, S, true, win, false)))
+			if ((rc = skm_build_level (h, S, true, win, win, false)))
 				return rc;
 			tr.mark ("  sub-slices");
 			a = b;
@@ -1201,8 +1260,8 @@ int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top)
 	return SDTGPU_OK;
 }
 
-int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, bool top)
-{
+int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, u64 n_est, bool top)
+{	// n_rec: records in the chains at most (room for the merged runs); n_est: about how many there are
 	int rc;
 	const SkmGeom g = h->geom;
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
@@ -1218,24 +1277,25 @@ int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, bool to
 			return rc;
 		L.out_cap = cap_b / rec;
 	}
-	if ((rc = launch_merge (h, L, has_mult, n_rec)))
+	if ((rc = launch_merge (h, L, has_mult, n_est)))
 		return rc;
-	CK (h, cudaMemcpyAsync (h->h_small + 4, small + 4, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-	CK (h, cudaMemcpyAsync (h->h_small + 6, L.d_cursor + 2, sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
-	CK (h, cudaStreamSynchronize (h->stream));
-	tr.mark (" merge");
-	const u32 n_items = (u32) std::min<u64> (h->h_small[6], L.cap_chains);
-	if (h->h_small[6] > L.cap_chains)
-		return fail (h, SDTGPU_ERANGE, "work item list overflow");
+	// the build takes the number of work items from the device: the host does not wait for the merge
 	if (!top)
-		return skm_build_runs (h, L, n_items, false);
-	h->n_items = n_items;
-	h->n_merged = n_rec ? h->h_small[4] : 0;
-	const u64 win_upper = h->h_small[5] + 1024;	// every node needs a window of its own
+		return skm_build_runs (h, L, L.cap_chains, false, L.d_cursor + 2);
+	u64 win_upper = ~0ull;
+	if (!h->table || h->cap < h->store_want)
+	{	// the node store has to be sized: by what the merge left (every node needs a window of its own)
+		CK (h, cudaMemcpyAsync (h->h_small + 4, small + 4, 2 * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
+		CK (h, cudaStreamSynchronize (h->stream));
+		tr.mark (" merge");
+		win_upper = h->h_small[5] + 1024;
+	}
+	const u32 n_items = L.cap_chains;
 	for (int attempt = 0;; attempt++)
 	{	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over.
 		// Its size: the hint's (or the estimate's) worth, never more than the windows the merge left
-		u64 want = std::min<u64> (h->store_want, win_upper);
+		u64 want = win_upper == ~0ull ? h->cap : std::min<u64> (h->store_want, win_upper);
+		if (want > h->cap || !h->table)
 		{	// no room for the node store beside the chains?  The chains are not needed any more (their records are
 			// merged): they go, and a later flush of this epoch emits the read log again
 			size_t fr = 0, tot = 0;
@@ -1259,9 +1319,10 @@ int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, bool to
 		CK (h, cudaMemsetAsync (small + 1, 0, 2 * sizeof (u64), h->stream));
 		CK (h, cudaMemsetAsync (&h->d_ctr->n_nodes, 0, 2 * sizeof (u64), h->stream));	// n_nodes, n_instances
 		h->n_retried = 0;
-		rc = skm_build_runs (h, L, n_items, true);
+		rc = skm_build_runs (h, L, n_items, true, L.d_cursor + 2);
 		if (rc != STORE_FULL)
 			break;
+		win_upper = h->win_left + 1024;	// (skm_build_runs has looked)
 		if (attempt == 1 || h->cap >= win_upper)
 			return fail (h, SDTGPU_ERANGE, "node store exhausted");
 		h->store_want = win_upper;	// the estimate was too low: a store that cannot run out, and once more
@@ -1368,6 +1429,7 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 		cudaDeviceProp prop;
 		CK (h, cudaGetDeviceProperties (&prop, device));
 		h->sm_count = prop.multiProcessorCount;
+		h->mem_total = prop.totalGlobalMem;
 		CK (h, cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking));
 		CK (h, cudaStreamCreateWithFlags (&h->copy_stream, cudaStreamNonBlocking));
 		for (auto &s : h->stage)
@@ -1394,6 +1456,7 @@ int sdtgpu_create (sdtgpu_t **out, int device, int K, int key_words, int max_rea
 			CK (h, cudaMalloc (&h->d_failed, (size_t) MAX_FAILED * sizeof (SkmWork)));
 			CK (h, cudaMalloc (&h->d_items, (size_t) MAX_FAILED * sizeof (SkmWork)));
 			CK (h, cudaMallocHost (&h->h_small, 160 * sizeof (u64)));
+			CK (h, cudaMallocHost (&h->h_failed, 4096 * sizeof (SkmWork)));
 			CK (h, cudaMemsetAsync (h->d_small, 0, 160 * sizeof (u64), h->stream));
 			CK (h, cudaStreamSynchronize (h->stream));
 			if (capacity_hint && (rc = skm_open_epoch (h)))	// (reports a bad geometry at create time)
@@ -1437,6 +1500,7 @@ void sdtgpu_destroy (sdtgpu_t *h)
 		level_free (L);
 	cudaFree (h->d_small); cudaFree (h->d_failed); cudaFree (h->d_items); cudaFree (h->rx);
 	if (h->h_small) cudaFreeHost (h->h_small);
+	if (h->h_failed) cudaFreeHost (h->h_failed);
 	cudaFree (h->table);
 	cudaFree (h->d_ctr);
 	if (h->h_ctr) cudaFreeHost (h->h_ctr);
@@ -1452,7 +1516,9 @@ int sdtgpu_reset (sdtgpu_t *h)
 	if (!h)
 		return SDTGPU_EINVAL;
 	CK (h, cudaSetDevice (h->device));
+	Trace tr (h);
 	CK (h, cudaMemsetAsync (h->d_ctr, 0, sizeof (Counters), h->stream));
+	tr.mark ("reset: counters");
 	if (h->sliced)
 	{	// records, their per-slice counts and the read log go; the store is rewritten by the next build
 		CK (h, cudaMemsetAsync (h->d_small, 0, 8 * sizeof (u64), h->stream));
@@ -1466,6 +1532,16 @@ int sdtgpu_reset (sdtgpu_t *h)
 			h->epoch_open = false;	// no hint: the next epoch's geometry comes from what is pushed then (skm_open_epoch empties the chains)
 		h->emitted = false;
 		h->chains_dropped = false;
+		{	// a node store that takes a large part of the memory would be in the way of the next epoch's records
+			if (h->table && (double) h->cap * slot_bytes (h->W) > 0.45 * (double) h->mem_total)
+			{
+				CK (h, cudaStreamSynchronize (h->stream));
+				CK (h, cudaFree (h->table));
+				h->table = nullptr;
+				h->cap = 0;
+			}
+		}
+		tr.mark ("reset: chains");
 		h->ord_bound_set = false;
 		h->log.clear ();
 		h->log_used[0] = h->log_used[1] = h->log_used[2] = 0;
@@ -1484,6 +1560,7 @@ int sdtgpu_reset (sdtgpu_t *h)
 		CK (h, cudaEventSynchronize (h->snap_ev));
 	h->snap_pending = false;
 	h->known_nodes = h->known_at = h->snap_pushed = 0;
+	tr.mark ("reset: rest");
 	return SDTGPU_OK;
 }
 
@@ -1635,15 +1712,18 @@ int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *starts, uint64_t 
 	if ((rc = skm_open_epoch (h)))
 		return rc;
 	ChainLevel &L = h->lv[0];
-	const u32 world = h->skm_world, per_owner = world > 1 ? h->n_local : L.n_chains;
+	const u32 world = h->skm_world, per_owner = world > 1 ? h->n_local / h->geom.send_group : L.n_chains;
 	u64 n_rec = 0;
 	h->emitted = true;	// (a rank without reads still takes part)
+	Trace tr (h);
 	if ((rc = skm_collect (h, &n_rec)))
 		return rc;
+	tr.mark ("stage: collect");
 	h->n_records = n_rec;
 	u64 n_blocks = 0;
 	if ((rc = level_list (h, L, &n_blocks)))
 		return rc;
+	tr.mark ("stage: list");
 	// records per owner (an upper bound of what survives the merge) -> where each owner's region starts
 	u64 *d_reg = h->d_small + 8;	// [world] region starts, [world] cursors
 	chain_owner_count_kernel<<<world, 256, 0, h->stream>>> (level_chains (h, L), per_owner, reinterpret_cast<unsigned long long *> (d_reg));
@@ -1668,10 +1748,12 @@ int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *starts, uint64_t 
 			return rc;
 		L.out_cap = cap_b / rec;
 	}
+	tr.mark ("stage: owner regions");
 	if ((rc = launch_merge (h, L, false, n_rec, per_owner, d_reg, d_reg + world)))
 		return rc;
 	CK (h, cudaMemcpyAsync (h->h_small + 8 + world, d_reg + world, world * sizeof (u64), cudaMemcpyDeviceToHost, h->stream));
 	CK (h, cudaStreamSynchronize (h->stream));
+	tr.mark ("stage: merge by owner");
 	for (u32 r = 0; r < world; r++)
 		counts[r] = h->h_small[8 + world + r];
 	*d_records = L.out;
@@ -1709,8 +1791,10 @@ int sdtgpu_skm_import (sdtgpu_t *h, uint64_t n_records)
 		return rc;
 	const u32 n_local = h->skm_world > 1 ? h->n_local : h->geom.n_slices;
 	ChainLevel &R = h->lv[2];
+	Trace tr (h);
 	if ((rc = level_create (h, R, n_local)))
 		return rc;
+	tr.mark ("import: chains reset");
 	const u64 hold = (u64) std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS) * CH_SB;
 	for (int attempt = 0;; attempt++)
 	{
@@ -1735,6 +1819,7 @@ int sdtgpu_skm_import (sdtgpu_t *h, uint64_t n_records)
 		CK (h, cudaStreamSynchronize (h->stream));
 		if (h->h_small[3] & OVF_FOREIGN)
 			return fail (h, SDTGPU_EINVAL, "super-k-mer exchange: a received record belongs to another rank's slices");
+		tr.mark ("import: append");
 		if (!(h->h_small[3] & OVF_RECORDS))
 			break;
 		if (attempt == 1)
@@ -1746,7 +1831,7 @@ int sdtgpu_skm_import (sdtgpu_t *h, uint64_t n_records)
 	h->n_store = 0;
 	if (!h->ord_bound_set && h->skm_world > 1)
 		h->ord_end = ~0ull;	// records of other ranks' reads: their ordinals are not bounded by what this rank pushed
-	return skm_build_level (h, R, true, n_records, true);
+	return skm_build_level (h, R, true, n_records, n_records, true);
 }
 
 size_t sdtgpu_record_bytes (const sdtgpu_t *h) { return h ? 8 * (size_t) (h->W + 1) : 0; }

@@ -230,6 +230,7 @@ class SkmExchange:
         self.world, self.rank, self.dev, self.group = world, rank, dev, group
         self.nvlink_bytes = 0
         self.collective_ms = 0.0        # device time of the counts + records exchange (CUDA events on the handle's stream)
+        self.host_ms = {}               # wall clock of the phases of flush (host side, this rank)
         self.rebind(g)
 
     def rebind(self, g):
@@ -260,10 +261,14 @@ class SkmExchange:
         self.inserted[b].record(self.main)          # the round's buffer is free again (the library keeps its own copy of the reads)
 
     def flush(self, g):
+        import time
+        t0 = time.perf_counter()
         bound = torch.tensor([self.reads_end], dtype=torch.int64, device=self.dev)
         dist.all_reduce(bound, op=dist.ReduceOp.MAX, group=self.group)
         g.skm_set_ordinal_bound(int(bound.item()))  # reads of all ranks this epoch: 32-bit ordinals in the slice images when they fit
+        t1 = time.perf_counter()
         ptr, starts, counts = g.skm_stage()         # merges this rank's copies, packs by owner; synchronises the handle's stream
+        t2 = time.perf_counter()
         rb, w8 = self.rec_bytes, self.rec_bytes // 8
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self.main):
@@ -272,6 +277,11 @@ class SkmExchange:
             total, _ = exchange_runs(send, w8, lambda n: _wrap(g.skm_import_buffer(n), n * rb, self.dev), group=self.group)
             e1.record(self.main)
             self.nvlink_bytes += (sum(counts) - counts[self.rank]) * rb
+        t3 = time.perf_counter()
         g.skm_import(total)                         # on the handle's stream, after the exchange (drains the stream)
+        t4 = time.perf_counter()
         self.collective_ms += e0.elapsed_time(e1)
+        for k, v in zip(("bound", "stage", "exchange", "import"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            self.host_ms[k] = self.host_ms.get(k, 0.0) + 1e3 * v
+        self.host_ms["flushes"] = self.host_ms.get("flushes", 0) + 1
         return total
