@@ -30,7 +30,10 @@ namespace sdt {
 // read, so the round trip of that reservation costs nothing.
 static constexpr int MG_NT = 512;	// 2 CTAs of 80-96 KB per SM
 static constexpr u32 MG_GMAX = 32;	// chains per group at most
-template <int W> struct MergeCfg { static constexpr u32 CHUNK = W == 1 ? 2048u : 1024u, TABLE = 2 * CHUNK; };
+#ifndef SDT_MERGE_CHUNK1
+#define SDT_MERGE_CHUNK1 2048u
+#endif
+template <int W> struct MergeCfg { static constexpr u32 CHUNK = W == 1 ? SDT_MERGE_CHUNK1 : 1024u, TABLE = 2 * CHUNK; };
 template <int W> __host__ __device__ inline size_t skm_merge_smem () { return (size_t) MergeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) MergeCfg<W>::TABLE * 4 + (MergeCfg<W>::CHUNK / CH_BLK + MG_GMAX + 4) * 4; }
 
 struct MergeOut
@@ -258,11 +261,68 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		c0 = owner * span + (u32) (grp % gpo) * G;
 		nch = min (min (G, owner * span + span - c0), ch.n_chains - c0);
 	};
+	// One GPU (no owners): a CTA takes a CONTIGUOUS range of groups and writes their survivors one behind the other
+	// into a region it reserves once (by its chains' record count), so that a work item can run across groups: the
+	// open item is carried from group to group and closed when the next chain would take it over the budget.
+	// Several GPUs, sending side: groups round robin, every group's survivors into its owner's region.
+	const bool contig = !mo.per_owner;
+	const u64 gpc = (n_groups + gridDim.x - 1) / gridDim.x;
+	const u64 g_first = contig ? blockIdx.x * gpc : blockIdx.x, g_step = contig ? 1 : gridDim.x;
+	const u64 g_end = contig ? min (n_groups, g_first + gpc) : n_groups;
+	u64 cta_base = 0, cta_out = 0;	// (uniform: every thread keeps the same values)
+	u64 open_r0 = 0;		// thread 0: the open work item (first record, records, windows)
+	u32 open_n = 0, open_w = 0;
+	auto close_item = [&]() {
+		if (!open_n)
+			return;
+		SkmWork it;
+		it.r0 = open_r0;
+		it.nrec = open_n;
+		it.wsum = open_w;
+		it.r = 0;
+		it.R = open_w > mo.oversize ? 0u : 1u;
+		const u64 ib = atomicAdd (mo.n_items, 1ull);
+		if (ib < mo.max_items)
+			mo.items[ib] = it;
+		open_n = open_w = 0;
+	};
+	auto add_chain = [&](u64 r0, u32 nrec, u32 w) {	// thread 0: a chain's survivors (they sit right behind the open item's)
+		if (!nrec)
+			return;
+		if (open_n && open_w + w > mo.budget)
+			close_item ();
+		if (!open_n)
+			open_r0 = r0;
+		open_n += nrec;
+		open_w += w;
+		if (open_w > mo.budget)
+			close_item ();	// a single chain beyond the budget: an item of its own
+	};
+	if (contig && g_first < g_end)
+	{	// this CTA's chains hold how many records?  (its region in out[]: an upper bound of what survives)
+		const u32 c_lo = (u32) (g_first * G), c_hi = (u32) min ((u64) ch.n_chains, g_end * G);
+		unsigned long long sum = 0;
+		for (u32 c = c_lo + tid; c < c_hi; c += MG_NT)
+			sum += (u64) ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1)
+			sum += __shfl_down_sync (0xFFFFFFFFu, sum, d);
+		if (tid == 0)
+			s_start = 0;
+		__syncthreads ();
+		if (lane == 0 && sum)
+			atomicAdd (&s_start, sum);
+		__syncthreads ();
+		if (tid == 0)
+			s_ibase = atomicAdd (mo.out_cursor, s_start);
+		__syncthreads ();
+		cta_base = s_ibase;
+	}
 	u32 pb = 0;	// which half of s_nraw / s_b0 holds this group's
-	if (blockIdx.x < n_groups)
+	if (g_first < g_end)
 	{
 		u32 owner, c0, nch;
-		geom (blockIdx.x, owner, c0, nch);
+		geom (g_first, owner, c0, nch);
 		if (tid < nch)
 		{
 			const u32 c = c0 + tid;
@@ -271,16 +331,16 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		}
 	}
 	__syncthreads ();
-	for (u64 grp = blockIdx.x; grp < n_groups; grp += gridDim.x, pb ^= MG_GMAX)
+	for (u64 grp = g_first; grp < g_end; grp += g_step, pb ^= MG_GMAX)
 	{
 		u32 owner, c0, nch;
 		geom (grp, owner, c0, nch);
 		u32 nx_raw = 0;
 		u64 nx_b0 = 0;
-		if (grp + gridDim.x < n_groups)
+		if (grp + g_step < g_end)
 		{
 			u32 o2, c2, n2;
-			geom (grp + gridDim.x, o2, c2, n2);
+			geom (grp + g_step, o2, c2, n2);
 			if (tid < n2)
 			{
 				const u32 c = c2 + tid;
@@ -297,9 +357,6 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 			total_raw += s_nraw[g];
 		if (total_raw == 0)
 			break;
-		unsigned long long resv = 0;
-		if (tid == 0 && !mo.per_owner)
-			resv = atomicAdd (mo.out_cursor, (unsigned long long) total_raw);	// (looked at after the first chunk is merged)
 		if (total_raw <= CH && nch <= MG_GMAX)
 		{	// ---- the rule: the whole group in one chunk
 			{	// first record of every chain in the chunk; its blocks; the records (coalesced 16-byte loads)
@@ -333,10 +390,8 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 			}
 			__syncthreads ();
 			dedupe (total_raw);
-			if (tid == 0)
-				s_start = resv;
 			__syncthreads ();
-			u64 base = s_start;
+			u64 base = cta_base + cta_out;
 			if (mo.per_owner)
 			{	// exact space in the owner's region: count the survivors first
 				u32 k = 0;
@@ -376,45 +431,21 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 			{
 				kept_total += kept;
 				win_total += s_wtot;
-				if (!mo.per_owner && kept)
-				{	// work items: consecutive chains with at most `budget` windows between them
-					SkmWork it[MG_GMAX];
-					u32 n_it = 0, g0 = 0;
-					for (u32 g = 1; g <= nch; g++)
-						if (g == nch || s_wpre[g + 1] - s_wpre[g0] > mo.budget)
-						{	// chains g0 .. g - 1 are an item (one chain at least)
-							const u32 nrec = s_pos[g] - s_pos[g0], wsum = s_wpre[g] - s_wpre[g0];
-							if (nrec)
-							{
-								it[n_it].r0 = base + s_pos[g0];
-								it[n_it].nrec = nrec;
-								it[n_it].wsum = wsum;
-								it[n_it].r = 0;
-								it[n_it].R = wsum > mo.oversize ? 0u : 1u;
-								n_it++;
-							}
-							g0 = g;
-						}
-					const u64 ib = atomicAdd (mo.n_items, (unsigned long long) n_it);
-					for (u32 k = 0; k < n_it; k++)
-						if (ib + k < mo.max_items)
-							mo.items[ib + k] = it[k];
-				}
+				if (contig)	// work items: the chains in order, each behind the other
+					for (u32 g = 0; g < nch; g++)
+						add_chain (base + s_pos[g], s_pos[g + 1] - s_pos[g], s_wpre[g + 1] - s_wpre[g]);
 			}
+			cta_out += kept;
 			__syncthreads ();
 			break;
 		}
 		// ---- a group with more records than a chunk holds: chain by chain, a chain in as many chunks as it takes.
 		// Every chain is an item of its own (copies that sit in different chunks of a chain are not merged).
-		u64 outp = 0;	// survivors of the group so far
-		if (tid == 0 && !mo.per_owner)
-			s_start = resv;
-		__syncthreads ();
 		for (u32 g = 0; g < nch; g++)
 		{
 			const u32 n_raw = s_nraw[g];
 			const u64 b0 = s_b0[g];
-			u64 first = outp, item_base = 0;
+			const u64 first = cta_out, item_base = cta_base + cta_out;
 			u32 wsum = 0;
 			for (u32 q0 = 0; q0 < n_raw; q0 += CH)
 			{
@@ -463,33 +494,28 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 					base = s_start;
 				}
 				else
-					base = s_start + outp;
-				if (q0 == 0)
-					item_base = base;
+					base = cta_base + cta_out;
 				if (tid == 0)
 					s_tot = s_wtot = 0;
 				__syncthreads ();
 				const u32 kept = write_any (nrec, base, c0 + g);
-				outp += kept;
+				cta_out += kept;
 				wsum += s_wtot;
 				__syncthreads ();
 			}
 			if (tid == 0)
 			{
-				const u64 nrec = outp - first;
+				const u64 nrec = cta_out - first;
 				kept_total += nrec;
 				win_total += wsum;
-				if (!mo.per_owner && nrec)
-				{
-					SkmWork it;
-					it.r0 = item_base;
-					it.nrec = (u32) min (nrec, (u64) 0xFFFFFFFFu);
-					it.wsum = wsum;
-					it.r = 0;
-					it.R = wsum > mo.oversize ? 0u : 1u;
-					const u64 ib = atomicAdd (mo.n_items, 1ull);
-					if (ib < mo.max_items)
-						mo.items[ib] = it;
+				if (contig)
+				{	// a chain that took several chunks is an item of its own (copies in different chunks were not merged,
+					// but they sit in one item)
+					if (n_raw > CH)
+						close_item ();
+					add_chain (item_base, (u32) min (nrec, (u64) 0xFFFFFFFFu), wsum);
+					if (n_raw > CH)
+						close_item ();
 				}
 			}
 		}
@@ -503,6 +529,8 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		}
 		__syncthreads ();
 	}
+	if (tid == 0)
+		close_item ();
 	if (tid == 0 && kept_total)
 	{
 		atomicAdd (mo.n_kept, kept_total);

@@ -595,7 +595,7 @@ int skm_setup (sdtgpu *h, u64 hint)
 	// consecutive chains into work items up to an image's worth of windows, which evens out how lumpy chains are
 	// (K <= 31 with a hint: a chain is about an image's worth — 2 % faster on C2 than packing small chains;
 	// without a hint the chains are made small, so that a guess that is too low by 4x still gives items that fit)
-	double load = h->W == 1 ? (h->hint ? 0.45 : 0.25) : (h->W == 2 ? 0.12 : 0.2);	// (long k-mers: nearly every window is a k-mer of its own and chains are lumpy)
+	double load = h->W == 1 ? (h->hint ? 0.45 : 0.3) : (h->W == 2 ? 0.12 : 0.2);	// (long k-mers: nearly every window is a k-mer of its own and chains are lumpy)
 	if (const char *e = getenv ("SDTGPU_SLICE_LOAD"))
 		if (atof (e) > 0.01 && atof (e) < 0.95)
 			load = atof (e);
@@ -945,7 +945,7 @@ template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u6
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	CK (h, cudaMemsetAsync (small + 4, 0, 2 * sizeof (u64), h->stream));	// surviving records, their windows
 	CK (h, cudaMemsetAsync (L.d_cursor + 1, 0, 3 * sizeof (u64), h->stream));	// output cursor, work items, group cursor
-	double load = 0.9;	// windows per work item / slots of an image: an item has at most as many distinct k-mers as windows
+	double load = 0.95;	// windows per work item / slots of an image: an item has at most as many distinct k-mers as windows
 	if (const char *e = getenv ("SDTGPU_ITEM_LOAD"))
 		if (atof (e) > 0.05 && atof (e) < 4.0)
 			load = atof (e);
