@@ -371,6 +371,7 @@ def main():
             exch = ReplicatedReads(pkg, g, world, rank, dev, max_round_reads=min(batch, n_reads), stride=stride)
 
     host_t = {"reset": 0.0, "push": 0.0, "flush": 0.0, "sync": 0.0, "n": 0}
+    step_wall = []
 
     def one_step(gg):
         t0 = time.perf_counter()
@@ -391,6 +392,7 @@ def main():
         for k, v in zip(("reset", "push", "flush", "sync"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
             host_t[k] += 1e3 * v
         host_t["n"] += 1
+        step_wall.append(round(1e3 * (t4 - t0), 2))
 
     def barrier():
         if world > 1:
@@ -409,6 +411,7 @@ def main():
     g.kernel_time(reset=True)
     for k in host_t:
         host_t[k] = 0
+    step_wall.clear()
     if exch is not None and hasattr(exch, "collective_ms"):
         exch.collective_ms = 0.0
         exch.host_ms = {}
@@ -424,6 +427,7 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     ms = e0.elapsed_time(e1)
+    step_wall_timed = list(step_wall)       # host wall clock of every timed step (this rank): an outlier shows here
     host_ms = {k: v / max(host_t["n"], 1) for k, v in host_t.items() if k != "n"}      # wall clock of the host calls of a timed step (this rank)
     st = g.stats()
     distinct = int(st.n_nodes)
@@ -583,7 +587,7 @@ def main():
                                            "ceiling_instances_per_s_per_gpu": RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words],
                                            "frac_of_ceiling": (inst_per_launch / (ker_ms * 1e-3)) / (RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words]),
                                            "source": "tools/randacc_bench.cu, profiles/r1_randacc_bench.txt"}},
-            "host_call_ms_per_step_rank0": host_ms,
+            "host_call_ms_per_step_rank0": host_ms, "step_wall_ms_rank0": step_wall_timed,
             "collective_ms_per_step": collective_ms,
             "exchange_host_ms_per_step_rank0": ({k: v / max(exch.host_ms.get("flushes", 1), 1) for k, v in exch.host_ms.items() if k != "flushes"} if exch is not None and getattr(exch, "host_ms", None) else None),
             "cpu_baseline": cpu, "e2e": e2e, "e2e_from_files": from_files, "gpu_launches": int(all_launches),

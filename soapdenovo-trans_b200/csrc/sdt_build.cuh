@@ -378,23 +378,18 @@ skm_build2_kernel (typename SlotOf<W>::type *store, u64 store_cap, unsigned long
 				}
 				__syncwarp ();	// probe sequences differ in length: meet again before the update
 				const bool hit = idx < S;
-				// lanes of this step that meet in the same (slot, cell) with one instance each: the lowest one adds for all
-				const bool one = hit && st.add == 1;
-				const u32 peers = __match_any_sync (0xFFFFFFFFu, one ? idx * 32 + cellid : 0xFFFFFFFFu - lane);
+				// (lanes of a step that meet in the same (slot, cell) are left to the atomic unit: after the merge pass
+				// records are distinct, such meetings are rare, and finding them with match.any cost every step 10 %)
 				if (hit)
 				{
 					u32 *cw = im.cell + (cellid >> 1) * S + idx;
 					const u32 sh = 16 * (cellid & 1);
-					if (one)
+					if (st.add == 1)
 					{
-						if ((u32) (__ffs (peers) - 1) == lane)
-						{
-							const u32 cnt = __popc (peers);
-							if (((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
-								atomicAdd (im.extra + idx, cnt);
-							else
-								atomicAdd (cw, cnt << sh);
-						}
+						if (((*reinterpret_cast<volatile u32 *> (cw) >> sh) & 0xFFFFu) >= CELL_STOP)
+							atomicAdd (im.extra + idx, 1u);
+						else
+							atomicAdd (cw, 1u << sh);
 					}
 					else
 					{	// a multiplicity: the cell takes what can still matter to a 6-bit link counter, `extra` the rest

@@ -30,11 +30,12 @@ namespace sdt {
 // read, so the round trip of that reservation costs nothing.
 static constexpr int MG_NT = 512;	// 2 CTAs of 80-96 KB per SM
 static constexpr u32 MG_GMAX = 32;	// chains per group at most
+static constexpr u32 MG_ITEMS = 16;	// work items a CTA collects before it asks for their places in the list
 #ifndef SDT_MERGE_CHUNK1
 #define SDT_MERGE_CHUNK1 2048u
 #endif
 template <int W> struct MergeCfg { static constexpr u32 CHUNK = W == 1 ? SDT_MERGE_CHUNK1 : 1024u, TABLE = 2 * CHUNK; };
-template <int W> __host__ __device__ inline size_t skm_merge_smem () { return (size_t) MergeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) MergeCfg<W>::TABLE * 4 + (MergeCfg<W>::CHUNK / CH_BLK + MG_GMAX + 4) * 4; }
+template <int W> __host__ __device__ inline size_t skm_merge_smem () { return (size_t) MergeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) MergeCfg<W>::TABLE * 4 + 2 * (MergeCfg<W>::CHUNK / CH_BLK + MG_GMAX + 4) * 4; }
 
 struct MergeOut
 {
@@ -55,7 +56,7 @@ struct MergeOut
 
 // HAS_MULT: word 2 of the incoming records already is a multiplicity (sub-records, records merged before an exchange)
 template <int W, bool HAS_MULT>
-__global__ void __launch_bounds__ (MG_NT)
+__global__ void __launch_bounds__ (MG_NT, 2)
 skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, u32 G)
 {
 	constexpr u32 RECW = SkmRec<W>::WORDS, CH = MergeCfg<W>::CHUNK, TS = MergeCfg<W>::TABLE, VEC = RECW / 4, RPT = CH / MG_NT;
@@ -63,12 +64,15 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	__shared__ u32 s_scan[MG_NT / 32], s_tot, s_wtot;
 	__shared__ u32 s_nraw2[2 * MG_GMAX], s_rs[MG_GMAX + 1], s_pos[MG_GMAX + 1], s_wpre[MG_GMAX + 1];	// per chain of the group: records (this group's and the next one's), first record in the chunk, first survivor, windows before it
 	__shared__ u64 s_b02[2 * MG_GMAX];
+	__shared__ u32 s_bs[MG_GMAX + 1];	// blocks in front of every chain of the group
+	__shared__ SkmWork s_items[MG_ITEMS];
 	u32 *s_nraw = s_nraw2;	// (the first group's)
 	u64 *s_b0 = s_b02;
 	__shared__ unsigned long long s_start, s_ibase;
 	u32 *st = smem;			// [CH * RECW]: the chunk's records
 	u32 *tab = smem + CH * RECW;	// [TS]: record index + 1, 0 = free
 	u32 *sbl = tab + TS;		// [CH / CH_BLK + G]: the chunk's blocks
+	u32 *sbd = sbl + CH / CH_BLK + MG_GMAX + 4;	// [same]: where a block's records go in st[] | how many << 16
 	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const u32 owners = mo.per_owner ? (ch.n_chains + mo.per_owner - 1) / mo.per_owner : 1;
 	const u32 span = mo.per_owner ? mo.per_owner : ch.n_chains;	// groups do not straddle owners
@@ -272,6 +276,16 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	u64 cta_base = 0, cta_out = 0;	// (uniform: every thread keeps the same values)
 	u64 open_r0 = 0;		// thread 0: the open work item (first record, records, windows)
 	u32 open_n = 0, open_w = 0;
+	u32 n_staged = 0;		// thread 0: items in s_items[]
+	auto flush_items = [&]() {	// (one round trip to the list's counter per MG_ITEMS items instead of one per item)
+		if (!n_staged)
+			return;
+		const u64 ib = atomicAdd (mo.n_items, (unsigned long long) n_staged);
+		for (u32 k = 0; k < n_staged; k++)
+			if (ib + k < mo.max_items)
+				mo.items[ib + k] = s_items[k];
+		n_staged = 0;
+	};
 	auto close_item = [&]() {
 		if (!open_n)
 			return;
@@ -281,9 +295,9 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		it.wsum = open_w;
 		it.r = 0;
 		it.R = open_w > mo.oversize ? 0u : 1u;
-		const u64 ib = atomicAdd (mo.n_items, 1ull);
-		if (ib < mo.max_items)
-			mo.items[ib] = it;
+		s_items[n_staged++] = it;
+		if (n_staged == MG_ITEMS)
+			flush_items ();
 		open_n = open_w = 0;
 	};
 	auto add_chain = [&](u64 r0, u32 nrec, u32 w) {	// thread 0: a chain's survivors (they sit right behind the open item's)
@@ -359,33 +373,75 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 			break;
 		if (total_raw <= CH && nch <= MG_GMAX)
 		{	// ---- the rule: the whole group in one chunk
-			{	// first record of every chain in the chunk; its blocks; the records (coalesced 16-byte loads)
-				if (tid == 0)
+			{	// first record and first block of every chain in the chunk (warp 0, a scan); the table is cleared meanwhile
+				if (wid == 0)
 				{
-					u32 r = 0;
-					for (u32 g = 0; g < nch; g++)
+					const u32 n = lane < nch ? s_nraw[lane] : 0u;
+					u32 incl = (((n + CH_BLK - 1) / CH_BLK) << 16) | n;	// blocks << 16 | records (<= CH < 2^16)
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1)
 					{
-						s_rs[g] = r;
-						r += s_nraw[g];
+						const u32 y = __shfl_up_sync (0xFFFFFFFFu, incl, d);
+						if (lane >= (u32) d)
+							incl += y;
 					}
-					s_rs[nch] = r;
+					const u32 excl = incl - ((((n + CH_BLK - 1) / CH_BLK) << 16) | n);
+					if (lane < nch)
+					{
+						s_rs[lane] = excl & 0xFFFFu;
+						s_bs[lane] = excl >> 16;
+					}
+					if (lane == nch - 1)
+					{
+						s_rs[nch] = incl & 0xFFFFu;
+						s_bs[nch] = incl >> 16;
+					}
 				}
 				for (u32 v = tid; v < TS; v += MG_NT)
 					tab[v] = 0u;
 				__syncthreads ();
-				for (u32 g = 0; g < nch; g++)
+				// the chunk's blocks: where each one is, where its records go, how many it holds
+				const u32 nbt = s_bs[nch];
+				if (tid < nbt)
 				{
-					const u32 n = s_nraw[g], r0 = s_rs[g];
-					uint4 *dst = reinterpret_cast<uint4 *> (st + (size_t) r0 * RECW);
-					for (u32 v = tid; v < n * VEC; v += MG_NT)
+					u32 g = 0;
+					while (s_bs[g + 1] <= tid)
+						g++;
+					const u32 j = tid - s_bs[g];
+					sbl[tid] = j == 0 ? c0 + g : __ldg (blist + s_b0[g] + j - 1);
+					sbd[tid] = (s_rs[g] + CH_BLK * j) | (min (CH_BLK, s_nraw[g] - CH_BLK * j) << 16);
+				}
+				__syncthreads ();
+				// the records: one flat loop over (block, record, 16-byte part), four loads in flight per thread
+				constexpr u32 SLOTS = CH_BLK * VEC;
+				const u32 tot = nbt * SLOTS;
+				uint4 *dst = reinterpret_cast<uint4 *> (st);
+				for (u32 v0 = tid; v0 < tot; v0 += 4 * MG_NT)
+				{
+					uint4 x[4];
+					u32 di[4];
+#pragma unroll
+					for (u32 k = 0; k < 4; k++)
 					{
-						const u32 i = v / VEC, part = v - i * VEC, j = i / CH_BLK;
-						const u32 blk = j == 0 ? c0 + g : __ldg (blist + s_b0[g] + j - 1);
-						uint4 x = ldg_stream (reinterpret_cast<const uint4 *> (ch.recs + ((u64) blk * CH_BLK + (i & (CH_BLK - 1))) * RECW) + part);
-						if (!HAS_MULT && part == 0)
-							x.z = 1u;
-						dst[v] = x;
+						const u32 v = v0 + k * MG_NT;
+						di[k] = 0xFFFFFFFFu;
+						if (v < tot)
+						{
+							const u32 b = v / SLOTS, w = v - b * SLOTS, i = w / VEC, part = w - i * VEC;
+							const u32 d = sbd[b];
+							if (i < (d >> 16))
+							{
+								x[k] = ldg_stream (reinterpret_cast<const uint4 *> (ch.recs + ((u64) sbl[b] * CH_BLK + i) * RECW) + part);
+								if (!HAS_MULT && part == 0)
+									x[k].z = 1u;
+								di[k] = ((d & 0xFFFFu) + i) * VEC + part;
+							}
+						}
 					}
+#pragma unroll
+					for (u32 k = 0; k < 4; k++)
+						if (di[k] != 0xFFFFFFFFu)
+							dst[di[k]] = x[k];
 				}
 			}
 			__syncthreads ();
@@ -530,7 +586,10 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		__syncthreads ();
 	}
 	if (tid == 0)
+	{
 		close_item ();
+		flush_items ();
+	}
 	if (tid == 0 && kept_total)
 	{
 		atomicAdd (mo.n_kept, kept_total);

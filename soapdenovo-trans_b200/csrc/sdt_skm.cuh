@@ -59,8 +59,10 @@ __host__ __device__ __forceinline__ u32 fmix32 (u32 h)
 	h ^= h >> 16;
 	return h;
 }
-// hash of a canonical m-mer code; the window's minimizer value is the minimum of these
-__host__ __device__ __forceinline__ u32 mmer_hash (u32 code) { return fmix32 (code ^ 0x5bd1e995u); }
+// hash of a canonical m-mer code, 31 bits; the window's minimizer value is the minimum of these.  Only the ORDER of
+// the values matters (the slice comes from a full mix of the minimum, slice_of_min), and the high bits of an odd
+// multiple depend on every bit of the code: one multiply is enough, and it runs once per base of every read.
+__host__ __device__ __forceinline__ u32 mmer_hash (u32 code) { return ((code ^ 0x5bd1e995u) * 0x9E3779B1u) >> 1; }
 #ifdef __CUDACC__
 __device__ __forceinline__ u32 slice_of_min (u32 minval, u32 n_slices) { return __umulhi (fmix32 (minval + 0x9E3779B9u), n_slices); }
 #endif
@@ -150,7 +152,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 	ReadTile<NMODE> rt;
 	tile_setup<NMODE> (rt, smem, rb);
 	u32 *mhs = smem + tile_words (rb, NMODE);	// [tile_reads * npad + 16]: m-mer hashes, later descriptors (read | first window << 8 | (n - 1) << 24) of the records
-	u32 *sls = mhs + (size_t) rb.tile_reads * g.npad + 16;	// [tile_reads * npad]: slice of every window (| SKM_NFLAG)
+	u32 *sls = mhs + (size_t) rb.tile_reads * g.npad + 16;	// [tile_reads * npad]: minimizer value of every window (31 bits | SKM_NFLAG); its slice is computed once per record
 	const u32 maxwin = g.npos - g.wfull + 1;	// windows of the longest read
 	const u32 gpr = (maxwin + 3) >> 2, spr = (maxwin + EMIT_SEG - 1) / EMIT_SEG;	// groups of 4 windows, segments of EMIT_SEG windows per read
 	const u32 m_npos = 0xFFFFFFFFu / g.npos + 1, m_gpr = 0xFFFFFFFFu / gpr + 1, m_spr = 0xFFFFFFFFu / spr + 1;	// x / d = (x * m) >> 32 for x < 65536
@@ -174,7 +176,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			}
 		}
 		__syncthreads ();
-		// ---- 2. slice of every window = slice of its minimizer value: the smallest hash among the CENTRAL w of the
+		// ---- 2. minimizer value of every window (its slice follows from it): the smallest hash among the CENTRAL w of the
 		// window's m-mers, positions lo .. lo + w - 1 (a set that is the same for a k-mer and its reverse
 		// complement).  For K <= 31 that is every m-mer of the window; for long k-mers it keeps a minimizer from
 		// gathering the windows of 50 or 110 consecutive positions in one slice (K = 63: 11 % of the slices overflowed).
@@ -230,15 +232,15 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			for (u32 q = 0; q < 4; q++)
 				if (j0 + q < nwin)
 				{
-					u32 v = slice_of_min (mv[q], g.n_slices);
+					u32 v = mv[q];
 					if constexpr (NMODE)
 						if (mask_any (rt.mtile + r * rt.mw, j0 + q, j0 + q + K))
-							v = g.slice_a | SKM_NFLAG;
+							v = mmer_hash (0) | SKM_NFLAG;	// with the all-A k-mer (key 0), whose every m-mer has code 0
 					sl[q] = v;
 				}
 		}
 		__syncthreads ();
-		// ---- 3. runs of windows with the same slice -> record descriptors in mhs[], which is free now.
+		// ---- 3. runs of windows with the same minimizer value -> record descriptors in mhs[], which is free now.
 		// One thread per segment of EMIT_SEG windows of a read walks them in order and reports the runs
 		// that END in its segment (a run that started before the segment is traced back to its start).
 		for (u32 x = tid; x < rt.nr * spr; x += EMIT_NT)
@@ -257,7 +259,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			u32 ends = 0;
 			for (u32 j = js; j < je; j++)
 			{
-				const u32 nxt = j + 1 < nwin ? sl[j + 1] : 0xFFFFFFFFu;	// no slice has this number (bit 31 is the N flag, 30 bits of slice)
+				const u32 nxt = j + 1 < nwin ? sl[j + 1] : 0xFFFFFFFFu;	// no window has this value (mmer_hash (0) is not 2^31 - 1)
 				ends |= (nxt != s ? 1u : 0u) << (j - js);
 				s = nxt;
 			}
@@ -265,8 +267,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			{
 				const u32 j = js + (u32) __ffs (ends) - 1;	// windows start .. j are a run
 				ends &= ends - 1;
-				const u32 rs = sl[j];
-				if (rb.owner_ranks <= 1 || (rs & ~SKM_NFLAG) % rb.owner_ranks == rb.owner_rank)
+				if (rb.owner_ranks <= 1 || slice_of_min (sl[j] & ~SKM_NFLAG, g.n_slices) % rb.owner_ranks == rb.owner_rank)
 				{
 					const u32 n = j - start + 1;
 					const u32 nrec = (n + NMAX - 1) / NMAX;
@@ -301,6 +302,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 		{
 			d_nx = mhs[tid];
 			s_nx = sls[(d_nx & 0xFFu) * g.npad + ((d_nx >> 8) & 0xFFFFu)];
+			s_nx = slice_of_min (s_nx & ~SKM_NFLAG, g.n_slices) | (s_nx & SKM_NFLAG);
 			tk_nx = chain_ticket (ch, (s_nx & ~SKM_NFLAG) / g.send_group);
 		}
 		for (u32 rid = tid; rid < n_out; rid += EMIT_NT)
@@ -312,6 +314,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			{
 				d_nx = mhs[rid + EMIT_NT];
 				s_nx = sls[(d_nx & 0xFFu) * g.npad + ((d_nx >> 8) & 0xFFFFu)];
+				s_nx = slice_of_min (s_nx & ~SKM_NFLAG, g.n_slices) | (s_nx & SKM_NFLAG);
 				tk_nx = chain_ticket (ch, (s_nx & ~SKM_NFLAG) / g.send_group);
 			}
 			const u32 r = d & 0xFFu, j0 = (d >> 8) & 0xFFFFu, n = (d >> 24) + 1;
@@ -337,18 +340,15 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			wd[0] = (u32) ord;
 			wd[1] = (u32) (ord >> 32) | ((n - 1) << 8) | (has_left << 14) | ((nrun ? 1u : 0u) << 15) | (nb << 16);
 			wd[2] = 0;
-			const u32 nbw = (nb + 15) >> 4;
 #pragma unroll
 			for (u32 q = 0; q < RECW - SKM_HDR; q++)
 			{
-				u32 v = 0;
-				if (q < nbw)
-				{
-					const u32 b = first + 16 * q, wq = b >> 4, sh = 2 * (b & 15);
-					v = __funnelshift_l (rd[wq + 1], rd[wq], sh);
-					if (q == nbw - 1 && (nb & 15))
-						v &= 0xFFFFFFFFu << (32 - 2 * (nb & 15));	// nothing of the read beyond the record's bases
-				}
+				// (no branch on the record's length: the words past its bases are read from whatever follows in the
+				// tile — shared memory of this CTA in any case — and masked away, so the warp stays converged)
+				const u32 b = first + 16 * q, wq = b >> 4, sh = 2 * (b & 15);
+				u32 v = __funnelshift_l (rd[wq + 1], rd[wq], sh);
+				const u32 left = nb > 16 * q ? nb - 16 * q : 0;	// bases of the record from this word on
+				v = left >= 16 ? v : left ? v & (0xFFFFFFFFu << (32 - 2 * left)) : 0;	// nothing of the read beyond the record's bases
 				const u32 o = SKM_HDR + q;
 				if (q == RECW - SKM_HDR - 1 && g.send_group > 1)
 					v = s & ~SKM_NFLAG;	// (the last word is never used by bases: the slice travels there)

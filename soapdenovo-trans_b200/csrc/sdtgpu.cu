@@ -551,8 +551,6 @@ struct Trace
 			cudaMemGetInfo (&fr, &tot);
 		fprintf (stderr, "[sdtgpu] %-28s %8.3f ms   (%.1f GB free)\n", what, std::chrono::duration<double, std::milli> (t1 - t0).count (), fr / 1e9);
 		t0 = std::chrono::steady_clock::now ();
-		return;
-		t0 = t1;
 	}
 };
 
@@ -1250,6 +1248,8 @@ int skm_build_runs (sdtgpu *h, ChainLevel &L, u32 n_items, bool top, const u64 *
 			CK (h, cudaStreamSynchronize (h->stream));	// `splits` is pageable host memory; d_items is reused below
 			if (h->h_small[3] & OVF_RECORDS)
 				return fail (h, SDTGPU_ERANGE, "sub-slice pool overflow");
+			if (tr.on)
+				fprintf (stderr, "[sdtgpu]   split: %zu pieces of %zu, %llu sub-slices, %llu windows\n", b - a, splits.size (), (unsigned long long) (q1 - q0), (unsigned long long) win);
 			tr.mark ("  split");
 			if ((rc = skm_build_level (h, S, true, win, win, false)))
 				return rc;
