@@ -65,6 +65,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	__shared__ u32 s_nraw2[2 * MG_GMAX], s_rs[MG_GMAX + 1], s_pos[MG_GMAX + 1], s_wpre[MG_GMAX + 1];	// per chain of the group: records (this group's and the next one's), first record in the chunk, first survivor, windows before it
 	__shared__ u64 s_b02[2 * MG_GMAX];
 	__shared__ u32 s_bs[MG_GMAX + 1];	// blocks in front of every chain of the group
+	__shared__ u32 s_traw[2], s_nch[2];	// records and chains of this group and of the next one
 	__shared__ SkmWork s_items[MG_ITEMS];
 	u32 *s_nraw = s_nraw2;	// (the first group's)
 	u64 *s_b0 = s_b02;
@@ -77,7 +78,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	const u32 owners = mo.per_owner ? (ch.n_chains + mo.per_owner - 1) / mo.per_owner : 1;
 	const u32 span = mo.per_owner ? mo.per_owner : ch.n_chains;	// groups do not straddle owners
 	const u32 gpo = (span + G - 1) / G;
-	const u64 n_groups = (u64) gpo * owners;
+	const u32 n_groups = gpo * owners;	// (32-bit on purpose: a 64-bit division per group and thread was a fifth of the kernel's instructions)
 	u64 kept_total = 0, win_total = 0;	// thread 0
 
 	// dedupe of the nrec records staged in st[]
@@ -260,9 +261,9 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 
 	// groups are dealt to the CTAs round robin; the chains' record counts and block lists of the NEXT group are
 	// loaded while this one is merged (two dependent round trips less per group)
-	auto geom = [&](u64 grp, u32 &owner, u32 &c0, u32 &nch) {
-		owner = (u32) (grp / gpo);
-		c0 = owner * span + (u32) (grp % gpo) * G;
+	auto geom = [&](u32 grp, u32 &owner, u32 &c0, u32 &nch) {
+		owner = mo.per_owner ? grp / gpo : 0u;
+		c0 = owner * span + (grp - owner * gpo) * G;
 		nch = min (min (G, owner * span + span - c0), ch.n_chains - c0);
 	};
 	// One GPU (no owners): a CTA takes a CONTIGUOUS range of groups and writes their survivors one behind the other
@@ -270,9 +271,11 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	// open item is carried from group to group and closed when the next chain would take it over the budget.
 	// Several GPUs, sending side: groups round robin, every group's survivors into its owner's region.
 	const bool contig = !mo.per_owner;
-	const u64 gpc = (n_groups + gridDim.x - 1) / gridDim.x;
-	const u64 g_first = contig ? blockIdx.x * gpc : blockIdx.x, g_step = contig ? 1 : gridDim.x;
-	const u64 g_end = contig ? min (n_groups, g_first + gpc) : n_groups;
+	const u32 g_first = blockIdx.x, g_step = gridDim.x, g_end = n_groups;	// (several GPUs)
+	// one GPU: the CTA's chains [c_lo, c_hi); a group is as many consecutive chains as fit a chunk (found by warp 0
+	// when the chains' record counts arrive, a group ahead), at most MG_GMAX
+	const u32 cpc = (ch.n_chains + gridDim.x - 1) / gridDim.x;
+	const u32 c_lo = (u32) min ((u64) ch.n_chains, (u64) blockIdx.x * cpc), c_hi = (u32) min ((u64) ch.n_chains, (u64) c_lo + cpc);
 	u64 cta_base = 0, cta_out = 0;	// (uniform: every thread keeps the same values)
 	u64 open_r0 = 0;		// thread 0: the open work item (first record, records, windows)
 	u32 open_n = 0, open_w = 0;
@@ -312,9 +315,8 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		if (open_w > mo.budget)
 			close_item ();	// a single chain beyond the budget: an item of its own
 	};
-	if (contig && g_first < g_end)
+	if (contig && c_lo < c_hi)
 	{	// this CTA's chains hold how many records?  (its region in out[]: an upper bound of what survives)
-		const u32 c_lo = (u32) (g_first * G), c_hi = (u32) min ((u64) ch.n_chains, g_end * G);
 		unsigned long long sum = 0;
 		for (u32 c = c_lo + tid; c < c_hi; c += MG_NT)
 			sum += (u64) ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);
@@ -333,42 +335,79 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		cta_base = s_ibase;
 	}
 	u32 pb = 0;	// which half of s_nraw / s_b0 holds this group's
-	if (g_first < g_end)
+	// warp 0: the record counts of up to 32 chains (lane l: chain l of the window, 0 beyond it) -> chains of the
+	// group and their records.  One GPU: the longest prefix that fits a chunk (at least one chain); else all `wn`.
+	auto plan = [&](u32 n, u32 wn, u32 half) {
+		u32 incl = min (n, 0x4000000u);	// (only "fits a chunk" matters beyond that)
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const u32 y = __shfl_up_sync (0xFFFFFFFFu, incl, d);
+			if (lane >= (u32) d)
+				incl += y;
+		}
+		u32 k = wn;
+		if (contig)
+			k = max (1u, (u32) __popc (__ballot_sync (0xFFFFFFFFu, lane < wn && incl <= CH)));
+		k = min (k, wn);
+		const u32 tot = __shfl_sync (0xFFFFFFFFu, incl, k ? k - 1 : 0);
+		if (lane == 0)
+		{
+			s_nch[half] = k;
+			s_traw[half] = k ? tot : 0u;
+		}
+	};
+	u32 grp = g_first, c0 = c_lo, owner = 0;
+	bool more = contig ? c_lo < c_hi : g_first < g_end;
+	if (more)
 	{
-		u32 owner, c0, nch;
-		geom (g_first, owner, c0, nch);
-		if (tid < nch)
+		u32 wn;
+		if (contig)
+			wn = min (MG_GMAX, c_hi - c0);
+		else
+			geom (grp, owner, c0, wn);
+		u32 n = 0;
+		if (tid < wn)
 		{
 			const u32 c = c0 + tid;
-			s_nraw[tid] = ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);	// (a chain of 2^32 records or more is not supported)
+			n = ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);	// (a chain of 2^32 records or more is not supported)
+			s_nraw[tid] = n;
 			s_b0[tid] = boff[c];
 		}
+		if (wid == 0)
+			plan (n, wn, 0);
 	}
 	__syncthreads ();
-	for (u64 grp = g_first; grp < g_end; grp += g_step, pb ^= MG_GMAX)
+	for (; more; pb ^= MG_GMAX)
 	{
-		u32 owner, c0, nch;
-		geom (grp, owner, c0, nch);
+		const u32 nch = s_nch[pb ? 1 : 0];
+		// the next group: where it starts is known now; its chains' counts travel while this group is merged
+		u32 nx_c0 = c0 + nch, nx_owner = owner, nx_wn = 0;
+		bool nx_more;
+		if (contig)
+		{
+			nx_more = nx_c0 < c_hi;
+			nx_wn = nx_more ? min (MG_GMAX, c_hi - nx_c0) : 0u;
+		}
+		else
+		{
+			nx_more = grp + g_step < g_end;
+			if (nx_more)
+				geom (grp + g_step, nx_owner, nx_c0, nx_wn);
+		}
 		u32 nx_raw = 0;
 		u64 nx_b0 = 0;
-		if (grp + g_step < g_end)
+		if (tid < nx_wn)
 		{
-			u32 o2, c2, n2;
-			geom (grp + g_step, o2, c2, n2);
-			if (tid < n2)
-			{
-				const u32 c = c2 + tid;
-				nx_raw = ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);
-				nx_b0 = boff[c];
-			}
+			const u32 c = nx_c0 + tid;
+			nx_raw = ch.bcount[c] * CH_BLK + min ((u32) ch.head[c], CH_BLK);
+			nx_b0 = boff[c];
 		}
 		s_nraw = s_nraw2 + pb;
 		s_b0 = s_b02 + pb;
 		do
 		{
-		u32 total_raw = 0;
-		for (u32 g = 0; g < nch; g++)
-			total_raw += s_nraw[g];
+		const u32 total_raw = s_traw[pb ? 1 : 0];
 		if (total_raw == 0)
 			break;
 		if (total_raw <= CH && nch <= MG_GMAX)
@@ -582,8 +621,13 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		{
 			s_nraw2[(pb ^ MG_GMAX) + tid] = nx_raw;
 			s_b02[(pb ^ MG_GMAX) + tid] = nx_b0;
+			plan (nx_raw, nx_wn, pb ? 0 : 1);
 		}
 		__syncthreads ();
+		c0 = nx_c0;
+		owner = nx_owner;
+		more = nx_more;
+		grp += g_step;
 	}
 	if (tid == 0)
 	{

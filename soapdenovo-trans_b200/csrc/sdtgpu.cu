@@ -939,7 +939,8 @@ template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u6
 	const u32 G = env_u32 ("SDTGPU_MERGE_GROUP", (u32) std::min<double> (MG_GMAX, std::max (1.0, std::floor (0.5 * MergeCfg<W>::CHUNK / avg))));
 	const u32 span = per_owner ? per_owner : L.n_chains;
 	const u64 n_groups = (u64) ((span + G - 1) / G) * (per_owner ? (L.n_chains + per_owner - 1) / per_owner : 1);
-	const unsigned grid = (unsigned) std::min<u64> (std::max<u64> (n_groups, 1), (u64) h->sm_count * occ);
+	// (one GPU: the kernel forms the groups itself, as many consecutive chains as fit a chunk; G only matters to the sending side)
+	const unsigned grid = (unsigned) std::min<u64> (std::max<u64> (per_owner ? n_groups : L.n_chains, 1), (u64) h->sm_count * occ);
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	CK (h, cudaMemsetAsync (small + 4, 0, 2 * sizeof (u64), h->stream));	// surviving records, their windows
 	CK (h, cudaMemsetAsync (L.d_cursor + 1, 0, 3 * sizeof (u64), h->stream));	// output cursor, work items, group cursor
