@@ -35,7 +35,20 @@ static constexpr u32 MG_ITEMS = 16;	// work items a CTA collects before it asks 
 #define SDT_MERGE_CHUNK1 2048u
 #endif
 template <int W> struct MergeCfg { static constexpr u32 CHUNK = W == 1 ? SDT_MERGE_CHUNK1 : 1024u, TABLE = 2 * CHUNK; };
-template <int W> __host__ __device__ inline size_t skm_merge_smem () { return (size_t) MergeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) MergeCfg<W>::TABLE * 4 + 2 * (MergeCfg<W>::CHUNK / CH_BLK + MG_GMAX + 4) * 4; }
+template <int W> __host__ __device__ inline size_t skm_merge_smem () { return (size_t) MergeCfg<W>::CHUNK * SkmRec<W>::WORDS * 4 + (size_t) MergeCfg<W>::TABLE * 4 + 2 * (MergeCfg<W>::CHUNK / CH_BLK + MG_GMAX + 4) * 4 + MergeCfg<W>::CHUNK; }
+// Where the 16-byte part `part` of staged record `rec` sits in the chunk.  Threads of a warp work on consecutive
+// records; with records of 32 (64) bytes laid out plainly every access would meet 2 (4) of its quarter-warp in the
+// same banks (and word-wise accesses 8 to 32: the shared-memory pipe was the kernel's busiest unit), so the parts
+// of every other group of records are swapped around.  Records are only ever touched 16 bytes at a time.
+template <int W> __device__ __forceinline__ u32 mg_swz (u32 rec, u32 part)
+{
+	constexpr u32 VEC = SkmRec<W>::WORDS / 4;
+	if (W == 1)
+		return rec * VEC + (part ^ ((rec >> 2) & 1u));
+	if (W == 4)
+		return rec * VEC + (part ^ ((rec >> 1) & 3u));
+	return rec * VEC + part;	// 48 bytes: no two of eight consecutive records share a bank
+}
 
 struct MergeOut
 {
@@ -74,6 +87,8 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	u32 *tab = smem + CH * RECW;	// [TS]: record index + 1, 0 = free
 	u32 *sbl = tab + TS;		// [CH / CH_BLK + G]: the chunk's blocks
 	u32 *sbd = sbl + CH / CH_BLK + MG_GMAX + 4;	// [same]: where a block's records go in st[] | how many << 16
+	unsigned char *flg = reinterpret_cast<unsigned char *> (sbd + CH / CH_BLK + MG_GMAX + 4);	// [CH]: after the dedupe, 0 = the record is a copy and goes, else its windows
+	uint4 *st4 = reinterpret_cast<uint4 *> (st);
 	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const u32 owners = mo.per_owner ? (ch.n_chains + mo.per_owner - 1) / mo.per_owner : 1;
 	const u32 span = mo.per_owner ? mo.per_owner : ch.n_chains;	// groups do not straddle owners
@@ -85,14 +100,27 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	auto dedupe = [&](u32 nrec) {
 		for (u32 i = tid; i < nrec; i += MG_NT)
 		{
-			u32 *me = st + i * RECW;
-			const u32 h1 = me[1];
-			if ((h1 >> 15) & 1u)
-				continue;	// an N-run stays as it is
-			u32 hsh = h1 & ~0xFFu;
+			uint4 r[VEC];
 #pragma unroll
-			for (u32 q = SKM_HDR; q < RECW; q++)
-				hsh = (hsh ^ me[q]) * 0x9E3779B1u + (hsh >> 15);
+			for (u32 q = 0; q < VEC; q++)
+				r[q] = st4[mg_swz<W> (i, q)];
+			const u32 h1 = r[0].y;
+			if ((h1 >> 15) & 1u)
+			{	// an N-run stays as it is
+				flg[i] = 1;
+				continue;
+			}
+			const u32 nw = ((h1 >> 8) & 63u) + 1;
+			u32 hsh = h1 & ~0xFFu;
+			hsh = (hsh ^ r[0].w) * 0x9E3779B1u + (hsh >> 15);
+#pragma unroll
+			for (u32 q = 1; q < VEC; q++)
+			{
+				hsh = (hsh ^ r[q].x) * 0x9E3779B1u + (hsh >> 15);
+				hsh = (hsh ^ r[q].y) * 0x9E3779B1u + (hsh >> 15);
+				hsh = (hsh ^ r[q].z) * 0x9E3779B1u + (hsh >> 15);
+				hsh = (hsh ^ r[q].w) * 0x9E3779B1u + (hsh >> 15);
+			}
 			u32 slot = fmix32 (hsh) & (TS - 1);
 			for (;;)
 			{
@@ -100,19 +128,26 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 				if (e == 0u)
 					e = atomicCAS (tab + slot, 0u, i + 1);
 				if (e == 0u)
-					break;	// first of its kind
-				u32 *rep = st + (e - 1) * RECW;
-				bool same = ((*reinterpret_cast<volatile u32 *> (rep + 1) ^ h1) & ~0xFFu) == 0u;	// the low 8 bits are ordinal bits and change
+				{	// first of its kind
+					flg[i] = (unsigned char) nw;
+					break;
+				}
+				uint4 *rep = st4 + mg_swz<W> (e - 1, 0);
+				const uint4 c = *rep;	// (words 0-2 of a representative change under it: only the constant bits are compared)
+				bool same = ((c.y ^ h1) & ~0xFFu) == 0u && c.w == r[0].w;	// the low 8 bits are ordinal bits and change
 #pragma unroll
-				for (u32 q = SKM_HDR; q < RECW; q++)
-					same &= rep[q] == me[q];
+				for (u32 q = 1; q < VEC; q++)
+				{
+					const uint4 d = st4[mg_swz<W> (e - 1, q)];
+					same &= d.x == r[q].x && d.y == r[q].y && d.z == r[q].z && d.w == r[q].w;
+				}
 				if (same)
 				{	// words 0-1 as one 64-bit number: the header bits above the ordinal are equal, so the minimum is the ordinal's
-					atomicAdd (rep + 2, HAS_MULT ? me[2] : 1u);
-					const u64 mine = *reinterpret_cast<const u64 *> (me);
+					atomicAdd (reinterpret_cast<u32 *> (rep) + 2, HAS_MULT ? r[0].z : 1u);
+					const u64 mine = (u64) r[0].x | ((u64) r[0].y << 32);
 					if (mine < *reinterpret_cast<volatile u64 *> (rep))
 						atomicMin (reinterpret_cast<unsigned long long *> (rep), mine);
-					me[2] = 0u;	// dropped
+					flg[i] = 0;	// dropped
 					break;
 				}
 				slot = (slot + 1) & (TS - 1);
@@ -122,15 +157,13 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	// survivors of st[0 .. nrec) to out[base ..] in order; returns their number, s_wtot their windows;
 	// the survivors / windows in front of the records listed in s_rs[0 .. nb] go to s_pos / s_wpre
 	auto write_out = [&](u32 nrec, u64 base, u32 nb, u32 slice0) -> u32 {
-		u32 keep[RPT], nw[RPT], packed = 0;	// thread t: records RPT * t .. RPT * t + RPT - 1; windows << 12 | records
+		u32 packed = 0;	// thread t: records RPT * t .. RPT * t + RPT - 1; windows << 12 | records
 #pragma unroll
 		for (u32 k = 0; k < RPT; k++)
 		{
 			const u32 i = RPT * tid + k;
-			keep[k] = i < nrec && st[i * RECW + 2] != 0u;
-			const u32 h1 = i < nrec ? st[i * RECW + 1] : 0u;
-			nw[k] = keep[k] ? (((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1) : 0u;
-			packed += (nw[k] << 12) | keep[k];
+			const u32 f = i < nrec ? flg[i] : 0u;
+			packed += (f << 12) | (f != 0u);
 		}
 		u32 incl = packed;
 #pragma unroll
@@ -162,23 +195,29 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 				s_wtot = total >> 12;
 			}
 		}
-		u32 run = lower + incl - packed;	// survivors / windows in front of this thread's first record
-		tab[tid] = run;	// (the table is free after the dedupe)
+		tab[tid] = lower + incl - packed;	// survivors / windows in front of this thread's first record (the table is free after the dedupe)
+		__syncthreads ();
+		// the copy runs over the records in staging order, a warp on 32 consecutive ones (no bank conflicts, and
+		// consecutive survivors go to consecutive places): a record's place is its scan thread's plus the survivors
+		// among that thread's earlier records
 #pragma unroll
 		for (u32 k = 0; k < RPT; k++)
 		{
-			const u32 i = RPT * tid + k;
-			if (keep[k])
+			const u32 i = k * MG_NT + tid;
+			if (i < nrec && flg[i])
 			{
-				const u64 pos = base + (run & 0xFFFu);
+				const u32 t = i / RPT;
+				u32 below = 0;
+				for (u32 k2 = RPT * t; k2 < i; k2++)
+					below += flg[k2] != 0;
+				const u64 pos = base + (tab[t] & 0xFFFu) + below;
 				if (pos < mo.out_cap)
 				{
-					const uint4 *src = reinterpret_cast<const uint4 *> (st + i * RECW);
 					uint4 *dst = reinterpret_cast<uint4 *> (mo.out + pos * RECW);
 #pragma unroll
 					for (u32 q = 0; q < VEC; q++)
 					{
-						uint4 x = src[q];
+						uint4 x = st4[mg_swz<W> (i, q)];
 						if (mo.per_owner && !mo.tagged && q == VEC - 1)
 						{	// the last base word is never used (80 / 144 / 208 bases of room for 64 / 128 / 192): the slice travels there
 							u32 g = 0;
@@ -190,9 +229,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 					}
 				}
 			}
-			run += (nw[k] << 12) | keep[k];
 		}
-		__syncthreads ();
 		if (tid <= nb)
 		{	// survivors / windows in front of the first record of chain `tid` (tid == nb: all)
 			const u32 i = min (s_rs[tid], nrec);
@@ -204,11 +241,8 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 				const u32 t = i / RPT;
 				v = tab[t];
 				for (u32 k = RPT * t; k < i; k++)
-					if (st[k * RECW + 2] != 0u)
-					{
-						const u32 h1 = st[k * RECW + 1];
-						v += ((((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1) << 12) | 1u;
-					}
+					if (flg[k])
+						v += ((u32) flg[k] << 12) | 1u;
 			}
 			s_pos[tid] = v & 0xFFFu;
 			s_wpre[tid] = v >> 12;
@@ -224,7 +258,8 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		for (u32 b = 0; b < nrec; b += MG_NT)
 		{
 			const u32 i = b + tid;
-			const bool keep = i < nrec && st[i * RECW + 2] != 0u;
+			const u32 f = i < nrec ? flg[i] : 0u;
+			const bool keep = f != 0u;
 			const u32 bal = __ballot_sync (0xFFFFFFFFu, keep);
 			u32 wb = 0;
 			if (lane == 0 && bal)
@@ -235,19 +270,17 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 				const u64 pos = base + wb + __popc (bal & ((1u << lane) - 1u));
 				if (pos < mo.out_cap)
 				{
-					const uint4 *src = reinterpret_cast<const uint4 *> (st + i * RECW);
 					uint4 *dst = reinterpret_cast<uint4 *> (mo.out + pos * RECW);
 #pragma unroll
 					for (u32 q = 0; q < VEC; q++)
 					{
-						uint4 x = src[q];
+						uint4 x = st4[mg_swz<W> (i, q)];
 						if (mo.per_owner && !mo.tagged && q == VEC - 1)
 							x.w = slice;
 						dst[q] = x;
 					}
 				}
-				const u32 h1 = st[i * RECW + 1];
-				wsum += ((h1 >> 15) & 1u) ? 1u : ((h1 >> 8) & 63u) + 1;
+				wsum += f;
 			}
 		}
 #pragma unroll
@@ -454,7 +487,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 				// the records: one flat loop over (block, record, 16-byte part), four loads in flight per thread
 				constexpr u32 SLOTS = CH_BLK * VEC;
 				const u32 tot = nbt * SLOTS;
-				uint4 *dst = reinterpret_cast<uint4 *> (st);
+				uint4 *dst = st4;
 				for (u32 v0 = tid; v0 < tot; v0 += 4 * MG_NT)
 				{
 					uint4 x[4];
@@ -473,7 +506,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 								x[k] = ldg_stream (reinterpret_cast<const uint4 *> (ch.recs + ((u64) sbl[b] * CH_BLK + i) * RECW) + part);
 								if (!HAS_MULT && part == 0)
 									x[k].z = 1u;
-								di[k] = ((d & 0xFFFFu) + i) * VEC + part;
+								di[k] = mg_swz<W> ((d & 0xFFFFu) + i, part);
 							}
 						}
 					}
@@ -491,7 +524,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 			{	// exact space in the owner's region: count the survivors first
 				u32 k = 0;
 				for (u32 i = tid; i < total_raw; i += MG_NT)
-					k += st[i * RECW + 2] != 0u;
+					k += flg[i] != 0;
 #pragma unroll
 				for (int d = 16; d > 0; d >>= 1)
 					k += __shfl_down_sync (0xFFFFFFFFu, k, d);
@@ -556,14 +589,13 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 					s_rs[1] = nrec;
 				}
 				__syncthreads ();
-				uint4 *dst = reinterpret_cast<uint4 *> (st);
 				for (u32 v = tid; v < nrec * VEC; v += MG_NT)
 				{
 					const u32 i = v / VEC, part = v - i * VEC;
 					uint4 x = ldg_stream (reinterpret_cast<const uint4 *> (ch.recs + ((u64) sbl[i / CH_BLK] * CH_BLK + (i & (CH_BLK - 1))) * RECW) + part);
 					if (!HAS_MULT && part == 0)
 						x.z = 1u;
-					dst[v] = x;
+					st4[mg_swz<W> (i, part)] = x;
 				}
 				__syncthreads ();
 				dedupe (nrec);
@@ -573,7 +605,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 				{
 					u32 k = 0;
 					for (u32 i = tid; i < nrec; i += MG_NT)
-						k += st[i * RECW + 2] != 0u;
+						k += flg[i] != 0;
 #pragma unroll
 					for (int d = 16; d > 0; d >>= 1)
 						k += __shfl_down_sync (0xFFFFFFFFu, k, d);
