@@ -30,6 +30,7 @@ namespace sdt {
 // read, so the round trip of that reservation costs nothing.
 static constexpr int MG_NT = 512;	// 2 CTAs of 80-96 KB per SM
 static constexpr u32 MG_GMAX = 32;	// chains per group at most
+static constexpr u32 MG_PIECE = 128;	// several GPUs, sending side: consecutive chains of one owner that a CTA takes at a time
 static constexpr u32 MG_ITEMS = 16;	// work items a CTA collects before it asks for their places in the list
 #ifndef SDT_MERGE_CHUNK1
 #define SDT_MERGE_CHUNK1 2048u
@@ -70,7 +71,7 @@ struct MergeOut
 // HAS_MULT: word 2 of the incoming records already is a multiplicity (sub-records, records merged before an exchange)
 template <int W, bool HAS_MULT>
 __global__ void __launch_bounds__ (MG_NT, 2)
-skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, u32 G)
+skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo)
 {
 	constexpr u32 RECW = SkmRec<W>::WORDS, CH = MergeCfg<W>::CHUNK, TS = MergeCfg<W>::TABLE, VEC = RECW / 4, RPT = CH / MG_NT;
 	extern __shared__ __align__(16) u32 smem[];
@@ -92,8 +93,8 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const u32 owners = mo.per_owner ? (ch.n_chains + mo.per_owner - 1) / mo.per_owner : 1;
 	const u32 span = mo.per_owner ? mo.per_owner : ch.n_chains;	// groups do not straddle owners
-	const u32 gpo = (span + G - 1) / G;
-	const u32 n_groups = gpo * owners;	// (32-bit on purpose: a 64-bit division per group and thread was a fifth of the kernel's instructions)
+	const u32 ppo = (span + MG_PIECE - 1) / MG_PIECE;	// pieces per owner
+	const u32 n_pieces = ppo * owners;	// (32-bit on purpose: a 64-bit division per group and thread was a fifth of the kernel's instructions)
 	u64 kept_total = 0, win_total = 0;	// thread 0
 
 	// dedupe of the nrec records staged in st[]
@@ -292,19 +293,18 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		return s_tot;
 	};
 
-	// groups are dealt to the CTAs round robin; the chains' record counts and block lists of the NEXT group are
-	// loaded while this one is merged (two dependent round trips less per group)
-	auto geom = [&](u32 grp, u32 &owner, u32 &c0, u32 &nch) {
-		owner = mo.per_owner ? grp / gpo : 0u;
-		c0 = owner * span + (grp - owner * gpo) * G;
-		nch = min (min (G, owner * span + span - c0), ch.n_chains - c0);
-	};
-	// One GPU (no owners): a CTA takes a CONTIGUOUS range of groups and writes their survivors one behind the other
+	// One GPU (no owners): a CTA takes a CONTIGUOUS range of chains and writes their survivors one behind the other
 	// into a region it reserves once (by its chains' record count), so that a work item can run across groups: the
 	// open item is carried from group to group and closed when the next chain would take it over the budget.
-	// Several GPUs, sending side: groups round robin, every group's survivors into its owner's region.
+	// Several GPUs, sending side: the chains of every owner in pieces of MG_PIECE, dealt to the CTAs round robin;
+	// every group's survivors go into its owner's region.
+	// The chains' record counts and block lists of the NEXT group are loaded while this one is merged.
 	const bool contig = !mo.per_owner;
-	const u32 g_first = blockIdx.x, g_step = gridDim.x, g_end = n_groups;	// (several GPUs)
+	auto piece = [&](u32 p, u32 &owner, u32 &lo, u32 &hi) {
+		owner = p / ppo;
+		lo = min (ch.n_chains, owner * span + (p - owner * ppo) * MG_PIECE);
+		hi = min (min (lo + MG_PIECE, owner * span + span), ch.n_chains);
+	};
 	// one GPU: the CTA's chains [c_lo, c_hi); a group is as many consecutive chains as fit a chunk (found by warp 0
 	// when the chains' record counts arrive, a group ahead), at most MG_GMAX
 	const u32 cpc = (ch.n_chains + gridDim.x - 1) / gridDim.x;
@@ -369,7 +369,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	}
 	u32 pb = 0;	// which half of s_nraw / s_b0 holds this group's
 	// warp 0: the record counts of up to 32 chains (lane l: chain l of the window, 0 beyond it) -> chains of the
-	// group and their records.  One GPU: the longest prefix that fits a chunk (at least one chain); else all `wn`.
+	// group and their records: the longest prefix that fits a chunk (at least one chain).
 	auto plan = [&](u32 n, u32 wn, u32 half) {
 		u32 incl = min (n, 0x4000000u);	// (only "fits a chunk" matters beyond that)
 #pragma unroll
@@ -379,10 +379,7 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 			if (lane >= (u32) d)
 				incl += y;
 		}
-		u32 k = wn;
-		if (contig)
-			k = max (1u, (u32) __popc (__ballot_sync (0xFFFFFFFFu, lane < wn && incl <= CH)));
-		k = min (k, wn);
+		const u32 k = min (wn, max (1u, (u32) __popc (__ballot_sync (0xFFFFFFFFu, lane < wn && incl <= CH))));
 		const u32 tot = __shfl_sync (0xFFFFFFFFu, incl, k ? k - 1 : 0);
 		if (lane == 0)
 		{
@@ -390,15 +387,13 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 			s_traw[half] = k ? tot : 0u;
 		}
 	};
-	u32 grp = g_first, c0 = c_lo, owner = 0;
-	bool more = contig ? c_lo < c_hi : g_first < g_end;
+	u32 pc = blockIdx.x, c0 = c_lo, p_hi = c_hi, owner = 0;	// the piece, the next chain, the piece's end
+	bool more = contig ? c_lo < c_hi : pc < n_pieces;
 	if (more)
 	{
-		u32 wn;
-		if (contig)
-			wn = min (MG_GMAX, c_hi - c0);
-		else
-			geom (grp, owner, c0, wn);
+		if (!contig)
+			piece (pc, owner, c0, p_hi);
+		const u32 wn = min (MG_GMAX, p_hi - c0);
 		u32 n = 0;
 		if (tid < wn)
 		{
@@ -415,19 +410,16 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 	{
 		const u32 nch = s_nch[pb ? 1 : 0];
 		// the next group: where it starts is known now; its chains' counts travel while this group is merged
-		u32 nx_c0 = c0 + nch, nx_owner = owner, nx_wn = 0;
-		bool nx_more;
-		if (contig)
-		{
-			nx_more = nx_c0 < c_hi;
-			nx_wn = nx_more ? min (MG_GMAX, c_hi - nx_c0) : 0u;
-		}
-		else
-		{
-			nx_more = grp + g_step < g_end;
+		u32 nx_c0 = c0 + nch, nx_owner = owner, nx_hi = p_hi, nx_pc = pc;
+		bool nx_more = true;
+		if (nx_c0 >= p_hi)
+		{	// the piece is through
+			nx_pc = pc + gridDim.x;
+			nx_more = !contig && nx_pc < n_pieces;
 			if (nx_more)
-				geom (grp + g_step, nx_owner, nx_c0, nx_wn);
+				piece (nx_pc, nx_owner, nx_c0, nx_hi);
 		}
+		const u32 nx_wn = nx_more ? min (MG_GMAX, nx_hi - nx_c0) : 0u;
 		u32 nx_raw = 0;
 		u64 nx_b0 = 0;
 		if (tid < nx_wn)
@@ -658,8 +650,9 @@ skm_merge_kernel (SkmChains ch, const u64 *boff, const u32 *blist, MergeOut mo, 
 		__syncthreads ();
 		c0 = nx_c0;
 		owner = nx_owner;
+		p_hi = nx_hi;
+		pc = nx_pc;
 		more = nx_more;
-		grp += g_step;
 	}
 	if (tid == 0)
 	{

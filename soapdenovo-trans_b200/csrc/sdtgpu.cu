@@ -934,13 +934,11 @@ template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u6
 	CK (h, cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, kern, MG_NT, smem));
 	if (occ < 1)
 		return fail (h, SDTGPU_ECUDA, "skm_merge_kernel does not fit");
-	// chains per group: half a chunk's worth of records on average, so that most groups fit one chunk
-	const double avg = std::max (1.0, (double) n_rec / (double) std::max<u32> (L.n_chains, 1));
-	const u32 G = env_u32 ("SDTGPU_MERGE_GROUP", (u32) std::min<double> (MG_GMAX, std::max (1.0, std::floor (0.5 * MergeCfg<W>::CHUNK / avg))));
+	// (the kernel forms the groups itself: as many consecutive chains as fit a chunk.  One GPU: a CTA takes a contiguous
+	// range of chains; sending side: pieces of MG_PIECE chains of an owner, round robin)
 	const u32 span = per_owner ? per_owner : L.n_chains;
-	const u64 n_groups = (u64) ((span + G - 1) / G) * (per_owner ? (L.n_chains + per_owner - 1) / per_owner : 1);
-	// (one GPU: the kernel forms the groups itself, as many consecutive chains as fit a chunk; G only matters to the sending side)
-	const unsigned grid = (unsigned) std::min<u64> (std::max<u64> (per_owner ? n_groups : L.n_chains, 1), (u64) h->sm_count * occ);
+	const u64 n_pieces = (u64) ((span + MG_PIECE - 1) / MG_PIECE) * (per_owner ? (L.n_chains + per_owner - 1) / per_owner : 1);
+	const unsigned grid = (unsigned) std::min<u64> (std::max<u64> (per_owner ? n_pieces : L.n_chains, 1), (u64) h->sm_count * occ);
 	unsigned long long *small = reinterpret_cast<unsigned long long *> (h->d_small);
 	CK (h, cudaMemsetAsync (small + 4, 0, 2 * sizeof (u64), h->stream));	// surviving records, their windows
 	CK (h, cudaMemsetAsync (L.d_cursor + 1, 0, 3 * sizeof (u64), h->stream));	// output cursor, work items, group cursor
@@ -964,7 +962,7 @@ template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u6
 	mo.rcur = reinterpret_cast<unsigned long long *> (rcur);
 	{
 		TimedLaunch tl (h, 3);
-		kern<<<grid, MG_NT, smem, h->stream>>> (level_chains (h, L), L.boff, L.blist, mo, std::min (G, MG_GMAX));
+		kern<<<grid, MG_NT, smem, h->stream>>> (level_chains (h, L), L.boff, L.blist, mo);
 	}
 	CK (h, cudaGetLastError ());
 	return SDTGPU_OK;

@@ -15,4 +15,4 @@ PY
 }
 run "X=1" ""
 
-run "SDTGPU_SLICE_LOAD=0.4" "--no-parity"
+run "X=C5" "--config C5"
