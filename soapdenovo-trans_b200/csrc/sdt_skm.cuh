@@ -155,6 +155,9 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 	u32 *sls = mhs + (size_t) rb.tile_reads * g.npad + 16;	// [tile_reads * npad]: minimizer value of every window (31 bits | SKM_NFLAG); its slice is computed once per record
 	const u32 maxwin = g.npos - g.wfull + 1;	// windows of the longest read
 	const u32 gpr = (maxwin + 3) >> 2, spr = (maxwin + EMIT_SEG - 1) / EMIT_SEG;	// groups of 4 windows, segments of EMIT_SEG windows per read
+	unsigned char *endb = reinterpret_cast<unsigned char *> (sls + (size_t) rb.tile_reads * g.npad);	// [tile_reads * 4 * spr]: per group of 4 windows, bit q: a run of windows ends at its window q
+	for (u32 v = tid; v < rb.tile_reads * spr; v += EMIT_NT)
+		reinterpret_cast<u32 *> (endb)[v] = 0u;	// (the groups beyond a row's last one are never written)
 	const u32 m_npos = 0xFFFFFFFFu / g.npos + 1, m_gpr = 0xFFFFFFFFu / gpr + 1, m_spr = 0xFFFFFFFFu / spr + 1;	// x / d = (x * m) >> 32 for x < 65536
 	const u64 n_tiles = (rb.n_reads + rb.tile_reads - 1) / rb.tile_reads;
 	for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x)
@@ -188,21 +191,26 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			const u32 r = gpr == 1 ? x : __umulhi (x, m_gpr), j0 = 4 * (x - r * gpr);	// (the multiplier of 1 does not fit 32 bits)
 			const u32 nwin = rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r];
 			if (j0 >= nwin)
+			{
+				endb[(r * spr << 2) + (j0 >> 2)] = 0;	// (the row's read in the previous tile may have been longer)
 				continue;
+			}
 			const uint4 *mh = reinterpret_cast<const uint4 *> (mhs + r * g.npad + j0 + g.lo);	// (lo is a multiple of 4)
 			const uint4 c0 = mh[0];
 			const u32 a2 = c0.z, a1 = min (c0.y, a2), a0 = min (c0.x, a1);	// hashes 0..2 belong to the first windows only
-			u32 common = g.w > 3 ? c0.w : 0xFFFFFFFFu;	// hashes 3 .. w-1: in all four windows
-			u32 b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;	// running minima of hashes w, w..w+1, w..w+2
+			// hash 3 and hashes 4 .. w-1 apart: the FIFTH window (the next group's first; computed here only to
+			// tell whether a run of windows ends at this group's fourth) does without hash 3
+			u32 c3 = g.w > 3 ? c0.w : 0xFFFFFFFFu, common4 = 0xFFFFFFFFu;
+			u32 b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu, b3 = 0xFFFFFFFFu;	// running minima of hashes w, w..w+1, w..w+2, w..w+3
 			if (g.w == 3)
-				b0 = b1 = b2 = c0.w;
-			const u32 nv = (g.w + 6) >> 2;	// 16-byte chunks that hold hashes 0 .. w+2
+				b0 = b1 = b2 = b3 = c0.w;
+			const u32 nv = (g.w + 7) >> 2;	// 16-byte chunks that hold hashes 0 .. w+3
 			for (u32 k = 1; k < nv; k++)
 			{
 				const uint4 c = mh[k];
 				const u32 e = 4 * k;
 				if (e + 3 < g.w)
-					common = min (common, min (min (c.x, c.y), min (c.z, c.w)));
+					common4 = min (common4, min (min (c.x, c.y), min (c.z, c.w)));
 				else
 				{	// the chunk reaches past hash w-1
 					const u32 v[4] = { c.x, c.y, c.z, c.w };
@@ -211,7 +219,7 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 					{
 						const u32 idx = e + q;
 						if (idx < g.w)
-							common = min (common, v[q]);
+							common4 = min (common4, v[q]);
 						else
 						{
 							if (idx == g.w)
@@ -220,24 +228,34 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 								b1 = min (b1, v[q]);
 							if (idx <= g.w + 2)
 								b2 = min (b2, v[q]);
+							if (idx <= g.w + 3)
+								b3 = min (b3, v[q]);
 						}
 					}
 				}
 			}
 			b1 = min (b1, b0);
 			b2 = min (b2, b1);
-			const u32 mv[4] = { min (common, a0), min (min (common, a1), b0), min (min (common, a2), b1), min (common, b2) };
+			b3 = min (b3, b2);
+			const u32 common = min (c3, common4);
+			u32 mv[5] = { min (common, a0), min (min (common, a1), b0), min (min (common, a2), b1), min (common, b2), min (common4, b3) };
+			if constexpr (NMODE)
+			{
+#pragma unroll
+				for (u32 q = 0; q < 5; q++)
+					if (j0 + q < nwin && mask_any (rt.mtile + r * rt.mw, j0 + q, j0 + q + K))
+						mv[q] = mmer_hash (0) | SKM_NFLAG;	// with the all-A k-mer (key 0), whose every m-mer has code 0
+			}
 			u32 *sl = sls + r * g.npad + j0;
+			u32 eb = 0;
 #pragma unroll
 			for (u32 q = 0; q < 4; q++)
 				if (j0 + q < nwin)
 				{
-					u32 v = mv[q];
-					if constexpr (NMODE)
-						if (mask_any (rt.mtile + r * rt.mw, j0 + q, j0 + q + K))
-							v = mmer_hash (0) | SKM_NFLAG;	// with the all-A k-mer (key 0), whose every m-mer has code 0
-					sl[q] = v;
+					sl[q] = mv[q];
+					eb |= (j0 + q + 1 >= nwin || mv[q + 1] != mv[q] ? 1u : 0u) << q;
 				}
+			endb[(r * spr << 2) + (j0 >> 2)] = (unsigned char) eb;
 		}
 		__syncthreads ();
 		// ---- 3. runs of windows with the same minimizer value -> record descriptors in mhs[], which is free now.
@@ -249,23 +267,21 @@ skm_emit_kernel (ReadBatch rb, SkmGeom g, SkmChains ch, unsigned long long *rec_
 			const u32 nwin = rt.uniform ? rt.nwin_u : rt.prefix[r + 1] - rt.prefix[r];
 			if (js >= nwin)
 				continue;
-			const u32 je = min (js + EMIT_SEG, nwin);
 			const u32 *sl = sls + r * g.npad;
-			u32 s = sl[js], start = js;
-			while (start > 0 && sl[start - 1] == s)
-				start--;
-			// first mark where runs end (a tight, convergent loop), then report them: reporting inside the
-			// walk made every step of the warp pay for the few lanes that had a run to report
-			u32 ends = 0;
-			for (u32 j = js; j < je; j++)
-			{
-				const u32 nxt = j + 1 < nwin ? sl[j + 1] : 0xFFFFFFFFu;	// no window has this value (mmer_hash (0) is not 2^31 - 1)
-				ends |= (nxt != s ? 1u : 0u) << (j - js);
-				s = nxt;
-			}
+			const u32 *ew = reinterpret_cast<const u32 *> (endb) + r * spr;	// a segment's four groups: one word, byte b bit q = window js + 4 b + q
+			u32 ends = ew[js / EMIT_SEG], start = 0;
+			// the run that is open at the segment's first window started behind the last end before the segment
+			for (int w = (int) (js / EMIT_SEG) - 1; w >= 0; w--)
+				if (const u32 e2 = ew[w])
+				{
+					const u32 p = 31 - __clz (e2);
+					start = EMIT_SEG * (u32) w + ((p >> 3) << 2) + (p & 7u) + 1;
+					break;
+				}
 			while (ends)
 			{
-				const u32 j = js + (u32) __ffs (ends) - 1;	// windows start .. j are a run
+				const u32 p = (u32) __ffs (ends) - 1;
+				const u32 j = js + ((p >> 3) << 2) + (p & 7u);	// windows start .. j are a run
 				ends &= ends - 1;
 				if (rb.owner_ranks <= 1 || slice_of_min (sl[j] & ~SKM_NFLAG, g.n_slices) % rb.owner_ranks == rb.owner_rank)
 				{

@@ -780,7 +780,7 @@ template <int W, bool NMODE> int launch_emit_t (sdtgpu *h, ReadBatch rb)
 	const SkmGeom &g = h->geom;
 	rb.tile_reads = g.tile_reads;
 	auto kern = skm_emit_kernel<W, NMODE>;
-	const size_t smem = 4 * (tile_words (rb, NMODE) + 2 * (size_t) g.tile_reads * g.npad + 16);
+	const size_t smem = 4 * (tile_words (rb, NMODE) + 2 * (size_t) g.tile_reads * g.npad + 16 + (size_t) g.tile_reads * ((g.npos - g.wfull + 1 + EMIT_SEG - 1) / EMIT_SEG) + 4);
 	if (smem > 48 * 1024)
 		CK (h, cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int occ = 0;
