@@ -251,6 +251,8 @@ def main():
     ap.add_argument("--path", default="sliced", choices=["auto", "direct", "sliced"],
                     help="insert path: the sliced build (super-k-mer records -> chains -> work items built in shared memory; every config) "
                          "or the single-pass upsert (direct)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="several GPUs: weak = the config's reads PER GPU (the driver's contract); strong = the config's reads in total, split over the GPUs")
     ap.add_argument("--hint", type=int, default=-1, help="capacity_hint for the handle (-1: none on one GPU, the closed-form estimate on several)")
     args = ap.parse_args()
     if args.path == "auto":
@@ -266,6 +268,8 @@ def main():
         cfg_d["n_transcripts"] = args.transcripts
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "strong" and world > 1:
+        cfg_d["n_pairs"] = cfg_d["n_pairs"] // world      # the config's reads in total: rank r takes pairs [r, r + 1) x n_pairs / world
     if os.environ.get("BENCH_TRACE_RANK0") and rank == 0:
         os.environ["SDTGPU_TRACE"] = "1"
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -567,7 +571,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers sharded by slice owner ({'super-k-mer records merged per sender and exchanged over NCCL, one all-to-all per step' if exch_kind == 'skm' else ('packed reads all-gathered over NCCL, every rank inserts the k-mers it owns' if args.exchange != 'records' else 'k-mer records exchanged over NCCL')})" if world > 1 else ""),
                        "instances_per_step": total_instances, "distinct_kmers": total_nodes,

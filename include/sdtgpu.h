@@ -190,7 +190,9 @@ int sdtgpu_kernel_times (sdtgpu_t *h, int reset, double ms[3], uint64_t launches
 int sdtgpu_phase_times (sdtgpu_t *h, int reset, double ms[8], uint64_t launches[8]);
 /* SDTGPU_F_SLICED only: out = { slices, slots per slice image, minimizer length m, m-mers per window,
  * bytes per super-k-mer record, records held, nodes in the store, work items retried by the last build,
- * records left after identical ones were merged (last build), 0, 0, 0 } */
+ * records left after identical ones were merged (last build), work items of the last build,
+ * epochs whose records had to be made a second time since create (the block pool was too small),
+ * device buffers (re)allocated since create } */
 int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[12]);
 
 /* debug (library built with -DSDT_BUILD_PROF; zeros otherwise): phase clocks of the slice build kernel,

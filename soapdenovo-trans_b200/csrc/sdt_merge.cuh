@@ -709,29 +709,56 @@ skm_append_kernel (SkmChains ch, const u32 *rec, u64 n, u32 lo)
 		if (threadIdx.x == 0)
 			pool_refill (ch, s_pool, 128);
 		__syncthreads ();
+		// A thread takes AP_TILE / AP_NT CONSECUTIVE records: the records of a slice arrive next to each other (a
+		// sender's run of a few dozen), and threads that append to the same chain at the same time wait for each
+		// other at every block boundary (with one record per thread and turn, 16 threads met in a chain: the
+		// pass took four times as long on 8 GPUs as on 2).  The next record's position is drawn while this one is written.
 		if (s_pool[1] != 0)
-			for (u64 i = t * AP_TILE + threadIdx.x; i < min (n, (t + 1) * AP_TILE); i += AP_NT)
-			{
+		{
+			constexpr u32 PER = AP_TILE / AP_NT, VEC = RECW / 4;
+			const u64 i0 = t * AP_TILE + (u64) threadIdx.x * PER, i1 = min (n, i0 + PER);
+			uint4 nx[VEC];
+			u32 s_nx = 0;
+			u64 tk_nx = 0;
+			bool ok_nx = false;
+			auto fetch = [&](u64 i) {
 				const uint4 *src = reinterpret_cast<const uint4 *> (rec + i * RECW);
-				uint4 v[RECW / 4];
 #pragma unroll
-				for (int q = 0; q < RECW / 4; q++)
-					v[q] = ldg_stream (src + q);
-				const u32 s = v[RECW / 4 - 1].w - lo;
-				if (s >= ch.n_chains)
-				{	// not this rank's: the exchange went wrong
+				for (u32 q = 0; q < VEC; q++)
+					nx[q] = ldg_stream (src + q);
+				s_nx = nx[VEC - 1].w - lo;
+				nx[VEC - 1].w = 0;
+				ok_nx = s_nx < ch.n_chains;
+				if (ok_nx)
+					tk_nx = chain_ticket (ch, s_nx);
+				else	// not this rank's: the exchange went wrong
 					atomicOr (reinterpret_cast<unsigned long long *> (&ch.ctr->overflow), (unsigned long long) OVF_FOREIGN);
+			};
+			if (i0 < i1)
+				fetch (i0);
+			for (u64 i = i0; i < i1; i++)
+			{
+				uint4 v[VEC];
+#pragma unroll
+				for (u32 q = 0; q < VEC; q++)
+					v[q] = nx[q];
+				const u32 sl = s_nx;
+				const u64 tk = tk_nx;
+				const bool ok = ok_nx;
+				ok_nx = false;
+				if (i + 1 < i1)
+					fetch (i + 1);
+				if (!ok)
 					continue;
-				}
-				v[RECW / 4 - 1].w = 0;
-				u32 *dst = chain_append (ch, s, s_pool);
+				u32 *dst = chain_place (ch, sl, tk, s_pool, ok_nx ? &tk_nx : nullptr, s_nx);
 				if (dst)
 				{
 #pragma unroll
-					for (int q = 0; q < RECW / 4; q++)
+					for (u32 q = 0; q < VEC; q++)
 						reinterpret_cast<uint4 *> (dst)[q] = v[q];
 				}
 			}
+		}
 		__syncthreads ();
 	}
 	pool_end (ch, s_pool);

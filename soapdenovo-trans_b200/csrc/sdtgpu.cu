@@ -106,6 +106,7 @@ struct sdtgpu
 	u32 *rx = nullptr;	// records received from other ranks
 	u64 rx_cap = 0;
 	u32 skm_world = 1, skm_rank = 0, n_local = 0;	// super-k-mer exchange (sdtgpu_skm_set_world): slices per rank; geom.n_slices = n_local * skm_world
+	u64 n_reemit = 0, n_alloc = 0;	// since create: epochs whose records were made a second time (block pool too small); device buffers (re)allocated after the first flush
 	u64 n_store = 0, n_records = 0, n_retried = 0, n_merged = 0, n_items = 0;	// nodes in the store after the last build
 	bool dirty = false;	// records were emitted since the last build
 	u32 n_epochs = 0;
@@ -629,6 +630,7 @@ int grow_device (sdtgpu *h, void **mem, size_t *cap, size_t keep, size_t need, c
 		return SDTGPU_OK;
 	size_t ncap = std::max (*cap + *cap / 2, need + (4u << 20));
 	void *neu = nullptr;
+	h->n_alloc++;
 	if (!keep && *mem)
 	{	// nothing to keep: the old buffer goes first
 		CK (h, cudaStreamSynchronize (h->stream));
@@ -997,6 +999,7 @@ int launch_split (sdtgpu *h, ChainLevel &sub, const u32 *rec, const SkmSplit *ch
 int skm_emit_all (sdtgpu *h, u64 records)
 {
 	int rc;
+	h->n_reemit++;
 	ChainLevel &L = h->lv[0];
 	const u64 hold = (u64) std::min<u64> ((u64) h->sm_count * 8, MAX_CTAS) * CH_SB;
 	if ((rc = level_reset (h, L)))
@@ -2223,7 +2226,7 @@ int sdtgpu_slice_geometry (const sdtgpu_t *h, uint64_t out[12])
 		return SDTGPU_ESTATE;
 	out[0] = h->geom.n_slices; out[1] = h->geom.slice_slots; out[2] = h->geom.m; out[3] = h->geom.w;
 	out[4] = 4 * (uint64_t) h->geom.recw; out[5] = h->n_records; out[6] = h->n_store; out[7] = h->n_retried;
-	out[8] = h->n_merged; out[9] = h->n_items; out[10] = out[11] = 0;
+	out[8] = h->n_merged; out[9] = h->n_items; out[10] = h->n_reemit; out[11] = h->n_alloc;
 	return SDTGPU_OK;
 }
 

@@ -322,7 +322,8 @@ class PregraphGPU:
         out = (C.c_uint64 * 12)()
         self._ck(self.L.sdtgpu_slice_geometry(self.h, out))
         return dict(n_slices=out[0], slice_slots=out[1], m=out[2], mmers_per_window=out[3], record_bytes=out[4],
-                    n_records=out[5], n_nodes=out[6], retried_items=out[7], n_records_merged=out[8], work_items=out[9])
+                    n_records=out[5], n_nodes=out[6], retried_items=out[7], n_records_merged=out[8], work_items=out[9],
+                    epochs_emitted_again=out[10], device_allocations=out[11])
 
     def kernel_times(self, reset: bool = True):
         """(ms[3], launches[3]) for insert / partition-count / partition-scatter kernels."""
