@@ -375,7 +375,7 @@ def main():
             exch = ReplicatedReads(pkg, g, world, rank, dev, max_round_reads=min(batch, n_reads), stride=stride)
 
     host_t = {"reset": 0.0, "push": 0.0, "flush": 0.0, "sync": 0.0, "n": 0}
-    step_wall = []
+    step_wall, step_events = [], []       # per step: wall clock; [epochs emitted again, device allocations (both cumulative), retried items, work items]
 
     def one_step(gg):
         t0 = time.perf_counter()
@@ -397,6 +397,11 @@ def main():
             host_t[k] += 1e3 * v
         host_t["n"] += 1
         step_wall.append(round(1e3 * (t4 - t0), 2))
+        if sliced:
+            geo_s = gg.slice_geometry()
+            ph_s = gg.phase_times(reset=False)      # cumulative kernel times per phase: the difference between two steps tells which phase an outlier sat in
+            step_events.append([geo_s["epochs_emitted_again"], geo_s["device_allocations"], geo_s["retried_items"], geo_s["work_items"],
+                                {k: round(v[0], 1) for k, v in ph_s.items() if v[0]}])
 
     def barrier():
         if world > 1:
@@ -416,9 +421,11 @@ def main():
     for k in host_t:
         host_t[k] = 0
     step_wall.clear()
+    step_events.clear()
     if exch is not None and hasattr(exch, "collective_ms"):
         exch.collective_ms = 0.0
         exch.host_ms = {}
+        exch.host_log = []
     sampler = ClockSampler(local_rank if rank == 0 else -1)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -432,6 +439,8 @@ def main():
     sampler.join()
     ms = e0.elapsed_time(e1)
     step_wall_timed = list(step_wall)       # host wall clock of every timed step (this rank): an outlier shows here
+    step_events_timed = list(step_events)
+    exch_log_timed = list(getattr(exch, "host_log", []) or [])      # per timed step: [bound, stage, exchange, import] ms on the host
     host_ms = {k: v / max(host_t["n"], 1) for k, v in host_t.items() if k != "n"}      # wall clock of the host calls of a timed step (this rank)
     st = g.stats()
     distinct = int(st.n_nodes)
@@ -591,7 +600,8 @@ def main():
                                            "ceiling_instances_per_s_per_gpu": RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words],
                                            "frac_of_ceiling": (inst_per_launch / (ker_ms * 1e-3)) / (RANDOM_REQUESTS_PER_S / MIN_REQUESTS_PER_INSTANCE[st.device_key_words]),
                                            "source": "tools/randacc_bench.cu, profiles/r1_randacc_bench.txt"}},
-            "host_call_ms_per_step_rank0": host_ms, "step_wall_ms_rank0": step_wall_timed,
+            "host_call_ms_per_step_rank0": host_ms, "step_wall_ms_rank0": step_wall_timed, "step_events_rank0": step_events_timed,
+            "exchange_host_ms_steps_rank0": exch_log_timed or None,
             "collective_ms_per_step": collective_ms,
             "exchange_host_ms_per_step_rank0": ({k: v / max(exch.host_ms.get("flushes", 1), 1) for k, v in exch.host_ms.items() if k != "flushes"} if exch is not None and getattr(exch, "host_ms", None) else None),
             "cpu_baseline": cpu, "e2e": e2e, "e2e_from_files": from_files, "gpu_launches": int(all_launches),

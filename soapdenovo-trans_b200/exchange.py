@@ -231,6 +231,7 @@ class SkmExchange:
         self.nvlink_bytes = 0
         self.collective_ms = 0.0        # device time of the counts + records exchange (CUDA events on the handle's stream)
         self.host_ms = {}               # wall clock of the phases of flush (host side, this rank)
+        self.host_log = []
         self.rebind(g)
 
     def rebind(self, g):
@@ -284,4 +285,5 @@ class SkmExchange:
         for k, v in zip(("bound", "stage", "exchange", "import"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
             self.host_ms[k] = self.host_ms.get(k, 0.0) + 1e3 * v
         self.host_ms["flushes"] = self.host_ms.get("flushes", 0) + 1
+        self.host_log.append([round(1e3 * (b - a), 2) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4))])   # per flush: bound, stage, exchange, import
         return total
