@@ -77,6 +77,24 @@ static long long hash_file (hasher_t * hs, const char *path1, const char *path2,
 	sdtpack_reader *rd;
 	long long seen = 0;
 	int64_t n;
+	{	/* The reference as shipped reads a .gz library as PLAIN TEXT: the popen ("gzip -dc") branch of its
+		 * openFile4read is commented out (readseq1by1.c:638-676).  This stage does the same bytes the same
+		 * way; say so once, on stderr (stdout is compared with the reference's) */
+		static int warned;
+		const char *p[2] = { path1, path2 };
+		int q;
+		for (q = 0; q < 2 && !warned; q++)
+		{
+			size_t l = p[q] ? strlen (p[q]) : 0;
+			while (l && p[q][l - 1] == ' ')
+				l--;	/* the reference's trailing-space rule, readseq1by1.c:808-812 */
+			if (l > 3 && !strncmp (p[q] + l - 3, ".gz", 3))
+			{
+				fprintf (stderr, "warning: %s looks gzip-compressed; like the reference, pregraph reads it as plain text — decompress it first\n", p[q]);
+				warned = 1;
+			}
+		}
+	}
 	if (sdtpack_open (&rd, path1, path2, fastq, 0))
 	{
 		printf ("Cannot open %s%s%s\n", path1, path2 ? " / " : "", path2 ? path2 : "");
