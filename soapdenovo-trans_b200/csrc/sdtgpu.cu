@@ -624,11 +624,13 @@ int skm_setup (sdtgpu *h, u64 hint)
 static constexpr u32 MAX_FAILED = 1u << 21;
 static constexpr u32 MAX_CTAS = 148 * 16 + 64;	// CTAs that keep a block range between launches (SkmChains::cta_pool)
 
-int grow_device (sdtgpu *h, void **mem, size_t *cap, size_t keep, size_t need, const char *what = "buffer")
-{	// *mem holds `keep` live bytes; make room for `need`
+int grow_device (sdtgpu *h, void **mem, size_t *cap, size_t keep, size_t need, const char *what = "buffer", bool slack = false)
+{	// *mem holds `keep` live bytes; make room for `need`.  slack: a buffer whose need varies a little from epoch to
+	// epoch on the same input (sub-slices, received records: which items overflow depends on the order records
+	// arrive in) gets an eighth more the first time, so that the next epoch does not allocate again
 	if (need <= *cap)
 		return SDTGPU_OK;
-	size_t ncap = std::max (*cap + *cap / 2, need + (4u << 20));
+	size_t ncap = std::max (*cap + *cap / 2, need + (slack ? need / 8 : 0) + (4u << 20));
 	void *neu = nullptr;
 	h->n_alloc++;
 	if (!keep && *mem)
@@ -758,7 +760,8 @@ int level_reserve (sdtgpu *h, ChainLevel &L, u64 blocks)
 	const size_t bb = (size_t) CH_BLK * h->geom.recw * 4;
 	const u64 old = L.pool_blocks;
 	size_t cap_r = old * bb, cap_c = old * 4, cap_s = old * 4;
-	if ((rc = grow_device (h, (void **) &L.recs, &cap_r, old * bb, blocks * bb, "record pool")))
+	const bool slack = &L != &h->lv[0];	// (the slices' own pool is sized by a formula of the reads pushed: it does not wander)
+	if ((rc = grow_device (h, (void **) &L.recs, &cap_r, old * bb, blocks * bb, "record pool", slack)))
 		return rc;
 	const u64 neu = cap_r / bb;
 	if ((rc = grow_device (h, (void **) &L.bchain, &cap_c, old * 4, neu * 4)) || (rc = grow_device (h, (void **) &L.bseq, &cap_s, old * 4, neu * 4)))
@@ -913,7 +916,7 @@ int level_list (sdtgpu *h, ChainLevel &L, u64 *n_blocks)
 	// (no look at the counts: the list is given room for every block of the pool, the kernel reads the cursor itself)
 	const u64 linked = L.pool_blocks > L.n_chains ? L.pool_blocks - L.n_chains : 0, cursor = L.pool_blocks;
 	size_t cap_b = L.blist_cap * 4;
-	if ((rc = grow_device (h, (void **) &L.blist, &cap_b, 0, std::max<u64> (linked, 1) * 4, "block list")))
+	if ((rc = grow_device (h, (void **) &L.blist, &cap_b, 0, std::max<u64> (linked, 1) * 4, "block list", &L != &h->lv[0])))
 		return rc;
 	L.blist_cap = cap_b / 4;
 	if (cursor > L.n_chains)
@@ -1275,7 +1278,7 @@ int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, u64 n_e
 	{	// the merged runs: at most as many records as went in
 		const size_t rec = 4 * (size_t) g.recw;
 		size_t cap_b = L.out_cap * rec;
-		if ((rc = grow_device (h, (void **) &L.out, &cap_b, 0, std::max<u64> (n_rec, 1) * rec, "merged records")))
+		if ((rc = grow_device (h, (void **) &L.out, &cap_b, 0, std::max<u64> (n_rec, 1) * rec, "merged records", &L != &h->lv[0])))
 			return rc;
 		L.out_cap = cap_b / rec;
 	}
@@ -1772,7 +1775,7 @@ int sdtgpu_skm_import_buffer (sdtgpu_t *h, uint64_t n_records, void **d_buffer)
 	CK (h, cudaSetDevice (h->device));
 	const size_t rec = 4 * (size_t) h->geom.recw;
 	size_t cap_b = h->rx_cap * rec;
-	if ((rc = grow_device (h, (void **) &h->rx, &cap_b, 0, std::max<u64> (n_records, 1) * rec)))
+	if ((rc = grow_device (h, (void **) &h->rx, &cap_b, 0, std::max<u64> (n_records, 1) * rec, "receive buffer", true)))
 		return rc;
 	h->rx_cap = cap_b / rec;
 	*d_buffer = h->rx;
