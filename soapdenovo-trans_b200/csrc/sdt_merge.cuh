@@ -16,18 +16,21 @@ namespace sdt {
 // counters take the multiplicity (update_kmer, newhash.c:71-96, is a sum) and the node's first
 // ordinal the minimum.
 //
-// A CTA takes MG_G consecutive chains at a time.  If their records fit one chunk (the rule) they are
-// staged together, a table of record indices keyed by the record's content finds the copies, and
-// the survivors are written out IN ORDER (block scan), so that consecutive chains are adjacent.
-// Then the CTA cuts the group into WORK ITEMS for skm_build_kernel at chain boundaries: as many
-// consecutive chains as have at most `budget` windows left between them.  Every instance of a k-mer
-// is in one chain, so an item holds all instances of its k-mers; an item has at most as many distinct
-// k-mers as windows, so with budget < image slots it CANNOT overflow an image, whatever the number of
-// slices was guessed to be (too many slices only make the chains short).  Only a single chain with
-// more windows than that — a highly expressed locus — becomes an item that the build may have to
-// split (R = 0 tells it not even to try when the chain is far beyond an image).
-// The space in out[] is reserved by the group's record count (an upper bound) before the records are
-// read, so the round trip of that reservation costs nothing.
+// A CTA walks a contiguous range of chains in GROUPS: as many consecutive chains as fit one chunk (found
+// by warp 0 from the chains' record counts, one group ahead, while the current group is merged).  The
+// group's records are staged together (16 bytes at a time, swizzled against bank conflicts, mg_swz), a
+// table of record indices keyed by the record's content finds the copies, and the survivors are written
+// out IN ORDER (block scan), so that consecutive chains are adjacent.  Then the CTA cuts the stream of
+// chains into WORK ITEMS for skm_build_kernel at chain boundaries — an open item is carried from group
+// to group: as many consecutive chains as have at most `budget` windows left between them.  Every
+// instance of a k-mer is in one chain, so an item holds all instances of its k-mers; an item has at most
+// as many distinct k-mers as windows, so with budget < image slots it CANNOT overflow an image, whatever
+// the number of slices was guessed to be (too many slices only make the chains short).  Only a single
+// chain with more windows than that — a highly expressed locus — becomes an item that the build may
+// have to split (R = 0 tells it not even to try when the chain is far beyond an image).
+// The CTA's space in out[] is reserved once, by its chains' record count (an upper bound), before the
+// records are read.  Several GPUs, sending side (per_owner): the chains of an owner in pieces of MG_PIECE,
+// every group's survivors into the owner's region, no work items.
 static constexpr int MG_NT = 512;	// 2 CTAs of 80-96 KB per SM
 static constexpr u32 MG_GMAX = 32;	// chains per group at most
 static constexpr u32 MG_PIECE = 128;	// several GPUs, sending side: consecutive chains of one owner that a CTA takes at a time

@@ -38,19 +38,17 @@ struct SkmGeom
 	u32 lo, wfull;		// first of them, K - m + 1
 	u32 nmax;		// windows per record at most (32 for 1-word keys, else 64)
 	u32 recw;		// u32 words per record (8, 12, 16)
-	u32 slice_a;		// slice of the all-A k-mer (key 0): where the -n N-windows go
+	u32 slice_a;		// slice of the all-A k-mer (key 0), where the -n N-windows go (informational: the emit kernel gives N-windows that k-mer's minimizer value)
 	u32 send_group;		// several GPUs, sending side: a chain holds this many consecutive slices and every record carries its slice in its last word (1: a chain is a slice)
 	u32 tile_reads;		// reads per shared-memory tile of skm_emit_kernel
 	u32 npos;		// m-mer positions per read at most (max_read_len - m + 1)
 	u32 npad;		// row stride of the per-read arrays of skm_emit_kernel (a multiple of 4, >= npos)
-	u32 build_nt;		// threads per CTA of skm_build_kernel: 1024 (one CTA per SM) or 512 (two)
 };
 
 static constexpr u32 SKM_HDR = 3;		// header words: ord low | ord high, n-1, flags, bases | slice
 static constexpr u32 SKM_NFLAG = 0x80000000u;	// in the per-window slice array: window contains an N (-n)
 static constexpr int EMIT_NT = 256;
 static constexpr u32 EMIT_SEG = 16;	// windows per thread in the run detection of skm_emit_kernel
-static constexpr int SCAT_NT = 256;
 
 __host__ __device__ __forceinline__ u32 fmix32 (u32 h)
 {

@@ -576,7 +576,6 @@ u64 estimate_distinct (u64 instances, int K)
 int skm_setup (sdtgpu *h, u64 hint)
 {
 	SkmGeom g;
-	g.build_nt = 0;
 	// default: what fits one CTA per SM (227 KB) beside the staging areas: 72 / 84 / 100 bytes per slot for 1- / 2- / 4-word keys
 	const u32 dflt = skm_build2_max_slots (h->W);
 	g.slice_slots = env_u32 ("SDTGPU_SLICE_SLOTS", dflt);
@@ -930,7 +929,7 @@ int level_list (sdtgpu *h, ChainLevel &L, u64 *n_blocks)
 	return SDTGPU_OK;
 }
 
-template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u64 n_rec, u32 per_owner, const u64 *region, u64 *rcur)
+template <int W, bool HAS_MULT> int launch_merge_t (sdtgpu *h, ChainLevel &L, u64 /* n_rec: the kernel forms its groups from the chains' own counts */, u32 per_owner, const u64 *region, u64 *rcur)
 {
 	auto kern = skm_merge_kernel<W, HAS_MULT>;
 	const size_t smem = skm_merge_smem<W> ();
