@@ -87,6 +87,8 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
                 self.nvml = pynvml
+                self._sample_nvml()      # the first queries initialise things inside NVML: not inside the timed region
+                self.samples.clear()
             except Exception:
                 self.nvml = None
 
@@ -248,6 +250,8 @@ def main():
     ap.add_argument("--batch-reads", type=int, default=1 << 22)
     ap.add_argument("--exchange", default="reads", choices=["reads", "records", "reads-replicated"],
                     help="multi-GPU sharding of --path direct: all-gather the packed reads and insert owned k-mers (default) or exchange k-mer records")
+    ap.add_argument("--skm-exchange", default="native", choices=["native", "torch"],
+                    help="several GPUs, sliced build: the exchange inside the library (sdtgpu_skm_exchange: NCCL bound by libsdtgpu.so) or driven from Python over torch.distributed")
     ap.add_argument("--path", default="sliced", choices=["auto", "direct", "sliced"],
                     help="insert path: the sliced build (super-k-mer records -> chains -> work items built in shared memory; every config) "
                          "or the single-pass upsert (direct)")
@@ -368,7 +372,7 @@ def main():
     if world > 1:
         from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads, SkmExchange
         if sliced:
-            exch, exch_kind = SkmExchange(pkg, g, world, rank, dev), "skm"
+            exch, exch_kind = SkmExchange(pkg, g, world, rank, dev, native=(args.skm_exchange == "native")), "skm"
         elif args.exchange == "records":
             exch = Exchange(pkg, g, world, rank, dev, max_round_instances=min(batch, n_reads) * nwin)
         else:
@@ -408,6 +412,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()        # (the first barrier of a process group sets up its communicator: before the warm-up, not next to the timed region)
     for _ in range(args.warmup):
         one_step(g)
     barrier()
@@ -582,7 +587,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers sharded by slice owner ({'super-k-mer records merged per sender and exchanged over NCCL, one all-to-all per step' if exch_kind == 'skm' else ('packed reads all-gathered over NCCL, every rank inserts the k-mers it owns' if args.exchange != 'records' else 'k-mer records exchanged over NCCL')})" if world > 1 else ""),
+            "config": {"workload": workload + (f" per GPU x {world} GPUs, k-mers sharded by slice owner ({('super-k-mer records merged per sender and exchanged over NCCL inside the library (sdtgpu_skm_exchange), one grouped send/recv per step' if args.skm_exchange == 'native' else 'super-k-mer records merged per sender and exchanged over NCCL (torch.distributed), one grouped send/recv per step') if exch_kind == 'skm' else ('packed reads all-gathered over NCCL, every rank inserts the k-mers it owns' if args.exchange != 'records' else 'k-mer records exchanged over NCCL')})" if world > 1 else ""),
                        "instances_per_step": total_instances, "distinct_kmers": total_nodes,
                        "capacity_hint": hint, "hint_source": ("none: sized inside the timed region from the number of windows pushed" if hint == 0 else
                                                               ("closed form, instances x (1 - 0.99^K) x 1.05: no pass over the data" if args.hint < 0 else "--hint")),

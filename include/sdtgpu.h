@@ -222,6 +222,24 @@ int sdtgpu_skm_stage (sdtgpu_t *h, void **d_records, uint64_t *starts /* world *
 int sdtgpu_skm_import_buffer (sdtgpu_t *h, uint64_t n_records, void **d_buffer);
 int sdtgpu_skm_import (sdtgpu_t *h, uint64_t n_records);
 
+/* ---- the same exchange in ONE call, NCCL inside the library (csrc/sdt_nccl.cu).  NCCL is bound at run time
+ * (dlopen of libnccl.so.2), so single-GPU users never load it.  A communicator is made once per process:
+ *   rank 0:      sdtgpu_comm_unique_id (id);  hand the 128 bytes to every rank (MPI_Bcast, a file, a socket ...)
+ *   every rank:  sdtgpu_comm_create (&c, device, id, rank, world);
+ * and per epoch, after sdtgpu_skm_set_world and this rank's pushes:
+ *   sdtgpu_skm_exchange (h, c, reads_end, &n_received, &collective_ms)
+ * = all-reduce of the ordinal bound (reads_end: one past the largest global read ordinal this rank pushed),
+ * sdtgpu_skm_stage, all-gather of the counts, one grouped ncclSend / ncclRecv of the records straight into the
+ * import buffer, sdtgpu_skm_import.  collective_ms (may be NULL): device time of counts + records, CUDA events.
+ * Collective: every rank of the communicator must make the call. */
+#define SDTGPU_COMM_ID_BYTES 128
+typedef struct sdtgpu_comm sdtgpu_comm_t;
+int sdtgpu_comm_unique_id (uint8_t id[SDTGPU_COMM_ID_BYTES]);
+int sdtgpu_comm_create (sdtgpu_comm_t **out, int device, const uint8_t id[SDTGPU_COMM_ID_BYTES], int rank, int world);
+int sdtgpu_comm_destroy (sdtgpu_comm_t *c);
+const char *sdtgpu_comm_last_error (const sdtgpu_comm_t *c);	/* c may be NULL: last failure without a communicator */
+int sdtgpu_skm_exchange (sdtgpu_t *h, sdtgpu_comm_t *c, uint64_t reads_end_this_rank, uint64_t *n_received, double *collective_ms);
+
 /* ---- synthetic reads on the device (bench/test utility; bit-identical to synth.py).
  * d_tr_bases: uint8 codes of all transcripts; d_starts u64[T]; d_lengths u32[T]; d_cum u64[T]. */
 int sdtgpu_synth_reads_device (int device, void *stream, const uint8_t *d_tr_bases, const uint64_t *d_starts,

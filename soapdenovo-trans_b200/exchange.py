@@ -226,8 +226,17 @@ class SkmExchange:
     rank's reads (the emit kernel runs, nothing crosses the fabric yet); `flush` groups the records by
     slice, exchanges counts and records with two all-to-alls and builds this rank's slices."""
 
-    def __init__(self, pkg, g, world: int, rank: int, dev, group=None):
+    def __init__(self, pkg, g, world: int, rank: int, dev, group=None, native: bool = False):
+        """native: the exchange runs inside the library (sdtgpu_skm_exchange, NCCL bound by the library itself);
+        torch.distributed then only carries the communicator's 128-byte id to the ranks, once."""
         self.world, self.rank, self.dev, self.group = world, rank, dev, group
+        self.comm = None
+        if native:
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(pkg.pregraph.SkmComm.unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+            self.comm = pkg.pregraph.SkmComm(torch.device(dev).index or 0, bytes(uid.cpu().numpy().tobytes()), rank, world)
         self.nvlink_bytes = 0
         self.collective_ms = 0.0        # device time of the counts + records exchange (CUDA events on the handle's stream)
         self.host_ms = {}               # wall clock of the phases of flush (host side, this rank)
@@ -264,6 +273,14 @@ class SkmExchange:
     def flush(self, g):
         import time
         t0 = time.perf_counter()
+        if self.comm is not None:
+            total, ms = g.skm_exchange(self.comm, self.reads_end)
+            t4 = time.perf_counter()
+            self.collective_ms += ms
+            self.host_ms["native"] = self.host_ms.get("native", 0.0) + 1e3 * (t4 - t0)
+            self.host_ms["flushes"] = self.host_ms.get("flushes", 0) + 1
+            self.host_log.append([round(1e3 * (t4 - t0), 2)])
+            return total
         bound = torch.tensor([self.reads_end], dtype=torch.int64, device=self.dev)
         dist.all_reduce(bound, op=dist.ReduceOp.MAX, group=self.group)
         g.skm_set_ordinal_bound(int(bound.item()))  # reads of all ranks this epoch: 32-bit ordinals in the slice images when they fit

@@ -83,6 +83,12 @@ def library() -> C.CDLL:
     L.sdtgpu_skm_set_ordinal_bound.argtypes = [vp, u64]
     L.sdtgpu_skm_import_buffer.argtypes = [vp, u64, C.POINTER(vp)]
     L.sdtgpu_skm_import.argtypes = [vp, u64]
+    L.sdtgpu_comm_unique_id.argtypes = [vp]
+    L.sdtgpu_comm_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32]
+    L.sdtgpu_comm_destroy.argtypes = [vp]
+    L.sdtgpu_comm_last_error.restype = C.c_char_p
+    L.sdtgpu_comm_last_error.argtypes = [vp]
+    L.sdtgpu_skm_exchange.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(C.c_double)]
     L.sdtgpu_record_bytes.restype = C.c_size_t
     L.sdtgpu_record_bytes.argtypes = [vp]
     L.sdtgpu_bucket_reads_device.argtypes = [vp, vp, vp, vp, u64, u32, u32, u64, i32, vp, u64, vp]
@@ -263,6 +269,15 @@ class PregraphGPU:
     def skm_import(self, n_records: int):
         self._ck(self.L.sdtgpu_skm_import(self.h, n_records))
 
+    def skm_exchange(self, comm: "SkmComm", reads_end: int):
+        """include/sdtgpu.h sdtgpu_skm_exchange: the whole exchange of an epoch in one call (NCCL inside the library).
+        -> (records received, device ms of the counts + records collectives)."""
+        n, ms = C.c_uint64(), C.c_double()
+        rc = self.L.sdtgpu_skm_exchange(self.h, comm.c, reads_end, C.byref(n), C.byref(ms))
+        if rc:
+            raise SdtGpuError(rc, (self.L.sdtgpu_comm_last_error(comm.c) or b"").decode())
+        return int(n.value), float(ms.value)
+
     def record_bytes(self) -> int:
         return int(self.L.sdtgpu_record_bytes(self.h))
 
@@ -330,6 +345,35 @@ class PregraphGPU:
         ms, nl = (C.c_double * 3)(), (C.c_uint64 * 3)()
         self._ck(self.L.sdtgpu_kernel_times(self.h, int(reset), ms, nl))
         return list(ms), list(nl)
+
+
+class SkmComm:
+    """include/sdtgpu.h sdtgpu_comm_*: the NCCL communicator of the super-k-mer exchange, owned by the library.
+    `unique_id()` on rank 0, the 128 bytes to every rank by whatever means the host has, then SkmComm(...)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import torch      # noqa: F401  (its NCCL must be in the process FIRST: the library binds whatever libnccl.so.2 is loaded, else the system's — and torch cannot live with an older one)
+        L = library()
+        buf = (C.c_uint8 * 128)()
+        rc = L.sdtgpu_comm_unique_id(buf)
+        if rc:
+            raise SdtGpuError(rc, (L.sdtgpu_comm_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def __init__(self, device: int, unique_id: bytes, rank: int, world: int):
+        import torch      # noqa: F401  (see unique_id)
+        self.L = library()
+        self.c = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        rc = self.L.sdtgpu_comm_create(C.byref(self.c), device, buf, rank, world)
+        if rc:
+            raise SdtGpuError(rc, (self.L.sdtgpu_comm_last_error(None) or b"").decode())
+
+    def close(self):
+        if self.c:
+            self.L.sdtgpu_comm_destroy(self.c)
+            self.c = C.c_void_p()
 
 
 def synth_reads_device(tr_dev: dict, seed: int, first_pair: int, n_pairs: int, read_len: int, stride_bytes: int,

@@ -39,9 +39,9 @@ def _worker(rank, world, port, K, kw, L, d, out_dir, mode):
     stride = synth.stride_bytes(L)
     d_packed = torch.from_numpy(synth.pack_reads(reads[lo:hi], lens[lo:hi], stride)).to(dev)
     d_lens = torch.from_numpy(lens[lo:hi].astype(np.int32)).to(dev)
-    g = pkg.PregraphGPU(K, kw, L, capacity_hint=1_500_000, device=rank, sliced=(mode == "skm"))
-    if mode == "skm":
-        ex = SkmExchange(pkg, g, world, rank, dev)
+    g = pkg.PregraphGPU(K, kw, L, capacity_hint=1_500_000, device=rank, sliced=mode.startswith("skm"))
+    if mode.startswith("skm"):      # skm_native: the exchange inside the library (sdtgpu_skm_exchange), NCCL bound by libsdtgpu.so itself
+        ex = SkmExchange(pkg, g, world, rank, dev, native=(mode == "skm_native"))
     elif mode == "records":
         ex = Exchange(pkg, g, world, rank, dev, max_round_instances=2048 * (L - K + 1))
     else:
@@ -61,7 +61,7 @@ def _worker(rank, world, port, K, kw, L, d, out_dir, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["reads", "records", "skm"])
+@pytest.mark.parametrize("mode", ["reads", "records", "skm", "skm_native"])
 @pytest.mark.parametrize("K,kw,L,d", [(25, 1, 100, 0), (63, 4, 100, 1), (127, 4, 150, 0)])
 def test_two_gpu_union_matches_oracle(pkg, oracle, tmp_path, K, kw, L, d, mode):
     import torch
