@@ -379,6 +379,7 @@ def main():
             exch = ReplicatedReads(pkg, g, world, rank, dev, max_round_reads=min(batch, n_reads), stride=stride)
 
     host_t = {"reset": 0.0, "push": 0.0, "flush": 0.0, "sync": 0.0, "n": 0}
+    step_calls = []
     step_wall, step_events = [], []       # per step: wall clock; [epochs emitted again, device allocations (both cumulative), retried items, work items]
 
     def one_step(gg):
@@ -401,6 +402,7 @@ def main():
             host_t[k] += 1e3 * v
         host_t["n"] += 1
         step_wall.append(round(1e3 * (t4 - t0), 2))
+        step_calls.append([round(1e3 * v, 2) for v in (t1 - t0, t2 - t1, t3 - t2, t4 - t3)])      # reset, push, flush, sync
         if sliced:
             geo_s = gg.slice_geometry()
             ph_s = gg.phase_times(reset=False)      # cumulative kernel times per phase: the difference between two steps tells which phase an outlier sat in
@@ -427,6 +429,7 @@ def main():
         host_t[k] = 0
     step_wall.clear()
     step_events.clear()
+    step_calls.clear()
     if exch is not None and hasattr(exch, "collective_ms"):
         exch.collective_ms = 0.0
         exch.host_ms = {}
@@ -446,6 +449,10 @@ def main():
     step_wall_timed = list(step_wall)       # host wall clock of every timed step (this rank): an outlier shows here
     step_events_timed = list(step_events)
     exch_log_timed = list(getattr(exch, "host_log", []) or [])      # per timed step: [bound, stage, exchange, import] ms on the host
+    if os.environ.get("BENCH_STEP_LOG"):     # diagnosis of outlier steps: every rank leaves its own per-step record
+        with open(os.path.join(os.environ["BENCH_STEP_LOG"], f"steps_rank{rank}.json"), "w") as f:
+            json.dump({"rank": rank, "step_wall_ms": step_wall_timed, "host_calls_ms": step_calls, "exchange_host_ms": exch_log_timed,
+                       "events": [e[:4] for e in step_events_timed]}, f)
     host_ms = {k: v / max(host_t["n"], 1) for k, v in host_t.items() if k != "n"}      # wall clock of the host calls of a timed step (this rank)
     st = g.stats()
     distinct = int(st.n_nodes)

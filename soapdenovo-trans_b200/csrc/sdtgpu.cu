@@ -1067,6 +1067,7 @@ int ensure_store (sdtgpu *h, u64 slots)
 		CK (h, cudaFree (h->table));
 	h->table = nullptr;
 	h->cap = 0;
+	h->n_alloc++;
 	CK (h, cudaMalloc (&h->table, slots * slot_bytes (h->W)));
 	h->cap = slots;
 	return SDTGPU_OK;
@@ -1298,7 +1299,12 @@ int skm_build_level (sdtgpu *h, ChainLevel &L, bool has_mult, u64 n_rec, u64 n_e
 	for (int attempt = 0;; attempt++)
 	{	// the store is rebuilt from all records: node cursor, failed-item count and the two counters start over.
 		// Its size: the hint's (or the estimate's) worth, never more than the windows the merge left
-		u64 want = win_upper == ~0ull ? h->cap : std::min<u64> (h->store_want, win_upper);
+		// (the windows the merge leaves vary a little from epoch to epoch on the same input — which copies meet in a
+		// chunk depends on the order records arrive in — and a store sized to the window would be freed and allocated
+		// again, 18 GB of it, whenever an epoch leaves a few more: 3 % of head room)
+		u64 want = h->cap;
+		if (win_upper != ~0ull && (!h->table || std::min<u64> (h->store_want, win_upper) > h->cap))
+			want = std::min<u64> (h->store_want, win_upper + win_upper / 32 + 65536);
 		if (want > h->cap || !h->table)
 		{	// no room for the node store beside the chains?  The chains are not needed any more (their records are
 			// merged): they go, and a later flush of this epoch emits the read log again
