@@ -372,7 +372,23 @@ def main():
     if world > 1:
         from soapdenovo_trans_b200.exchange import Exchange, ReplicatedReads, SkmExchange
         if sliced:
-            exch, exch_kind = SkmExchange(pkg, g, world, rank, dev, native=(args.skm_exchange == "native")), "skm"
+            native = args.skm_exchange == "native"
+            if native:      # the library's own NCCL binding; if ANY rank cannot set it up, all ranks drive the same exchange over torch.distributed
+                try:
+                    exch = SkmExchange(pkg, g, world, rank, dev, native=True)
+                    ok = torch.ones(1, dtype=torch.int32, device=dev)
+                except Exception as e:      # noqa: BLE001
+                    print(f"[bench] rank {rank}: native exchange unavailable ({e}); using torch.distributed", file=sys.stderr)
+                    exch, ok = None, torch.zeros(1, dtype=torch.int32, device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0:
+                    if exch is not None and exch.comm is not None:
+                        exch.comm.close()
+                    exch, native = None, False
+                    args.skm_exchange = "torch"
+            if exch is None:
+                exch = SkmExchange(pkg, g, world, rank, dev, native=False)
+            exch_kind = "skm"
         elif args.exchange == "records":
             exch = Exchange(pkg, g, world, rank, dev, max_round_instances=min(batch, n_reads) * nwin)
         else:

@@ -232,10 +232,15 @@ class SkmExchange:
         self.world, self.rank, self.dev, self.group = world, rank, dev, group
         self.comm = None
         if native:
-            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            uid, why = torch.zeros(128, dtype=torch.uint8, device=dev), ""
             if rank == 0:
-                uid.copy_(torch.frombuffer(bytearray(pkg.pregraph.SkmComm.unique_id()), dtype=torch.uint8))
+                try:
+                    uid.copy_(torch.frombuffer(bytearray(pkg.pregraph.SkmComm.unique_id()), dtype=torch.uint8))
+                except Exception as e:      # noqa: BLE001  (the other ranks are waiting in the broadcast: tell them with an all-zero id)
+                    why = str(e)
             dist.broadcast(uid, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+            if not bool(uid.any()):
+                raise RuntimeError(f"SkmExchange(native=True): no NCCL id from rank 0 {why}")
             self.comm = pkg.pregraph.SkmComm(torch.device(dev).index or 0, bytes(uid.cpu().numpy().tobytes()), rank, world)
         self.nvlink_bytes = 0
         self.collective_ms = 0.0        # device time of the counts + records exchange (CUDA events on the handle's stream)
