@@ -42,6 +42,22 @@ def test_create_rejects_bad_arguments_without_a_gpu(pkg):
         assert e.value.code == 1
 
 
+def test_exchange_calls_reject_bad_arguments_without_a_gpu(pkg):
+    """sdtgpu_comm_* / sdtgpu_skm_exchange (the super-k-mer exchange behind the C ABI): argument errors are
+    reported before NCCL or CUDA are touched."""
+    import ctypes as C
+    L = pkg.library()
+    c = C.c_void_p()
+    uid = (C.c_uint8 * 128)()
+    assert L.sdtgpu_comm_unique_id(None) == 1                               # SDTGPU_EINVAL
+    for rank, world in ((0, 0), (2, 2), (-1, 2), (0, 65)):
+        assert L.sdtgpu_comm_create(C.byref(c), 0, uid, rank, world) == 1 and not c.value
+        assert b"rank" in L.sdtgpu_comm_last_error(None)
+    assert L.sdtgpu_comm_create(None, 0, uid, 0, 1) == 1
+    assert L.sdtgpu_skm_exchange(None, None, 0, None, None) == 1
+    assert L.sdtgpu_comm_destroy(None) == 0
+
+
 @pytest.mark.parametrize("K,kw,p", [(25, 1, 8), (31, 1, 3), (45, 2, 8), (63, 4, 5), (127, 4, 8)])
 def test_kmerset_builder_reproduces_reference_layout(pkg, oracle, tiny_transcriptome, K, kw, p):
     L_read = 150 if K > 63 else 100
